@@ -1,0 +1,154 @@
+"""BrushGpu: one context of the C-ABI library (one GPU, one thread)."""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+
+EDGE_TYPES = ("ff", "fr", "rf", "rr")  # Node.java:78
+
+EDGE_DTYPE = np.dtype([("node", "<u4"), ("nbr", "<u4"), ("ov", "<u2"), ("type", "u1"), ("pad", "u1")])
+NODE_DTYPE = np.dtype([("line", "<u4"), ("cov", "<u4")])
+
+
+class BrushGpuError(IOError):
+    """Raised for every non-zero return of the C ABI (the Java shim raises IOException)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"{L.ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+@dataclass
+class BrushConfig:
+    """The BrushConfig options the path reads (BrushConfig.java:55-84, :207-406)."""
+    k: int = 21            # -k
+    readlen: int = 36      # -readlen
+    up_kmer: int = 2000    # -kmerup
+    low_kmer: int = 1      # -kmerlow
+    majority: float = 0.6  # -maj
+    pwm_n: float = 0.1     # -N
+    device: int = 0
+    rank: int = 0
+    world: int = 1
+
+
+class BrushGpu:
+    def __init__(self, cfg: BrushConfig):
+        self._L = L.load()
+        c = L.cb_config()
+        self._L.cb_default_config(C.byref(c))
+        c.k, c.readlen = cfg.k, cfg.readlen
+        c.up_kmer, c.low_kmer = cfg.up_kmer, cfg.low_kmer
+        c.majority, c.pwm_n = cfg.majority, cfg.pwm_n
+        c.device, c.rank, c.world = cfg.device, cfg.rank, cfg.world
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        rc = self._L.cb_create(C.byref(c), C.byref(self._h))
+        if rc != 0:
+            self._h = None
+            raise BrushGpuError(rc, "cb_create failed (a CUDA device is required; there is no CPU fallback)")
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cb_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BrushGpuError(rc, self._L.cb_last_error(self._h).decode(errors="replace"))
+
+    # -- input ----------------------------------------------------------------------------
+    def load_sfa(self, path):
+        self._check(self._L.cb_load_sfa(self._h, str(path).encode()))
+
+    def load_sfa_buffer(self, buf):
+        """buf: bytes / bytearray / numpy uint8 array / pinned torch uint8 CPU tensor."""
+        if hasattr(buf, "data_ptr"):
+            ptr, n = buf.data_ptr(), buf.numel()
+        elif isinstance(buf, np.ndarray):
+            ptr, n = buf.ctypes.data, buf.nbytes
+        else:
+            b = bytes(buf)
+            self._keep = b
+            ptr, n = C.cast(C.c_char_p(b), C.c_void_p).value, len(b)
+        self._check(self._L.cb_load_sfa_buffer(self._h, ptr, n))
+
+    def load_sfa_device(self, dev_ptr, n):
+        self._check(self._L.cb_load_sfa_device(self._h, dev_ptr, n))
+
+    # -- the three stage groups (BrushAssembler.java:256-379) --------------------------------
+    def preprocess(self):
+        self._check(self._L.cb_preprocess(self._h))
+
+    def build_overlap(self):
+        self._check(self._L.cb_build_overlap(self._h))
+
+    def string_graph(self):
+        self._check(self._L.cb_string_graph(self._h))
+
+    def run(self):
+        self.preprocess()
+        self.build_overlap()
+        self.string_graph()
+
+    # -- results --------------------------------------------------------------------------
+    def counter(self, name):
+        v = C.c_int64()
+        self._check(self._L.cb_get_counter(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+    def edges(self, checkpoint):
+        """structured array (node, nbr, ov, type) sorted by (node, type, nbr, ov)."""
+        n = C.c_size_t()
+        self._check(self._L.cb_export_edges(self._h, checkpoint, None, 0, C.byref(n)))
+        out = np.zeros(n.value, EDGE_DTYPE)
+        if n.value:
+            self._check(self._L.cb_export_edges(self._h, checkpoint, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def edge_rows(self, checkpoint):
+        """int64[n,4] rows (node line, type, nbr line, ov) -- the oracle's canonical form."""
+        e = self.edges(checkpoint)
+        return np.stack([e["node"].astype(np.int64), e["type"].astype(np.int64), e["nbr"].astype(np.int64),
+                         e["ov"].astype(np.int64)], axis=1) if len(e) else np.zeros((0, 4), np.int64)
+
+    def num_edges(self, checkpoint):
+        n = C.c_size_t()
+        self._check(self._L.cb_export_edges(self._h, checkpoint, None, 0, C.byref(n)))
+        return n.value
+
+    def nodes(self):
+        n = C.c_size_t()
+        self._check(self._L.cb_export_nodes(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, NODE_DTYPE)
+        if n.value:
+            self._check(self._L.cb_export_nodes(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def write_nodes(self, checkpoint, out_dir):
+        self._check(self._L.cb_write_nodes(self._h, checkpoint, str(out_dir).encode()))
+
+    def time_ms(self, what):
+        v = C.c_double()
+        self._check(self._L.cb_get_time_ms(self._h, what.encode(), C.byref(v)))
+        return v.value
+
+    def launch_count(self):
+        v = C.c_int64()
+        self._L.cb_get_launch_count(self._h, C.byref(v))
+        return v.value

@@ -1,0 +1,441 @@
+// capi.cu -- the C ABI of include/cloudbrush_gpu.h: context, input, counters, export, node text.
+#include <dirent.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+
+#include "ctx.cuh"
+
+namespace cb {
+
+void timer_start(cb_ctx* c, const char* name) {
+  Timer& t = c->timers[name];
+  if (!t.a) {
+    cudaEventCreate(&t.a);
+    cudaEventCreate(&t.b);
+  }
+  t.done = false;
+  cudaEventRecord(t.a, c->stream);
+}
+void timer_stop(cb_ctx* c, const char* name) {
+  Timer& t = c->timers[name];
+  cudaEventRecord(t.b, c->stream);
+  t.done = true;
+}
+
+void download_counters(cb_ctx* c) {
+  CB_CUDA(cudaMemcpyAsync(c->hcount, c->dcount.p, DC_COUNT * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+  CB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// canonical export order (node, type, nbr, ov): re-encode, sort, decode
+__global__ void __launch_bounds__(256) export_encode_kernel(const u64* __restrict__ in, size_t n, EdgeLayout lay,
+                                                            int K, u64* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 k = in[i];
+  u64 type = (u64)lay.x(k) * 2 + lay.y(k);
+  u64 ovf = (u64)(lay.ov(k) - (u32)K);  // K <= ov <= L, so ov - K fits ob bits
+  out[i] = ((u64)lay.node(k) << (lay.nb + lay.ob + 2)) | (type << (lay.nb + lay.ob)) | ((u64)lay.nbr(k) << lay.ob) | ovf;
+}
+__global__ void __launch_bounds__(256) export_decode_kernel(const u64* __restrict__ in, size_t n, EdgeLayout lay,
+                                                            int K, const u32* __restrict__ node_line,
+                                                            cb_edge* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 k = in[i];
+  cb_edge e;
+  e.node = node_line[(u32)(k >> (lay.nb + lay.ob + 2))];
+  e.type = (uint8_t)((k >> (lay.nb + lay.ob)) & 3);
+  e.nbr = node_line[(u32)((k >> lay.ob) & ((1ull << lay.nb) - 1))];
+  e.ov = (uint16_t)((u32)(k & ((1ull << lay.ob) - 1)) + (u32)K);
+  e.pad = 0;
+  out[i] = e;
+}
+
+__global__ void __launch_bounds__(256) export_nodes_kernel(const u32* __restrict__ node_line,
+                                                           const u32* __restrict__ node_cov, u32 n,
+                                                           cb_node* __restrict__ out) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cb_node v;
+  v.line = node_line[i];
+  v.cov = node_cov[i];
+  out[i] = v;
+}
+
+static const EdgeSet* edge_set(cb_ctx* c, int ck) {
+  switch (ck) {
+    case CB_CK_OVERLAP: return c->overlapped ? &c->ckA : nullptr;
+    case CB_CK_CHL2: return c->reduced ? (c->ckC_is_A ? &c->ckA : &c->ckC) : nullptr;
+    case CB_CK_RE: return c->reduced ? &c->ckB : nullptr;
+  }
+  return nullptr;
+}
+
+static void export_edges_host(cb_ctx* c, const EdgeSet& es, std::vector<cb_edge>& out) {
+  cudaStream_t s = c->stream;
+  out.resize(es.n);
+  if (es.n == 0) return;
+  DevBuf<u64> a, b;
+  a.alloc(es.n, s);
+  b.alloc(es.n, s);
+  export_encode_kernel<<<div_up(es.n, 256), 256, 0, s>>>(es.keys.p, es.n, c->lay, c->K, a.p);
+  int w = radix_sort(a.p, b.p, nullptr, nullptr, es.n, 0, c->lay.total_bits(), s, c->lc);
+  DevBuf<cb_edge> d;
+  d.alloc(es.n, s);
+  export_decode_kernel<<<div_up(es.n, 256), 256, 0, s>>>(w ? b.p : a.p, es.n, c->lay, c->K, c->node_line.p, d.p);
+  c->lc.n += 2;
+  CB_CUDA(cudaMemcpyAsync(out.data(), d.p, es.n * sizeof(cb_edge), cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+}
+
+static void read_file(const std::string& path, std::vector<char>& out) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw Error(CB_E_IO, "cannot open " + path);
+  f.seekg(0, std::ios::end);
+  std::streamoff sz = f.tellg();
+  f.seekg(0);
+  size_t at = out.size();
+  out.resize(at + (size_t)sz);
+  if (sz) f.read(out.data() + at, sz);
+  if (!out.empty() && out.back() != '\n' && out.back() != '\r') out.push_back('\n');  // files are split separately
+}
+
+// Node.str2dna (Node.java:186-211) over a 2-bit packed row
+static std::string encode_dna(const u64* row, int L) {
+  auto code = [&](int i) { return (int)((row[i >> 5] >> (62 - 2 * (i & 31))) & 3); };
+  std::string o;
+  int i = 0;
+  while (i < L) {
+    int r = L - i;
+    if (r >= 2) { o.push_back((char)('A' + 5 * code(i) + 1 + code(i + 1))); i += 2; }
+    else { o.push_back((char)('A' + 5 * code(i))); i += 1; }
+  }
+  return o;
+}
+
+static void reset_after_load(cb_ctx* c) {
+  c->loaded = true;
+  c->preprocessed = c->overlapped = c->reduced = false;
+  c->host_text.clear();
+  c->counters.clear();
+  c->ckA = EdgeSet();
+  c->ckC = EdgeSet();
+  c->ckB = EdgeSet();
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+#define CB_API_BEGIN(ctx)            \
+  if (!(ctx)) return CB_E_INVALID;   \
+  try {                              \
+    cudaSetDevice((ctx)->cfg.device);
+
+#define CB_API_END(ctx)                        \
+  }                                            \
+  catch (const cb::Error& e) {                 \
+    (ctx)->err = e.what();                     \
+    return e.code;                             \
+  }                                            \
+  catch (const std::bad_alloc&) {              \
+    (ctx)->err = "host allocation failed";     \
+    return CB_E_NOMEM;                         \
+  }                                            \
+  catch (const std::exception& e) {            \
+    (ctx)->err = e.what();                     \
+    return CB_E_INVALID;                       \
+  }                                            \
+  return CB_OK;
+
+extern "C" {
+
+const char* cb_version(void) { return "cloudbrush-b200 0.1 (sm_100a)"; }
+
+void cb_default_config(cb_config* cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->abi_version = CB_ABI_VERSION;
+  cfg->k = 21;
+  cfg->readlen = 36;
+  cfg->up_kmer = 2000;  // BrushConfig.java:84
+  cfg->low_kmer = 1;    // BrushConfig.java:83
+  cfg->majority = 0.6f; // BrushConfig.java:62
+  cfg->pwm_n = 0.1f;    // BrushConfig.java:63
+  cfg->device = 0;
+  cfg->rank = 0;
+  cfg->world = 1;
+}
+
+int cb_create(const cb_config* cfg, cb_ctx** out) {
+  if (!cfg || !out) return CB_E_INVALID;
+  *out = nullptr;
+  if (cfg->abi_version != CB_ABI_VERSION) return CB_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CB_E_NODEVICE;  // no CPU fallback
+  if (cfg->device < 0 || cfg->device >= ndev) return CB_E_NODEVICE;
+  cb_ctx* c = new (std::nothrow) cb_ctx();
+  if (!c) return CB_E_NOMEM;
+  c->cfg = *cfg;
+  if (cudaSetDevice(cfg->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return CB_E_CUDA;
+  }
+  // keep freed blocks in the pool: repeated runs must not pay cudaMalloc again
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = c;
+  return CB_OK;
+}
+
+void cb_destroy(cb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->timers) {
+    if (kv.second.a) cudaEventDestroy(kv.second.a);
+    if (kv.second.b) cudaEventDestroy(kv.second.b);
+  }
+  cudaStream_t s = c->stream;
+  delete c;  // DevBufs free stream-ordered
+  cudaStreamSynchronize(s);
+  cudaStreamDestroy(s);
+}
+
+const char* cb_last_error(const cb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int cb_load_sfa_device(cb_ctx* c, const void* dev_buf, size_t n) {
+  CB_API_BEGIN(c)
+  if (!dev_buf && n) throw Error(CB_E_INVALID, "null buffer");
+  c->text.alloc(n + 32, c->stream);
+  c->text_n = n;
+  if (n) CB_CUDA(cudaMemcpyAsync(c->text.p, dev_buf, n, cudaMemcpyDeviceToDevice, c->stream));
+  CB_CUDA(cudaMemsetAsync(c->text.p + n, 0, 32, c->stream));
+  reset_after_load(c);
+  CB_API_END(c)
+}
+
+int cb_load_sfa_buffer(cb_ctx* c, const char* buf, size_t n) {
+  CB_API_BEGIN(c)
+  if (!buf && n) throw Error(CB_E_INVALID, "null buffer");
+  c->text.alloc(n + 32, c->stream);
+  c->text_n = n;
+  if (n) CB_CUDA(cudaMemcpyAsync(c->text.p, buf, n, cudaMemcpyHostToDevice, c->stream));
+  CB_CUDA(cudaMemsetAsync(c->text.p + n, 0, 32, c->stream));
+  CB_CUDA(cudaStreamSynchronize(c->stream));  // the caller's buffer is only borrowed for the call
+  reset_after_load(c);
+  CB_API_END(c)
+}
+
+int cb_load_sfa(cb_ctx* c, const char* path) {
+  CB_API_BEGIN(c)
+  if (!path) throw Error(CB_E_INVALID, "null path");
+  struct stat st;
+  if (stat(path, &st) != 0) throw Error(CB_E_IO, std::string("cannot stat ") + path);
+  std::vector<char> all;
+  if (S_ISDIR(st.st_mode)) {
+    std::vector<std::string> names;
+    DIR* d = opendir(path);
+    if (!d) throw Error(CB_E_IO, std::string("cannot open directory ") + path);
+    while (dirent* de = readdir(d)) {
+      std::string nm = de->d_name;
+      if (nm.empty() || nm[0] == '.' || nm[0] == '_') continue;  // Hadoop hides . and _ files
+      std::string full = std::string(path) + "/" + nm;
+      struct stat fs;
+      if (stat(full.c_str(), &fs) == 0 && S_ISREG(fs.st_mode)) names.push_back(full);
+    }
+    closedir(d);
+    std::sort(names.begin(), names.end());
+    for (const std::string& f : names) read_file(f, all);
+  } else {
+    read_file(path, all);
+  }
+  int rc = cb_load_sfa_buffer(c, all.data(), all.size());
+  if (rc != CB_OK) return rc;
+  c->host_text.swap(all);
+  CB_API_END(c)
+}
+
+int cb_preprocess(cb_ctx* c) {
+  CB_API_BEGIN(c)
+  if (!c->loaded) throw Error(CB_E_INVALID, "cb_preprocess: no input loaded");
+  c->preprocessed = c->overlapped = c->reduced = false;
+  timer_start(c, "preprocess");
+  stage_parse_and_pack(c);
+  timer_stop(c, "preprocess");
+  c->preprocessed = true;
+  CB_API_END(c)
+}
+
+int cb_build_overlap(cb_ctx* c) {
+  CB_API_BEGIN(c)
+  if (!c->preprocessed) throw Error(CB_E_INVALID, "cb_build_overlap: call cb_preprocess first");
+  c->overlapped = c->reduced = false;
+  timer_start(c, "overlap");
+  stage_build_overlap(c);
+  timer_stop(c, "overlap");
+  c->overlapped = true;
+  CB_API_END(c)
+}
+
+int cb_string_graph(cb_ctx* c) {
+  CB_API_BEGIN(c)
+  if (!c->overlapped) throw Error(CB_E_INVALID, "cb_string_graph: call cb_build_overlap first");
+  c->reduced = false;
+  timer_start(c, "string");
+  stage_string_graph(c);
+  timer_stop(c, "string");
+  c->reduced = true;
+  CB_API_END(c)
+}
+
+int cb_get_counter(cb_ctx* c, const char* name, int64_t* value) {
+  if (!c || !name || !value) return CB_E_INVALID;
+  auto it = c->counters.find(name);
+  if (it == c->counters.end()) {
+    c->err = std::string("unknown counter ") + name;
+    return CB_E_INVALID;
+  }
+  *value = it->second;
+  return CB_OK;
+}
+
+int cb_export_edges(cb_ctx* c, int checkpoint, cb_edge* out, size_t cap, size_t* n) {
+  CB_API_BEGIN(c)
+  if (!n) throw Error(CB_E_INVALID, "null size pointer");
+  const EdgeSet* es = edge_set(c, checkpoint);
+  if (!es) throw Error(CB_E_INVALID, "checkpoint not available");
+  *n = es->n;
+  if (out && cap >= es->n && es->n) {
+    std::vector<cb_edge> tmp;
+    export_edges_host(c, *es, tmp);
+    memcpy(out, tmp.data(), tmp.size() * sizeof(cb_edge));
+  }
+  CB_API_END(c)
+}
+
+int cb_export_nodes(cb_ctx* c, cb_node* out, size_t cap, size_t* n) {
+  CB_API_BEGIN(c)
+  if (!n) throw Error(CB_E_INVALID, "null size pointer");
+  if (!c->preprocessed) throw Error(CB_E_INVALID, "nodes not available");
+  *n = c->n_nodes;
+  if (out && cap >= c->n_nodes && c->n_nodes) {
+    DevBuf<cb_node> d;
+    d.alloc(c->n_nodes, c->stream);
+    export_nodes_kernel<<<div_up(c->n_nodes, 256), 256, 0, c->stream>>>(c->node_line.p, c->node_cov.p, c->n_nodes, d.p);
+    c->lc.n++;
+    CB_CUDA(cudaMemcpyAsync(out, d.p, (size_t)c->n_nodes * sizeof(cb_node), cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  CB_API_END(c)
+}
+
+int cb_write_nodes(cb_ctx* c, int checkpoint, const char* out_dir) {
+  CB_API_BEGIN(c)
+  if (!out_dir) throw Error(CB_E_INVALID, "null path");
+  if (!c->preprocessed) throw Error(CB_E_INVALID, "nodes not available");
+  const EdgeSet* es = nullptr;
+  if (checkpoint != CB_CK_PREPROCESS) {
+    es = edge_set(c, checkpoint);
+    if (!es) throw Error(CB_E_INVALID, "checkpoint not available");
+  }
+  cudaStream_t s = c->stream;
+  if (c->host_text.empty() && c->text_n) {
+    c->host_text.resize(c->text_n);
+    CB_CUDA(cudaMemcpyAsync(c->host_text.data(), c->text.p, c->text_n, cudaMemcpyDeviceToHost, s));
+  }
+  const u32 nn = c->n_nodes;
+  std::vector<u32> line_start((size_t)c->n_lines + 1), node_line(nn), node_cov(nn);
+  std::vector<u64> seq((size_t)nn * c->NW);
+  CB_CUDA(cudaMemcpyAsync(line_start.data(), c->line_start.p, line_start.size() * 4, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaMemcpyAsync(node_line.data(), c->node_line.p, (size_t)nn * 4, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaMemcpyAsync(node_cov.data(), c->node_cov.p, (size_t)nn * 4, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaMemcpyAsync(seq.data(), c->node_seq.p, seq.size() * 8, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  std::vector<cb_edge> edges;
+  if (es) export_edges_host(c, *es, edges);
+  auto id_of = [&](u32 line) {
+    const char* p = c->host_text.data() + line_start[line];
+    const char* e = c->host_text.data() + line_start[line + 1];
+    const char* q = p;
+    while (q < e && *q != '\t') q++;
+    return std::string(p, q - p);
+  };
+  // FileSystem.delete(outputPath, true) then one part file (e.g. VerifyOverlap.java:379)
+  std::string dir(out_dir);
+  {
+    std::string part = dir + "/part-00000";
+    unlink(part.c_str());
+    DIR* d = opendir(dir.c_str());
+    if (d) {
+      while (dirent* de = readdir(d)) {
+        std::string nm = de->d_name;
+        if (nm == "." || nm == "..") continue;
+        unlink((dir + "/" + nm).c_str());
+      }
+      closedir(d);
+    }
+    mkdir(dir.c_str(), 0777);
+  }
+  std::ofstream f(dir + "/part-00000", std::ios::binary);
+  if (!f) throw Error(CB_E_IO, "cannot write " + dir + "/part-00000");
+  static const char* TY[4] = {"ff", "fr", "rf", "rr"};
+  size_t ei = 0;
+  std::string rec;
+  for (u32 i = 0; i < nn; i++) {
+    u32 line = node_line[i];
+    rec.clear();
+    rec += id_of(line);
+    rec += "\tN\t*s\t";
+    rec += encode_dna(seq.data() + (size_t)i * c->NW, c->L);
+    rec += "\t*v\t";
+    rec += std::to_string(node_cov[i]);
+    rec += ".00";  // DecimalFormat("0.00") of an integral coverage (Node.java:1761,1775)
+    int cur_type = -1;
+    while (ei < edges.size() && edges[ei].node == line) {
+      if ((int)edges[ei].type != cur_type) {
+        cur_type = edges[ei].type;
+        rec += "\t*";
+        rec += TY[cur_type];
+      }
+      rec += "\t";
+      rec += id_of(edges[ei].nbr);
+      rec += "!";
+      rec += std::to_string(edges[ei].ov);
+      ei++;
+    }
+    rec += "\n";
+    f.write(rec.data(), (std::streamsize)rec.size());
+  }
+  f.close();
+  if (!f) throw Error(CB_E_IO, "write failed in " + dir);
+  CB_API_END(c)
+}
+
+int cb_get_time_ms(cb_ctx* c, const char* what, double* ms) {
+  CB_API_BEGIN(c)
+  if (!what || !ms) throw Error(CB_E_INVALID, "null argument");
+  auto it = c->timers.find(what);
+  if (it == c->timers.end() || !it->second.done) throw Error(CB_E_INVALID, std::string("no such timer: ") + what);
+  CB_CUDA(cudaEventSynchronize(it->second.b));
+  float f = 0;
+  CB_CUDA(cudaEventElapsedTime(&f, it->second.a, it->second.b));
+  *ms = f;
+  CB_API_END(c)
+}
+
+int cb_get_launch_count(cb_ctx* c, int64_t* n) {
+  if (!c || !n) return CB_E_INVALID;
+  *n = c->lc.n;
+  return CB_OK;
+}
+
+}  // extern "C"

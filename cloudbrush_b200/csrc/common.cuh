@@ -1,0 +1,178 @@
+// common.cuh -- shared host/device helpers of the CloudBrush B200 path (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <stdexcept>
+
+#include "../../include/cloudbrush_gpu.h"
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef unsigned long long ull;
+
+namespace cb {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CB_CUDA(expr)                                                                           \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      throw cb::Error(_e == cudaErrorMemoryAllocation ? CB_E_NOMEM : CB_E_CUDA,                 \
+                      std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " + __FILE__ +  \
+                          ":" + std::to_string(__LINE__));                                      \
+  } while (0)
+
+// Stream-ordered device buffer (cudaMallocAsync pool: repeated runs reuse the same pages).
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t count, cudaStream_t stream) {
+    release();
+    s = stream;
+    n = count;
+    if (count) CB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), stream));
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+inline int div_up(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// 2-bit DNA words.  A read of L bases is ceil(L/32) u64 words, base i in word i/32 at bits
+// [63-2*(i%32)-1, 63-2*(i%32)] (MSB first), codes A=0 C=1 G=2 T=3, so that unsigned word-wise
+// comparison equals String.compareTo on the ACGT strings the reference compares
+// (e.g. MatchPrefix.java:122, GenNonContainedReads.java:193).  Unused low bits are zero.
+// ---------------------------------------------------------------------------------------------
+
+// reverse the order of the 32 2-bit groups of x and complement every base (A<->T, C<->G)
+__host__ __device__ __forceinline__ u64 revcomp_word(u64 x) {
+#ifdef __CUDA_ARCH__
+  u64 y = __brevll(x);
+#else
+  u64 y = 0;
+  for (int i = 0; i < 64; i++) y |= ((x >> i) & 1ull) << (63 - i);
+#endif
+  y = ((y & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((y & 0x5555555555555555ull) << 1);
+  return ~y;
+}
+
+// shift an NW-word base string left by nb bases (0 <= nb <= 32*NW), zero fill
+template <int NW>
+__host__ __device__ __forceinline__ void shl_bases(u64 (&a)[NW], int nb) {
+  int ws = nb >> 5, bs = (nb & 31) * 2;
+  u64 t[NW];
+#pragma unroll
+  for (int i = 0; i < NW; i++) {
+    int j = i + ws;
+    u64 hi = (j < NW) ? a[j < NW ? j : 0] : 0ull;
+    u64 lo = (j + 1 < NW) ? a[(j + 1) < NW ? (j + 1) : 0] : 0ull;
+    t[i] = bs ? ((hi << bs) | (lo >> (64 - bs))) : hi;
+  }
+#pragma unroll
+  for (int i = 0; i < NW; i++) a[i] = t[i];
+}
+
+// out = reverse complement of the L-base string in `in`
+template <int NW>
+__host__ __device__ __forceinline__ void revcomp_read(const u64 (&in)[NW], u64 (&out)[NW], int L) {
+#pragma unroll
+  for (int i = 0; i < NW; i++) out[i] = revcomp_word(in[NW - 1 - i]);
+  shl_bases<NW>(out, NW * 32 - L);
+}
+
+// keep the first nb bases, zero the rest
+template <int NW>
+__host__ __device__ __forceinline__ void keep_prefix(u64 (&a)[NW], int nb) {
+#pragma unroll
+  for (int i = 0; i < NW; i++) {
+    int lo = i * 32;
+    if (nb <= lo) a[i] = 0;
+    else if (nb < lo + 32) a[i] &= ~0ull << (64 - 2 * (nb - lo));
+  }
+}
+
+// do the first nb bases of a and b agree?
+template <int NW>
+__host__ __device__ __forceinline__ bool prefix_equal(const u64 (&a)[NW], const u64 (&b)[NW], int nb) {
+  u64 diff = 0;
+#pragma unroll
+  for (int i = 0; i < NW; i++) {
+    int lo = i * 32;
+    u64 x = a[i] ^ b[i];
+    if (nb <= lo) x = 0;
+    else if (nb < lo + 32) x &= ~0ull << (64 - 2 * (nb - lo));
+    diff |= x;
+  }
+  return diff == 0;
+}
+
+// the K-mer (K <= 31) starting at base `pos`, right aligned in 2K bits
+template <int NW>
+__host__ __device__ __forceinline__ u64 extract_kmer(const u64 (&a)[NW], int pos, int K) {
+  int w = pos >> 5, off = (pos & 31) * 2;
+  u64 hi = 0, lo = 0;
+#pragma unroll
+  for (int i = 0; i < NW; i++) {
+    if (i == w) hi = a[i];
+    if (i == w + 1) lo = a[i];
+  }
+  u64 top = off ? ((hi << off) | (lo >> (64 - off))) : hi;
+  return top >> (64 - 2 * K);
+}
+
+__host__ __device__ __forceinline__ u64 revcomp_kmer(u64 kmer, int K) {
+  return revcomp_word(kmer) >> (64 - 2 * K);
+}
+
+// lexicographic compare of NW-word strings (same length): -1/0/1
+template <int NW>
+__host__ __device__ __forceinline__ int cmp_words(const u64 (&a)[NW], const u64 (&b)[NW]) {
+#pragma unroll
+  for (int i = 0; i < NW; i++) {
+    if (a[i] < b[i]) return -1;
+    if (a[i] > b[i]) return 1;
+  }
+  return 0;
+}
+
+__host__ __device__ __forceinline__ u64 mix64(u64 x) {  // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+
+// 16-byte id key: the id bytes big-endian, zero padded.  Unsigned (hi, lo) order equals
+// String.compareTo for ASCII ids of <= 16 bytes (shorter-is-smaller on a common prefix).
+struct IdKey {
+  u64 hi, lo;
+};
+__host__ __device__ __forceinline__ bool idkey_less(const IdKey& a, const IdKey& b) {
+  return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+}
+
+}  // namespace cb

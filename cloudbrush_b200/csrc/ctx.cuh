@@ -1,0 +1,128 @@
+// ctx.cuh -- the context object behind the C ABI (include/cloudbrush_gpu.h) and the stage
+// entry points implemented in the stage_*.cu files.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "primitives.cuh"
+
+namespace cb {
+
+// device-side counters (one u64 each), downloaded after every stage group
+enum DevCounter {
+  DC_READS_GOOD = 0,
+  DC_READS_GOODBP,
+  DC_READS_SHORT,
+  DC_READS_SKIPPED,
+  DC_LINES_INVALID,
+  DC_LEN_MISMATCH,     // good reads whose length != -readlen (unsupported)
+  DC_LONG_ID,          // ids longer than 16 bytes (unsupported in this round)
+  DC_SURVIVORS,
+  DC_MAX_COV,
+  DC_TUPLES_INVALID,   // window slots that emit nothing (poly-A interior windows, palindromes)
+  DC_POLYA_WEIGHT,     // BuildHighKmerList weight of the all-A / all-T k-mer
+  DC_HKMER,
+  DC_EDGES_RAW,        // records appended by the join (edge + mirror)
+  DC_CAND_VERIFIED,    // verified, maximal candidates (|S|)
+  DC_UPKMER_LISTS,     // k-mer groups larger than UP_KMER (order dependent in the reference)
+  DC_EDGE_REMOVAL,
+  DC_TRANS_EDGE,
+  DC_CONTAINED_EDGE,
+  DC_TR_OVERFLOW,      // kept-list capacity of the literal TR scan exceeded
+  DC_SLOW_LISTS,       // (node, direction) lists that took the literal path
+  DC_COUNT
+};
+
+// Bit layout of one directed adjacency record in a u64, most significant field first:
+//   node | x | (L - ov) | y | nbr        x, y: 0 = 'f', 1 = 'r'
+// so that an ascending sort groups by node, then direction x, then overlap DEscending -- the
+// order CutChimericLinks / TransitiveReduction scan in (TransitiveReduction.java:175-221).
+struct EdgeLayout {
+  int nb = 0;  // bits of a node index
+  int ob = 0;  // bits of (L - ov)
+  int L = 0;
+  __host__ __device__ int total_bits() const { return 2 * nb + ob + 2; }
+  __host__ __device__ u64 encode(u32 node, u32 x, u32 ov, u32 y, u32 nbr) const {
+    return ((u64)node << (nb + ob + 2)) | ((u64)x << (nb + ob + 1)) | ((u64)(L - ov) << (nb + 1)) |
+           ((u64)y << nb) | (u64)nbr;
+  }
+  __host__ __device__ u32 node(u64 k) const { return (u32)(k >> (nb + ob + 2)); }
+  __host__ __device__ u32 x(u64 k) const { return (u32)(k >> (nb + ob + 1)) & 1u; }
+  __host__ __device__ u32 ov(u64 k) const { return (u32)L - ((u32)(k >> (nb + 1)) & ((1u << ob) - 1)); }
+  __host__ __device__ u32 y(u64 k) const { return (u32)(k >> nb) & 1u; }
+  __host__ __device__ u32 nbr(u64 k) const { return (u32)(k & ((1ull << nb) - 1)); }
+  __host__ __device__ u32 list(u64 k) const { return (u32)(k >> (nb + ob + 1)); }  // node*2 + x
+  __host__ __device__ u64 mirror(u64 k) const {  // Node.flip_link: xy -> flip(y) flip(x)
+    return encode(nbr(k), y(k) ^ 1u, ov(k), x(k) ^ 1u, node(k));
+  }
+};
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  bool done = false;
+};
+
+struct EdgeSet {
+  DevBuf<u64> keys;      // sorted, unique
+  DevBuf<u32> adj_off;   // [2*n_nodes + 1] start of list (node, x)
+  size_t n = 0;
+  bool valid = false;
+};
+
+}  // namespace cb
+
+struct cb_ctx {
+  cb_config cfg;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  cb::LaunchCounter lc;
+  std::map<std::string, int64_t> counters;
+  std::map<std::string, cb::Timer> timers;
+
+  // input text
+  cb::DevBuf<char> text;
+  size_t text_n = 0;
+  std::vector<char> host_text;  // filled lazily (ids are only needed when node text is written)
+  bool loaded = false, preprocessed = false, overlapped = false, reduced = false;
+
+  // parse
+  u32 n_lines = 0;
+  int L = 0, K = 0, NW = 0, W = 0;  // read length, k, words per read, windows per read
+  cb::DevBuf<u32> line_start;       // [n_lines + 1]
+  cb::DevBuf<uint8_t> status;       // [n_lines] 0 good, 1 invalid, 2 skipped, 3 short
+  cb::DevBuf<u64> reads;            // [n_lines][NW]
+  cb::DevBuf<cb::IdKey> idkey;      // [n_lines]
+  cb::DevBuf<u64> dcount;           // [DC_COUNT]
+  uint64_t hcount[cb::DC_COUNT] = {0};
+
+  // nodes (00-preprocess)
+  u32 n_nodes = 0;
+  cb::DevBuf<u32> node_line;
+  cb::DevBuf<u64> node_seq;         // [n_nodes][NW]
+  cb::DevBuf<cb::IdKey> node_idkey;
+  cb::DevBuf<u32> node_cov;
+
+  // graph
+  cb::EdgeLayout lay;
+  cb::EdgeSet ckA, ckC, ckB;        // 01-overlap, 01-overlap.chl2, 01-overlap.re
+  bool ckC_is_A = false;
+};
+
+namespace cb {
+
+void timer_start(cb_ctx* c, const char* name);
+void timer_stop(cb_ctx* c, const char* name);
+void download_counters(cb_ctx* c);
+
+// stage_preprocess.cu
+void stage_parse_and_pack(cb_ctx* c);
+void stage_dedupe(cb_ctx* c);
+// stage_overlap.cu
+void stage_build_overlap(cb_ctx* c);
+// stage_string.cu
+void build_adjacency(cb_ctx* c, EdgeSet& es);
+void stage_string_graph(cb_ctx* c);
+
+}  // namespace cb

@@ -1,0 +1,298 @@
+// primitives.cu -- device-wide exclusive scan and LSD radix sort for the shuffle replacement.
+//
+// The Hadoop shuffle of MatchPrefix (reference: JobClient.runJob at MatchPrefix.java:468 --
+// HashPartitioner + sort by Text key + group) is replaced by a stable LSD radix sort of
+// (canonical k-mer key, payload) tuples.  One pass over an 8-bit digit is:
+//   rs_upsweep   per-tile digit histogram (shared-memory staged, warp-aggregated atomics)
+//   rs_chunk_sums / rs_chunk_scan / rs_apply   column-wise exclusive scan of the tile histograms
+//   rs_scatter   stable in-tile ranking with __match_any_sync, shared-memory staged so that each
+//                digit run leaves the SM as one contiguous, coalesced store
+// HBM traffic per pass: 8 B (keys, histogram) + 12 B read + 12 B write per tuple.
+#include "primitives.cuh"
+
+namespace cb {
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan
+// ------------------------------------------------------------------------------------------
+constexpr int SC_THREADS = 512;
+constexpr int SC_ITEMS = 8;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
+
+__device__ __forceinline__ u32 warp_incl_scan(u32 v) {
+  int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    u32 t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one value per thread across the block; `total` receives the block sum.
+// tmp must hold (blockDim.x / 32) u32.
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32* tmp, u32& total) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  u32 inc = warp_incl_scan(v);
+  if (lane == 31) tmp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    u32 w = lane < nw ? tmp[lane] : 0;
+    u32 wi = warp_incl_scan(w);
+    if (lane < nw) tmp[lane] = wi - w;
+    if (lane == nw - 1) tmp[nw] = wi;
+  }
+  __syncthreads();
+  u32 r = tmp[warp] + inc - v;
+  total = tmp[nw];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) scan_tile_kernel(const u32* __restrict__ in, u32* __restrict__ out,
+                                                               u32* __restrict__ block_sums, size_t n) {
+  __shared__ u32 tmp[SC_THREADS / 32 + 1];
+  size_t base = (size_t)blockIdx.x * SC_TILE + (size_t)threadIdx.x * SC_ITEMS;
+  u32 v[SC_ITEMS];
+  u32 sum = 0;
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++) {
+    v[i] = (base + i < n) ? in[base + i] : 0;
+    sum += v[i];
+  }
+  u32 total;
+  u32 ex = block_excl_scan(sum, tmp, total);
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++) {
+    if (base + i < n) out[base + i] = ex;
+    ex += v[i];
+  }
+  if (threadIdx.x == 0 && block_sums) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) scan_add_kernel(u32* __restrict__ out, const u32* __restrict__ block_offs,
+                                                              size_t n) {
+  size_t base = (size_t)blockIdx.x * SC_TILE + (size_t)threadIdx.x * SC_ITEMS;
+  u32 o = block_offs[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SC_ITEMS; i++)
+    if (base + i < n) out[base + i] += o;
+}
+
+void exclusive_scan_u32(const u32* in, u32* out, size_t n, cudaStream_t s, LaunchCounter& lc) {
+  if (n == 0) return;
+  size_t nb = (n + SC_TILE - 1) / SC_TILE;
+  if (nb == 1) {
+    scan_tile_kernel<<<1, SC_THREADS, 0, s>>>(in, out, nullptr, n);
+    lc.n++;
+    CB_CUDA(cudaGetLastError());
+    return;
+  }
+  DevBuf<u32> sums;
+  sums.alloc(nb, s);
+  scan_tile_kernel<<<(unsigned)nb, SC_THREADS, 0, s>>>(in, out, sums.p, n);
+  lc.n++;
+  CB_CUDA(cudaGetLastError());
+  exclusive_scan_u32(sums.p, sums.p, nb, s, lc);
+  scan_add_kernel<<<(unsigned)nb, SC_THREADS, 0, s>>>(out, sums.p, n);
+  lc.n++;
+  CB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------
+// radix sort
+// ------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_SUB = RS_THREADS * RS_ITEMS;  // 4096 elements ranked at a time
+constexpr int RS_SUBTILES = 4;
+constexpr int RS_TILE = RS_SUB * RS_SUBTILES;  // 16384 elements per block
+
+__global__ void __launch_bounds__(RS_THREADS) rs_upsweep(const u64* __restrict__ kin, u32* __restrict__ hist, size_t n,
+                                                         int shift, u32 mask) {
+  __shared__ u32 h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  size_t base = (size_t)blockIdx.x * RS_TILE;
+  int lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int i = 0; i < RS_TILE / RS_THREADS; i++) {
+    size_t idx = base + (size_t)i * RS_THREADS + threadIdx.x;
+    bool valid = idx < n;
+    u32 d = valid ? (u32)((kin[valid ? idx : 0] >> shift) & mask) : 0xffffffffu;
+    u32 peers = __match_any_sync(0xffffffffu, d);
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(&h[d], __popc(peers));
+  }
+  __syncthreads();
+  hist[(size_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
+}
+
+// column sums of hist rows [r0, r1) of chunk blockIdx.x
+__global__ void __launch_bounds__(256) rs_chunk_sums(const u32* __restrict__ hist, u32* __restrict__ chunk_sum,
+                                                     int tiles, int rows_per_chunk) {
+  int r0 = blockIdx.x * rows_per_chunk, r1 = min(tiles, r0 + rows_per_chunk);
+  u32 s = 0;
+  for (int r = r0; r < r1; r++) s += hist[(size_t)r * 256 + threadIdx.x];
+  chunk_sum[(size_t)blockIdx.x * 256 + threadIdx.x] = s;
+}
+
+// one block: chunk_sum[c][d] -> exclusive base of (digit d, chunk c) in the sorted output
+__global__ void __launch_bounds__(256) rs_chunk_scan(u32* __restrict__ chunk_sum, int chunks) {
+  __shared__ u32 tmp[256 / 32 + 1];
+  u32 run = 0;
+  for (int c = 0; c < chunks; c++) {
+    u32 v = chunk_sum[(size_t)c * 256 + threadIdx.x];
+    chunk_sum[(size_t)c * 256 + threadIdx.x] = run;
+    run += v;
+  }
+  u32 total;
+  u32 dbase = block_excl_scan(run, tmp, total);
+  for (int c = 0; c < chunks; c++) chunk_sum[(size_t)c * 256 + threadIdx.x] += dbase;
+}
+
+__global__ void __launch_bounds__(256) rs_apply(u32* __restrict__ hist, const u32* __restrict__ chunk_base, int tiles,
+                                                int rows_per_chunk) {
+  int r0 = blockIdx.x * rows_per_chunk, r1 = min(tiles, r0 + rows_per_chunk);
+  u32 run = chunk_base[(size_t)blockIdx.x * 256 + threadIdx.x];
+  for (int r = r0; r < r1; r++) {
+    u32 v = hist[(size_t)r * 256 + threadIdx.x];
+    hist[(size_t)r * 256 + threadIdx.x] = run;
+    run += v;
+  }
+}
+
+template <bool HAS_VALS>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const u64* __restrict__ kin, u64* __restrict__ kout,
+                                                         const u32* __restrict__ vin, u32* __restrict__ vout,
+                                                         const u32* __restrict__ offsets, size_t n, int shift,
+                                                         u32 mask) {
+  __shared__ u32 warp_hist[RS_WARPS][256];
+  __shared__ u32 digit_base[256];
+  __shared__ u32 sub_start[256];
+  __shared__ u32 scan_tmp[RS_WARPS + 1];
+  __shared__ u64 stage[RS_SUB];
+  __shared__ unsigned char sorted_digit[RS_SUB];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt_mask = (1u << lane) - 1;
+  digit_base[tid] = offsets[(size_t)blockIdx.x * 256 + tid];
+
+  for (int sub = 0; sub < RS_SUBTILES; sub++) {
+    size_t base = (size_t)blockIdx.x * RS_TILE + (size_t)sub * RS_SUB;
+    if (base >= n) break;  // uniform across the block
+    int nvalid = (int)min((size_t)RS_SUB, n - base);
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) warp_hist[w][tid] = 0;
+    __syncthreads();
+
+    u64 key[RS_ITEMS];
+    u32 pos[RS_ITEMS];
+    // warp-striped: element order inside the sub-tile is (warp, item, lane) == ascending index
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+      int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
+      key[i] = (e < nvalid) ? kin[base + e] : ~0ull;
+    }
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+      int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
+      u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;  // padding ranks last
+      u32 peers = __match_any_sync(0xffffffffu, d);
+      u32 prev = warp_hist[warp][d];
+      __syncwarp();
+      if (lane == __ffs(peers) - 1) warp_hist[warp][d] = prev + __popc(peers);
+      __syncwarp();
+      pos[i] = prev + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+    // per digit (thread tid): exclusive scan over the warps, then over the digits
+    u32 run = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) {
+      u32 c = warp_hist[w][tid];
+      warp_hist[w][tid] = run;
+      run += c;
+    }
+    u32 total;
+    u32 dstart = block_excl_scan(run, scan_tmp, total);
+    sub_start[tid] = dstart;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+      int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
+      u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;
+      pos[i] += sub_start[d] + warp_hist[warp][d];
+      stage[pos[i]] = key[i];
+      sorted_digit[pos[i]] = (unsigned char)d;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < RS_ITEMS; j++) {
+      int p = j * RS_THREADS + tid;
+      if (p < nvalid) {
+        u32 d = sorted_digit[p];
+        kout[digit_base[d] + (p - sub_start[d])] = stage[p];
+      }
+    }
+    if (HAS_VALS) {
+      __syncthreads();
+      u32* vstage = reinterpret_cast<u32*>(stage);
+#pragma unroll
+      for (int i = 0; i < RS_ITEMS; i++) {
+        int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
+        vstage[pos[i]] = (e < nvalid) ? vin[base + e] : 0u;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int j = 0; j < RS_ITEMS; j++) {
+        int p = j * RS_THREADS + tid;
+        if (p < nvalid) {
+          u32 d = sorted_digit[p];
+          vout[digit_base[d] + (p - sub_start[d])] = vstage[p];
+        }
+      }
+    }
+    __syncthreads();
+    digit_base[tid] += run;  // padding only inflates digit 255 of the very last sub-tile
+    __syncthreads();
+  }
+}
+
+int radix_sort(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int begin_bit, int end_bit,
+               cudaStream_t s, LaunchCounter& lc) {
+  if (n == 0 || end_bit <= begin_bit) return 0;
+  if (n >= (1ull << 32)) throw Error(CB_E_CAPACITY, "radix_sort: more than 2^32-1 elements");
+  int tiles = (int)((n + RS_TILE - 1) / RS_TILE);
+  int chunks = tiles < 4 * kNumSMs ? tiles : 4 * kNumSMs;
+  int rows_per_chunk = (tiles + chunks - 1) / chunks;
+  chunks = (tiles + rows_per_chunk - 1) / rows_per_chunk;
+  DevBuf<u32> hist, chunk;
+  hist.alloc((size_t)tiles * 256, s);
+  chunk.alloc((size_t)chunks * 256, s);
+  u64* kin = keys_a;
+  u64* kout = keys_b;
+  u32* vin = vals_a;
+  u32* vout = vals_b;
+  int where = 0;
+  for (int bit = begin_bit; bit < end_bit; bit += 8) {
+    int nbits = end_bit - bit < 8 ? end_bit - bit : 8;
+    u32 mask = (1u << nbits) - 1;
+    rs_upsweep<<<tiles, RS_THREADS, 0, s>>>(kin, hist.p, n, bit, mask);
+    rs_chunk_sums<<<chunks, 256, 0, s>>>(hist.p, chunk.p, tiles, rows_per_chunk);
+    rs_chunk_scan<<<1, 256, 0, s>>>(chunk.p, chunks);
+    rs_apply<<<chunks, 256, 0, s>>>(hist.p, chunk.p, tiles, rows_per_chunk);
+    if (vin)
+      rs_scatter<true><<<tiles, RS_THREADS, 0, s>>>(kin, kout, vin, vout, hist.p, n, bit, mask);
+    else
+      rs_scatter<false><<<tiles, RS_THREADS, 0, s>>>(kin, kout, nullptr, nullptr, hist.p, n, bit, mask);
+    lc.n += 5;
+    CB_CUDA(cudaGetLastError());
+    u64* tk = kin; kin = kout; kout = tk;
+    u32* tv = vin; vin = vout; vout = tv;
+    where ^= 1;
+  }
+  return where;
+}
+
+}  // namespace cb

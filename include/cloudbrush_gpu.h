@@ -1,0 +1,141 @@
+/* cloudbrush_gpu.h -- C ABI of the B200 overlap-discovery + transitive-reduction path.
+ *
+ * This is the drop-in boundary for the Brush stages of CloudBrush's hot path
+ * (reference: src/Brush/BrushAssembler.java:256-379):
+ *
+ *   cb_preprocess      replaces  GenNonContainedReads.run   (GenNonContainedReads.java:256-289)
+ *                                RedundantRemoval.run       (RedundantRemoval.java:107-139)
+ *                                BuildHighKmerList.run      (BuildHighKmerList.java:121-153)
+ *   cb_build_overlap   replaces  MatchPrefix.run            (MatchPrefix.java:435-469)
+ *                                VerifyOverlap.run          (VerifyOverlap.java:348-382)
+ *                                GenReverseEdge.run         (GenReverseEdge.java:248-280)
+ *   cb_string_graph    replaces  CutChimericLinks.run x<=2  (CutChimericLinks.java:415-450)
+ *                                EdgeRemoval.run x<=3       (EdgeRemoval.java:207-242)
+ *                                TransitiveReduction.run    (TransitiveReduction.java:549-583)
+ *   cb_get_counter     replaces  RunningJob.getCounters().findCounter("Brush", name)
+ *                                                           (BrushAssembler.java:124-127)
+ *   cb_write_nodes     replaces  the TextOutputFormat part files of 00-preprocess, 01-overlap,
+ *                                01-overlap.chl2, 01-overlap.re in Node.toNodeMsg format
+ *                                                           (Node.java:1757-1982)
+ *   cb_load_sfa*       replaces  TextInputFormat over the -reads directory (id \t SEQ lines,
+ *                                data/preprocessor.pl:27-52)
+ *
+ * Conventions: plain C types only; every function returns 0 (CB_OK) or a negative CB_E* code
+ * and never throws or exits; one context per thread; a context owns all device memory and one
+ * CUDA stream; host buffers passed in are borrowed for the duration of the call only.  There is
+ * NO CPU fallback: without a CUDA device cb_create fails with CB_E_NODEVICE.
+ *
+ * The Java side (java/Brush/GpuOverlap.java + java/jni/cloudbrush_jni.c)
+ * maps a non-zero return to IOException so BrushAssembler.end(job) behaves as before.
+ */
+#ifndef CLOUDBRUSH_GPU_H
+#define CLOUDBRUSH_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_ABI_VERSION 1
+
+enum {
+  CB_OK = 0,
+  CB_E_INVALID = -1,      /* bad argument / call order */
+  CB_E_NODEVICE = -2,     /* no CUDA device / driver */
+  CB_E_CUDA = -3,         /* CUDA runtime error (message in cb_last_error) */
+  CB_E_NOMEM = -4,        /* device or host allocation failed */
+  CB_E_IO = -5,           /* file could not be read / written */
+  CB_E_NOREADS = -6,      /* reads_good == 0  (BrushAssembler.java:273-276 "No good reads") */
+  CB_E_UNSUPPORTED = -7,  /* input outside the supported contract */
+  CB_E_CAPACITY = -8      /* an internal fixed capacity was exceeded */
+};
+
+/* Checkpoints (directories under <asm>.tmp/ in the reference, BrushAssembler.java:75-89). */
+enum {
+  CB_CK_PREPROCESS = 0, /* 00-preprocess      : nodes, no edges            */
+  CB_CK_OVERLAP = 1,    /* 01-overlap         : checkpoint A               */
+  CB_CK_CHL2 = 2,       /* 01-overlap.chl2    : after CutChimericLinks     */
+  CB_CK_RE = 3          /* 01-overlap.re      : checkpoint B               */
+};
+
+/* BrushConfig.java:55-84 -- the options the path reads (defaults in cb_default_config). */
+typedef struct cb_config {
+  int32_t abi_version; /* CB_ABI_VERSION */
+  int32_t k;           /* -k        (BrushConfig.K)        odd, 1 <= k <= 31           */
+  int32_t readlen;     /* -readlen  (BrushConfig.READLEN)                              */
+  int64_t up_kmer;     /* -kmerup   (UP_KMER  = 2000)                                  */
+  int64_t low_kmer;    /* -kmerlow  (LOW_KMER = 1)                                     */
+  float majority;      /* -maj      (MAJORITY = 0.6f)                                  */
+  float pwm_n;         /* -N        (PWM_N    = 0.1f)                                  */
+  int32_t device;      /* CUDA device ordinal                                          */
+  int32_t rank;        /* this process' shard index   (0 for a single GPU)             */
+  int32_t world;       /* number of shards / GPUs     (1 for a single GPU)             */
+  int32_t reserved[5];
+} cb_config;
+
+/* One directed adjacency entry: the last `ov` bases of read `node` in orientation x equal the
+ * first `ov` bases of read `nbr` in orientation y; type = 0 ff, 1 fr, 2 rf, 3 rr (Node.java:78).
+ * `node` / `nbr` are 0-based line indices of the SFA input. */
+typedef struct cb_edge {
+  uint32_t node;
+  uint32_t nbr;
+  uint16_t ov;
+  uint8_t type;
+  uint8_t pad;
+} cb_edge;
+
+/* One node of the graph (00-preprocess and later): SFA line, coverage (*v). */
+typedef struct cb_node {
+  uint32_t line;
+  uint32_t cov;
+} cb_node;
+
+typedef struct cb_ctx cb_ctx;
+
+void cb_default_config(cb_config* cfg);
+int cb_create(const cb_config* cfg, cb_ctx** out);
+void cb_destroy(cb_ctx* ctx);
+const char* cb_last_error(const cb_ctx* ctx); /* library-owned, valid until the next call */
+const char* cb_version(void);
+
+/* Input: SFA text ("id\tSEQ[\tQ]\n" lines).  cb_load_sfa reads a file or every regular file of
+ * a directory (sorted by name); cb_load_sfa_buffer copies a caller-owned host buffer to the
+ * device; cb_load_sfa_device adopts nothing and copies from a caller-owned DEVICE buffer. */
+int cb_load_sfa(cb_ctx* ctx, const char* path_or_dir);
+int cb_load_sfa_buffer(cb_ctx* ctx, const char* buf, size_t n);
+int cb_load_sfa_device(cb_ctx* ctx, const void* dev_buf, size_t n);
+
+/* The three stage groups, run to completion on the calling thread (see top of file). */
+int cb_preprocess(cb_ctx* ctx);
+int cb_build_overlap(cb_ctx* ctx);
+int cb_string_graph(cb_ctx* ctx);
+
+/* Hadoop counters of group "Brush" with the reference's names: reads_good, reads_goodbp,
+ * reads_short, reads_skipped, input_lines_invalid, contained, nodecount, redundant, nodes,
+ * hkmer, edge_removal, edge_removal_1, edge_removal_2, trans_edge, contained_edge; plus the
+ * library's own: tuples, candidates_verified, edges_overlap, edges_chl2, edges_re,
+ * order_dependent, upkmer_truncated_lists.  Unknown name -> CB_E_INVALID. */
+int cb_get_counter(cb_ctx* ctx, const char* name, int64_t* value);
+
+/* Size query then fill (out == NULL or cap too small -> *n is set, nothing is written).
+ * Edges come sorted by (node, type, nbr, ov); nodes by line. */
+int cb_export_edges(cb_ctx* ctx, int checkpoint, cb_edge* out, size_t cap, size_t* n);
+int cb_export_nodes(cb_ctx* ctx, cb_node* out, size_t cap, size_t* n);
+
+/* Writes <out_dir>/part-00000 in Node.toNodeMsg format (out_dir is deleted first, like
+ * FileSystem.delete(outputPath, true) in every stage's run()). */
+int cb_write_nodes(cb_ctx* ctx, int checkpoint, const char* out_dir);
+
+/* Device time (ms, CUDA events) of the last run of a stage group: "preprocess", "overlap",
+ * "string", or one of the per-kernel-group names listed in DESIGN.md ("sort_tuples", ...). */
+int cb_get_time_ms(cb_ctx* ctx, const char* what, double* ms);
+
+/* Number of kernel launches issued by this context since creation. */
+int cb_get_launch_count(cb_ctx* ctx, int64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOUDBRUSH_GPU_H */
