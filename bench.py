@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the CloudBrush overlap-discovery + transitive-reduction hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config cfg2] [--genome G]
+
+A "step" is one pass of the whole hot path (SFA text -> checkpoint-B edge list) over one batch of
+synthetic reads.  At N=1 the workload is BASELINE.json configs[1]
+("synthetic E. coli-size (4.6 Mb) random genome, 36 bp reads at 100x, k=21").
+
+  value   reads/s with the ASCII SFA bytes already resident in HBM when the timed region starts
+          (device time, CUDA events on the library's stream: preprocess + overlap + string groups)
+  e2e     reads/s through the public C-ABI call sequence with HOST buffers: pinned-host SFA ->
+          cb_load_sfa_buffer (H2D) -> cb_preprocess/cb_build_overlap/cb_string_graph ->
+          cb_export_edges(checkpoint B) + cb_export_nodes (D2H), wall clock
+  roofline  the dominant kernel (rs_scatter of the k-mer tuple sort): algorithmic bytes per launch
+          (24 B per tuple: 12 B read + 12 B written) / its mean CUDA-event duration, against the
+          measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the CPU restatement oracle ("port", 1 core) on a bounded sample of the same workload
+
+`--impl reference` times the reference's CPU algorithm (the oracle port -- the reference itself is
+Java/Hadoop and cannot run in this image) on all host cores over bounded samples.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads_per_sec"
+UNIT = "reads/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------
+def make_workload(name, genome=None, seed_shift=0):
+    from cloudbrush_b200 import synth
+    G, L, cov, both, k, seed = synth.CONFIGS[name]
+    if genome:
+        G = genome
+    codes = synth.synth_reads(G, L, cov, both, seed + seed_shift)
+    sfa = synth.sfa_bytes(codes)
+    return sfa, dict(genome=G, readlen=L, coverage=cov, both_strands=both, k=k, n_reads=int(codes.shape[0]))
+
+
+def cpu_sample_genome(meta, target_reads=250_000):
+    g = int(target_reads * meta["readlen"] / meta["coverage"])
+    return max(10_000, min(g, meta["genome"]))
+
+
+def run_oracle_once(sfa_bytes_, k, L):
+    from oracle import oracle as O
+    t = time.perf_counter()
+    r = O.OracleRun(sfa_bytes_, k, L)
+    dt = time.perf_counter() - t
+    if r.error:
+        raise RuntimeError(r.error)
+    ea = r.counter("GenReverseEdge:nodes")  # forces nothing; edges counted below
+    n_edges_a = len(r.edges(O.CK_A))
+    r.close()
+    return dt, n_edges_a
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the CPU algorithm on all host cores, bounded samples
+# --------------------------------------------------------------------------------------------
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    name = args.config
+    from cloudbrush_b200 import synth
+    G, L, cov, both, k, seed = synth.CONFIGS[name]
+    meta = dict(genome=args.genome or G, readlen=L, coverage=cov, both_strands=both, k=k)
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, args.ref_threads or cores, 32))
+    sample_g = cpu_sample_genome(meta, target_reads=args.ref_sample_reads)
+    samples = []
+    for t in range(threads):  # one independent sample (own genome seed) per host thread
+        sfa, m = make_workload(name, genome=sample_g, seed_shift=1000 + t)
+        samples.append((bytes(sfa), m))
+    n_reads = sum(m["n_reads"] for _, m in samples)
+
+    def step():
+        res = [None] * threads
+
+        def work(i):
+            res[i] = run_oracle_once(samples[i][0], k, L)
+
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        return time.perf_counter() - t0, sum(r[1] for r in res)
+
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        step()
+    times, edges = [], 0
+    for _ in range(args.steps):
+        dt, e = step()
+        times.append(dt)
+        edges = e
+    t = float(np.mean(times))
+    value = n_reads / t
+    sample_desc = (f"{threads} independent samples (one per host thread) of {samples[0][1]['n_reads']} reads each: "
+                   f"{sample_g} bp random genome, {L} bp reads at {cov}x, k={k}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"{name}: {meta['genome']} bp random genome, {L} bp reads at {cov}x, k={k} "
+                               f"(timed on bounded samples)", "sample": sample_desc},
+        "edges_per_sec": edges / t,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+KERNELS = ["parse_lines", "dedupe_runs", "keygen", "join_verify", "cut", "tr",
+           "rs_scatter:dedupe", "rs_upsweep:dedupe", "rs_scatter:tuples", "rs_upsweep:tuples",
+           "rs_scatter:edges", "rs_upsweep:edges", "rs_scatter:export", "rs_upsweep:export"]
+
+
+def bench_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cloudbrush_b200 import BrushConfig, BrushGpu
+    from cloudbrush_b200 import _lib as L_
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    name = args.config
+    t0 = time.time()
+    sfa_np, meta = make_workload(name, genome=args.genome)
+    log(f"[rank {rank}] workload {name}: {meta} ({len(sfa_np)/1e6:.1f} MB SFA) generated in {time.time()-t0:.1f}s")
+    k, L = meta["k"], meta["readlen"]
+    n_reads = meta["n_reads"]
+
+    host = torch.from_numpy(sfa_np).pin_memory()
+    dev = host.cuda(non_blocking=False)
+    g = BrushGpu(BrushConfig(k=k, readlen=L, device=local_rank, rank=rank, world=world))
+
+    def step_resident():
+        g.borrow_sfa_device(dev.data_ptr(), dev.numel())
+        g.run()
+        return g.time_ms("preprocess") + g.time_ms("overlap") + g.time_ms("string")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    g.set_profile(True)
+    l0 = g.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    w0 = time.perf_counter()
+    dev_ms = []
+    for _ in range(args.steps):
+        dev_ms.append(step_resident())
+    barrier()
+    wall = (time.perf_counter() - w0) / args.steps
+    clocks = sampler.stop()
+    launches = g.launch_count() - l0
+    stats = {kn: g.kernel_stat(kn) for kn in KERNELS}
+    g.set_profile(False)
+    ms = float(np.mean(dev_ms))
+    counters = {c: g.counter(c) for c in ["reads_good", "nodes", "tuples", "candidates_verified", "edges_overlap",
+                                          "edges_chl2", "edges_re", "trans_edge", "edge_removal_1", "slow_lists"]}
+    stage_ms = {t: g.time_ms(t) for t in ["parse", "dedupe", "keygen", "sort_tuples", "join_verify", "sort_edges",
+                                          "cut", "tr"]}
+
+    # ---- e2e through the C ABI with host buffers ----
+    e2e_t = []
+    d2h = 0
+    for i in range(max(1, min(args.steps, 3)) + 1):
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        g.load_sfa_buffer(host)
+        g.run()
+        eb = g.edges(L_.CK_RE)
+        nd = g.nodes()
+        dt = time.perf_counter() - t1
+        d2h = eb.nbytes + nd.nbytes
+        if i > 0:  # first one warms the export path
+            e2e_t.append(dt)
+    e2e_s = float(np.mean(e2e_t))
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1]) / 1e3
+        tot = torch.tensor([n_reads, counters["edges_overlap"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        total_reads, total_edges = float(tot[0]), float(tot[1])
+    else:
+        total_reads, total_edges = float(n_reads), float(counters["edges_overlap"])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        # dominant kernel
+        W = L - k + 1
+        T_slots = counters["nodes"] * W
+        st = stats.get("rs_scatter:tuples")
+        roof = None
+        if st and st[1] > 0:
+            per_launch_ms = st[0] / st[1]
+            alg_bytes = 24.0 * T_slots
+            achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+            traffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                traffic = tj.get("rs_scatter:tuples", {}).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+            roof = {"bound": "hbm", "kernel": "rs_scatter<pairs> (k-mer tuple sort, one 8-bit LSD pass)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
+                    "ms_per_launch": per_launch_ms, "launches_per_step": st[1] / args.steps,
+                    "share_of_step": st[0] / args.steps / ms}
+        kern = {kn: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+                for kn, v in stats.items() if v}
+        # ---- CPU baseline (oracle port, 1 core, bounded sample) ----
+        cpu = None
+        if not args.no_cpu_baseline:
+            sg = cpu_sample_genome(meta, target_reads=args.cpu_sample_reads)
+            ssfa, sm = make_workload(name, genome=sg, seed_shift=1000)
+            dt, _ = run_oracle_once(bytes(ssfa), k, L)
+            cpu = {"value": sm["n_reads"] / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{sm['n_reads']} reads: {sg} bp random genome, {L} bp reads at {meta['coverage']}x, "
+                             f"k={k} (oracle/brush_oracle.cpp, single thread, {dt:.1f}s)"}
+        line = {
+            "metric": METRIC, "value": total_reads / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{name}: {meta['genome']} bp random genome, {L} bp reads at "
+                                   f"{meta['coverage']}x{' both strands' if meta['both_strands'] else ''}, k={k}, "
+                                   f"{n_reads} reads per GPU",
+                       "l2": "inputs larger than L2 (SFA text and tuple arrays exceed 126 MB)" if len(sfa_np) > 126e6
+                             else "input smaller than L2 (reduced run)",
+                       "sharding": "one shard per GPU" if world > 1 else "single GPU"},
+            "edges_per_sec": total_edges / (ms * 1e-3),
+            "wall_ms_per_step": wall * 1e3,
+            "e2e": {"value": total_reads / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(len(sfa_np)),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "counters": counters,
+            "stage_ms": stage_ms,
+            "kernels": kern,
+        }
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--genome", type=int, default=None, help="override the genome length (reduced runs)")
+    ap.add_argument("--cpu-sample-reads", type=int, default=250_000)
+    ap.add_argument("--ref-sample-reads", type=int, default=120_000)
+    ap.add_argument("--ref-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,19 @@ class BrushGpu:
     def load_sfa_device(self, dev_ptr, n):
         self._check(self._L.cb_load_sfa_device(self._h, dev_ptr, n))
 
+    def borrow_sfa_device(self, dev_ptr, n):
+        """Zero-copy: the context reads the caller's device buffer in place."""
+        self._check(self._L.cb_borrow_sfa_device(self._h, dev_ptr, n))
+
+    def set_profile(self, on=True):
+        self._check(self._L.cb_set_profile(self._h, 1 if on else 0))
+
+    def kernel_stat(self, name):
+        """(total ms, launches) of one instrumented kernel since set_profile(True); None if never launched."""
+        ms, n = C.c_double(), C.c_int64()
+        rc = self._L.cb_get_kernel_stat(self._h, name.encode(), C.byref(ms), C.byref(n))
+        return (ms.value, n.value) if rc == 0 else None
+
     # -- the three stage groups (BrushAssembler.java:256-379) --------------------------------
     def preprocess(self):
         self._check(self._L.cb_preprocess(self._h))

@@ -84,7 +84,7 @@ static void export_edges_host(cb_ctx* c, const EdgeSet& es, std::vector<cb_edge>
   a.alloc(es.n, s);
   b.alloc(es.n, s);
   export_encode_kernel<<<div_up(es.n, 256), 256, 0, s>>>(es.keys.p, es.n, c->lay, c->K, a.p);
-  int w = radix_sort(a.p, b.p, nullptr, nullptr, es.n, 0, c->lay.total_bits(), s, c->lc);
+  int w = radix_sort(a.p, b.p, nullptr, nullptr, es.n, 0, c->lay.total_bits(), s, c->lc, "export");
   DevBuf<cb_edge> d;
   d.alloc(es.n, s);
   export_decode_kernel<<<div_up(es.n, 256), 256, 0, s>>>(w ? b.p : a.p, es.n, c->lay, c->K, c->node_line.p, d.p);
@@ -192,6 +192,7 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
+  c->lc.stream = c->stream;
   *out = c;
   return CB_OK;
 }
@@ -219,8 +220,38 @@ int cb_load_sfa_device(cb_ctx* c, const void* dev_buf, size_t n) {
   c->text_n = n;
   if (n) CB_CUDA(cudaMemcpyAsync(c->text.p, dev_buf, n, cudaMemcpyDeviceToDevice, c->stream));
   CB_CUDA(cudaMemsetAsync(c->text.p + n, 0, 32, c->stream));
+  c->text_ptr = c->text.p;
   reset_after_load(c);
   CB_API_END(c)
+}
+
+int cb_borrow_sfa_device(cb_ctx* c, const void* dev_buf, size_t n) {
+  CB_API_BEGIN(c)
+  if (!dev_buf && n) throw Error(CB_E_INVALID, "null buffer");
+  c->text.release();
+  c->text_ptr = (const char*)dev_buf;
+  c->text_n = n;
+  reset_after_load(c);
+  CB_API_END(c)
+}
+
+int cb_set_profile(cb_ctx* c, int on) {
+  if (!c) return CB_E_INVALID;
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->stream);
+  c->lc.profile = on != 0;
+  c->lc.reset();
+  return CB_OK;
+}
+
+int cb_get_kernel_stat(cb_ctx* c, const char* name, double* total_ms, int64_t* launches) {
+  if (!c || !name || !total_ms || !launches) return CB_E_INVALID;
+  cudaSetDevice(c->cfg.device);
+  if (!c->lc.query(name, *total_ms, *launches)) {
+    c->err = std::string("no such kernel stat: ") + name;
+    return CB_E_INVALID;
+  }
+  return CB_OK;
 }
 
 int cb_load_sfa_buffer(cb_ctx* c, const char* buf, size_t n) {
@@ -231,6 +262,7 @@ int cb_load_sfa_buffer(cb_ctx* c, const char* buf, size_t n) {
   if (n) CB_CUDA(cudaMemcpyAsync(c->text.p, buf, n, cudaMemcpyHostToDevice, c->stream));
   CB_CUDA(cudaMemsetAsync(c->text.p + n, 0, 32, c->stream));
   CB_CUDA(cudaStreamSynchronize(c->stream));  // the caller's buffer is only borrowed for the call
+  c->text_ptr = c->text.p;
   reset_after_load(c);
   CB_API_END(c)
 }
@@ -350,7 +382,7 @@ int cb_write_nodes(cb_ctx* c, int checkpoint, const char* out_dir) {
   cudaStream_t s = c->stream;
   if (c->host_text.empty() && c->text_n) {
     c->host_text.resize(c->text_n);
-    CB_CUDA(cudaMemcpyAsync(c->host_text.data(), c->text.p, c->text_n, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaMemcpyAsync(c->host_text.data(), c->text_ptr, c->text_n, cudaMemcpyDeviceToHost, s));
   }
   const u32 nn = c->n_nodes;
   std::vector<u32> line_start((size_t)c->n_lines + 1), node_line(nn), node_cov(nn);

@@ -82,7 +82,8 @@ struct cb_ctx {
   std::map<std::string, cb::Timer> timers;
 
   // input text
-  cb::DevBuf<char> text;
+  cb::DevBuf<char> text;          // owned copy (cb_load_sfa / cb_load_sfa_buffer / cb_load_sfa_device)
+  const char* text_ptr = nullptr; // what the kernels read: text.p or a borrowed device buffer
   size_t text_n = 0;
   std::vector<char> host_text;  // filled lazily (ids are only needed when node text is written)
   bool loaded = false, preprocessed = false, overlapped = false, reduced = false;

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const u64* __restrict__
 }
 
 int radix_sort(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int begin_bit, int end_bit,
-               cudaStream_t s, LaunchCounter& lc) {
+               cudaStream_t s, LaunchCounter& lc, const char* tag) {
   if (n == 0 || end_bit <= begin_bit) return 0;
   if (n >= (1ull << 32)) throw Error(CB_E_CAPACITY, "radix_sort: more than 2^32-1 elements");
   int tiles = (int)((n + RS_TILE - 1) / RS_TILE);
@@ -270,6 +270,9 @@ int radix_sort(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int
   DevBuf<u32> hist, chunk;
   hist.alloc((size_t)tiles * 256, s);
   chunk.alloc((size_t)chunks * 256, s);
+  const std::string nm_up_s = std::string("rs_upsweep:") + tag, nm_sc_s = std::string("rs_scatter:") + tag;
+  const char* nm_up = nm_up_s.c_str();
+  const char* nm_sc = nm_sc_s.c_str();
   u64* kin = keys_a;
   u64* kout = keys_b;
   u32* vin = vals_a;
@@ -278,14 +281,18 @@ int radix_sort(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int
   for (int bit = begin_bit; bit < end_bit; bit += 8) {
     int nbits = end_bit - bit < 8 ? end_bit - bit : 8;
     u32 mask = (1u << nbits) - 1;
+    lc.begin(nm_up);
     rs_upsweep<<<tiles, RS_THREADS, 0, s>>>(kin, hist.p, n, bit, mask);
+    lc.end(nm_up);
     rs_chunk_sums<<<chunks, 256, 0, s>>>(hist.p, chunk.p, tiles, rows_per_chunk);
     rs_chunk_scan<<<1, 256, 0, s>>>(chunk.p, chunks);
     rs_apply<<<chunks, 256, 0, s>>>(hist.p, chunk.p, tiles, rows_per_chunk);
+    lc.begin(nm_sc);
     if (vin)
       rs_scatter<true><<<tiles, RS_THREADS, 0, s>>>(kin, kout, vin, vout, hist.p, n, bit, mask);
     else
       rs_scatter<false><<<tiles, RS_THREADS, 0, s>>>(kin, kout, nullptr, nullptr, hist.p, n, bit, mask);
+    lc.end(nm_sc);
     lc.n += 5;
     CB_CUDA(cudaGetLastError());
     u64* tk = kin; kin = kout; kout = tk;

@@ -364,8 +364,10 @@ void stage_build_overlap(cb_ctx* c) {
     int blocks = div_up((size_t)nn * 32, 256);
     int cap = kNumSMs * 8 * 4;
     if (blocks > cap) blocks = cap;
+    c->lc.begin("keygen");
     CB_DISPATCH_NW(c->NW, (keygen_kernel<NW_><<<blocks, 256, 0, s>>>(c->node_seq.p, c->node_cov.p, nn, L, K, W, pb,
                                                                     keys[0].p, vals[0].p, (ull*)c->dcount.p)));
+    c->lc.end("keygen");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
   }
@@ -373,7 +375,7 @@ void stage_build_overlap(cb_ctx* c) {
 
   // ---- shuffle replacement ----
   timer_start(c, "sort_tuples");
-  int where = radix_sort(keys[0].p, keys[1].p, vals[0].p, vals[1].p, Tmax, 0, 2 * K, s, c->lc);
+  int where = radix_sort(keys[0].p, keys[1].p, vals[0].p, vals[1].p, Tmax, 0, 2 * K, s, c->lc, "tuples");
   timer_stop(c, "sort_tuples");
   download_counters(c);
   const u32 T = (u32)(Tmax - c->hcount[DC_TUPLES_INVALID]);
@@ -407,7 +409,9 @@ void stage_build_overlap(cb_ctx* c) {
     int blocks = kNumSMs * 8;
     int need = div_up(((size_t)T + 31) / 32, JN_WARPS);
     if (need < blocks) blocks = need > 0 ? need : 1;
+    c->lc.begin("join_verify");
     CB_DISPATCH_NW(c->NW, (join_verify_kernel<NW_><<<blocks, JN_WARPS * 32, 0, s>>>(P)));
+    c->lc.end("join_verify");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
     download_counters(c);
@@ -435,7 +439,7 @@ void stage_build_overlap(cb_ctx* c) {
   timer_start(c, "sort_edges");
   DevBuf<u64> raw2;
   raw2.alloc(n_raw, s);
-  int w2 = radix_sort(raw.p, raw2.p, nullptr, nullptr, n_raw, 0, c->lay.total_bits(), s, c->lc);
+  int w2 = radix_sort(raw.p, raw2.p, nullptr, nullptr, n_raw, 0, c->lay.total_bits(), s, c->lc, "edges");
   u64* sorted = w2 ? raw2.p : raw.p;
   DevBuf<u32> flag;
   flag.alloc(n_raw, s);

@@ -306,21 +306,21 @@ void stage_parse_and_pack(cb_ctx* c) {
   DevBuf<u32> bcnt, boff;
   bcnt.alloc(nb, s);
   boff.alloc(nb, s);
-  count_terms_kernel<<<nb, PT_THREADS, 0, s>>>(c->text.p, n, bcnt.p);
+  count_terms_kernel<<<nb, PT_THREADS, 0, s>>>(c->text_ptr, n, bcnt.p);
   c->lc.n++;
   exclusive_scan_u32(bcnt.p, boff.p, nb, s, c->lc);
   u32 last_cnt = 0, last_off = 0;
   char last_byte = 0;
   CB_CUDA(cudaMemcpyAsync(&last_cnt, bcnt.p + nb - 1, 4, cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaMemcpyAsync(&last_off, boff.p + nb - 1, 4, cudaMemcpyDeviceToHost, s));
-  CB_CUDA(cudaMemcpyAsync(&last_byte, c->text.p + n - 1, 1, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaMemcpyAsync(&last_byte, c->text_ptr + n - 1, 1, cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
   u32 terms = last_cnt + last_off;
   bool last_is_term = (last_byte == '\n' || last_byte == '\r');
   c->n_lines = terms + (last_is_term ? 0 : 1);
   c->line_start.alloc((size_t)c->n_lines + 1, s);
   set_u32_kernel<<<1, 1, 0, s>>>(c->line_start.p, 0u);
-  fill_line_starts_kernel<<<nb, PT_THREADS, 0, s>>>(c->text.p, n, boff.p, c->line_start.p);
+  fill_line_starts_kernel<<<nb, PT_THREADS, 0, s>>>(c->text_ptr, n, boff.p, c->line_start.p);
   set_u32_kernel<<<1, 1, 0, s>>>(c->line_start.p + c->n_lines, (u32)n);
   c->lc.n += 3;
 
@@ -333,9 +333,11 @@ void stage_parse_and_pack(cb_ctx* c) {
   DevBuf<u32> hv[2];
   {
     for (int i = 0; i < 2; i++) { hk[i].alloc(nl, s); hv[i].alloc(nl, s); }
+    c->lc.begin("parse_lines");
     CB_DISPATCH_NW(c->NW, (parse_lines_kernel<NW_><<<div_up(nl, 128), 128, 0, s>>>(
-                              c->text.p, c->line_start.p, nl, c->K, c->L, c->status.p, c->reads.p, c->idkey.p,
+                              c->text_ptr, c->line_start.p, nl, c->K, c->L, c->status.p, c->reads.p, c->idkey.p,
                               hk[0].p, hv[0].p, (ull*)c->dcount.p)));
+    c->lc.end("parse_lines");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
     timer_stop(c, "parse");
@@ -354,15 +356,17 @@ void stage_parse_and_pack(cb_ctx* c) {
     int hb = ((bits + 16 + 7) / 8) * 8;
     if (hb > 64) hb = 64;
     const u64 keymask = hb == 64 ? ~0ull : ((1ull << hb) - 1);
-    int where = radix_sort(hk[0].p, hk[1].p, hv[0].p, hv[1].p, nl, 0, hb, s, c->lc);
+    int where = radix_sort(hk[0].p, hk[1].p, hv[0].p, hv[1].p, nl, 0, hb, s, c->lc, "dedupe");
     DevBuf<u32> surv_flag, surv_idx, cov;
     surv_flag.alloc(nl, s);
     surv_idx.alloc(nl, s);
     cov.alloc(nl, s);
     CB_CUDA(cudaMemsetAsync(surv_flag.p, 0, (size_t)nl * 4, s));
+    c->lc.begin("dedupe_runs");
     CB_DISPATCH_NW(c->NW, (dedupe_runs_kernel<NW_><<<div_up(n_good, 128), 128, 0, s>>>(
                               hk[where].p, hv[where].p, n_good, keymask, c->reads.p, c->idkey.p, c->L, surv_flag.p,
                               cov.p, (ull*)c->dcount.p)));
+    c->lc.end("dedupe_runs");
     c->lc.n++;
     exclusive_scan_u32(surv_flag.p, surv_idx.p, nl, s, c->lc);
     download_counters(c);

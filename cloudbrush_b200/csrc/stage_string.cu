@@ -414,7 +414,9 @@ static int64_t cut_round(cb_ctx* c, const EdgeSet& in, EdgeSet& out, bool& chang
   CB_CUDA(cudaMemsetAsync(removed.p, 0, in.n, s));
   StringParams P = make_params(c, in);
   P.removed = removed.p;
+  c->lc.begin("cut");
   CB_DISPATCH_NW(c->NW, (cut_kernel<NW_><<<list_grid(P.n_lists), ST_WARPS * 32, 0, s>>>(P)));
+  c->lc.end("cut");
   c->lc.n++;
   CB_CUDA(cudaGetLastError());
   download_counters(c);
@@ -468,7 +470,9 @@ void stage_string_graph(cb_ctx* c) {
     CB_CUDA(cudaMemsetAsync(kept.p, 0, C.n, s));
     StringParams P = make_params(c, C);
     P.kept = kept.p;
+    c->lc.begin("tr");
     CB_DISPATCH_NW(c->NW, (tr_kernel<NW_><<<list_grid(P.n_lists), ST_WARPS * 32, 0, s>>>(P)));
+    c->lc.end("tr");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
     DevBuf<u32> flag;

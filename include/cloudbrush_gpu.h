@@ -106,6 +106,9 @@ const char* cb_version(void);
 int cb_load_sfa(cb_ctx* ctx, const char* path_or_dir);
 int cb_load_sfa_buffer(cb_ctx* ctx, const char* buf, size_t n);
 int cb_load_sfa_device(cb_ctx* ctx, const void* dev_buf, size_t n);
+/* Zero-copy variant: the context reads the caller's DEVICE buffer in place; it must stay valid
+ * and unchanged until the next cb_load_* / cb_borrow_* / cb_destroy. */
+int cb_borrow_sfa_device(cb_ctx* ctx, const void* dev_buf, size_t n);
 
 /* The three stage groups, run to completion on the calling thread (see top of file). */
 int cb_preprocess(cb_ctx* ctx);
@@ -134,6 +137,14 @@ int cb_get_time_ms(cb_ctx* ctx, const char* what, double* ms);
 
 /* Number of kernel launches issued by this context since creation. */
 int cb_get_launch_count(cb_ctx* ctx, int64_t* n);
+
+/* Per-kernel device timing.  cb_set_profile(ctx, 1) clears the statistics and makes every
+ * instrumented kernel launch be bracketed by CUDA events on the context's stream;
+ * cb_get_kernel_stat returns the summed duration and the launch count of one kernel
+ * ("rs_scatter:<sort>" and "rs_upsweep:<sort>" with <sort> in tuples, dedupe, edges, export; "parse_lines",
+ * "dedupe_runs", "keygen", "join_verify", "cut", "tr"). */
+int cb_set_profile(cb_ctx* ctx, int on);
+int cb_get_kernel_stat(cb_ctx* ctx, const char* name, double* total_ms, int64_t* launches);
 
 #ifdef __cplusplus
 }
