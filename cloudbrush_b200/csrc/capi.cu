@@ -31,15 +31,25 @@ void download_counters(cb_ctx* c) {
   CB_CUDA(cudaStreamSynchronize(c->stream));
 }
 
-// canonical export order (node, type, nbr, ov): re-encode, sort, decode
-__global__ void __launch_bounds__(256) export_encode_kernel(const u64* __restrict__ in, size_t n, EdgeLayout lay,
+// canonical export order (node, type, nbr, ov): gather the lists, re-encode, sort, decode
+__global__ void __launch_bounds__(256) export_gather_kernel(const u64* __restrict__ keys,
+                                                            const u32* __restrict__ adj_off,
+                                                            const u32* __restrict__ cnt,
+                                                            const u32* __restrict__ coff, u32 n_lists, EdgeLayout lay,
                                                             int K, u64* __restrict__ out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  u64 k = in[i];
-  u64 type = (u64)lay.x(k) * 2 + lay.y(k);
-  u64 ovf = (u64)(lay.ov(k) - (u32)K);  // K <= ov <= L, so ov - K fits ob bits
-  out[i] = ((u64)lay.node(k) << (lay.nb + lay.ob + 2)) | (type << (lay.nb + lay.ob)) | ((u64)lay.nbr(k) << lay.ob) | ovf;
+  const int lane = threadIdx.x & 31;
+  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 lid = warp_global; lid < n_lists; lid += nwarps) {
+    const u32 n = cnt[lid], src = adj_off[lid], dst = coff[lid];
+    for (u32 t = lane; t < n; t += 32) {
+      u64 k = keys[src + t];
+      u64 type = (u64)lay.x(k) * 2 + lay.y(k);
+      u64 ovf = (u64)(lay.ov(k) - (u32)K);  // K <= ov <= L, so ov - K fits ob bits
+      out[dst + t] = ((u64)lay.node(k) << (lay.nb + lay.ob + 2)) | (type << (lay.nb + lay.ob)) |
+                     ((u64)lay.nbr(k) << lay.ob) | ovf;
+    }
+  }
 }
 __global__ void __launch_bounds__(256) export_decode_kernel(const u64* __restrict__ in, size_t n, EdgeLayout lay,
                                                             int K, const u32* __restrict__ node_line,
@@ -80,10 +90,18 @@ static void export_edges_host(cb_ctx* c, const EdgeSet& es, std::vector<cb_edge>
   cudaStream_t s = c->stream;
   out.resize(es.n);
   if (es.n == 0) return;
+  const u32 n_lists = 2 * c->n_nodes;
+  DevBuf<u32> coff;
+  coff.alloc((size_t)n_lists + 1, s);
+  CB_CUDA(cudaMemcpyAsync(coff.p, es.cnt.p, (size_t)n_lists * 4, cudaMemcpyDeviceToDevice, s));
+  CB_CUDA(cudaMemsetAsync(coff.p + n_lists, 0, 4, s));
+  exclusive_scan_u32(coff.p, coff.p, (size_t)n_lists + 1, s, c->lc);
   DevBuf<u64> a, b;
   a.alloc(es.n, s);
   b.alloc(es.n, s);
-  export_encode_kernel<<<div_up(es.n, 256), 256, 0, s>>>(es.keys.p, es.n, c->lay, c->K, a.p);
+  int blocks = div_up((size_t)n_lists, 8);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  export_gather_kernel<<<blocks, 256, 0, s>>>(es.keys.p, c->adj_off.p, es.cnt.p, coff.p, n_lists, c->lay, c->K, a.p);
   int w = radix_sort(a.p, b.p, nullptr, nullptr, es.n, 0, c->lay.total_bits(), s, c->lc, "export");
   DevBuf<cb_edge> d;
   d.alloc(es.n, s);
@@ -135,7 +153,8 @@ using namespace cb;
 #define CB_API_BEGIN(ctx)            \
   if (!(ctx)) return CB_E_INVALID;   \
   try {                              \
-    cudaSetDevice((ctx)->cfg.device);
+    cudaSetDevice((ctx)->cfg.device); \
+    cb::current_arena() = &(ctx)->arena;
 
 #define CB_API_END(ctx)                        \
   }                                            \
@@ -186,12 +205,6 @@ int cb_create(const cb_config* cfg, cb_ctx** out) {
     delete c;
     return CB_E_CUDA;
   }
-  // keep freed blocks in the pool: repeated runs must not pay cudaMalloc again
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
   c->lc.stream = c->stream;
   *out = c;
   return CB_OK;
@@ -206,8 +219,7 @@ void cb_destroy(cb_ctx* c) {
     if (kv.second.b) cudaEventDestroy(kv.second.b);
   }
   cudaStream_t s = c->stream;
-  delete c;  // DevBufs free stream-ordered
-  cudaStreamSynchronize(s);
+  delete c;  // DevBufs return to the arena, the arena returns everything to the driver
   cudaStreamDestroy(s);
 }
 
@@ -331,6 +343,8 @@ int cb_string_graph(cb_ctx* c) {
 
 int cb_get_counter(cb_ctx* c, const char* name, int64_t* value) {
   if (!c || !name || !value) return CB_E_INVALID;
+  if (!strcmp(name, "pool_reserved_bytes")) { *value = (int64_t)c->arena.reserved; return CB_OK; }
+  if (!strcmp(name, "pool_used_bytes")) { *value = (int64_t)c->arena.in_use; return CB_OK; }
   auto it = c->counters.find(name);
   if (it == c->counters.end()) {
     c->err = std::string("unknown counter ") + name;

@@ -3,8 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
 #include <string>
 #include <stdexcept>
+#include <unordered_map>
 
 #include "../../include/cloudbrush_gpu.h"
 
@@ -30,29 +32,95 @@ struct Error : public std::runtime_error {
                           ":" + std::to_string(__LINE__));                                      \
   } while (0)
 
-// Stream-ordered device buffer (cudaMallocAsync pool: repeated runs reuse the same pages).
+// Per-context caching device allocator.  Every stage of the path allocates the same buffer
+// sizes run after run, so freed blocks are kept in a size-ordered free list and handed out again
+// (all work of a context is on one stream, so reuse right after free is stream-ordered and
+// safe).  cudaMalloc/cudaFree are only paid while the cache warms up.  (The driver's
+// cudaMallocAsync pool showed sporadic ~0.8 s remapping stalls on this workload.)
+struct Arena {
+  std::multimap<size_t, void*> free_;
+  std::unordered_map<void*, size_t> size_;
+  size_t reserved = 0, in_use = 0;
+  static size_t round_up(size_t b) {
+    if (b < 512) return 512;
+    size_t g = b >= (8u << 20) ? (2u << 20) : 512;
+    return (b + g - 1) / g * g;
+  }
+  void* alloc(size_t bytes) {
+    bytes = round_up(bytes);
+    auto it = free_.lower_bound(bytes);
+    if (it != free_.end() && it->first <= bytes + bytes / 8 + 4096) {
+      void* p = it->second;
+      in_use += it->first;
+      free_.erase(it);
+      return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      trim();
+      e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      throw cb::Error(CB_E_NOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    size_[p] = bytes;
+    reserved += bytes;
+    in_use += bytes;
+    return p;
+  }
+  void free(void* p) {
+    auto it = size_.find(p);
+    if (it == size_.end()) return;
+    in_use -= it->second;
+    free_.insert({it->second, p});
+  }
+  void trim() {  // give every cached block back to the driver
+    for (auto& kv : free_) {
+      cudaFree(kv.second);
+      reserved -= kv.first;
+      size_.erase(kv.second);
+    }
+    free_.clear();
+  }
+  ~Arena() {
+    trim();
+    for (auto& kv : size_) cudaFree(kv.first);
+  }
+};
+
+// the arena of the context whose API call is running on this thread (set by CB_API_BEGIN)
+inline Arena*& current_arena() {
+  static thread_local Arena* a = nullptr;
+  return a;
+}
+
+// Device buffer owned by the current context's arena.
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
-  cudaStream_t s = 0;
+  Arena* a = nullptr;
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), a(o.a) { o.p = nullptr; o.n = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; a = o.a; o.p = nullptr; o.n = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
-  void alloc(size_t count, cudaStream_t stream) {
+  void alloc(size_t count, cudaStream_t) {
     release();
-    s = stream;
+    a = current_arena();
+    if (!a) throw cb::Error(CB_E_INVALID, "device allocation outside an API call");
     n = count;
-    if (count) CB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), stream));
+    if (count) p = (T*)a->alloc(count * sizeof(T));
   }
   void release() {
-    if (p) cudaFreeAsync(p, s);
+    if (p && a) a->free(p);
     p = nullptr;
     n = 0;
   }

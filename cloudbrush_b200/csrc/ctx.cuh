@@ -24,7 +24,9 @@ enum DevCounter {
   DC_TUPLES_INVALID,   // window slots that emit nothing (poly-A interior windows, palindromes)
   DC_POLYA_WEIGHT,     // BuildHighKmerList weight of the all-A / all-T k-mer
   DC_HKMER,
-  DC_EDGES_RAW,        // records appended by the join (edge + mirror)
+  DC_EDGES_RAW,        // side-buffer records of the join (edges whose mirror may not be proposed)
+  DC_EDGES_M,          // mirror records written straight into their adjacency list
+  DC_EDGES_A,          // edges of checkpoint A after assembly
   DC_CAND_VERIFIED,    // verified, maximal candidates (|S|)
   DC_UPKMER_LISTS,     // k-mer groups larger than UP_KMER (order dependent in the reference)
   DC_EDGE_REMOVAL,
@@ -32,6 +34,9 @@ enum DevCounter {
   DC_CONTAINED_EDGE,
   DC_TR_OVERFLOW,      // kept-list capacity of the literal TR scan exceeded
   DC_SLOW_LISTS,       // (node, direction) lists that took the literal path
+  DC_EDGES_C,          // edges after CutChimericLinks + EdgeRemoval
+  DC_EDGES_B,          // edges of checkpoint B
+  DC_MAX_LIST,         // longest adjacency list
   DC_COUNT
 };
 
@@ -64,16 +69,20 @@ struct Timer {
   bool done = false;
 };
 
+// One checkpoint of the graph as a gapped CSR: adjacency list `lid` = node*2 + x occupies
+// keys[adj_off[lid] .. adj_off[lid] + cnt[lid]), ordered by overlap descending (ties in any
+// order).  All checkpoints share cb_ctx::adj_off, so "removing edges" is a per-list rewrite.
 struct EdgeSet {
-  DevBuf<u64> keys;      // sorted, unique
-  DevBuf<u32> adj_off;   // [2*n_nodes + 1] start of list (node, x)
-  size_t n = 0;
+  DevBuf<u64> keys;  // [slots]
+  DevBuf<u32> cnt;   // [n_lists]
+  size_t n = 0;      // sum of cnt
   bool valid = false;
 };
 
 }  // namespace cb
 
 struct cb_ctx {
+  cb::Arena arena;  // declared first: destroyed after every DevBuf below
   cb_config cfg;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -107,6 +116,9 @@ struct cb_ctx {
 
   // graph
   cb::EdgeLayout lay;
+  cb::DevBuf<u32> adj_off;          // [2*n_nodes + 1] slot offset of list node*2 + x
+  size_t slots = 0;
+  cb::DevBuf<uint8_t> list_flag;    // [2*n_nodes] 1: all overhangs nest (consistent), 0: not, 2: unknown
   cb::EdgeSet ckA, ckC, ckB;        // 01-overlap, 01-overlap.chl2, 01-overlap.re
   bool ckC_is_A = false;
 };
@@ -123,7 +135,6 @@ void stage_dedupe(cb_ctx* c);
 // stage_overlap.cu
 void stage_build_overlap(cb_ctx* c);
 // stage_string.cu
-void build_adjacency(cb_ctx* c, EdgeSet& es);
 void stage_string_graph(cb_ctx* c);
 
 }  // namespace cb

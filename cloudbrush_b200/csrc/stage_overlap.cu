@@ -74,7 +74,18 @@ __global__ void __launch_bounds__(256) keygen_kernel(const u64* __restrict__ nod
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6+K7+K8: segmented join fused with the packed-word overlap check.
+// K6+K7+K8+K9: segmented join fused with the packed-word overlap check and with the
+// GenReverseEdge mirror.
+//
+// Node entry (b, y) -- the window-0 tuple of b for y = f, the window-(L-K) tuple for y = r --
+// lives in exactly one k-mer group, and every verified edge (a,x,ov) -> (b,y) of that group has
+// its mirror (b, flip y) -> (a, flip x) in the SAME adjacency list (b, flip y).  The join
+// therefore writes the mirror records straight into that list's slot range (sized by
+// slot_count_kernel: one slot per tuple of the group).  The edge itself belongs to list (a, x);
+// that list is produced by a's own node entry (a, flip x) iff the mirror is proposed and kept
+// there, which is decided locally (see `certain` below).  Only edges for which that is not
+// certain go through the small side buffer X; duplicates are dropped when the lists are
+// assembled.
 // ---------------------------------------------------------------------------------------------
 struct JoinParams {
   const u64* keys;
@@ -87,13 +98,17 @@ struct JoinParams {
   u32 max_cov;
   long long low_kmer, up_kmer;
   EdgeLayout lay;
-  u64* edges_out;
-  u64 edges_cap;
+  u32* slotcnt;        // slot_count_kernel output [n_lists]
+  const u32* off1;     // slot offsets of the temporary list storage
+  u64* mtmp;           // temporary list storage
+  u32* cntM;           // records written per list
+  u64* xbuf;           // side buffer
+  u64 xcap;
   ull* dcount;
 };
 
 constexpr int JN_WARPS = 8;
-constexpr int JN_EB = 256;  // staged edge records per warp
+constexpr int JN_EB = 256;  // staged side-buffer records per warp
 
 __device__ __forceinline__ u64 tuple_meta(const JoinParams& P, u32 j) {
   return ((P.keys[j] >> (2 * P.K)) << 32) | (u64)P.vals[j];
@@ -108,13 +123,65 @@ __device__ __forceinline__ void entry_of(int L, int K, int pos, int d, int sel, 
   else ovc = d == 0 ? L - pos : K + pos;
   x = sel ? (d ^ 1) : d;
   ov = sel ? (L + K - ovc) : ovc;
-  if ((pos == 0 || pos == L - K) && sel) ov = K;
+}
+
+// walks the k-mer groups whose head lies in this warp's 32-tuple chunks
+#define CB_FOR_EACH_SEGMENT(P, ...)                                                          \
+  {                                                                                          \
+    const u32 nchunks_ = ((P).T + 31) / 32;                                                  \
+    for (u32 chunk_ = warp_global; chunk_ < nchunks_; chunk_ += nwarps) {                    \
+      u32 i_ = chunk_ * 32 + lane;                                                           \
+      bool valid_ = i_ < (P).T;                                                              \
+      u64 ki_ = valid_ ? ((P).keys[i_] & (P).kmask) : 0;                                     \
+      u64 kprev_ = (valid_ && i_ > 0) ? ((P).keys[i_ - 1] & (P).kmask) : ~ki_;               \
+      u32 heads_ = __ballot_sync(0xffffffffu, valid_ && ki_ != kprev_);                      \
+      while (heads_) {                                                                       \
+        int h_ = __ffs(heads_) - 1;                                                          \
+        heads_ &= heads_ - 1;                                                                \
+        const u32 s = chunk_ * 32 + h_;                                                      \
+        const u64 kseg = __shfl_sync(0xffffffffu, ki_, h_);                                  \
+        u32 e = s + 1;                                                                       \
+        for (;;) {                                                                           \
+          u32 j_ = e + lane;                                                                 \
+          bool diff_ = (j_ >= (P).T) || (((P).keys[j_ < (P).T ? j_ : 0] & (P).kmask) != kseg); \
+          u32 b_ = __ballot_sync(0xffffffffu, diff_);                                        \
+          if (b_) { e += __ffs(b_) - 1; break; }                                             \
+          e += 32;                                                                           \
+        }                                                                                    \
+        __VA_ARGS__                                                                               \
+      }                                                                                      \
+    }                                                                                        \
+  }
+
+// one slot per tuple of the group for every node entry of a group the reducer processes
+__global__ void __launch_bounds__(JN_WARPS * 32) slot_count_kernel(JoinParams P) {
+  const int lane = threadIdx.x & 31;
+  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  const u32 posmask = (1u << P.pb) - 1;
+  CB_FOR_EACH_SEGMENT(P, {
+    (void)kseg;
+    const u32 g = e - s;
+    if ((long long)g > P.low_kmer) {
+      for (u32 j = s + lane; j < e; j += 32) {
+        u64 m = tuple_meta(P, j);
+        int pos = (int)((m >> 1) & posmask);
+        if (pos == 0 || pos == P.L - P.K) {
+          u32 b = (u32)(m >> (P.pb + 1));
+          u32 y = pos == 0 ? 0u : 1u;
+          P.slotcnt[2 * b + (y ^ 1u)] = g;
+        }
+      }
+    }
+  })
 }
 
 template <int NW>
 __global__ void __launch_bounds__(JN_WARPS * 32) join_verify_kernel(JoinParams P) {
   __shared__ u64 s_B[JN_WARPS][32][NW];
   __shared__ u32 s_Bmeta[JN_WARPS][32];
+  __shared__ u32 s_Bbase[JN_WARPS][32];
+  __shared__ u32 s_Bcnt[JN_WARPS][32];
   __shared__ u64 s_edges[JN_WARPS][JN_EB];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -123,7 +190,7 @@ __global__ void __launch_bounds__(JN_WARPS * 32) join_verify_kernel(JoinParams P
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
   const int L = P.L, K = P.K;
   const u32 posmask = (1u << P.pb) - 1;
-  u32 ebuf = 0;        // staged records (warp uniform)
+  u32 ebuf = 0;        // staged side-buffer records (warp uniform)
   u32 n_verified = 0;  // lane-local count of maximal verified candidates
 
   auto flush = [&]() {
@@ -132,158 +199,167 @@ __global__ void __launch_bounds__(JN_WARPS * 32) join_verify_kernel(JoinParams P
     if (lane == 0) base = atomicAdd(&P.dcount[DC_EDGES_RAW], (ull)ebuf);
     base = __shfl_sync(0xffffffffu, base, 0);
     for (u32 t = lane; t < ebuf; t += 32)
-      if (base + t < P.edges_cap) P.edges_out[base + t] = s_edges[warp][t];
+      if (base + t < P.xcap) P.xbuf[base + t] = s_edges[warp][t];
     __syncwarp();
     ebuf = 0;
   };
 
-  const u32 nchunks = (P.T + 31) / 32;
-  for (u32 chunk = warp_global; chunk < nchunks; chunk += nwarps) {
-    u32 i = chunk * 32 + lane;
-    bool valid = i < P.T;
-    u64 ki = valid ? (P.keys[i] & P.kmask) : 0;
-    u64 kprev = (valid && i > 0) ? (P.keys[i - 1] & P.kmask) : ~ki;
-    u32 heads = __ballot_sync(0xffffffffu, valid && ki != kprev);
-    while (heads) {
-      int h = __ffs(heads) - 1;
-      heads &= heads - 1;
-      const u32 s = chunk * 32 + h;
-      const u64 kseg = __shfl_sync(0xffffffffu, ki, h);
-      u32 e = s + 1;
-      for (;;) {
-        u32 j = e + lane;
-        bool diff = (j >= P.T) || ((P.keys[j < P.T ? j : 0] & P.kmask) != kseg);
-        u32 b = __ballot_sync(0xffffffffu, diff);
-        if (b) { e += __ffs(b) - 1; break; }
-        e += 32;
+  CB_FOR_EACH_SEGMENT(P, {
+    const u32 g = e - s;
+    // BuildHighKmerList.java:96-117: weighted count over windows [0, L-K) above UP_KMER
+    if (kseg != 0 && (long long)g * (long long)P.max_cov > P.up_kmer) {
+      ull sum = 0;
+      for (u32 j = s + lane; j < e; j += 32) {
+        u64 m = tuple_meta(P, j);
+        int pos = (int)((m >> 1) & posmask);
+        if (pos < L - K) sum += P.node_cov[(u32)(m >> (P.pb + 1))];
       }
-      const u32 g = e - s;
-      // BuildHighKmerList.java:96-117: weighted count over windows [0, L-K) above UP_KMER
-      if (kseg != 0 && (long long)g * (long long)P.max_cov > P.up_kmer) {
-        ull sum = 0;
-        for (u32 j = s + lane; j < e; j += 32) {
-          u64 m = tuple_meta(P, j);
-          int pos = (int)((m >> 1) & posmask);
-          if (pos < L - K) sum += P.node_cov[(u32)(m >> (P.pb + 1))];
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0 && (long long)sum > P.up_kmer) atomicAdd(&P.dcount[DC_HKMER], 1ull);
-      }
-      if ((long long)g <= P.low_kmer) continue;  // MatchPrefix.java:366
-      if ((long long)g > P.up_kmer && lane == 0) atomicAdd(&P.dcount[DC_UPKMER_LISTS], 1ull);
-
-      u32 scan_pos = s;
-      for (;;) {
-        // ---- collect the next batch of <= 32 node entries (tuples of window 0 / L-K) ----
-        u32 nB = 0;
-        while (scan_pos < e && nB < 32) {
-          u32 j = scan_pos + lane;
-          u64 m = (j < e) ? tuple_meta(P, j) : 0;
-          int pos = (int)((m >> 1) & posmask);
-          bool isn = (j < e) && (pos == 0 || pos == L - K);
-          u32 bal = __ballot_sync(0xffffffffu, isn);
-          u32 cnt = __popc(bal);
-          u32 advance = 32;
-          if (nB + cnt > 32) {
-            u32 need = 32 - nB, tb = bal;
-            int last = 0;
-            for (u32 t = 0; t < need; t++) { last = __ffs(tb) - 1; tb &= tb - 1; }
-            bal &= (last == 31) ? 0xffffffffu : ((2u << last) - 1);
-            cnt = need;
-            advance = (u32)last + 1;
-          }
-          if (isn && ((bal >> lane) & 1u)) {
-            u32 slot = nB + __popc(bal & lt_mask);
-            u32 b = (u32)(m >> (P.pb + 1));
-            int d = (int)(m & 1);
-            int y = pos == 0 ? 0 : 1;          // prefix entry: b^f starts with X; suffix entry: b^r
-            int sel = pos == 0 ? d : (d ^ 1);  // MatchPrefix.java:275-296
-            u64 r[NW], rcw[NW];
-            load_read_b<NW>(P.node_seq, b, r);
-            if (y) revcomp_read<NW>(r, rcw, L);
-#pragma unroll
-            for (int w = 0; w < NW; w++) s_B[warp][slot][w] = y ? rcw[w] : r[w];
-            s_Bmeta[warp][slot] = b | ((u32)y << 28) | ((u32)sel << 29);
-          }
-          nB += cnt;
-          scan_pos += advance;
-        }
-        if (nB == 0) break;
-        __syncwarp();
-        // ---- every tuple of the group against the batch ----
-        for (u32 j0 = s; j0 < e; j0 += 32) {
-          u32 j = j0 + lane;
-          bool act = j < e;
-          u64 m = act ? tuple_meta(P, j) : 0;
-          u32 a = (u32)(m >> (P.pb + 1));
-          int pos = (int)((m >> 1) & posmask);
-          int d = (int)(m & 1);
-          u64 R[NW], Rc[NW];
-          if (act) load_read_b<NW>(P.node_seq, a, R);
-          else {
-#pragma unroll
-            for (int w = 0; w < NW; w++) R[w] = 0;
-          }
-          revcomp_read<NW>(R, Rc, L);
-          // does a neighbouring tuple of the group belong to the same read?  (tuples of one read
-          // are contiguous: the sort is stable and keygen emits in (node, window) order)
-          bool same_l = act && j > s && (u32)(tuple_meta(P, j - 1) >> (P.pb + 1)) == a;
-          bool same_r = act && j + 1 < e && (u32)(tuple_meta(P, j + 1) >> (P.pb + 1)) == a;
-          for (u32 n = 0; n < nB; n++) {
-            u32 bm = s_Bmeta[warp][n];
-            u32 b = bm & 0x0fffffffu;
-            int y = (bm >> 28) & 1, sel = (bm >> 29) & 1;
-            int x, ov;
-            entry_of(L, K, pos, d, sel, x, ov);
-            u64 A[NW], B[NW];
-#pragma unroll
-            for (int w = 0; w < NW; w++) { A[w] = x ? Rc[w] : R[w]; B[w] = s_B[warp][n][w]; }
-            shl_bases<NW>(A, L - ov);
-            // VerifyOverlap.java:295-309: a^x[L-ov:] == b^y[0:ov]; self candidates skipped at
-            // MatchPrefix.java:405-407
-            bool ok = act && a != b && prefix_equal<NW>(A, B, ov);
-            if (ok && (same_l || same_r)) {
-              // maximal-overlap filter, VerifyOverlap.java:275-283: a larger verified overlap of
-              // the same (a, x) with the same (b, y) wins
-              for (int dirn = -1; dirn <= 1 && ok; dirn += 2) {
-                long long jj = (long long)j + dirn;
-                while (jj >= (long long)s && jj < (long long)e) {
-                  u64 m2 = tuple_meta(P, (u32)jj);
-                  if ((u32)(m2 >> (P.pb + 1)) != a) break;
-                  int x2, ov2;
-                  entry_of(L, K, (int)((m2 >> 1) & posmask), (int)(m2 & 1), sel, x2, ov2);
-                  if (x2 == x && ov2 > ov) {
-                    u64 A2[NW];
-#pragma unroll
-                    for (int w = 0; w < NW; w++) A2[w] = x ? Rc[w] : R[w];
-                    shl_bases<NW>(A2, L - ov2);
-                    if (prefix_equal<NW>(A2, B, ov2)) { ok = false; break; }
-                  }
-                  jj += dirn;
-                }
-              }
-            }
-            u32 bal = __ballot_sync(0xffffffffu, ok);
-            if (bal) {
-              u32 cnt = __popc(bal);
-              if (ebuf + 2 * cnt > JN_EB) flush();
-              if (ok) {
-                u32 r = ebuf + 2 * __popc(bal & lt_mask);
-                s_edges[warp][r] = P.lay.encode(a, (u32)x, (u32)ov, (u32)y, b);
-                s_edges[warp][r + 1] = P.lay.encode(b, (u32)(y ^ 1), (u32)ov, (u32)(x ^ 1), a);  // GenReverseEdge
-                n_verified++;
-              }
-              ebuf += 2 * cnt;
-              __syncwarp();
-            }
-          }
-        }
-        __syncwarp();
-        if (scan_pos >= e) break;
-      }
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0 && (long long)sum > P.up_kmer) atomicAdd(&P.dcount[DC_HKMER], 1ull);
     }
-  }
+    if ((long long)g <= P.low_kmer) continue;  // MatchPrefix.java:366
+    if ((long long)g > P.up_kmer && lane == 0) atomicAdd(&P.dcount[DC_UPKMER_LISTS], 1ull);
+
+    u32 scan_pos = s;
+    for (;;) {
+      // ---- collect the next batch of <= 32 node entries (tuples of window 0 / L-K) ----
+      u32 nB = 0;
+      while (scan_pos < e && nB < 32) {
+        u32 j = scan_pos + lane;
+        u64 m = (j < e) ? tuple_meta(P, j) : 0;
+        int pos = (int)((m >> 1) & posmask);
+        bool isn = (j < e) && (pos == 0 || pos == L - K);
+        u32 bal = __ballot_sync(0xffffffffu, isn);
+        u32 cnt = __popc(bal);
+        u32 advance = 32;
+        if (nB + cnt > 32) {
+          u32 need = 32 - nB, tb = bal;
+          int last = 0;
+          for (u32 t = 0; t < need; t++) { last = __ffs(tb) - 1; tb &= tb - 1; }
+          bal &= (last == 31) ? 0xffffffffu : ((2u << last) - 1);
+          cnt = need;
+          advance = (u32)last + 1;
+        }
+        if (isn && ((bal >> lane) & 1u)) {
+          u32 slot = nB + __popc(bal & lt_mask);
+          u32 b = (u32)(m >> (P.pb + 1));
+          int d = (int)(m & 1);
+          int y = pos == 0 ? 0 : 1;          // prefix entry: b^f starts with X; suffix entry: b^r
+          int sel = pos == 0 ? d : (d ^ 1);  // MatchPrefix.java:275-296
+          u64 r[NW], rcw[NW];
+          load_read_b<NW>(P.node_seq, b, r);
+          if (y) revcomp_read<NW>(r, rcw, L);
+#pragma unroll
+          for (int w = 0; w < NW; w++) s_B[warp][slot][w] = y ? rcw[w] : r[w];
+          s_Bmeta[warp][slot] = b | ((u32)y << 28) | ((u32)sel << 29);
+          s_Bbase[warp][slot] = P.off1[2 * b + (u32)(y ^ 1)];
+          s_Bcnt[warp][slot] = 0;
+        }
+        nB += cnt;
+        scan_pos += advance;
+      }
+      if (nB == 0) break;
+      __syncwarp();
+      // ---- every tuple of the group against the batch ----
+      for (u32 j0 = s; j0 < e; j0 += 32) {
+        u32 j = j0 + lane;
+        bool act = j < e;
+        u64 m = act ? tuple_meta(P, j) : 0;
+        u32 a = (u32)(m >> (P.pb + 1));
+        int pos = (int)((m >> 1) & posmask);
+        int d = (int)(m & 1);
+        u64 R[NW], Rc[NW];
+        if (act) load_read_b<NW>(P.node_seq, a, R);
+        else {
+#pragma unroll
+          for (int w = 0; w < NW; w++) R[w] = 0;
+        }
+        revcomp_read<NW>(R, Rc, L);
+        // last k-mers of a^f and a^r: the group of the mirror candidate is keyed by their rc
+        const u64 ksuf_f = extract_kmer<NW>(R, L - K, K), ksuf_r = extract_kmer<NW>(Rc, L - K, K);
+        // does a neighbouring tuple of the group belong to the same read?  (tuples of one read
+        // are contiguous: the sort is stable and keygen emits in (node, window) order)
+        bool same_l = act && j > s && (u32)(tuple_meta(P, j - 1) >> (P.pb + 1)) == a;
+        bool same_r = act && j + 1 < e && (u32)(tuple_meta(P, j + 1) >> (P.pb + 1)) == a;
+        for (u32 n = 0; n < nB; n++) {
+          u32 bm = s_Bmeta[warp][n];
+          u32 b = bm & 0x0fffffffu;
+          int y = (bm >> 28) & 1, sel = (bm >> 29) & 1;
+          int x, ov;
+          entry_of(L, K, pos, d, sel, x, ov);
+          u64 A[NW], B[NW];
+#pragma unroll
+          for (int w = 0; w < NW; w++) { A[w] = x ? Rc[w] : R[w]; B[w] = s_B[warp][n][w]; }
+          shl_bases<NW>(A, L - ov);
+          // VerifyOverlap.java:295-309: a^x[L-ov:] == b^y[0:ov]; self candidates skipped at
+          // MatchPrefix.java:405-407
+          bool ok = act && a != b && prefix_equal<NW>(A, B, ov);
+          if (ok && (same_l || same_r)) {
+            // maximal-overlap filter, VerifyOverlap.java:275-283: a larger verified overlap of
+            // the same (a, x) with the same (b, y) wins; an identical entry of an earlier tuple
+            // (MatchPrefix.java:409 hasEdge) is emitted only once
+            for (int dirn = -1; dirn <= 1 && ok; dirn += 2) {
+              long long jj = (long long)j + dirn;
+              while (jj >= (long long)s && jj < (long long)e) {
+                u64 m2 = tuple_meta(P, (u32)jj);
+                if ((u32)(m2 >> (P.pb + 1)) != a) break;
+                int x2, ov2;
+                entry_of(L, K, (int)((m2 >> 1) & posmask), (int)(m2 & 1), sel, x2, ov2);
+                if (x2 == x && ov2 == ov && dirn < 0) { ok = false; break; }
+                if (x2 == x && ov2 > ov) {
+                  u64 A2[NW];
+#pragma unroll
+                  for (int w = 0; w < NW; w++) A2[w] = x ? Rc[w] : R[w];
+                  shl_bases<NW>(A2, L - ov2);
+                  if (prefix_equal<NW>(A2, B, ov2)) { ok = false; break; }
+                }
+                jj += dirn;
+              }
+            }
+          }
+          u32 bal = __ballot_sync(0xffffffffu, ok);
+          if (bal) {
+            u32 cnt = __popc(bal);
+            u32 rank = __popc(bal & lt_mask);
+            u32 mbase = s_Bbase[warp][n] + s_Bcnt[warp][n];
+            // Is the mirror candidate (b, flip y, ov) -> (a, flip x) certain to be proposed and
+            // kept in the group of X' = a^(flip x)[0:K]?  Then a's own node entry writes this
+            // edge into list (a, x) and it need not travel.  (SURVEY.md 8a': proposed iff
+            // ov > K and X' not poly-A/T, or ov == K and X' > rc(X'); kept iff no larger TRUE
+            // overlap, which would show as another tuple of a in this group.)
+            bool certain = false;
+            if (ok) {
+              const u64 ksuf = x ? ksuf_r : ksuf_f;
+              const u64 xp = revcomp_kmer(ksuf, K);
+              const bool proposed = (ov > K) ? ((xp < ksuf ? xp : ksuf) != 0) : (xp > ksuf);
+              certain = proposed && kseg != 0 && !same_l && !same_r && P.low_kmer == 1;
+            }
+            u32 xbal = __ballot_sync(0xffffffffu, ok && !certain);
+            u32 xcnt = __popc(xbal);
+            if (xcnt && ebuf + xcnt > JN_EB) flush();
+            if (ok) {
+              P.mtmp[mbase + rank] = P.lay.encode(b, (u32)(y ^ 1), (u32)ov, (u32)(x ^ 1), a);  // GenReverseEdge
+              if (!certain) s_edges[warp][ebuf + __popc(xbal & lt_mask)] = P.lay.encode(a, (u32)x, (u32)ov, (u32)y, b);
+              n_verified++;
+            }
+            ebuf += xcnt;
+            __syncwarp();
+            if (lane == 0) s_Bcnt[warp][n] += cnt;
+            __syncwarp();
+          }
+        }
+      }
+      __syncwarp();
+      if ((u32)lane < nB) {
+        u32 bm = s_Bmeta[warp][lane];
+        u32 b = bm & 0x0fffffffu, y = (bm >> 28) & 1;
+        P.cntM[2 * b + (y ^ 1u)] = s_Bcnt[warp][lane];
+      }
+      __syncwarp();
+      if (scan_pos >= e) break;
+    }
+  })
   flush();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_verified += __shfl_xor_sync(0xffffffffu, n_verified, o);
@@ -291,37 +367,116 @@ __global__ void __launch_bounds__(JN_WARPS * 32) join_verify_kernel(JoinParams P
 }
 
 // ---------------------------------------------------------------------------------------------
-// unique + compaction of a sorted key array
+// list assembly: list = records written by the list's own node entry (M) + side-buffer records
+// addressed to it (X, sorted so that a list's records are contiguous), without duplicates,
+// counting-sorted by overlap descending.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) unique_flags_kernel(const u64* __restrict__ k, size_t n,
-                                                           u32* __restrict__ flag) {
+__global__ void __launch_bounds__(256) list_bounds_kernel(const u64* __restrict__ xs, size_t n, EdgeLayout lay,
+                                                          u32 n_lists, u32* __restrict__ xoff) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flag[i] = (i == 0 || k[i] != k[i - 1]) ? 1u : 0u;
+  if (i >= n) return;
+  u32 p = lay.list(xs[i]);
+  long long prev = i > 0 ? (long long)lay.list(xs[i - 1]) : -1;
+  for (long long q = prev + 1; q <= (long long)p; q++) xoff[q] = (u32)i;
+  if (i == n - 1)
+    for (u32 q = p + 1; q <= n_lists; q++) xoff[q] = (u32)n;
 }
 
-__global__ void __launch_bounds__(256) compact_kernel(const u64* __restrict__ k, const u32* __restrict__ flag,
-                                                      const u32* __restrict__ idx, size_t n, u64* __restrict__ out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && flag[i]) out[idx[i]] = k[i];
+__global__ void __launch_bounds__(256) list_total_kernel(const u32* __restrict__ cntM, const u32* __restrict__ xoff,
+                                                         u32 n_lists, u32* __restrict__ tot, ull* __restrict__ dcount) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 t = 0;
+  if (i < n_lists) {
+    t = cntM[i] + (xoff[i + 1] - xoff[i]);
+    tot[i] = t;
+  } else if (i == n_lists) tot[i] = 0;
+  // longest list (for diagnostics)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
+  if ((threadIdx.x & 31) == 0 && t) atomicMax(&dcount[DC_MAX_LIST], (ull)t);
 }
 
-// keeps k[i] where flag[i] != 0; returns the number kept (synchronises the stream)
-size_t compact_by_flags(cb_ctx* c, const u64* k, const u32* flag, size_t n, DevBuf<u64>& out) {
-  cudaStream_t s = c->stream;
-  if (n == 0) { out.alloc(0, s); return 0; }
-  DevBuf<u32> idx;
-  idx.alloc(n, s);
-  exclusive_scan_u32(flag, idx.p, n, s, c->lc);
-  u32 last_idx = 0, last_flag = 0;
-  CB_CUDA(cudaMemcpyAsync(&last_idx, idx.p + n - 1, 4, cudaMemcpyDeviceToHost, s));
-  CB_CUDA(cudaMemcpyAsync(&last_flag, flag + n - 1, 4, cudaMemcpyDeviceToHost, s));
-  CB_CUDA(cudaStreamSynchronize(s));
-  size_t m = (size_t)last_idx + (last_flag ? 1 : 0);
-  out.alloc(m, s);
-  compact_kernel<<<div_up(n, 256), 256, 0, s>>>(k, flag, idx.p, n, out.p);
-  c->lc.n++;
-  CB_CUDA(cudaGetLastError());
-  return m;
+constexpr int AS_WARPS = 8;
+
+__global__ void __launch_bounds__(AS_WARPS * 32) assemble_kernel(const u64* __restrict__ mtmp,
+                                                                 const u32* __restrict__ off1,
+                                                                 const u32* __restrict__ cntM,
+                                                                 const u64* __restrict__ xs,
+                                                                 const u32* __restrict__ xoff,
+                                                                 const u32* __restrict__ off2, u64* __restrict__ out,
+                                                                 u32* __restrict__ cnt_out, EdgeLayout lay,
+                                                                 u32 n_lists, ull* __restrict__ dcount) {
+  __shared__ u32 s_hist[AS_WARPS][257];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  const u32 nbins = 1u << lay.ob;
+  const u32 ovmask = nbins - 1;
+  ull total_edges = 0;
+  for (u32 lid = warp_global; lid < n_lists; lid += nwarps) {
+    const u32 m = cntM[lid], x0 = xoff[lid], q = xoff[lid + 1] - x0;
+    const u32 n = m + q;
+    if (n == 0) {
+      if (lane == 0) cnt_out[lid] = 0;
+      continue;
+    }
+    const u64* M = mtmp + off1[lid];
+    const u64* X = xs + x0;
+    u64* O = out + off2[lid];
+    if (q == 0 && n <= 32) {
+      // common case: one record per lane, ordered with a warp-wide rank by (L - ov)
+      u64 key = lane < (int)n ? M[lane] : ~0ull;
+      u32 bin = (u32)(key >> (lay.nb + 1)) & ovmask;
+      u32 rank = 0;
+#pragma unroll 8
+      for (int t = 0; t < 32; t++) {
+        u32 ob = __shfl_sync(0xffffffffu, bin, t);
+        bool ov_valid = t < (int)n;
+        if (ov_valid && (ob < bin || (ob == bin && t < lane))) rank++;
+      }
+      if (lane < (int)n) O[rank] = key;
+      if (lane == 0) { cnt_out[lid] = n; total_edges += n; }
+      continue;
+    }
+    for (u32 t = lane; t < nbins; t += 32) s_hist[warp][t] = 0;
+    __syncwarp();
+    for (u32 i = lane; i < n; i += 32) {
+      u64 key = i < m ? M[i] : X[i - m];
+      bool valid = true;
+      if (i >= m)
+        for (u32 t = 0; t < m; t++)
+          if (M[t] == key) { valid = false; break; }
+      if (valid) atomicAdd(&s_hist[warp][(u32)(key >> (lay.nb + 1)) & ovmask], 1u);
+    }
+    __syncwarp();
+    u32 carry = 0;
+    for (u32 base = 0; base < nbins; base += 32) {
+      u32 v = (base + lane < nbins) ? s_hist[warp][base + lane] : 0;
+      u32 inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (base + lane < nbins) s_hist[warp][base + lane] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+    for (u32 i = lane; i < n; i += 32) {
+      u64 key = i < m ? M[i] : X[i - m];
+      bool valid = true;
+      if (i >= m)
+        for (u32 t = 0; t < m; t++)
+          if (M[t] == key) { valid = false; break; }
+      if (valid) {
+        u32 p = atomicAdd(&s_hist[warp][(u32)(key >> (lay.nb + 1)) & ovmask], 1u);
+        O[p] = key;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) { cnt_out[lid] = carry; total_edges += carry; }
+  }
+  if (lane == 0 && total_edges) atomicAdd(&dcount[DC_EDGES_A], total_edges);
 }
 
 static int bits_for(u64 nvalues) {  // bits needed to store values 0 .. nvalues-1
@@ -339,6 +494,13 @@ static int bits_for(u64 nvalues) {  // bits needed to store values 0 .. nvalues-
     default: throw Error(CB_E_UNSUPPORTED, "read length above 256 bases");   \
   }
 
+static u32 read_u32(cb_ctx* c, const u32* p) {
+  u32 v = 0;
+  CB_CUDA(cudaMemcpyAsync(&v, p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CB_CUDA(cudaStreamSynchronize(c->stream));
+  return v;
+}
+
 void stage_build_overlap(cb_ctx* c) {
   cudaStream_t s = c->stream;
   const u32 nn = c->n_nodes;
@@ -353,6 +515,7 @@ void stage_build_overlap(cb_ctx* c) {
   c->lay.nb = nbits;
   c->lay.ob = bits_for((u64)(L - K + 1));
   c->lay.L = L;
+  const u32 n_lists = 2 * nn;
 
   // ---- keygen ----
   timer_start(c, "keygen");
@@ -398,27 +561,48 @@ void stage_build_overlap(cb_ctx* c) {
   P.up_kmer = c->cfg.up_kmer;
   P.lay = c->lay;
   P.dcount = (ull*)c->dcount.p;
-  DevBuf<u64> raw;
-  u64 cap = (u64)T * 4 + 1024;
-  u64 n_raw = 0;
-  for (int attempt = 0; attempt < 2; attempt++) {
-    raw.alloc(cap, s);
-    P.edges_out = raw.p;
-    P.edges_cap = cap;
-    CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_HKMER, 0, (DC_EDGE_REMOVAL - DC_HKMER) * sizeof(u64), s));
-    int blocks = kNumSMs * 8;
+  int jblocks = kNumSMs * 8;
+  {
     int need = div_up(((size_t)T + 31) / 32, JN_WARPS);
-    if (need < blocks) blocks = need > 0 ? need : 1;
+    if (need < jblocks) jblocks = need > 0 ? need : 1;
+  }
+  // slots: one per tuple of the group for every node entry
+  DevBuf<u32> slotcnt, off1, cntM;
+  slotcnt.alloc((size_t)n_lists + 1, s);
+  off1.alloc((size_t)n_lists + 1, s);
+  cntM.alloc(n_lists, s);
+  CB_CUDA(cudaMemsetAsync(slotcnt.p, 0, ((size_t)n_lists + 1) * 4, s));
+  CB_CUDA(cudaMemsetAsync(cntM.p, 0, (size_t)n_lists * 4, s));
+  P.slotcnt = slotcnt.p;
+  c->lc.begin("slot_count");
+  slot_count_kernel<<<jblocks, JN_WARPS * 32, 0, s>>>(P);
+  c->lc.end("slot_count");
+  c->lc.n++;
+  exclusive_scan_u32(slotcnt.p, off1.p, (size_t)n_lists + 1, s, c->lc);
+  const size_t slots1 = read_u32(c, off1.p + n_lists);
+  slotcnt.release();
+  DevBuf<u64> mtmp, xbuf;
+  mtmp.alloc(slots1 ? slots1 : 1, s);
+  P.off1 = off1.p;
+  P.mtmp = mtmp.p;
+  P.cntM = cntM.p;
+  u64 xcap = (u64)T / 4 + 4096;
+  u64 n_x = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    xbuf.alloc(xcap, s);
+    P.xbuf = xbuf.p;
+    P.xcap = xcap;
+    CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_HKMER, 0, (DC_EDGE_REMOVAL - DC_HKMER) * sizeof(u64), s));
     c->lc.begin("join_verify");
-    CB_DISPATCH_NW(c->NW, (join_verify_kernel<NW_><<<blocks, JN_WARPS * 32, 0, s>>>(P)));
+    CB_DISPATCH_NW(c->NW, (join_verify_kernel<NW_><<<jblocks, JN_WARPS * 32, 0, s>>>(P)));
     c->lc.end("join_verify");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
     download_counters(c);
-    n_raw = c->hcount[DC_EDGES_RAW];
-    if (n_raw <= cap) break;
-    if (attempt == 1) throw Error(CB_E_CAPACITY, "edge buffer overflow");
-    cap = n_raw;  // exact size known now: run again
+    n_x = c->hcount[DC_EDGES_RAW];
+    if (n_x <= xcap) break;
+    if (attempt == 1) throw Error(CB_E_CAPACITY, "side buffer overflow");
+    xcap = n_x;  // exact size known now: run again
   }
   timer_stop(c, "join_verify");
   keys[where].release();
@@ -428,6 +612,7 @@ void stage_build_overlap(cb_ctx* c) {
   int64_t hkmer = (int64_t)c->hcount[DC_HKMER] + ((long long)c->hcount[DC_POLYA_WEIGHT] > c->cfg.up_kmer ? 1 : 0);
   c->counters["hkmer"] = hkmer;
   c->counters["candidates_verified"] = (int64_t)c->hcount[DC_CAND_VERIFIED];
+  c->counters["side_buffer_edges"] = (int64_t)n_x;
   c->counters["upkmer_truncated_lists"] = (int64_t)c->hcount[DC_UPKMER_LISTS];
   c->counters["order_dependent"] = (int64_t)c->hcount[DC_UPKMER_LISTS];
   if (hkmer > 0)
@@ -435,23 +620,48 @@ void stage_build_overlap(cb_ctx* c) {
                 "non-empty high-frequency k-mer list: the reference's stopword loader (MatchPrefix.java:81) is "
                 "ill-defined for it, parity undefined");
 
-  // ---- S u mirror(S): sort + unique ----
-  timer_start(c, "sort_edges");
-  DevBuf<u64> raw2;
-  raw2.alloc(n_raw, s);
-  int w2 = radix_sort(raw.p, raw2.p, nullptr, nullptr, n_raw, 0, c->lay.total_bits(), s, c->lc, "edges");
-  u64* sorted = w2 ? raw2.p : raw.p;
-  DevBuf<u32> flag;
-  flag.alloc(n_raw, s);
-  if (n_raw) {
-    unique_flags_kernel<<<div_up(n_raw, 256), 256, 0, s>>>(sorted, n_raw, flag.p);
+  // ---- assemble the adjacency lists of checkpoint A ----
+  timer_start(c, "assemble");
+  DevBuf<u64> xalt;
+  xalt.alloc(n_x ? n_x : 1, s);
+  int wx = radix_sort(xbuf.p, xalt.p, nullptr, nullptr, n_x, c->lay.nb + c->lay.ob + 1, c->lay.total_bits(), s, c->lc,
+                      "edges");
+  const u64* xs = wx ? xalt.p : xbuf.p;
+  DevBuf<u32> xoff, tot;
+  xoff.alloc((size_t)n_lists + 1, s);
+  tot.alloc((size_t)n_lists + 1, s);
+  if (n_x) {
+    list_bounds_kernel<<<div_up(n_x, 256), 256, 0, s>>>(xs, n_x, c->lay, n_lists, xoff.p);
     c->lc.n++;
+  } else {
+    CB_CUDA(cudaMemsetAsync(xoff.p, 0, ((size_t)n_lists + 1) * 4, s));
   }
-  c->ckA.n = compact_by_flags(c, sorted, flag.p, n_raw, c->ckA.keys);
+  list_total_kernel<<<div_up((size_t)n_lists + 1, 256), 256, 0, s>>>(cntM.p, xoff.p, n_lists, tot.p,
+                                                                    (ull*)c->dcount.p);
+  c->lc.n++;
+  c->adj_off.alloc((size_t)n_lists + 1, s);
+  exclusive_scan_u32(tot.p, c->adj_off.p, (size_t)n_lists + 1, s, c->lc);
+  c->slots = read_u32(c, c->adj_off.p + n_lists);
+  c->ckA.keys.alloc(c->slots ? c->slots : 1, s);
+  c->ckA.cnt.alloc(n_lists, s);
+  {
+    int blocks = div_up((size_t)n_lists, AS_WARPS);
+    int cap = kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    c->lc.begin("assemble");
+    assemble_kernel<<<blocks, AS_WARPS * 32, 0, s>>>(mtmp.p, off1.p, cntM.p, xs, xoff.p, c->adj_off.p, c->ckA.keys.p,
+                                                    c->ckA.cnt.p, c->lay, n_lists, (ull*)c->dcount.p);
+    c->lc.end("assemble");
+    c->lc.n++;
+    CB_CUDA(cudaGetLastError());
+  }
+  download_counters(c);
+  c->ckA.n = (size_t)c->hcount[DC_EDGES_A];
   c->ckA.valid = true;
-  timer_stop(c, "sort_edges");
-  build_adjacency(c, c->ckA);
+  timer_stop(c, "assemble");
   c->counters["edges_overlap"] = (int64_t)c->ckA.n;
+  c->counters["max_list"] = (int64_t)c->hcount[DC_MAX_LIST];
 }
 
 }  // namespace cb

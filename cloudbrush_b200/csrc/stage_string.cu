@@ -35,18 +35,19 @@ __device__ __forceinline__ void load_read_c(const u64* __restrict__ reads, u32 i
 }
 
 struct StringParams {
-  const u64* edges;
-  const u32* adj_off;
-  u32 n_lists;  // 2 * n_nodes
-  size_t n_edges;
+  const u64* edges;    // gapped CSR keys
+  const u32* adj_off;  // [n_lists + 1]
+  const u32* cnt;      // [n_lists]
+  u32 n_lists;         // 2 * n_nodes
   EdgeLayout lay;
   const u64* node_seq;
   const IdKey* node_idkey;
   const u32* node_cov;
   int L, K;
   float majority, pwm_n;
-  uint8_t* removed;  // cut_kernel output
-  uint8_t* kept;     // tr_kernel output
+  uint8_t* removed;    // cut_kernel output, per slot
+  uint8_t* kept;       // tr_kernel output, per slot
+  uint8_t* list_flag;  // per list: 1 consistent, 0 not, 2 unknown
   ull* dcount;
 };
 
@@ -74,17 +75,25 @@ __device__ __forceinline__ int base_at(const u64 (&h)[NW], int j) {
   return (int)((w >> (62 - 2 * (j & 31))) & 3);
 }
 
-// index of `key` in the sorted edge array or -1
+// slot index of `key` in its list or -1.  Lists are ordered by (L - ov) ascending; entries of
+// equal overlap are in no particular order, so the equal-overlap run is scanned.
 __device__ __forceinline__ long long find_edge(const StringParams& P, u64 key) {
-  u32 list = P.lay.list(key);
-  u32 lo = P.adj_off[list], hi = P.adj_off[list + 1];
+  const u32 list = P.lay.list(key);
+  const u32 base = P.adj_off[list], n = P.cnt[list];
+  const u32 sh = P.lay.nb + 1, msk = (1u << P.lay.ob) - 1;
+  const u32 target = (u32)(key >> sh) & msk;
+  u32 lo = 0, hi = n;
   while (lo < hi) {
     u32 mid = (lo + hi) >> 1;
-    u64 k = P.edges[mid];
-    if (k < key) lo = mid + 1;
+    if (((u32)(P.edges[base + mid] >> sh) & msk) < target) lo = mid + 1;
     else hi = mid;
   }
-  return (lo < P.adj_off[list + 1] && P.edges[lo] == key) ? (long long)lo : -1;
+  for (u32 t = lo; t < n; t++) {
+    u64 k = P.edges[base + t];
+    if (((u32)(k >> sh) & msk) != target) break;
+    if (k == key) return (long long)(base + t);
+  }
+  return -1;
 }
 
 // are all overhangs of [lo, hi) prefixes of the longest one (the last entry)?
@@ -143,10 +152,15 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
   const int L = P.L;
   for (u32 list = warp_global; list < P.n_lists; list += nwarps) {
-    const u32 lo = P.adj_off[list], hi = P.adj_off[list + 1];
-    const u32 n = hi - lo;
-    if (n <= 1) continue;  // CutChimericLinks.java:306 "flist.size() > 1"
-    if (P.majority < 1.0f && list_consistent<NW>(P, lo, hi, lane)) continue;
+    const u32 n = P.cnt[list];
+    const u32 lo = P.adj_off[list], hi = lo + n;
+    if (n <= 1) {  // CutChimericLinks.java:306 "flist.size() > 1"
+      if (lane == 0) P.list_flag[list] = 1;
+      continue;
+    }
+    const bool cons = list_consistent<NW>(P, lo, hi, lane);
+    if (lane == 0) P.list_flag[list] = cons ? 1 : 0;
+    if (cons && P.majority < 1.0f) continue;
     if (lane == 0) atomicAdd(&P.dcount[DC_SLOW_LISTS], 1ull);
     const u32 x = list & 1;
     // ---- entries 0 and 1 of the Consensus order (Node.java:1295-1320) ----
@@ -232,6 +246,40 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
   }
 }
 
+// EdgeRemoval (EdgeRemoval.java:121-202): per list, copy the entries that are not flagged.
+// A list that loses an entry has its consistency flag reset to "unknown".
+__global__ void __launch_bounds__(ST_WARPS * 32) filter_lists_kernel(const u64* __restrict__ in,
+                                                                     const u32* __restrict__ adj_off,
+                                                                     const u32* __restrict__ cnt_in,
+                                                                     const uint8_t* __restrict__ drop, u32 n_lists,
+                                                                     u64* __restrict__ out, u32* __restrict__ cnt_out,
+                                                                     uint8_t* __restrict__ list_flag,
+                                                                     ull* __restrict__ dcount, int counter) {
+  const int lane = threadIdx.x & 31;
+  const u32 lt_mask = (1u << lane) - 1;
+  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  ull total = 0;
+  for (u32 list = warp_global; list < n_lists; list += nwarps) {
+    const u32 n = cnt_in[list], lo = adj_off[list];
+    u32 w = 0;
+    for (u32 t0 = 0; t0 < n; t0 += 32) {
+      u32 t = t0 + lane;
+      bool keep = t < n && !drop[lo + t];
+      u64 k = keep ? in[lo + t] : 0;
+      u32 bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) out[lo + w + __popc(bal & lt_mask)] = k;
+      w += __popc(bal);
+    }
+    if (lane == 0) {
+      cnt_out[list] = w;
+      if (w != n && list_flag) list_flag[list] = 2;
+      total += w;
+    }
+  }
+  if (lane == 0 && total) atomicAdd(&dcount[counter], total);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K11: TransitiveReduction
 // ---------------------------------------------------------------------------------------------
@@ -247,9 +295,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
   const int L = P.L;
   u32 trans = 0, contained = 0;
   for (u32 list = warp_global; list < P.n_lists; list += nwarps) {
-    const u32 lo = P.adj_off[list], hi = P.adj_off[list + 1];
-    if (hi == lo) continue;
-    if (list_consistent<NW>(P, lo, hi, lane)) {
+    const u32 n = P.cnt[list];
+    if (n == 0) continue;
+    const u32 lo = P.adj_off[list], hi = lo + n;
+    const uint8_t fl = P.list_flag[list];
+    const bool cons = fl == 1 ? true : list_consistent<NW>(P, lo, hi, lane);
+    if (cons) {
       // all overhangs nest: the scan keeps the entries of maximal overlap and drops the rest
       const u32 ovmax = P.lay.ov(P.edges[lo]);
       for (u32 t0 = lo; t0 < hi; t0 += 32) {
@@ -322,49 +373,34 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
   }
 }
 
-// EdgeRemoval after TransitiveReduction: an edge survives iff both endpoints kept it
-__global__ void __launch_bounds__(256) tr_final_flags_kernel(StringParams P, u32* __restrict__ flag) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= P.n_edges) return;
-  u32 f = 0;
-  if (P.kept[t]) {
-    long long mi = find_edge(P, P.lay.mirror(P.edges[t]));
-    f = (mi >= 0) ? (P.kept[mi] ? 1u : 0u) : 1u;  // no mirror: nobody can ask for the removal
+// EdgeRemoval after TransitiveReduction: an edge survives iff both endpoints kept it.
+// Writes the surviving entries of every list (checkpoint B) at the list's own offset.
+__global__ void __launch_bounds__(ST_WARPS * 32) tr_final_kernel(StringParams P, u64* __restrict__ out,
+                                                                 u32* __restrict__ cnt_out) {
+  const int lane = threadIdx.x & 31;
+  const u32 lt_mask = (1u << lane) - 1;
+  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  ull total = 0;
+  for (u32 list = warp_global; list < P.n_lists; list += nwarps) {
+    const u32 n = P.cnt[list], lo = P.adj_off[list];
+    u32 w = 0;
+    for (u32 t0 = 0; t0 < n; t0 += 32) {
+      u32 t = t0 + lane;
+      bool keep = false;
+      u64 k = 0;
+      if (t < n && P.kept[lo + t]) {
+        k = P.edges[lo + t];
+        long long mi = find_edge(P, P.lay.mirror(k));
+        keep = (mi >= 0) ? (P.kept[mi] != 0) : true;  // no mirror: nobody can ask for the removal
+      }
+      u32 bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) out[lo + w + __popc(bal & lt_mask)] = k;
+      w += __popc(bal);
+    }
+    if (lane == 0) { cnt_out[list] = w; total += w; }
   }
-  flag[t] = f;
-}
-
-__global__ void __launch_bounds__(256) not_removed_flags_kernel(const uint8_t* __restrict__ removed, size_t n,
-                                                                u32* __restrict__ flag) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) flag[t] = removed[t] ? 0u : 1u;
-}
-
-// adj_off[q] = first edge index whose list id (node*2 + x) is >= q
-__global__ void __launch_bounds__(256) adjacency_kernel(const u64* __restrict__ edges, size_t n, EdgeLayout lay,
-                                                        u32 n_lists, u32* __restrict__ adj_off) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  u32 p = lay.list(edges[i]);
-  long long prev = i > 0 ? (long long)lay.list(edges[i - 1]) : -1;
-  for (long long q = prev + 1; q <= (long long)p; q++) adj_off[q] = (u32)i;
-  if (i == n - 1)
-    for (u32 q = p + 1; q <= n_lists; q++) adj_off[q] = (u32)n;
-}
-
-size_t compact_by_flags(cb_ctx* c, const u64* k, const u32* flag, size_t n, DevBuf<u64>& out);
-
-void build_adjacency(cb_ctx* c, EdgeSet& es) {
-  cudaStream_t s = c->stream;
-  u32 n_lists = 2 * c->n_nodes;
-  es.adj_off.alloc((size_t)n_lists + 1, s);
-  if (es.n == 0) {
-    CB_CUDA(cudaMemsetAsync(es.adj_off.p, 0, ((size_t)n_lists + 1) * 4, s));
-    return;
-  }
-  adjacency_kernel<<<div_up(es.n, 256), 256, 0, s>>>(es.keys.p, es.n, c->lay, n_lists, es.adj_off.p);
-  c->lc.n++;
-  CB_CUDA(cudaGetLastError());
+  if (lane == 0 && total) atomicAdd(&P.dcount[DC_EDGES_B], total);
 }
 
 #define CB_DISPATCH_NW(nw, CALL)                                             \
@@ -379,9 +415,9 @@ void build_adjacency(cb_ctx* c, EdgeSet& es) {
 static StringParams make_params(cb_ctx* c, const EdgeSet& es) {
   StringParams P;
   P.edges = es.keys.p;
-  P.adj_off = es.adj_off.p;
+  P.adj_off = c->adj_off.p;
+  P.cnt = es.cnt.p;
   P.n_lists = 2 * c->n_nodes;
-  P.n_edges = es.n;
   P.lay = c->lay;
   P.node_seq = c->node_seq.p;
   P.node_idkey = c->node_idkey.p;
@@ -392,6 +428,7 @@ static StringParams make_params(cb_ctx* c, const EdgeSet& es) {
   P.pwm_n = c->cfg.pwm_n;
   P.removed = nullptr;
   P.kept = nullptr;
+  P.list_flag = c->list_flag.p;
   P.dcount = (ull*)c->dcount.p;
   return P;
 }
@@ -409,9 +446,10 @@ static int64_t cut_round(cb_ctx* c, const EdgeSet& in, EdgeSet& out, bool& chang
   changed = false;
   CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGE_REMOVAL, 0, sizeof(u64), s));
   if (in.n == 0) return 0;
+  const u32 n_lists = 2 * c->n_nodes;
   DevBuf<uint8_t> removed;
-  removed.alloc(in.n, s);
-  CB_CUDA(cudaMemsetAsync(removed.p, 0, in.n, s));
+  removed.alloc(c->slots, s);
+  CB_CUDA(cudaMemsetAsync(removed.p, 0, c->slots, s));
   StringParams P = make_params(c, in);
   P.removed = removed.p;
   c->lc.begin("cut");
@@ -422,13 +460,17 @@ static int64_t cut_round(cb_ctx* c, const EdgeSet& in, EdgeSet& out, bool& chang
   download_counters(c);
   int64_t cuts = (int64_t)c->hcount[DC_EDGE_REMOVAL];
   if (cuts > 0) {
-    DevBuf<u32> flag;
-    flag.alloc(in.n, s);
-    not_removed_flags_kernel<<<div_up(in.n, 256), 256, 0, s>>>(removed.p, in.n, flag.p);
+    out.keys.alloc(c->slots, s);
+    out.cnt.alloc(n_lists, s);
+    CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGES_C, 0, sizeof(u64), s));
+    filter_lists_kernel<<<list_grid(n_lists), ST_WARPS * 32, 0, s>>>(in.keys.p, c->adj_off.p, in.cnt.p, removed.p,
+                                                                    n_lists, out.keys.p, out.cnt.p, c->list_flag.p,
+                                                                    (ull*)c->dcount.p, (int)DC_EDGES_C);
     c->lc.n++;
-    out.n = compact_by_flags(c, in.keys.p, flag.p, in.n, out.keys);
+    CB_CUDA(cudaGetLastError());
+    download_counters(c);
+    out.n = (size_t)c->hcount[DC_EDGES_C];
     out.valid = true;
-    build_adjacency(c, out);
     changed = true;
   }
   return cuts;
@@ -436,7 +478,10 @@ static int64_t cut_round(cb_ctx* c, const EdgeSet& in, EdgeSet& out, bool& chang
 
 void stage_string_graph(cb_ctx* c) {
   cudaStream_t s = c->stream;
+  const u32 n_lists = 2 * c->n_nodes;
   CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGE_REMOVAL, 0, (DC_COUNT - DC_EDGE_REMOVAL) * sizeof(u64), s));
+  c->list_flag.alloc(n_lists ? n_lists : 1, s);
+  CB_CUDA(cudaMemsetAsync(c->list_flag.p, 2, n_lists ? n_lists : 1, s));
   // ---- CutChimericLinks x <= 2 (BrushAssembler.java:347-367) ----
   timer_start(c, "cut");
   EdgeSet tmp1, tmp2;
@@ -461,13 +506,15 @@ void stage_string_graph(cb_ctx* c) {
 
   // ---- TransitiveReduction + EdgeRemoval (BrushAssembler.java:370-379) ----
   timer_start(c, "tr");
+  c->ckB.keys.alloc(c->slots ? c->slots : 1, s);
+  c->ckB.cnt.alloc(n_lists ? n_lists : 1, s);
   if (C.n == 0) {
-    c->ckB.keys.alloc(0, s);
+    CB_CUDA(cudaMemsetAsync(c->ckB.cnt.p, 0, (size_t)(n_lists ? n_lists : 1) * 4, s));
     c->ckB.n = 0;
   } else {
     DevBuf<uint8_t> kept;
-    kept.alloc(C.n, s);
-    CB_CUDA(cudaMemsetAsync(kept.p, 0, C.n, s));
+    kept.alloc(c->slots, s);
+    CB_CUDA(cudaMemsetAsync(kept.p, 0, c->slots, s));
     StringParams P = make_params(c, C);
     P.kept = kept.p;
     c->lc.begin("tr");
@@ -475,16 +522,16 @@ void stage_string_graph(cb_ctx* c) {
     c->lc.end("tr");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
-    DevBuf<u32> flag;
-    flag.alloc(C.n, s);
-    tr_final_flags_kernel<<<div_up(C.n, 256), 256, 0, s>>>(P, flag.p);
+    c->lc.begin("tr_final");
+    tr_final_kernel<<<list_grid(P.n_lists), ST_WARPS * 32, 0, s>>>(P, c->ckB.keys.p, c->ckB.cnt.p);
+    c->lc.end("tr_final");
     c->lc.n++;
-    c->ckB.n = compact_by_flags(c, C.keys.p, flag.p, C.n, c->ckB.keys);
+    CB_CUDA(cudaGetLastError());
   }
-  c->ckB.valid = true;
-  build_adjacency(c, c->ckB);
   timer_stop(c, "tr");
   download_counters(c);
+  c->ckB.n = (size_t)c->hcount[DC_EDGES_B];
+  c->ckB.valid = true;
   if (c->hcount[DC_TR_OVERFLOW]) throw Error(CB_E_CAPACITY, "TransitiveReduction kept-list capacity exceeded");
   c->counters["trans_edge"] = (int64_t)c->hcount[DC_TRANS_EDGE];
   c->counters["contained_edge"] = (int64_t)c->hcount[DC_CONTAINED_EDGE];
