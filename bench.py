@@ -190,7 +190,7 @@ def bench_reference(args):
 # --------------------------------------------------------------------------------------------
 KERNELS = ["parse_lines", "dedupe_runs", "keygen", "join_verify", "cut", "tr",
            "rs_scatter:dedupe", "rs_upsweep:dedupe", "rs_scatter:tuples", "rs_upsweep:tuples",
-           "rs_scatter:edges", "rs_upsweep:edges", "rs_scatter:export", "rs_upsweep:export", "slot_count", "assemble", "tr_final"]
+           "rs_scatter:edges", "rs_upsweep:edges", "rs_scatter:export", "rs_upsweep:export", "slot_count", "side_insert", "consistency", "tr_fast", "tr_final"]
 
 
 def bench_ours(args):
@@ -250,7 +250,7 @@ def bench_ours(args):
     ms = float(np.mean(dev_ms))
     counters = {c: g.counter(c) for c in ["reads_good", "nodes", "tuples", "candidates_verified", "edges_overlap",
                                           "edges_chl2", "edges_re", "trans_edge", "edge_removal_1", "slow_lists"]}
-    stage_ms = {t: g.time_ms(t) for t in ["parse", "dedupe", "keygen", "sort_tuples", "join_verify", "assemble",
+    stage_ms = {t: g.time_ms(t) for t in ["parse", "dedupe", "keygen", "sort_tuples", "join_verify",
                                           "cut", "tr"]}
 
     # ---- e2e through the C ABI with host buffers ----

@@ -363,120 +363,43 @@ __global__ void __launch_bounds__(JN_WARPS * 32) join_verify_kernel(JoinParams P
   flush();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_verified += __shfl_xor_sync(0xffffffffu, n_verified, o);
-  if (lane == 0 && n_verified) atomicAdd(&P.dcount[DC_CAND_VERIFIED], (ull)n_verified);
+  if (lane == 0 && n_verified) {
+    atomicAdd(&P.dcount[DC_CAND_VERIFIED], (ull)n_verified);
+    atomicAdd(&P.dcount[DC_EDGES_M], (ull)n_verified);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-// list assembly: list = records written by the list's own node entry (M) + side-buffer records
-// addressed to it (X, sorted so that a list's records are contiguous), without duplicates,
-// counting-sorted by overlap descending.
+// Side-buffer records: edge (a,x,ov,y,b) goes into list (a,x) unless a's own node entry already
+// wrote it.  One thread per record: scan the list's own records, then claim a free slot.  A
+// record that does not fit (only possible around poly-A/T k-mers, whose interior windows have no
+// tuple and therefore no slot) is counted in extra[list]; the host then re-runs the join with
+// enlarged slot ranges.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) list_bounds_kernel(const u64* __restrict__ xs, size_t n, EdgeLayout lay,
-                                                          u32 n_lists, u32* __restrict__ xoff) {
+__global__ void __launch_bounds__(256) side_insert_kernel(const u64* __restrict__ xs, size_t n, EdgeLayout lay,
+                                                          const u32* __restrict__ off, const u32* __restrict__ cntM,
+                                                          u32* __restrict__ cnt, u64* __restrict__ keys,
+                                                          u32* __restrict__ extra, ull* __restrict__ dcount) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  u32 p = lay.list(xs[i]);
-  long long prev = i > 0 ? (long long)lay.list(xs[i - 1]) : -1;
-  for (long long q = prev + 1; q <= (long long)p; q++) xoff[q] = (u32)i;
-  if (i == n - 1)
-    for (u32 q = p + 1; q <= n_lists; q++) xoff[q] = (u32)n;
-}
-
-__global__ void __launch_bounds__(256) list_total_kernel(const u32* __restrict__ cntM, const u32* __restrict__ xoff,
-                                                         u32 n_lists, u32* __restrict__ tot, ull* __restrict__ dcount) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  u32 t = 0;
-  if (i < n_lists) {
-    t = cntM[i] + (xoff[i + 1] - xoff[i]);
-    tot[i] = t;
-  } else if (i == n_lists) tot[i] = 0;
-  // longest list (for diagnostics)
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
-  if ((threadIdx.x & 31) == 0 && t) atomicMax(&dcount[DC_MAX_LIST], (ull)t);
-}
-
-constexpr int AS_WARPS = 8;
-
-__global__ void __launch_bounds__(AS_WARPS * 32) assemble_kernel(const u64* __restrict__ mtmp,
-                                                                 const u32* __restrict__ off1,
-                                                                 const u32* __restrict__ cntM,
-                                                                 const u64* __restrict__ xs,
-                                                                 const u32* __restrict__ xoff,
-                                                                 const u32* __restrict__ off2, u64* __restrict__ out,
-                                                                 u32* __restrict__ cnt_out, EdgeLayout lay,
-                                                                 u32 n_lists, ull* __restrict__ dcount) {
-  __shared__ u32 s_hist[AS_WARPS][257];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-  const u32 nbins = 1u << lay.ob;
-  const u32 ovmask = nbins - 1;
-  ull total_edges = 0;
-  for (u32 lid = warp_global; lid < n_lists; lid += nwarps) {
-    const u32 m = cntM[lid], x0 = xoff[lid], q = xoff[lid + 1] - x0;
-    const u32 n = m + q;
-    if (n == 0) {
-      if (lane == 0) cnt_out[lid] = 0;
-      continue;
-    }
-    const u64* M = mtmp + off1[lid];
-    const u64* X = xs + x0;
-    u64* O = out + off2[lid];
-    if (q == 0 && n <= 32) {
-      // common case: one record per lane, ordered with a warp-wide rank by (L - ov)
-      u64 key = lane < (int)n ? M[lane] : ~0ull;
-      u32 bin = (u32)(key >> (lay.nb + 1)) & ovmask;
-      u32 rank = 0;
-#pragma unroll 8
-      for (int t = 0; t < 32; t++) {
-        u32 ob = __shfl_sync(0xffffffffu, bin, t);
-        bool ov_valid = t < (int)n;
-        if (ov_valid && (ob < bin || (ob == bin && t < lane))) rank++;
-      }
-      if (lane < (int)n) O[rank] = key;
-      if (lane == 0) { cnt_out[lid] = n; total_edges += n; }
-      continue;
-    }
-    for (u32 t = lane; t < nbins; t += 32) s_hist[warp][t] = 0;
-    __syncwarp();
-    for (u32 i = lane; i < n; i += 32) {
-      u64 key = i < m ? M[i] : X[i - m];
-      bool valid = true;
-      if (i >= m)
-        for (u32 t = 0; t < m; t++)
-          if (M[t] == key) { valid = false; break; }
-      if (valid) atomicAdd(&s_hist[warp][(u32)(key >> (lay.nb + 1)) & ovmask], 1u);
-    }
-    __syncwarp();
-    u32 carry = 0;
-    for (u32 base = 0; base < nbins; base += 32) {
-      u32 v = (base + lane < nbins) ? s_hist[warp][base + lane] : 0;
-      u32 inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        u32 t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (base + lane < nbins) s_hist[warp][base + lane] = carry + inc - v;
-      carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    __syncwarp();
-    for (u32 i = lane; i < n; i += 32) {
-      u64 key = i < m ? M[i] : X[i - m];
-      bool valid = true;
-      if (i >= m)
-        for (u32 t = 0; t < m; t++)
-          if (M[t] == key) { valid = false; break; }
-      if (valid) {
-        u32 p = atomicAdd(&s_hist[warp][(u32)(key >> (lay.nb + 1)) & ovmask], 1u);
-        O[p] = key;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) { cnt_out[lid] = carry; total_edges += carry; }
+  const u64 key = xs[i];
+  const u32 lid = lay.list(key);
+  const u32 base = off[lid], m = cntM[lid], cap = off[lid + 1] - base;
+  for (u32 t = 0; t < m; t++)
+    if (keys[base + t] == key) return;
+  u32 pos = atomicAdd(&cnt[lid], 1u);
+  if (pos < cap) {
+    keys[base + pos] = key;
+    atomicAdd(&dcount[DC_EDGES_A], 1ull);
+  } else {
+    atomicAdd(&extra[lid], 1u);
+    atomicAdd(&dcount[DC_MAX_LIST], 1ull);  // reused as the overflow count of this attempt
   }
-  if (lane == 0 && total_edges) atomicAdd(&dcount[DC_EDGES_A], total_edges);
+}
+
+__global__ void __launch_bounds__(256) add_u32_kernel(u32* __restrict__ a, const u32* __restrict__ b, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
 }
 
 static int bits_for(u64 nvalues) {  // bits needed to store values 0 .. nvalues-1
@@ -579,20 +502,24 @@ void stage_build_overlap(cb_ctx* c) {
   c->lc.end("slot_count");
   c->lc.n++;
   exclusive_scan_u32(slotcnt.p, off1.p, (size_t)n_lists + 1, s, c->lc);
-  const size_t slots1 = read_u32(c, off1.p + n_lists);
-  slotcnt.release();
+  size_t slots1 = read_u32(c, off1.p + n_lists);
   DevBuf<u64> mtmp, xbuf;
-  mtmp.alloc(slots1 ? slots1 : 1, s);
-  P.off1 = off1.p;
-  P.mtmp = mtmp.p;
+  DevBuf<u32> cnt, extra;
+  cnt.alloc(n_lists ? n_lists : 1, s);
+  extra.alloc(n_lists ? n_lists : 1, s);
   P.cntM = cntM.p;
   u64 xcap = (u64)T / 4 + 4096;
   u64 n_x = 0;
-  for (int attempt = 0; attempt < 2; attempt++) {
+  for (int attempt = 0;; attempt++) {
+    mtmp.alloc(slots1 ? slots1 : 1, s);
+    CB_CUDA(cudaMemsetAsync(mtmp.p, 0xff, (slots1 ? slots1 : 1) * sizeof(u64), s));  // free slots read as ~0
     xbuf.alloc(xcap, s);
+    P.off1 = off1.p;
+    P.mtmp = mtmp.p;
     P.xbuf = xbuf.p;
     P.xcap = xcap;
     CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_HKMER, 0, (DC_EDGE_REMOVAL - DC_HKMER) * sizeof(u64), s));
+    CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_MAX_LIST, 0, sizeof(u64), s));
     c->lc.begin("join_verify");
     CB_DISPATCH_NW(c->NW, (join_verify_kernel<NW_><<<jblocks, JN_WARPS * 32, 0, s>>>(P)));
     c->lc.end("join_verify");
@@ -600,9 +527,30 @@ void stage_build_overlap(cb_ctx* c) {
     CB_CUDA(cudaGetLastError());
     download_counters(c);
     n_x = c->hcount[DC_EDGES_RAW];
-    if (n_x <= xcap) break;
-    if (attempt == 1) throw Error(CB_E_CAPACITY, "side buffer overflow");
-    xcap = n_x;  // exact size known now: run again
+    if (n_x > xcap) {  // side buffer too small: its exact size is known now
+      if (attempt >= 3) throw Error(CB_E_CAPACITY, "side buffer overflow");
+      xcap = n_x;
+      continue;
+    }
+    // side-buffer records into their lists
+    CB_CUDA(cudaMemcpyAsync(cnt.p, cntM.p, (size_t)n_lists * 4, cudaMemcpyDeviceToDevice, s));
+    CB_CUDA(cudaMemsetAsync(extra.p, 0, (size_t)n_lists * 4, s));
+    if (n_x) {
+      c->lc.begin("side_insert");
+      side_insert_kernel<<<div_up(n_x, 256), 256, 0, s>>>(xbuf.p, n_x, c->lay, off1.p, cntM.p, cnt.p, mtmp.p, extra.p,
+                                                         (ull*)c->dcount.p);
+      c->lc.end("side_insert");
+      c->lc.n++;
+      CB_CUDA(cudaGetLastError());
+    }
+    download_counters(c);
+    if (c->hcount[DC_MAX_LIST] == 0) break;
+    if (attempt >= 3) throw Error(CB_E_CAPACITY, "adjacency slot overflow");
+    // enlarge the slot ranges of the lists that overflowed and run the join again
+    add_u32_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(slotcnt.p, extra.p, n_lists);
+    c->lc.n++;
+    exclusive_scan_u32(slotcnt.p, off1.p, (size_t)n_lists + 1, s, c->lc);
+    slots1 = read_u32(c, off1.p + n_lists);
   }
   timer_stop(c, "join_verify");
   keys[where].release();
@@ -620,48 +568,14 @@ void stage_build_overlap(cb_ctx* c) {
                 "non-empty high-frequency k-mer list: the reference's stopword loader (MatchPrefix.java:81) is "
                 "ill-defined for it, parity undefined");
 
-  // ---- assemble the adjacency lists of checkpoint A ----
-  timer_start(c, "assemble");
-  DevBuf<u64> xalt;
-  xalt.alloc(n_x ? n_x : 1, s);
-  int wx = radix_sort(xbuf.p, xalt.p, nullptr, nullptr, n_x, c->lay.nb + c->lay.ob + 1, c->lay.total_bits(), s, c->lc,
-                      "edges");
-  const u64* xs = wx ? xalt.p : xbuf.p;
-  DevBuf<u32> xoff, tot;
-  xoff.alloc((size_t)n_lists + 1, s);
-  tot.alloc((size_t)n_lists + 1, s);
-  if (n_x) {
-    list_bounds_kernel<<<div_up(n_x, 256), 256, 0, s>>>(xs, n_x, c->lay, n_lists, xoff.p);
-    c->lc.n++;
-  } else {
-    CB_CUDA(cudaMemsetAsync(xoff.p, 0, ((size_t)n_lists + 1) * 4, s));
-  }
-  list_total_kernel<<<div_up((size_t)n_lists + 1, 256), 256, 0, s>>>(cntM.p, xoff.p, n_lists, tot.p,
-                                                                    (ull*)c->dcount.p);
-  c->lc.n++;
-  c->adj_off.alloc((size_t)n_lists + 1, s);
-  exclusive_scan_u32(tot.p, c->adj_off.p, (size_t)n_lists + 1, s, c->lc);
-  c->slots = read_u32(c, c->adj_off.p + n_lists);
-  c->ckA.keys.alloc(c->slots ? c->slots : 1, s);
-  c->ckA.cnt.alloc(n_lists, s);
-  {
-    int blocks = div_up((size_t)n_lists, AS_WARPS);
-    int cap = kNumSMs * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    c->lc.begin("assemble");
-    assemble_kernel<<<blocks, AS_WARPS * 32, 0, s>>>(mtmp.p, off1.p, cntM.p, xs, xoff.p, c->adj_off.p, c->ckA.keys.p,
-                                                    c->ckA.cnt.p, c->lay, n_lists, (ull*)c->dcount.p);
-    c->lc.end("assemble");
-    c->lc.n++;
-    CB_CUDA(cudaGetLastError());
-  }
-  download_counters(c);
-  c->ckA.n = (size_t)c->hcount[DC_EDGES_A];
+  // checkpoint A: the slot array is the adjacency structure
+  c->adj_off = std::move(off1);
+  c->slots = slots1;
+  c->ckA.keys = std::move(mtmp);
+  c->ckA.cnt = std::move(cnt);
+  c->ckA.n = (size_t)(c->hcount[DC_EDGES_M] + c->hcount[DC_EDGES_A]);
   c->ckA.valid = true;
-  timer_stop(c, "assemble");
   c->counters["edges_overlap"] = (int64_t)c->ckA.n;
-  c->counters["max_list"] = (int64_t)c->hcount[DC_MAX_LIST];
 }
 
 }  // namespace cb

@@ -10,15 +10,16 @@
 //
 // The graph of checkpoint A is symmetric (S u mirror(S)), so the neighbour messages each
 // reducer rebuilds its lists from (DARKMSG / OVALMSG, sent by the mirror edge) are exactly the
-// node's own adjacency list; a list is the contiguous key range [adj_off[2a+x], adj_off[2a+x+1])
-// ordered by overlap descending.  The overhang of an entry is b^y[ov:], the bases of the
-// neighbour that extend past the node.
+// node's own adjacency list: the cnt[lid] records at keys[adj_off[lid] ...), lid = 2a + x, in no
+// particular order.  The overhang of an entry is b^y[ov:], the bases of the neighbour that extend
+// past the node.
 //
-// Both kernels first test whether every overhang of the list is a prefix of the longest one
-// ("consistent list").  Then (a) the PWM consensus equals that longest overhang wherever it is
-// defined, has no N, and cuts nothing (needs MAJORITY < 1); (b) the greedy scan of
-// TransitiveReduction keeps exactly the entries of maximal overlap.  Lists that are not
-// consistent (sequencing errors, repeats) take the literal path.
+// First every list is tested for "consistency": is every overhang a prefix of the longest one?
+// (one thread per record, consistency_kernel).  For a consistent list (a) the PWM consensus of
+// CutChimericLinks equals the longest overhang wherever it is defined, has no N and cuts nothing
+// (needs MAJORITY < 1); (b) the greedy scan of TransitiveReduction keeps exactly the entries of
+// maximal overlap (tr_fast_kernel, one thread per record).  Lists that are not consistent
+// (sequencing errors, repeats) go through work lists to the literal warp-per-list kernels.
 #include "ctx.cuh"
 
 namespace cb {
@@ -35,19 +36,26 @@ __device__ __forceinline__ void load_read_c(const u64* __restrict__ reads, u32 i
 }
 
 struct StringParams {
-  const u64* edges;    // gapped CSR keys
+  const u64* edges;    // gapped CSR keys (free slots hold ~0)
   const u32* adj_off;  // [n_lists + 1]
   const u32* cnt;      // [n_lists]
   u32 n_lists;         // 2 * n_nodes
+  size_t slots;
   EdgeLayout lay;
   const u64* node_seq;
   const IdKey* node_idkey;
   const u32* node_cov;
   int L, K;
   float majority, pwm_n;
-  uint8_t* removed;    // cut_kernel output, per slot
-  uint8_t* kept;       // tr_kernel output, per slot
-  uint8_t* list_flag;  // per list: 1 consistent, 0 not, 2 unknown
+  uint8_t* removed;    // cut output, per slot
+  uint8_t* kept;       // tr output, per slot
+  uint8_t* list_flag;  // per list: 1 consistent, 0 not, 2 dirty (lost an entry)
+  const u32* work;     // work list of list ids (literal kernels)
+  u32 n_work;
+  u32* work_out;       // lists that lost an entry in this round
+  u32* n_work_out;
+  int check_consistency;  // literal kernels: re-test the list first
+  int dirty_bit;          // 2 in the first cut round, 4 in the second
   ull* dcount;
 };
 
@@ -75,50 +83,57 @@ __device__ __forceinline__ int base_at(const u64 (&h)[NW], int j) {
   return (int)((w >> (62 - 2 * (j & 31))) & 3);
 }
 
-// slot index of `key` in its list or -1.  Lists are ordered by (L - ov) ascending; entries of
-// equal overlap are in no particular order, so the equal-overlap run is scanned.
+// slot index of `key` in its (unordered) list or -1
 __device__ __forceinline__ long long find_edge(const StringParams& P, u64 key) {
   const u32 list = P.lay.list(key);
   const u32 base = P.adj_off[list], n = P.cnt[list];
-  const u32 sh = P.lay.nb + 1, msk = (1u << P.lay.ob) - 1;
-  const u32 target = (u32)(key >> sh) & msk;
-  u32 lo = 0, hi = n;
-  while (lo < hi) {
-    u32 mid = (lo + hi) >> 1;
-    if (((u32)(P.edges[base + mid] >> sh) & msk) < target) lo = mid + 1;
-    else hi = mid;
-  }
-  for (u32 t = lo; t < n; t++) {
-    u64 k = P.edges[base + t];
-    if (((u32)(k >> sh) & msk) != target) break;
-    if (k == key) return (long long)(base + t);
-  }
+  for (u32 t = 0; t < n; t++)
+    if (P.edges[base + t] == key) return (long long)(base + t);
   return -1;
-}
-
-// are all overhangs of [lo, hi) prefixes of the longest one (the last entry)?
-template <int NW>
-__device__ __forceinline__ bool list_consistent(const StringParams& P, u32 lo, u32 hi, int lane) {
-  u64 H[NW];
-  int lenH;
-  load_overhang<NW>(P, P.edges[hi - 1], H, lenH);
-  bool good = true;
-  for (u32 t0 = lo; t0 < hi; t0 += 32) {
-    u32 t = t0 + lane;
-    if (t < hi) {
-      u64 h[NW];
-      int len;
-      load_overhang<NW>(P, P.edges[t], h, len);
-      good = good && prefix_equal<NW>(h, H, len);
-    }
-  }
-  return __all_sync(0xffffffffu, good);
 }
 
 constexpr int ST_WARPS = 8;
 
 // ---------------------------------------------------------------------------------------------
-// K10: CutChimericLinks
+// consistency of every list, one thread per record.  Threads of one list run in lock step over
+// the same addresses (broadcast loads), so the per-record list scan is cheap.
+// ---------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* __restrict__ work_out,
+                                                          u32* __restrict__ n_work_out, int force_slow) {
+  size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= P.slots) return;
+  const u64 k = P.edges[slot];
+  if (k == ~0ull) return;
+  const u32 lid = P.lay.list(k);
+  const u32 lo = P.adj_off[lid], n = P.cnt[lid];
+  if (n <= 1) return;  // flag stays 1
+  bool bad = force_slow != 0;
+  if (!bad) {
+    // the longest overhang: minimal overlap, first such record
+    u32 hidx = lo;
+    u32 hov = P.lay.ov(P.edges[lo]);
+    for (u32 t = 1; t < n; t++) {
+      u32 o = P.lay.ov(P.edges[lo + t]);
+      if (o < hov) { hov = o; hidx = lo + t; }
+    }
+    u64 H[NW], h[NW];
+    int lenH, len;
+    load_overhang<NW>(P, P.edges[hidx], H, lenH);
+    load_overhang<NW>(P, k, h, len);
+    bad = !prefix_equal<NW>(h, H, len);
+  }
+  if (bad) {
+    // first thread to clear the flag queues the list for the literal kernel
+    unsigned int* word = reinterpret_cast<unsigned int*>(P.list_flag + (lid & ~3u));
+    unsigned int bit = 0xffu << (8 * (lid & 3u));
+    unsigned int old = atomicAnd(word, ~bit);
+    if (old & bit) work_out[atomicAdd(n_work_out, 1u)] = lid;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K10: CutChimericLinks, literal path, one warp per queued list
 // ---------------------------------------------------------------------------------------------
 struct TopKey {  // order of Node.Consensus after the reducer's pre-sort: overhang length desc
   u32 ov;        // (= ov asc), then id asc for direction f / desc for direction r
@@ -144,6 +159,42 @@ __device__ __forceinline__ TopKey warp_top_min(TopKey v) {
   return v;
 }
 
+// warp version of the consistency test (lists that changed since consistency_kernel ran)
+template <int NW>
+__device__ __forceinline__ bool list_consistent_warp(const StringParams& P, u32 lo, u32 n, int lane) {
+  u32 hov = 0xffffffffu, hidx = 0xffffffffu;
+  for (u32 t = lane; t < n; t += 32) {
+    u32 o = P.lay.ov(P.edges[lo + t]);
+    if (o < hov) { hov = o; hidx = lo + t; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    u32 ov2 = __shfl_xor_sync(0xffffffffu, hov, o), ix2 = __shfl_xor_sync(0xffffffffu, hidx, o);
+    if (ov2 < hov || (ov2 == hov && ix2 < hidx)) { hov = ov2; hidx = ix2; }
+  }
+  u64 H[NW];
+  int lenH;
+  load_overhang<NW>(P, P.edges[hidx], H, lenH);
+  bool good = true;
+  for (u32 t = lane; t < n; t += 32) {
+    u64 h[NW];
+    int len;
+    load_overhang<NW>(P, P.edges[lo + t], h, len);
+    good = good && prefix_equal<NW>(h, H, len);
+  }
+  return __all_sync(0xffffffffu, good);
+}
+
+// sets this round's dirty bit of the list's flag byte; the first setter queues the list once.
+// Any dirty bit makes the flag differ from 1, so TransitiveReduction takes the literal path.
+__device__ __forceinline__ void mark_dirty(const StringParams& P, u32 lid) {
+  unsigned int* word = reinterpret_cast<unsigned int*>(P.list_flag + (lid & ~3u));
+  unsigned int sh = 8 * (lid & 3u);
+  unsigned int bit = (unsigned int)P.dirty_bit << sh;
+  unsigned int old = atomicOr(word, bit);
+  if (!(old & bit)) P.work_out[atomicAdd(P.n_work_out, 1u)] = lid;
+}
+
 template <int NW>
 __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
   __shared__ unsigned char s_cons[ST_WARPS][256];
@@ -151,25 +202,22 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
   const int L = P.L;
-  for (u32 list = warp_global; list < P.n_lists; list += nwarps) {
+  for (u32 wi = warp_global; wi < P.n_work; wi += nwarps) {
+    const u32 list = P.work[wi];
     const u32 n = P.cnt[list];
-    const u32 lo = P.adj_off[list], hi = lo + n;
-    if (n <= 1) {  // CutChimericLinks.java:306 "flist.size() > 1"
-      if (lane == 0) P.list_flag[list] = 1;
-      continue;
-    }
-    const bool cons = list_consistent<NW>(P, lo, hi, lane);
-    if (lane == 0) P.list_flag[list] = cons ? 1 : 0;
-    if (cons && P.majority < 1.0f) continue;
+    const u32 lo = P.adj_off[list];
+    if (n <= 1) continue;  // CutChimericLinks.java:306 "flist.size() > 1"
+    if (P.check_consistency && P.majority < 1.0f && list_consistent_warp<NW>(P, lo, n, lane)) continue;
     if (lane == 0) atomicAdd(&P.dcount[DC_SLOW_LISTS], 1ull);
     const u32 x = list & 1;
-    // ---- entries 0 and 1 of the Consensus order (Node.java:1295-1320) ----
-    TopKey best[2];
-    for (int r = 0; r < 2; r++) {
+    // ---- entries 0, 1 of the Consensus order and the overlap of entry 2 (Node.java:1295-1320) ----
+    TopKey best[3];
+    for (int r = 0; r < 3; r++) {
       TopKey mine;
       mine.ov = 0xffffffffu; mine.hi = ~0ull; mine.lo = ~0ull; mine.idx = 0xffffffffu;
-      for (u32 t = lo + lane; t < hi; t += 32) {
-        if (r == 1 && t == best[0].idx) continue;
+      for (u32 t = lo + lane; t < lo + n; t += 32) {
+        if (r >= 1 && t == best[0].idx) continue;
+        if (r >= 2 && t == best[1].idx) continue;
         u64 k = P.edges[t];
         IdKey ik = P.node_idkey[P.lay.nbr(k)];
         TopKey c;
@@ -184,15 +232,15 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
     const u32 cov0 = P.node_cov[P.lay.nbr(P.edges[best[0].idx])];
     const u32 cov1 = P.node_cov[P.lay.nbr(P.edges[best[1].idx])];
     int clen;
-    if (n == 2 || (float)cov0 + (float)cov1 > 2.0f) clen = L - (int)P.lay.ov(P.edges[hi - 2]);
-    else clen = L - (int)P.lay.ov(P.edges[hi - 3]);
+    if (n == 2 || (float)cov0 + (float)cov1 > 2.0f) clen = L - (int)best[1].ov;
+    else clen = L - (int)best[2].ov;
     // ---- position weight matrix, one lane per position (Node.java:1321-1364) ----
     int ncount = 0;
     for (int j0 = 0; j0 < clen; j0 += 32) {
       int j = j0 + lane;
       int cnt[4] = {0, 0, 0, 0};
       int sum = 0;
-      for (u32 t = lo; t < hi; t++) {
+      for (u32 t = lo; t < lo + n; t++) {
         u64 k = P.edges[t];
         u64 h[NW];
         int len;
@@ -221,9 +269,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
     // Node.java:1369-1371 (0/0 = NaN compares false, as in Java)
     if (__fdiv_rn((float)ncount, (float)clen) > P.pwm_n) continue;
     // ---- entries that disagree with the consensus (CutChimericLinks.java:337-381) ----
-    for (u32 t0 = lo; t0 < hi; t0 += 32) {
+    for (u32 t0 = lo; t0 < lo + n; t0 += 32) {
       u32 t = t0 + lane;
-      if (t < hi) {
+      if (t < lo + n) {
         u64 k = P.edges[t];
         u64 h[NW];
         int len;
@@ -236,8 +284,10 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
         }
         if (miss) {
           P.removed[t] = 1;
-          long long mi = find_edge(P, P.lay.mirror(k));
-          if (mi >= 0) P.removed[mi] = 1;
+          mark_dirty(P, list);
+          u64 mk = P.lay.mirror(k);
+          long long mi = find_edge(P, mk);
+          if (mi >= 0) { P.removed[mi] = 1; mark_dirty(P, P.lay.list(mk)); }
           atomicAdd(&P.dcount[DC_EDGE_REMOVAL], 1ull);
         }
       }
@@ -246,119 +296,163 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
   }
 }
 
-// EdgeRemoval (EdgeRemoval.java:121-202): per list, copy the entries that are not flagged.
-// A list that loses an entry has its consistency flag reset to "unknown".
-__global__ void __launch_bounds__(ST_WARPS * 32) filter_lists_kernel(const u64* __restrict__ in,
-                                                                     const u32* __restrict__ adj_off,
-                                                                     const u32* __restrict__ cnt_in,
-                                                                     const uint8_t* __restrict__ drop, u32 n_lists,
-                                                                     u64* __restrict__ out, u32* __restrict__ cnt_out,
-                                                                     uint8_t* __restrict__ list_flag,
-                                                                     ull* __restrict__ dcount, int counter) {
+// EdgeRemoval (EdgeRemoval.java:121-202) on the lists that lost an entry: in-place compaction.
+__global__ void __launch_bounds__(ST_WARPS * 32) remove_flagged_kernel(u64* __restrict__ keys,
+                                                                       const u32* __restrict__ adj_off,
+                                                                       u32* __restrict__ cnt,
+                                                                       uint8_t* __restrict__ drop,
+                                                                       const u32* __restrict__ work, u32 n_work,
+                                                                       ull* __restrict__ dcount) {
   const int lane = threadIdx.x & 31;
   const u32 lt_mask = (1u << lane) - 1;
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-  ull total = 0;
-  for (u32 list = warp_global; list < n_lists; list += nwarps) {
-    const u32 n = cnt_in[list], lo = adj_off[list];
+  ull removed_total = 0;
+  for (u32 wi = warp_global; wi < n_work; wi += nwarps) {
+    const u32 list = work[wi];
+    const u32 n = cnt[list], lo = adj_off[list];
     u32 w = 0;
     for (u32 t0 = 0; t0 < n; t0 += 32) {
       u32 t = t0 + lane;
       bool keep = t < n && !drop[lo + t];
-      u64 k = keep ? in[lo + t] : 0;
+      u64 k = t < n ? keys[lo + t] : 0;
+      __syncwarp();
       u32 bal = __ballot_sync(0xffffffffu, keep);
-      if (keep) out[lo + w + __popc(bal & lt_mask)] = k;
+      if (keep) keys[lo + w + __popc(bal & lt_mask)] = k;  // w <= t0: never overtakes the reads
+      if (t < n) drop[lo + t] = 0;
       w += __popc(bal);
+      __syncwarp();
     }
-    if (lane == 0) {
-      cnt_out[list] = w;
-      if (w != n && list_flag) list_flag[list] = 2;
-      total += w;
-    }
+    for (u32 t = w + lane; t < n; t += 32) keys[lo + t] = ~0ull;
+    if (lane == 0) { cnt[list] = w; removed_total += n - w; }
   }
-  if (lane == 0 && total) atomicAdd(&dcount[counter], total);
+  if (lane == 0 && removed_total) atomicAdd(&dcount[DC_EDGES_C], removed_total);
 }
 
 // ---------------------------------------------------------------------------------------------
 // K11: TransitiveReduction
 // ---------------------------------------------------------------------------------------------
+// consistent lists, one thread per record: keep the records of maximal overlap
+__global__ void __launch_bounds__(256) tr_fast_kernel(StringParams P) {
+  size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  u32 trans = 0, contained = 0;
+  if (slot < P.slots) {
+    const u64 k = P.edges[slot];
+    if (k != ~0ull) {
+      const u32 lid = P.lay.list(k);
+      if (P.list_flag[lid] == 1) {
+        const u32 lo = P.adj_off[lid], n = P.cnt[lid];
+        const u32 ov = P.lay.ov(k);
+        u32 ovmax = 0;
+        for (u32 t = 0; t < n; t++) ovmax = max(ovmax, P.lay.ov(P.edges[lo + t]));
+        if ((int)ov == P.L) contained = 1;  // TransitiveReduction.java:319-323 (equal-length reads)
+        if (ov == ovmax) P.kept[slot] = 1;
+        else {
+          // :325-334 an entry of the same type to the same neighbour already kept -> dropped
+          // without counting as transitive
+          bool step2 = false;
+          for (u32 t = 0; t < n; t++) {
+            u64 kq = P.edges[lo + t];
+            if (P.lay.ov(kq) == ovmax && P.lay.nbr(kq) == P.lay.nbr(k) && P.lay.y(kq) == P.lay.y(k)) { step2 = true; break; }
+          }
+          if (!step2) trans = 1;
+        }
+      }
+    }
+  }
+  u32 tb = __popc(__ballot_sync(0xffffffffu, trans)), cb_ = __popc(__ballot_sync(0xffffffffu, contained));
+  if ((threadIdx.x & 31) == 0) {
+    if (tb) atomicAdd(&P.dcount[DC_TRANS_EDGE], (ull)tb);
+    if (cb_) atomicAdd(&P.dcount[DC_CONTAINED_EDGE], (ull)cb_);
+  }
+}
+
+// lists whose flag is not "consistent" -> work list for the literal kernel
+__global__ void __launch_bounds__(256) tr_worklist_kernel(const uint8_t* __restrict__ list_flag,
+                                                          const u32* __restrict__ cnt, u32 n_lists,
+                                                          u32* __restrict__ work, u32* __restrict__ n_work) {
+  u32 lid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lid < n_lists && list_flag[lid] != 1 && cnt[lid] > 0) work[atomicAdd(n_work, 1u)] = lid;
+}
+
 constexpr int TR_KC = 64;  // kept entries per list in the literal scan
 
+// literal greedy scan (TransitiveReduction.java:300-409), one warp per queued list.  Entries are
+// visited by overlap descending; entries of equal overlap skip each other (:341-343) and cannot
+// be the same edge, so a whole overlap level is decided at once against the entries kept from
+// larger overlaps.
 template <int NW>
 __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
   __shared__ u64 s_kh[ST_WARPS][TR_KC][NW];
   __shared__ u64 s_kkey[ST_WARPS][TR_KC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 lt_mask = (1u << lane) - 1;
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
   const int L = P.L;
   u32 trans = 0, contained = 0;
-  for (u32 list = warp_global; list < P.n_lists; list += nwarps) {
-    const u32 n = P.cnt[list];
+  for (u32 wi = warp_global; wi < P.n_work; wi += nwarps) {
+    const u32 list = P.work[wi];
+    const u32 n = P.cnt[list], lo = P.adj_off[list];
     if (n == 0) continue;
-    const u32 lo = P.adj_off[list], hi = lo + n;
-    const uint8_t fl = P.list_flag[list];
-    const bool cons = fl == 1 ? true : list_consistent<NW>(P, lo, hi, lane);
-    if (cons) {
-      // all overhangs nest: the scan keeps the entries of maximal overlap and drops the rest
-      const u32 ovmax = P.lay.ov(P.edges[lo]);
-      for (u32 t0 = lo; t0 < hi; t0 += 32) {
-        u32 t = t0 + lane;
-        if (t < hi) {
-          u64 k = P.edges[t];
-          u32 ov = P.lay.ov(k);
-          if ((int)ov == L) contained++;  // TransitiveReduction.java:319-323 (equal-length reads)
-          if (ov == ovmax) P.kept[t] = 1;
-          else {
-            // :325-334 an entry of the same type to the same neighbour already kept -> dropped
-            // without counting as transitive
-            bool step2 = false;
-            for (u32 q = lo; q < hi && P.lay.ov(P.edges[q]) == ovmax; q++) {
-              u64 kq = P.edges[q];
-              if (P.lay.nbr(kq) == P.lay.nbr(k) && P.lay.y(kq) == P.lay.y(k)) { step2 = true; break; }
-            }
-            if (!step2) trans++;
-          }
-        }
-      }
-      continue;
-    }
     if (lane == 0) atomicAdd(&P.dcount[DC_SLOW_LISTS], 1ull);
-    // ---- literal greedy scan (TransitiveReduction.java:300-409) ----
     u32 nk = 0;
-    for (u32 t = lo; t < hi; t++) {
-      u64 k = P.edges[t];
-      u64 h[NW];
-      int len;
-      load_overhang<NW>(P, k, h, len);
-      const u32 ov = P.lay.ov(k), y = P.lay.y(k), nbr = P.lay.nbr(k);
-      if ((int)ov == L && lane == 0) contained++;
-      bool step2 = false, step3 = false;
-      for (u32 q = lane; q < nk; q += 32) {
-        u64 kq = s_kkey[warp][q];
-        if (P.lay.nbr(kq) == nbr && P.lay.y(kq) == y) step2 = true;
-        u32 ovq = P.lay.ov(kq);
-        if (ovq != ov) {  // :341-343 (equal length reads: same ov <=> same ov and same length)
-          u64 hq[NW];
+    int level = L + 1;  // overlap levels strictly below `level` are still to do
+    for (;;) {
+      // next level: the largest overlap below `level`
+      int nxt = -1;
+      for (u32 t = lane; t < n; t += 32) {
+        int o = (int)P.lay.ov(P.edges[lo + t]);
+        if (o < level && o > nxt) nxt = o;
+      }
 #pragma unroll
-          for (int w = 0; w < NW; w++) hq[w] = s_kh[warp][q][w];
-          if (prefix_equal<NW>(h, hq, L - (int)ovq)) step3 = true;  // prefix.startsWith(suffix) :345
+      for (int o = 16; o > 0; o >>= 1) nxt = max(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
+      if (nxt < 0) break;
+      level = nxt;
+      const u32 nk_level = nk;  // entries of this level are compared with earlier levels only
+      for (u32 t0 = 0; t0 < n; t0 += 32) {
+        u32 t = t0 + lane;
+        u64 k = t < n ? P.edges[lo + t] : ~0ull;
+        bool mine = t < n && (int)P.lay.ov(k) == level;
+        bool keep = false;
+        u64 h[NW];
+        if (mine) {
+          int len;
+          load_overhang<NW>(P, k, h, len);
+          if (level == L) contained++;
+          bool step2 = false, step3 = false;
+          for (u32 q = 0; q < nk_level; q++) {  // :325-334 comes before the transitive test
+            u64 kq = s_kkey[warp][q];
+            if (P.lay.nbr(kq) == P.lay.nbr(k) && P.lay.y(kq) == P.lay.y(k)) { step2 = true; break; }
+          }
+          for (u32 q = 0; q < nk_level && !step2; q++) {
+            u64 kq = s_kkey[warp][q];
+            u64 hq[NW];
+#pragma unroll
+            for (int w = 0; w < NW; w++) hq[w] = s_kh[warp][q][w];
+            if (prefix_equal<NW>(h, hq, L - (int)P.lay.ov(kq))) { step3 = true; break; }  // startsWith :345
+          }
+          if (step3) trans++;
+          keep = !step2 && !step3;
         }
-      }
-      step2 = __any_sync(0xffffffffu, step2);
-      step3 = __any_sync(0xffffffffu, step3);
-      if (step2) continue;
-      if (step3) { if (lane == 0) trans++; continue; }
-      if (nk >= TR_KC) { if (lane == 0) atomicAdd(&P.dcount[DC_TR_OVERFLOW], 1ull); continue; }
-      if (lane < NW) {
+        u32 bal = __ballot_sync(0xffffffffu, keep);
+        if (bal) {
+          u32 pos = nk + __popc(bal & lt_mask);
+          if (keep) {
+            if (pos < TR_KC) {
 #pragma unroll
-        for (int w = 0; w < NW; w++)
-          if (w == lane) s_kh[warp][nk][w] = h[w];
+              for (int w = 0; w < NW; w++) s_kh[warp][pos][w] = h[w];
+              s_kkey[warp][pos] = k;
+              P.kept[lo + t] = 1;
+            } else {
+              atomicAdd(&P.dcount[DC_TR_OVERFLOW], 1ull);
+            }
+          }
+          nk += __popc(bal);
+          if (nk > TR_KC) nk = TR_KC;
+        }
+        __syncwarp();
       }
-      if (lane == 0) { s_kkey[warp][nk] = k; P.kept[t] = 1; }
-      nk++;
-      __syncwarp();
     }
     __syncwarp();
   }
@@ -374,33 +468,32 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
 }
 
 // EdgeRemoval after TransitiveReduction: an edge survives iff both endpoints kept it.
-// Writes the surviving entries of every list (checkpoint B) at the list's own offset.
-__global__ void __launch_bounds__(ST_WARPS * 32) tr_final_kernel(StringParams P, u64* __restrict__ out,
-                                                                 u32* __restrict__ cnt_out) {
-  const int lane = threadIdx.x & 31;
-  const u32 lt_mask = (1u << lane) - 1;
-  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-  ull total = 0;
-  for (u32 list = warp_global; list < P.n_lists; list += nwarps) {
-    const u32 n = P.cnt[list], lo = P.adj_off[list];
-    u32 w = 0;
-    for (u32 t0 = 0; t0 < n; t0 += 32) {
-      u32 t = t0 + lane;
-      bool keep = false;
-      u64 k = 0;
-      if (t < n && P.kept[lo + t]) {
-        k = P.edges[lo + t];
-        long long mi = find_edge(P, P.lay.mirror(k));
-        keep = (mi >= 0) ? (P.kept[mi] != 0) : true;  // no mirror: nobody can ask for the removal
+// One thread per list writes the surviving records (checkpoint B) at the list's own offset.
+__global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __restrict__ out,
+                                                       u32* __restrict__ cnt_out) {
+  u32 lid = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 w = 0;
+  if (lid < P.n_lists) {
+    const u32 n = P.cnt[lid], lo = P.adj_off[lid];
+    for (u32 t = 0; t < n; t++) {
+      if (!P.kept[lo + t]) continue;
+      const u64 k = P.edges[lo + t];
+      const u64 mk = P.lay.mirror(k);
+      const u32 ml = P.lay.list(mk);
+      const u32 mlo = P.adj_off[ml], mn = P.cnt[ml];
+      bool found = false, keep = false;
+      for (u32 q = 0; q < mn; q++) {
+        if (P.edges[mlo + q] == mk) { found = true; keep = P.kept[mlo + q] != 0; break; }
       }
-      u32 bal = __ballot_sync(0xffffffffu, keep);
-      if (keep) out[lo + w + __popc(bal & lt_mask)] = k;
-      w += __popc(bal);
+      if (!found) keep = true;  // no mirror: nobody can ask for the removal
+      if (keep) out[lo + w++] = k;
     }
-    if (lane == 0) { cnt_out[list] = w; total += w; }
+    cnt_out[lid] = w;
   }
-  if (lane == 0 && total) atomicAdd(&P.dcount[DC_EDGES_B], total);
+  u32 tot = w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&P.dcount[DC_EDGES_B], (ull)tot);
 }
 
 #define CB_DISPATCH_NW(nw, CALL)                                             \
@@ -412,12 +505,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_final_kernel(StringParams P,
     default: throw Error(CB_E_UNSUPPORTED, "read length above 256 bases");   \
   }
 
-static StringParams make_params(cb_ctx* c, const EdgeSet& es) {
+static StringParams make_params(cb_ctx* c, const u64* keys, const u32* cnt) {
   StringParams P;
-  P.edges = es.keys.p;
+  P.edges = keys;
   P.adj_off = c->adj_off.p;
-  P.cnt = es.cnt.p;
+  P.cnt = cnt;
   P.n_lists = 2 * c->n_nodes;
+  P.slots = c->slots;
   P.lay = c->lay;
   P.node_seq = c->node_seq.p;
   P.node_idkey = c->node_idkey.p;
@@ -429,101 +523,147 @@ static StringParams make_params(cb_ctx* c, const EdgeSet& es) {
   P.removed = nullptr;
   P.kept = nullptr;
   P.list_flag = c->list_flag.p;
+  P.work = nullptr;
+  P.n_work = 0;
+  P.work_out = nullptr;
+  P.n_work_out = nullptr;
+  P.check_consistency = 0;
+  P.dirty_bit = 2;
   P.dcount = (ull*)c->dcount.p;
   return P;
 }
 
-static int list_grid(u32 n_lists) {
-  int blocks = div_up((size_t)n_lists, ST_WARPS);
+static int warp_grid(size_t n_items) {
+  int blocks = div_up(n_items, ST_WARPS);
   int cap = kNumSMs * 8;
   if (blocks > cap) blocks = cap;
   return blocks > 0 ? blocks : 1;
 }
 
-// one CutChimericLinks job + the EdgeRemoval that follows it; returns edge_removal
-static int64_t cut_round(cb_ctx* c, const EdgeSet& in, EdgeSet& out, bool& changed) {
-  cudaStream_t s = c->stream;
-  changed = false;
-  CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGE_REMOVAL, 0, sizeof(u64), s));
-  if (in.n == 0) return 0;
-  const u32 n_lists = 2 * c->n_nodes;
-  DevBuf<uint8_t> removed;
-  removed.alloc(c->slots, s);
-  CB_CUDA(cudaMemsetAsync(removed.p, 0, c->slots, s));
-  StringParams P = make_params(c, in);
-  P.removed = removed.p;
-  c->lc.begin("cut");
-  CB_DISPATCH_NW(c->NW, (cut_kernel<NW_><<<list_grid(P.n_lists), ST_WARPS * 32, 0, s>>>(P)));
-  c->lc.end("cut");
-  c->lc.n++;
-  CB_CUDA(cudaGetLastError());
-  download_counters(c);
-  int64_t cuts = (int64_t)c->hcount[DC_EDGE_REMOVAL];
-  if (cuts > 0) {
-    out.keys.alloc(c->slots, s);
-    out.cnt.alloc(n_lists, s);
-    CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGES_C, 0, sizeof(u64), s));
-    filter_lists_kernel<<<list_grid(n_lists), ST_WARPS * 32, 0, s>>>(in.keys.p, c->adj_off.p, in.cnt.p, removed.p,
-                                                                    n_lists, out.keys.p, out.cnt.p, c->list_flag.p,
-                                                                    (ull*)c->dcount.p, (int)DC_EDGES_C);
-    c->lc.n++;
-    CB_CUDA(cudaGetLastError());
-    download_counters(c);
-    out.n = (size_t)c->hcount[DC_EDGES_C];
-    out.valid = true;
-    changed = true;
-  }
-  return cuts;
+static u32 read_u32s(cb_ctx* c, const u32* p) {
+  u32 v = 0;
+  CB_CUDA(cudaMemcpyAsync(&v, p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CB_CUDA(cudaStreamSynchronize(c->stream));
+  return v;
 }
 
 void stage_string_graph(cb_ctx* c) {
   cudaStream_t s = c->stream;
   const u32 n_lists = 2 * c->n_nodes;
+  const size_t nl = n_lists ? n_lists : 1;
+  const size_t slots = c->slots ? c->slots : 1;
   CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGE_REMOVAL, 0, (DC_COUNT - DC_EDGE_REMOVAL) * sizeof(u64), s));
-  c->list_flag.alloc(n_lists ? n_lists : 1, s);
-  CB_CUDA(cudaMemsetAsync(c->list_flag.p, 2, n_lists ? n_lists : 1, s));
+  c->list_flag.alloc((nl + 3) & ~(size_t)3, s);
+  CB_CUDA(cudaMemsetAsync(c->list_flag.p, 1, (nl + 3) & ~(size_t)3, s));
+  DevBuf<u32> workA, workB, nwork;  // work lists: inconsistent lists / lists that lost an entry
+  workA.alloc(nl, s);
+  workB.alloc(nl, s);
+  nwork.alloc(4, s);
+  CB_CUDA(cudaMemsetAsync(nwork.p, 0, 16, s));
+  DevBuf<uint8_t> flags;  // per slot: "removed" during the cut rounds, then "kept" for TR
+  flags.alloc(slots, s);
+  CB_CUDA(cudaMemsetAsync(flags.p, 0, slots, s));
+
   // ---- CutChimericLinks x <= 2 (BrushAssembler.java:347-367) ----
   timer_start(c, "cut");
-  EdgeSet tmp1, tmp2;
-  const EdgeSet* cur = &c->ckA;
-  bool ch1 = false, ch2 = false;
-  int64_t e1 = cut_round(c, *cur, tmp1, ch1), e2 = 0;
-  if (ch1) cur = &tmp1;
-  c->counters["edge_removal_1"] = e1;
-  c->counters["edge_removal"] = e1;
-  if (e1 > 0) {
-    e2 = cut_round(c, *cur, tmp2, ch2);
-    if (ch2) cur = &tmp2;
-    c->counters["edge_removal"] = e2;
+  const u64* cur_keys = c->ckA.keys.p;
+  const u32* cur_cnt = c->ckA.cnt.p;
+  size_t cur_n = c->ckA.n;
+  c->ckC_is_A = true;
+  int64_t e1 = 0, e2 = 0;
+  if (c->ckA.n) {
+    StringParams P = make_params(c, cur_keys, cur_cnt);
+    c->lc.begin("consistency");
+    CB_DISPATCH_NW(c->NW, (consistency_kernel<NW_><<<div_up(c->slots, 256), 256, 0, s>>>(
+                              P, workA.p, nwork.p + 0, c->cfg.majority < 1.0f ? 0 : 1)));
+    c->lc.end("consistency");
+    c->lc.n++;
+    CB_CUDA(cudaGetLastError());
+    u32 n_bad = read_u32s(c, nwork.p + 0);
+    const u32* work = workA.p;
+    u32 n_work = n_bad;
+    for (int round = 1; round <= 2 && n_work > 0; round++) {
+      u32* dirty = (round == 1) ? workB.p : workA.p;  // round 2 reuses A's storage: its list is consumed
+      u32* n_dirty = nwork.p + round;
+      P = make_params(c, cur_keys, cur_cnt);
+      P.removed = flags.p;
+      P.work = work;
+      P.n_work = n_work;
+      P.work_out = dirty;
+      P.n_work_out = n_dirty;
+      P.check_consistency = round == 2;
+      P.dirty_bit = round == 1 ? 2 : 4;
+      CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGE_REMOVAL, 0, sizeof(u64), s));
+      c->lc.begin("cut");
+      CB_DISPATCH_NW(c->NW, (cut_kernel<NW_><<<warp_grid(n_work), ST_WARPS * 32, 0, s>>>(P)));
+      c->lc.end("cut");
+      c->lc.n++;
+      CB_CUDA(cudaGetLastError());
+      download_counters(c);
+      int64_t cuts = (int64_t)c->hcount[DC_EDGE_REMOVAL];
+      (round == 1 ? e1 : e2) = cuts;
+      if (cuts == 0) break;
+      // EdgeRemoval: checkpoint chl2 becomes a private copy of A that the dirty lists rewrite
+      if (c->ckC_is_A) {
+        c->ckC.keys.alloc(slots, s);
+        c->ckC.cnt.alloc(nl, s);
+        CB_CUDA(cudaMemcpyAsync(c->ckC.keys.p, c->ckA.keys.p, slots * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        CB_CUDA(cudaMemcpyAsync(c->ckC.cnt.p, c->ckA.cnt.p, nl * 4, cudaMemcpyDeviceToDevice, s));
+        c->ckC_is_A = false;
+        c->ckC.valid = true;
+      }
+      u32 nd = read_u32s(c, n_dirty);
+      CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGES_C, 0, sizeof(u64), s));
+      remove_flagged_kernel<<<warp_grid(nd), ST_WARPS * 32, 0, s>>>(c->ckC.keys.p, c->adj_off.p, c->ckC.cnt.p,
+                                                                   flags.p, dirty, nd, (ull*)c->dcount.p);
+      c->lc.n++;
+      CB_CUDA(cudaGetLastError());
+      download_counters(c);
+      cur_n -= (size_t)c->hcount[DC_EDGES_C];
+      c->ckC.n = cur_n;
+      cur_keys = c->ckC.keys.p;
+      cur_cnt = c->ckC.cnt.p;
+      // round 2 only has to look at the lists that changed: an unchanged list cuts nothing again
+      work = dirty;
+      n_work = nd;
+    }
   }
+  c->counters["edge_removal_1"] = e1;
   c->counters["edge_removal_2"] = e2;
+  c->counters["edge_removal"] = e1 > 0 ? e2 : e1;
   timer_stop(c, "cut");
-  c->ckC_is_A = (cur == &c->ckA);
-  if (cur == &tmp1) c->ckC = std::move(tmp1);
-  else if (cur == &tmp2) c->ckC = std::move(tmp2);
-  const EdgeSet& C = c->ckC_is_A ? c->ckA : c->ckC;
-  c->counters["edges_chl2"] = (int64_t)C.n;
+  c->counters["edges_chl2"] = (int64_t)cur_n;
 
   // ---- TransitiveReduction + EdgeRemoval (BrushAssembler.java:370-379) ----
   timer_start(c, "tr");
-  c->ckB.keys.alloc(c->slots ? c->slots : 1, s);
-  c->ckB.cnt.alloc(n_lists ? n_lists : 1, s);
-  if (C.n == 0) {
-    CB_CUDA(cudaMemsetAsync(c->ckB.cnt.p, 0, (size_t)(n_lists ? n_lists : 1) * 4, s));
-    c->ckB.n = 0;
+  c->ckB.keys.alloc(slots, s);
+  c->ckB.cnt.alloc(nl, s);
+  if (cur_n == 0) {
+    CB_CUDA(cudaMemsetAsync(c->ckB.cnt.p, 0, nl * 4, s));
   } else {
-    DevBuf<uint8_t> kept;
-    kept.alloc(c->slots, s);
-    CB_CUDA(cudaMemsetAsync(kept.p, 0, c->slots, s));
-    StringParams P = make_params(c, C);
-    P.kept = kept.p;
-    c->lc.begin("tr");
-    CB_DISPATCH_NW(c->NW, (tr_kernel<NW_><<<list_grid(P.n_lists), ST_WARPS * 32, 0, s>>>(P)));
-    c->lc.end("tr");
-    c->lc.n++;
+    // `flags` is all zero again here (remove_flagged_kernel clears what it consumed)
+    StringParams P = make_params(c, cur_keys, cur_cnt);
+    P.kept = flags.p;
+    c->lc.begin("tr_fast");
+    tr_fast_kernel<<<div_up(c->slots, 256), 256, 0, s>>>(P);
+    c->lc.end("tr_fast");
+    CB_CUDA(cudaMemsetAsync(nwork.p + 3, 0, 4, s));
+    tr_worklist_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(c->list_flag.p, cur_cnt, n_lists, workA.p,
+                                                                   nwork.p + 3);
+    c->lc.n += 2;
+    u32 n_slow = read_u32s(c, nwork.p + 3);
+    if (n_slow) {
+      P.work = workA.p;
+      P.n_work = n_slow;
+      c->lc.begin("tr");
+      CB_DISPATCH_NW(c->NW, (tr_kernel<NW_><<<warp_grid(n_slow), ST_WARPS * 32, 0, s>>>(P)));
+      c->lc.end("tr");
+      c->lc.n++;
+    }
     CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaMemsetAsync(c->ckB.keys.p, 0xff, slots * sizeof(u64), s));
     c->lc.begin("tr_final");
-    tr_final_kernel<<<list_grid(P.n_lists), ST_WARPS * 32, 0, s>>>(P, c->ckB.keys.p, c->ckB.cnt.p);
+    tr_final_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(P, c->ckB.keys.p, c->ckB.cnt.p);
     c->lc.end("tr_final");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());

@@ -25,7 +25,7 @@ def one(label, sfa, k, L):
         for c in ["nodes", "tuples", "candidates_verified", "edges_overlap", "edges_chl2", "edges_re", "edge_removal_1",
                   "edge_removal_2", "trans_edge", "slow_lists", "hkmer"]:
             print(" ", c, g.counter(c))
-        for tname in ["parse", "dedupe", "keygen", "sort_tuples", "join_verify", "assemble", "cut", "tr"]:
+        for tname in ["parse", "dedupe", "keygen", "sort_tuples", "join_verify", "cut", "tr"]:
             print(f"  t[{tname}] = {g.time_ms(tname):.3f} ms")
         d = compare(g, r, label)
         print("PARITY OK" if not d else "PARITY FAIL:\n  " + "\n  ".join(d), flush=True)

@@ -21,4 +21,4 @@ for it in range(5):
     row.append(f"reserved={g.counter('pool_reserved_bytes')/1e9:.2f}GB used={g.counter('pool_used_bytes')/1e9:.2f}GB")
     row.append(f"torch_alloc={torch.cuda.memory_allocated()/1e9:.2f}GB free={torch.cuda.mem_get_info()[0]/1e9:.1f}GB")
     print(it, " ".join(row), flush=True)
-    print("   ", {t: round(g.time_ms(t), 2) for t in ["parse", "dedupe", "keygen", "sort_tuples", "join_verify", "assemble", "cut", "tr"]}, flush=True)
+    print("   ", {t: round(g.time_ms(t), 2) for t in ["parse", "dedupe", "keygen", "sort_tuples", "join_verify", "cut", "tr"]}, flush=True)
