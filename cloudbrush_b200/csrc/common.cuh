@@ -151,17 +151,20 @@ __host__ __device__ __forceinline__ u64 revcomp_word(u64 x) {
 // shift an NW-word base string left by nb bases (0 <= nb <= 32*NW), zero fill
 template <int NW>
 __host__ __device__ __forceinline__ void shl_bases(u64 (&a)[NW], int nb) {
-  int ws = nb >> 5, bs = (nb & 31) * 2;
-  u64 t[NW];
+  // register arrays must only be indexed with compile-time constants (a dynamic index sends
+  // the array to local memory): the word shift is a binary cascade of predicated moves
+  const int ws = nb >> 5, bs = (nb & 31) * 2;
 #pragma unroll
-  for (int i = 0; i < NW; i++) {
-    int j = i + ws;
-    u64 hi = (j < NW) ? a[j < NW ? j : 0] : 0ull;
-    u64 lo = (j + 1 < NW) ? a[(j + 1) < NW ? (j + 1) : 0] : 0ull;
-    t[i] = bs ? ((hi << bs) | (lo >> (64 - bs))) : hi;
+  for (int step = 1; step < 2 * NW; step <<= 1) {
+    if (ws & step) {
+#pragma unroll
+      for (int i = 0; i < NW; i++) a[i] = (i + step < NW) ? a[(i + step < NW) ? i + step : 0] : 0ull;
+    }
   }
+  if (bs) {
 #pragma unroll
-  for (int i = 0; i < NW; i++) a[i] = t[i];
+    for (int i = 0; i < NW; i++) a[i] = (a[i] << bs) | ((i + 1 < NW) ? (a[(i + 1 < NW) ? i + 1 : 0] >> (64 - bs)) : 0ull);
+  }
 }
 
 // out = reverse complement of the L-base string in `in`

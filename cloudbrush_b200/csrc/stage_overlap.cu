@@ -381,19 +381,29 @@ __global__ void __launch_bounds__(256) side_insert_kernel(const u64* __restrict_
                                                           u32* __restrict__ cnt, u64* __restrict__ keys,
                                                           u32* __restrict__ extra, ull* __restrict__ dcount) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const u64 key = xs[i];
-  const u32 lid = lay.list(key);
-  const u32 base = off[lid], m = cntM[lid], cap = off[lid + 1] - base;
-  for (u32 t = 0; t < m; t++)
-    if (keys[base + t] == key) return;
-  u32 pos = atomicAdd(&cnt[lid], 1u);
-  if (pos < cap) {
-    keys[base + pos] = key;
-    atomicAdd(&dcount[DC_EDGES_A], 1ull);
-  } else {
-    atomicAdd(&extra[lid], 1u);
-    atomicAdd(&dcount[DC_MAX_LIST], 1ull);  // reused as the overflow count of this attempt
+  bool inserted = false, overflow = false;
+  if (i < n) {
+    const u64 key = xs[i];
+    const u32 lid = lay.list(key);
+    const u32 base = off[lid], m = cntM[lid], cap = off[lid + 1] - base;
+    bool dup = false;
+    for (u32 t = 0; t < m; t++)
+      if (keys[base + t] == key) { dup = true; break; }
+    if (!dup) {
+      u32 pos = atomicAdd(&cnt[lid], 1u);
+      if (pos < cap) {
+        keys[base + pos] = key;
+        inserted = true;
+      } else {
+        atomicAdd(&extra[lid], 1u);
+        overflow = true;
+      }
+    }
+  }
+  u32 ni = __popc(__ballot_sync(0xffffffffu, inserted)), no = __popc(__ballot_sync(0xffffffffu, overflow));
+  if ((threadIdx.x & 31) == 0) {
+    if (ni) atomicAdd(&dcount[DC_EDGES_A], (ull)ni);
+    if (no) atomicAdd(&dcount[DC_MAX_LIST], (ull)no);  // reused as the overflow count of this attempt
   }
 }
 

@@ -91,92 +91,102 @@ __global__ void __launch_bounds__(PT_THREADS) fill_line_starts_kernel(const char
 
 __global__ void set_u32_kernel(u32* p, u32 v) { *p = v; }
 
-// One thread per SFA line: Java split("\t") semantics, uppercase, ACGT filter, length filter,
-// 2-bit packing (row written with 16-byte vector stores), 16-byte id key, and the 64-bit hash
-// of the canonical read min(s, rc(s)) that keys the duplicate detection.
+// One thread per SFA line, one pass over the line's bytes in aligned 16-byte chunks (vector
+// loads; neighbouring threads share chunks through L1): Java split("\t") semantics, uppercase,
+// ACGT filter, length filter, 2-bit packing (row written with 16-byte vector stores), 16-byte id
+// key, and the 64-bit hash of the canonical read min(s, rc(s)) that keys the duplicate detection.
+//   code(c) = ((c >> 1) ^ (c >> 2)) & 3 maps A,C,G,T (either case) to 0,1,2,3
+//   valid(c): (c & 0xDF) - 'A' in {0, 2, 6, 19}
 template <int NW>
-__global__ void __launch_bounds__(128) parse_lines_kernel(const char* __restrict__ text,
+__global__ void __launch_bounds__(128) parse_lines_kernel(const char* __restrict__ text, size_t text_n,
                                                           const u32* __restrict__ line_start, u32 n_lines, int K,
                                                           int L, uint8_t* __restrict__ status,
                                                           u64* __restrict__ reads, IdKey* __restrict__ idkey,
                                                           u64* __restrict__ hkeys, u32* __restrict__ hvals,
                                                           ull* __restrict__ dcount) {
-  u32 line = blockIdx.x * blockDim.x + threadIdx.x;
-  if (line >= n_lines) return;
-  u32 s = line_start[line], e = line_start[line + 1];
-  if (e > s && text[e - 1] == '\n') e--;
-  if (e > s && text[e - 1] == '\r') e--;
-  // field boundaries; String.split drops trailing empty fields
-  u32 tab1 = e, tab2 = e;
+  // grid-stride over the lines; counters are accumulated per thread and flushed once per warp at
+  // the end (a same-address atomic per read would serialise the kernel at the L2 atomic unit)
+  u32 c_inv = 0, c_skip = 0, c_short = 0, c_good = 0, c_mis = 0, c_long = 0;
+  ull c_bp = 0;
+  for (u32 line = blockIdx.x * blockDim.x + threadIdx.x; line < n_lines; line += gridDim.x * blockDim.x) {
+  const u32 s = line_start[line];
+  u32 e = line_start[line + 1];
   int field = 0, last_nonempty = -1;
-  for (u32 p = s; p < e; p++) {
-    char c = text[p];
-    if (c == '\t') {
-      if (field == 0) tab1 = p;
-      else if (field == 1) tab2 = p;
-      field++;
-    } else {
-      last_nonempty = field;
-    }
-  }
-  int nf = last_nonempty + 1;
+  u32 idlen = 0;
+  int nb = 0;  // bytes of field 1
+  bool bad = false, done = false;
+  IdKey ik;
+  ik.hi = 0;
+  ik.lo = 0;
   u64 w[NW];
 #pragma unroll
   for (int i = 0; i < NW; i++) w[i] = 0;
+  u64 acc = 0;
+  for (u32 chunk = s & ~15u; chunk < e && !done; chunk += 16) {
+    u32 v[4];
+    if ((size_t)chunk + 16 <= text_n) {
+      uint4 q = *reinterpret_cast<const uint4*>(text + chunk);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      v[0] = v[1] = v[2] = v[3] = 0;
+      for (int j = 0; j < 16; j++)
+        if ((size_t)chunk + j < text_n) v[j >> 2] |= (u32)(unsigned char)text[chunk + j] << ((j & 3) * 8);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const u32 p = chunk + j;
+      const u32 c = (v[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+      if (p < s || p >= e || done) continue;
+      if (c == '\n' || c == '\r') { done = true; continue; }  // the terminator is the end of the line
+      if (c == '\t') { field++; continue; }
+      last_nonempty = field;
+      if (field == 0) {
+        if (idlen < 8) ik.hi |= (u64)c << (56 - 8 * idlen);
+        else if (idlen < 16) ik.lo |= (u64)c << (56 - 8 * (idlen - 8));
+        idlen++;
+      } else if (field == 1) {
+        u32 u = (c & 0xdfu) - 'A';
+        bool ok = u < 20u && ((0x80045u >> u) & 1u);
+        bad |= !ok;
+        acc = (acc << 2) | (u64)(((c >> 1) ^ (c >> 2)) & 3u);
+        nb++;
+        if ((nb & 31) == 0) {
+          int wi = (nb >> 5) - 1;
+#pragma unroll
+          for (int q = 0; q < NW; q++)
+            if (q == wi) w[q] = acc;
+        }
+      }
+    }
+  }
+  if (nb & 31) {  // left-align the last partial word
+    int wi = nb >> 5;
+    u64 last = acc << (64 - 2 * (nb & 31));
+#pragma unroll
+    for (int q = 0; q < NW; q++)
+      if (q == wi) w[q] = last;
+  }
+  const int nf = last_nonempty + 1;
   uint8_t st = 0;
   u64 hk = ~0ull;
-  if (nf != 2 && nf != 3) {  // GenNonContainedReads.java:64-69
-    st = 1;
-    atomicAdd(&dcount[DC_LINES_INVALID], 1ull);
-  } else {
-    u32 q0 = tab1 + 1, q1 = tab2;
-    int len = (int)(q1 - q0);
-    bool bad = false;
-    for (int i = 0; i < len; i++) {
-      char c = text[q0 + i];
-      if (c >= 'a' && c <= 'z') c = (char)(c - 32);  // toUpperCase :79
-      u64 code;
-      if (c == 'A') code = 0;
-      else if (c == 'C') code = 1;
-      else if (c == 'G') code = 2;
-      else if (c == 'T') code = 3;
-      else { bad = true; break; }
-      if (i < NW * 32) {
-        int wi = i >> 5;
+  if (nf != 2 && nf != 3) { st = 1; c_inv++; }  // GenNonContainedReads.java:64-69
+  else if (bad) { st = 2; c_skip++; }          // :102-107
+  else if (nb <= K) { st = 3; c_short++; }     // :110-115
+  else {
+    c_good++;
+    c_bp += (ull)nb;
+    if (nb != L) c_mis++;
+    if (idlen > 16) c_long++;
+  }
+  if (st == 0) {
+    idkey[line] = ik;
+    u64 rc[NW];
+    revcomp_read<NW>(w, rc, L);
+    bool fwd = cmp_words<NW>(w, rc) <= 0;
+    u64 h = 0x9e3779b97f4a7c15ull;
 #pragma unroll
-        for (int j = 0; j < NW; j++)
-          if (j == wi) w[j] |= code << (62 - 2 * (i & 31));
-      }
-    }
-    if (bad) {  // :102-107
-      st = 2;
-      atomicAdd(&dcount[DC_READS_SKIPPED], 1ull);
-    } else if (len <= K) {  // :110-115
-      st = 3;
-      atomicAdd(&dcount[DC_READS_SHORT], 1ull);
-    } else {
-      atomicAdd(&dcount[DC_READS_GOOD], 1ull);
-      atomicAdd(&dcount[DC_READS_GOODBP], (ull)len);
-      if (len != L) atomicAdd(&dcount[DC_LEN_MISMATCH], 1ull);
-      u32 idlen = tab1 - s;
-      if (idlen > 16) atomicAdd(&dcount[DC_LONG_ID], 1ull);
-      IdKey ik;
-      ik.hi = 0;
-      ik.lo = 0;
-      for (u32 i = 0; i < idlen && i < 16; i++) {
-        u64 b = (u64)(unsigned char)text[s + i];
-        if (i < 8) ik.hi |= b << (56 - 8 * i);
-        else ik.lo |= b << (56 - 8 * (i - 8));
-      }
-      idkey[line] = ik;
-      u64 rc[NW];
-      revcomp_read<NW>(w, rc, L);
-      bool fwd = cmp_words<NW>(w, rc) <= 0;
-      u64 h = 0x9e3779b97f4a7c15ull;
-#pragma unroll
-      for (int i = 0; i < NW; i++) h = mix64(h ^ (fwd ? w[i] : rc[i])) + 0x9e3779b97f4a7c15ull;
-      hk = h & ~1ull;  // bit 0 clear: never collides with the all-ones key of non-reads
-    }
+    for (int i = 0; i < NW; i++) h = mix64(h ^ (fwd ? w[i] : rc[i])) + 0x9e3779b97f4a7c15ull;
+    hk = h & ~1ull;  // bit 0 clear: never collides with the all-ones key of non-reads
   }
   status[line] = st;
   // packed row: NW is even, so the row is NW/2 aligned 16-byte stores
@@ -190,6 +200,27 @@ __global__ void __launch_bounds__(128) parse_lines_kernel(const char* __restrict
   }
   hkeys[line] = hk;
   hvals[line] = line;
+  }  // line loop
+  const u32 full = 0xffffffffu;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c_inv += __shfl_xor_sync(full, c_inv, o);
+    c_skip += __shfl_xor_sync(full, c_skip, o);
+    c_short += __shfl_xor_sync(full, c_short, o);
+    c_good += __shfl_xor_sync(full, c_good, o);
+    c_mis += __shfl_xor_sync(full, c_mis, o);
+    c_long += __shfl_xor_sync(full, c_long, o);
+    c_bp += __shfl_xor_sync(full, c_bp, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c_inv) atomicAdd(&dcount[DC_LINES_INVALID], (ull)c_inv);
+    if (c_skip) atomicAdd(&dcount[DC_READS_SKIPPED], (ull)c_skip);
+    if (c_short) atomicAdd(&dcount[DC_READS_SHORT], (ull)c_short);
+    if (c_good) atomicAdd(&dcount[DC_READS_GOOD], (ull)c_good);
+    if (c_bp) atomicAdd(&dcount[DC_READS_GOODBP], c_bp);
+    if (c_mis) atomicAdd(&dcount[DC_LEN_MISMATCH], (ull)c_mis);
+    if (c_long) atomicAdd(&dcount[DC_LONG_ID], (ull)c_long);
+  }
 }
 
 template <int NW>
@@ -215,45 +246,58 @@ __device__ __forceinline__ void load_canon(const u64* __restrict__ reads, u32 id
   for (int i = 0; i < NW; i++) canon[i] = c <= 0 ? r[i] : rc[i];
 }
 
-// Sorted by canonical-read hash: the head of every run of equal (masked) hashes resolves the
-// duplicate classes inside its run by exact comparison of the canonical reads.
+// Sorted by canonical-read hash: every read scans the run of equal (masked) hashes it lies in,
+// compares the canonical reads exactly wherever the full 64-bit hashes agree, and decides on its
+// own whether it is the survivor of its duplicate class (smallest id key) and what the class
+// size is.  Runs are as long as the duplicate classes (a few reads), so the scans are short and
+// every thread is busy.
 template <int NW>
 __global__ void __launch_bounds__(128) dedupe_runs_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals,
                                                           u32 n_good, u64 keymask, const u64* __restrict__ reads,
                                                           const IdKey* __restrict__ idkey, int L,
                                                           u32* __restrict__ surv_flag, u32* __restrict__ cov,
                                                           ull* __restrict__ dcount) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_good) return;
-  u64 k = keys[i] & keymask;
-  if (i > 0 && (keys[i - 1] & keymask) == k) return;
-  u32 e = i + 1;
-  while (e < n_good && (keys[e] & keymask) == k) e++;
-  for (u32 a = i; a < e; a++) {
-    u64 ca[NW], cb_[NW];
+  u32 ns = 0, mx = 0;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_good; i += gridDim.x * blockDim.x) {
+    bool survivor = false;
+    u32 cv = 0;
+    const u64 ki = keys[i], km = ki & keymask;
+    const u32 li = vals[i];
+    u64 ci[NW], cj[NW];
     bool self, self2;
-    load_canon<NW>(reads, vals[a], L, ca, self);
-    bool seen = false;
-    for (u32 b = i; b < a; b++) {
-      load_canon<NW>(reads, vals[b], L, cb_, self2);
-      if (cmp_words<NW>(ca, cb_) == 0) { seen = true; break; }
-    }
-    if (seen) continue;
-    u32 cnt = 1, best = vals[a];
-    IdKey bk = idkey[best];
-    for (u32 b = a + 1; b < e; b++) {
-      load_canon<NW>(reads, vals[b], L, cb_, self2);
-      if (cmp_words<NW>(ca, cb_) == 0) {
+    load_canon<NW>(reads, li, L, ci, self);
+    const IdKey mine = idkey[li];
+    u32 cnt = 1;
+    survivor = true;
+    for (int dirn = -1; dirn <= 1; dirn += 2) {
+      for (long long j = (long long)i + dirn; j >= 0 && j < (long long)n_good; j += dirn) {
+        const u64 kj = keys[j];
+        if ((kj & keymask) != km) break;
+        if (kj != ki) continue;
+        const u32 lj = vals[j];
+        load_canon<NW>(reads, lj, L, cj, self2);
+        if (cmp_words<NW>(ci, cj) != 0) continue;
         cnt++;
-        IdKey kb = idkey[vals[b]];
-        if (idkey_less(kb, bk)) { bk = kb; best = vals[b]; }
+        const IdKey other = idkey[lj];
+        if (idkey_less(other, mine) || (!idkey_less(mine, other) && lj < li)) survivor = false;
       }
     }
-    u32 cv = 1 + (cnt - 1) * (self ? 2u : 1u);  // GenNonContainedReads.java:176-201
-    surv_flag[best] = 1;
-    cov[best] = cv;
-    atomicAdd(&dcount[DC_SURVIVORS], 1ull);
-    atomicMax(&dcount[DC_MAX_COV], (ull)cv);
+    if (survivor) {
+      cv = 1 + (cnt - 1) * (self ? 2u : 1u);  // GenNonContainedReads.java:176-201
+      surv_flag[li] = 1;
+      cov[li] = cv;
+      ns++;
+      mx = max(mx, cv);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ns += __shfl_xor_sync(0xffffffffu, ns, o);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0 && ns) {
+    atomicAdd(&dcount[DC_SURVIVORS], (ull)ns);
+    atomicMax(&dcount[DC_MAX_COV], (ull)mx);
   }
 }
 
@@ -334,8 +378,8 @@ void stage_parse_and_pack(cb_ctx* c) {
   {
     for (int i = 0; i < 2; i++) { hk[i].alloc(nl, s); hv[i].alloc(nl, s); }
     c->lc.begin("parse_lines");
-    CB_DISPATCH_NW(c->NW, (parse_lines_kernel<NW_><<<div_up(nl, 128), 128, 0, s>>>(
-                              c->text_ptr, c->line_start.p, nl, c->K, c->L, c->status.p, c->reads.p, c->idkey.p,
+    CB_DISPATCH_NW(c->NW, (parse_lines_kernel<NW_><<<min(div_up(nl, 128), kNumSMs * 16), 128, 0, s>>>(
+                              c->text_ptr, n, c->line_start.p, nl, c->K, c->L, c->status.p, c->reads.p, c->idkey.p,
                               hk[0].p, hv[0].p, (ull*)c->dcount.p)));
     c->lc.end("parse_lines");
     c->lc.n++;
@@ -363,7 +407,7 @@ void stage_parse_and_pack(cb_ctx* c) {
     cov.alloc(nl, s);
     CB_CUDA(cudaMemsetAsync(surv_flag.p, 0, (size_t)nl * 4, s));
     c->lc.begin("dedupe_runs");
-    CB_DISPATCH_NW(c->NW, (dedupe_runs_kernel<NW_><<<div_up(n_good, 128), 128, 0, s>>>(
+    CB_DISPATCH_NW(c->NW, (dedupe_runs_kernel<NW_><<<min(div_up(n_good, 128), kNumSMs * 16), 128, 0, s>>>(
                               hk[where].p, hv[where].p, n_good, keymask, c->reads.p, c->idkey.p, c->L, surv_flag.p,
                               cov.p, (ull*)c->dcount.p)));
     c->lc.end("dedupe_runs");

@@ -334,9 +334,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32) remove_flagged_kernel(u64* __re
 // ---------------------------------------------------------------------------------------------
 // consistent lists, one thread per record: keep the records of maximal overlap
 __global__ void __launch_bounds__(256) tr_fast_kernel(StringParams P) {
-  size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   u32 trans = 0, contained = 0;
-  if (slot < P.slots) {
+  for (size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x; slot < P.slots;
+       slot += (size_t)gridDim.x * blockDim.x) {
     const u64 k = P.edges[slot];
     if (k != ~0ull) {
       const u32 lid = P.lay.list(k);
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) tr_fast_kernel(StringParams P) {
         const u32 ov = P.lay.ov(k);
         u32 ovmax = 0;
         for (u32 t = 0; t < n; t++) ovmax = max(ovmax, P.lay.ov(P.edges[lo + t]));
-        if ((int)ov == P.L) contained = 1;  // TransitiveReduction.java:319-323 (equal-length reads)
+        if ((int)ov == P.L) contained++;  // TransitiveReduction.java:319-323 (equal-length reads)
         if (ov == ovmax) P.kept[slot] = 1;
         else {
           // :325-334 an entry of the same type to the same neighbour already kept -> dropped
@@ -355,15 +355,19 @@ __global__ void __launch_bounds__(256) tr_fast_kernel(StringParams P) {
             u64 kq = P.edges[lo + t];
             if (P.lay.ov(kq) == ovmax && P.lay.nbr(kq) == P.lay.nbr(k) && P.lay.y(kq) == P.lay.y(k)) { step2 = true; break; }
           }
-          if (!step2) trans = 1;
+          if (!step2) trans++;
         }
       }
     }
   }
-  u32 tb = __popc(__ballot_sync(0xffffffffu, trans)), cb_ = __popc(__ballot_sync(0xffffffffu, contained));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    trans += __shfl_xor_sync(0xffffffffu, trans, o);
+    contained += __shfl_xor_sync(0xffffffffu, contained, o);
+  }
   if ((threadIdx.x & 31) == 0) {
-    if (tb) atomicAdd(&P.dcount[DC_TRANS_EDGE], (ull)tb);
-    if (cb_) atomicAdd(&P.dcount[DC_CONTAINED_EDGE], (ull)cb_);
+    if (trans) atomicAdd(&P.dcount[DC_TRANS_EDGE], (ull)trans);
+    if (contained) atomicAdd(&P.dcount[DC_CONTAINED_EDGE], (ull)contained);
   }
 }
 
@@ -471,9 +475,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
 // One thread per list writes the surviving records (checkpoint B) at the list's own offset.
 __global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __restrict__ out,
                                                        u32* __restrict__ cnt_out) {
-  u32 lid = blockIdx.x * blockDim.x + threadIdx.x;
-  u32 w = 0;
-  if (lid < P.n_lists) {
+  u32 tot = 0;
+  for (u32 lid = blockIdx.x * blockDim.x + threadIdx.x; lid < P.n_lists; lid += gridDim.x * blockDim.x) {
+    u32 w = 0;
     const u32 n = P.cnt[lid], lo = P.adj_off[lid];
     for (u32 t = 0; t < n; t++) {
       if (!P.kept[lo + t]) continue;
@@ -489,8 +493,8 @@ __global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __re
       if (keep) out[lo + w++] = k;
     }
     cnt_out[lid] = w;
+    tot += w;
   }
-  u32 tot = w;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
   if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&P.dcount[DC_EDGES_B], (ull)tot);
@@ -645,7 +649,7 @@ void stage_string_graph(cb_ctx* c) {
     StringParams P = make_params(c, cur_keys, cur_cnt);
     P.kept = flags.p;
     c->lc.begin("tr_fast");
-    tr_fast_kernel<<<div_up(c->slots, 256), 256, 0, s>>>(P);
+    tr_fast_kernel<<<min(div_up(c->slots, 256), kNumSMs * 8), 256, 0, s>>>(P);
     c->lc.end("tr_fast");
     CB_CUDA(cudaMemsetAsync(nwork.p + 3, 0, 4, s));
     tr_worklist_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(c->list_flag.p, cur_cnt, n_lists, workA.p,
@@ -663,7 +667,7 @@ void stage_string_graph(cb_ctx* c) {
     CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaMemsetAsync(c->ckB.keys.p, 0xff, slots * sizeof(u64), s));
     c->lc.begin("tr_final");
-    tr_final_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(P, c->ckB.keys.p, c->ckB.cnt.p);
+    tr_final_kernel<<<min(div_up((size_t)n_lists, 256), kNumSMs * 8), 256, 0, s>>>(P, c->ckB.keys.p, c->ckB.cnt.p);
     c->lc.end("tr_final");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
