@@ -1,0 +1,131 @@
+"""-m gpu: rule-by-rule micro cases, input edge cases, node text and size-independent properties,
+all through the C ABI and checked against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import all_cases
+from parity_util import compare, run_gpu, run_oracle
+
+pytestmark = pytest.mark.gpu
+CASES = all_cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_micro_case_parity(name):
+    buf, k, L = CASES[name]
+    r = run_oracle(buf, k, L)
+    g = run_gpu(buf, k, L)
+    assert compare(g, r, name) == []
+    g.close()
+
+
+def _canon_text(text):
+    """node text -> set of (id, seq, cov, frozenset(edges per type)) ; edge order is not part of the contract"""
+    out = set()
+    for line in text.split("\n"):
+        if not line:
+            continue
+        f = line.split("\t")
+        rec = {"id": f[0]}
+        cur = None
+        fields = {}
+        for tok in f[2:]:
+            if tok.startswith("*"):
+                cur = tok[1:]
+                fields[cur] = []
+            else:
+                fields[cur].append(tok)
+        out.add((f[0], f[1], tuple(fields["s"]), tuple(fields["v"]),
+                 tuple((t, tuple(sorted(fields.get(t, [])))) for t in ("ff", "fr", "rf", "rr") if t in fields)))
+    return out
+
+
+@pytest.mark.parametrize("name", ["tiling_both_strands", "branch", "line_formats"])
+def test_node_text_matches_to_node_msg(name, tmp_path):
+    from oracle import oracle as O
+    buf, k, L = CASES[name]
+    r = run_oracle(buf, k, L)
+    g = run_gpu(buf, k, L)
+    for gck, ock in ((0, O.CK_PREPROCESS), (1, O.CK_A), (2, O.CK_CHL2), (3, O.CK_B)):
+        d = tmp_path / f"ck{gck}"
+        g.write_nodes(gck, d)
+        got = open(d / "part-00000").read()
+        assert _canon_text(got) == _canon_text(r.node_text(ock))
+    g.close()
+
+
+def test_write_nodes_replaces_output_directory(tmp_path):
+    buf, k, L = CASES["chain3"]
+    g = run_gpu(buf, k, L)
+    d = tmp_path / "01-overlap"
+    os.makedirs(d)
+    open(d / "stale-file", "w").write("x")
+    g.write_nodes(1, d)
+    assert sorted(os.listdir(d)) == ["part-00000"]
+    g.close()
+
+
+def test_error_codes_for_bad_input():
+    from cloudbrush_b200 import BrushConfig, BrushGpu, BrushGpuError
+    g = BrushGpu(BrushConfig(k=21, readlen=40))
+    with pytest.raises(BrushGpuError) as e:
+        g.preprocess()                     # nothing loaded
+    assert e.value.code == -1
+    g.load_sfa_buffer(b"only\tNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN\n")
+    with pytest.raises(BrushGpuError) as e:
+        g.preprocess()                     # BrushAssembler.java:273-276 "No good reads"
+    assert e.value.code == -6
+    g.load_sfa_buffer(b"")
+    with pytest.raises(BrushGpuError) as e:
+        g.preprocess()
+    assert e.value.code == -6
+    g.load_sfa_buffer(b"a\t" + b"ACGT" * 10 + b"\nb\t" + b"ACGT" * 11 + b"\n")
+    with pytest.raises(BrushGpuError) as e:
+        g.preprocess()                     # mixed read lengths are outside the supported contract
+    assert e.value.code == -7
+    with pytest.raises(BrushGpuError) as e:
+        g.build_overlap()                  # stage order is enforced
+    assert e.value.code == -1
+    g.close()
+    g2 = BrushGpu(BrushConfig(k=20, readlen=40))
+    g2.load_sfa_buffer(CASES["chain3"][0])
+    with pytest.raises(BrushGpuError) as e:
+        g2.preprocess()                    # even k: palindromic k-mers, outside the parity contract
+    assert e.value.code == -7
+    g2.close()
+
+
+def test_rerun_is_deterministic_and_context_is_reusable():
+    buf, k, L = CASES["tiling_both_strands"]
+    g = run_gpu(buf, k, L)
+    a1, b1 = g.edge_rows(1), g.edge_rows(3)
+    g.load_sfa_buffer(CASES["branch"][0])
+    g.run()
+    g.load_sfa_buffer(buf)
+    g.run()
+    assert np.array_equal(a1, g.edge_rows(1)) and np.array_equal(b1, g.edge_rows(3))
+    g.close()
+
+
+def test_full_size_properties():
+    """Size-independent properties at a size the oracle is not run at: mirror closure of every
+    checkpoint, nesting B <= chl2 <= A, coverage sum == reads, two kept edges per direction at most
+    for an error-free forward-strand genome."""
+    from cloudbrush_b200 import synth
+    buf, meta = synth.make_config("cfg2", scale_genome=400_000)
+    g = run_gpu(bytes(buf), meta["k"], meta["readlen"])
+    assert int(g.nodes()["cov"].sum()) == meta["n_reads"] == g.counter("reads_good")
+    flip = np.array([3, 1, 2, 0])
+    sets = []
+    for ck in (1, 2, 3):
+        e = g.edge_rows(ck)
+        m = np.stack([e[:, 2], flip[e[:, 1]], e[:, 0], e[:, 3]], axis=1)
+        key = lambda x: x[np.lexsort((x[:, 3], x[:, 2], x[:, 1], x[:, 0]))]
+        assert np.array_equal(key(e), key(m)), f"checkpoint {ck} is not closed under flip_link mirroring"
+        sets.append({tuple(r) for r in e.tolist()})
+    assert sets[2] <= sets[1] <= sets[0]
+    assert g.counter("edges_overlap") == len(sets[0]) and g.counter("edges_re") == len(sets[2])
+    assert g.counter("trans_edge") + g.counter("edges_re") >= g.counter("edges_chl2") - g.counter("edges_re")
+    g.close()
