@@ -35,7 +35,7 @@ class cb_node(C.Structure):
 SYMBOLS = ["cb_default_config", "cb_create", "cb_destroy", "cb_last_error", "cb_version", "cb_load_sfa",
            "cb_load_sfa_buffer", "cb_load_sfa_device", "cb_preprocess", "cb_build_overlap", "cb_string_graph",
            "cb_get_counter", "cb_export_edges", "cb_export_nodes", "cb_write_nodes", "cb_get_time_ms",
-           "cb_get_launch_count", "cb_borrow_sfa_device", "cb_set_profile", "cb_get_kernel_stat"]
+           "cb_get_launch_count", "cb_borrow_sfa_device", "cb_set_profile", "cb_get_kernel_stat", "cb_set_exchange"]
 
 _lib = None
 
@@ -71,6 +71,7 @@ def load():
     L.cb_get_time_ms.argtypes = [P, C.c_char_p, C.POINTER(C.c_double)]
     L.cb_get_launch_count.argtypes = [P, C.POINTER(C.c_int64)]
     L.cb_borrow_sfa_device.argtypes = [P, C.c_void_p, C.c_size_t]
+    L.cb_set_exchange.argtypes = [P, C.c_void_p]
     L.cb_set_profile.argtypes = [P, C.c_int]
     L.cb_get_kernel_stat.argtypes = [P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = L

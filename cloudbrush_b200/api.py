@@ -95,6 +95,12 @@ class BrushGpu:
         """Zero-copy: the context reads the caller's device buffer in place."""
         self._check(self._L.cb_borrow_sfa_device(self._h, dev_ptr, n))
 
+    def set_exchange(self, exchange):
+        """exchange: cloudbrush_b200.dist.TorchExchange (required when cfg.world > 1)."""
+        self._exchange = exchange  # keeps the ctypes callbacks alive
+        st = exchange.as_struct()
+        self._check(self._L.cb_set_exchange(self._h, C.cast(C.byref(st), C.c_void_p)))
+
     def set_profile(self, on=True):
         self._check(self._L.cb_set_profile(self._h, 1 if on else 0))
 

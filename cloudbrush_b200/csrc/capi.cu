@@ -247,6 +247,13 @@ int cb_borrow_sfa_device(cb_ctx* c, const void* dev_buf, size_t n) {
   CB_API_END(c)
 }
 
+int cb_set_exchange(cb_ctx* c, const cb_exchange* ex) {
+  if (!c || !ex || !ex->exchange_counts || !ex->alltoallv || !ex->allgatherv || !ex->allreduce_u64) return CB_E_INVALID;
+  c->ex = *ex;
+  c->has_ex = true;
+  return CB_OK;
+}
+
 int cb_set_profile(cb_ctx* c, int on) {
   if (!c) return CB_E_INVALID;
   cudaSetDevice(c->cfg.device);

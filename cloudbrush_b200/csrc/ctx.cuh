@@ -90,6 +90,16 @@ struct cb_ctx {
   std::map<std::string, int64_t> counters;
   std::map<std::string, cb::Timer> timers;
 
+  // multi-GPU (cfg.world > 1): transport callbacks and the global numbering
+  cb_exchange ex = {};
+  bool has_ex = false;
+  int lg_world = 0;               // log2(world)
+  int pbit = 0;                   // k-mer groups are owned by rank (key >> pbit) & (world - 1)
+  u32 line_base = 0;              // global index of this shard's first SFA line
+  std::vector<u64> line_bases;    // [world + 1]
+  u32 node_lo = 0, node_hi = 0;   // nodes built from this shard (global node indices)
+  uint64_t gcount[cb::DC_COUNT] = {0};  // counters reduced over the ranks
+
   // input text
   cb::DevBuf<char> text;          // owned copy (cb_load_sfa / cb_load_sfa_buffer / cb_load_sfa_device)
   const char* text_ptr = nullptr; // what the kernels read: text.p or a borrowed device buffer
@@ -129,9 +139,25 @@ void timer_start(cb_ctx* c, const char* name);
 void timer_stop(cb_ctx* c, const char* name);
 void download_counters(cb_ctx* c);
 
+// dist.cu -- routing helpers of the multi-GPU path
+inline bool distributed(const cb_ctx* c) { return c->cfg.world > 1; }
+void ex_allreduce(cb_ctx* c, u64* vals, int n, int op);
+void ex_counts(cb_ctx* c, const u64* send, u64* recv, int n_per_rank);
+void ex_alltoallv(cb_ctx* c, const void* send, const u64* send_bytes, void* recv, const u64* recv_bytes);
+void ex_allgatherv(cb_ctx* c, const void* send, u64 send_bytes, void* recv, const u64* recv_bytes);
+// routes n records of elem_bytes (multiple of 4) to rank dest[i] (dest[i] == world: dropped);
+// out receives the records addressed to this rank, grouped by source rank
+void route_records(cb_ctx* c, const void* recs, size_t elem_bytes, const u32* dest, size_t n, DevBuf<char>& out,
+                   size_t& n_out);
+// all-gathers a per-rank array of `count` elements into `out` (rank order); counts[r] of every rank
+void gather_all(cb_ctx* c, const void* local, size_t elem_bytes, size_t count, const std::vector<u64>& counts,
+                void* out);
+// global counters (sum over ranks; max for the two maxima); identity on a single GPU
+void reduce_counters(cb_ctx* c);
+
 // stage_preprocess.cu
 void stage_parse_and_pack(cb_ctx* c);
-void stage_dedupe(cb_ctx* c);
+
 // stage_overlap.cu
 void stage_build_overlap(cb_ctx* c);
 // stage_string.cu

@@ -40,14 +40,16 @@ __device__ __forceinline__ void load_read_b(const u64* __restrict__ reads, u32 i
 // ---------------------------------------------------------------------------------------------
 template <int NW>
 __global__ void __launch_bounds__(256) keygen_kernel(const u64* __restrict__ node_seq,
-                                                     const u32* __restrict__ node_cov, u32 n_nodes, int L, int K,
-                                                     int W, int pb, u64* __restrict__ keys, u32* __restrict__ vals,
-                                                     ull* __restrict__ dcount) {
+                                                     const u32* __restrict__ node_cov, u32 node_lo, u32 n_nodes,
+                                                     int L, int K, int W, int pb, u64* __restrict__ keys,
+                                                     u32* __restrict__ vals, ull* __restrict__ dcount) {
   const int lane = threadIdx.x & 31;
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
   u32 invalid = 0;
-  for (u32 node = warp_global; node < n_nodes; node += nwarps) {
+  // nodes [node_lo, node_lo + n_nodes) are this rank's (all of them on a single GPU)
+  for (u32 loc = warp_global; loc < n_nodes; loc += nwarps) {
+    const u32 node = node_lo + loc;
     u64 r[NW];
     load_read_b<NW>(node_seq, node, r);
     for (int w0 = 0; w0 < W; w0 += 32) {
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(256) keygen_kernel(const u64* __restrict__ nod
         bool emit = (km != rk) && !(interior && canon == 0);
         if (canon == 0 && i < L - K) atomicAdd(&dcount[DC_POLYA_WEIGHT], (ull)node_cov[node]);
         u64 meta = ((u64)node << (pb + 1)) | ((u64)i << 1) | (fwd ? 0ull : 1ull);
-        size_t slot = (size_t)node * W + i;
+        size_t slot = (size_t)loc * W + i;
         keys[slot] = emit ? (canon | ((meta >> 32) << (2 * K))) : ~0ull;
         vals[slot] = emit ? (u32)meta : ~0u;
         if (!emit) invalid++;
@@ -407,6 +409,48 @@ __global__ void __launch_bounds__(256) side_insert_kernel(const u64* __restrict_
   }
 }
 
+// owner rank of adjacency list (a, x): the rank of the k-mer group of node entry (a, flip x),
+// i.e. of canon(last k-mer of a) for x = f and canon(first k-mer of a) for x = r
+template <int NW>
+__device__ __forceinline__ u32 list_owner(const u64* __restrict__ node_seq, u32 lid, int L, int K, int pbit,
+                                          u32 wmask) {
+  u64 r[NW];
+  load_read_b<NW>(node_seq, lid >> 1, r);
+  u64 km = extract_kmer<NW>(r, (lid & 1u) ? 0 : L - K, K);
+  u64 rk = revcomp_kmer(km, K);
+  u64 canon = km < rk ? km : rk;
+  return (u32)(canon >> pbit) & wmask;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(256) key_owner_kernel(const u64* __restrict__ keys, size_t n, EdgeLayout lay,
+                                                        const u64* __restrict__ node_seq, int L, int K, int pbit,
+                                                        u32 wmask, u32* __restrict__ dest) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dest[i] = list_owner<NW>(node_seq, lay.list(keys[i]), L, K, pbit, wmask);
+}
+
+__global__ void __launch_bounds__(256) tuple_dest_hist_kernel(const u64* __restrict__ keys, size_t n, int pbit,
+                                                              u32 wmask, ull* __restrict__ counts) {
+  __shared__ u32 h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    atomicAdd(&h[(u32)(keys[i] >> pbit) & wmask], 1u);
+  __syncthreads();
+  if (threadIdx.x <= wmask && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (ull)h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) count_invalid_kernel(const u64* __restrict__ keys, size_t n,
+                                                            ull* __restrict__ out) {
+  u32 c = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    if (keys[i] == ~0ull) c++;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (ull)c);
+}
+
 __global__ void __launch_bounds__(256) add_u32_kernel(u32* __restrict__ a, const u32* __restrict__ b, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] += b[i];
@@ -443,7 +487,10 @@ void stage_build_overlap(cb_ctx* c) {
   if (nbits > 27) throw Error(CB_E_CAPACITY, "more than 2^27 nodes per context");
   if (nbits + pb + 1 > 32 + (64 - 2 * K))
     throw Error(CB_E_CAPACITY, "node/window payload does not fit the 12-byte tuple for this k");
-  const size_t Tmax = (size_t)nn * W;
+  const u32 n_own = c->node_hi - c->node_lo;
+  const int world = c->cfg.world;
+  const u32 wmask = (u32)world - 1;
+  size_t Tmax = (size_t)n_own * W;  // tuple slots generated here
   if (Tmax >= (1ull << 32)) throw Error(CB_E_CAPACITY, "more than 2^32 k-mer tuples per context");
   c->lay.nb = nbits;
   c->lay.ob = bits_for((u64)(L - K + 1));
@@ -454,15 +501,16 @@ void stage_build_overlap(cb_ctx* c) {
   timer_start(c, "keygen");
   DevBuf<u64> keys[2];
   DevBuf<u32> vals[2];
-  for (int i = 0; i < 2; i++) { keys[i].alloc(Tmax, s); vals[i].alloc(Tmax, s); }
+  for (int i = 0; i < 2; i++) { keys[i].alloc(Tmax ? Tmax : 1, s); vals[i].alloc(Tmax ? Tmax : 1, s); }
   CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_TUPLES_INVALID, 0, (DC_COUNT - DC_TUPLES_INVALID) * sizeof(u64), s));
-  {
-    int blocks = div_up((size_t)nn * 32, 256);
+  if (n_own) {
+    int blocks = div_up((size_t)n_own * 32, 256);
     int cap = kNumSMs * 8 * 4;
     if (blocks > cap) blocks = cap;
     c->lc.begin("keygen");
-    CB_DISPATCH_NW(c->NW, (keygen_kernel<NW_><<<blocks, 256, 0, s>>>(c->node_seq.p, c->node_cov.p, nn, L, K, W, pb,
-                                                                    keys[0].p, vals[0].p, (ull*)c->dcount.p)));
+    CB_DISPATCH_NW(c->NW, (keygen_kernel<NW_><<<blocks, 256, 0, s>>>(c->node_seq.p, c->node_cov.p, c->node_lo, n_own, L,
+                                                                    K, W, pb, keys[0].p, vals[0].p,
+                                                                    (ull*)c->dcount.p)));
     c->lc.end("keygen");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
@@ -470,12 +518,56 @@ void stage_build_overlap(cb_ctx* c) {
   timer_stop(c, "keygen");
 
   // ---- shuffle replacement ----
+  if (distributed(c)) {
+    // partition by owner rank (one stable radix pass over the owner bits of the key), then the
+    // all-to-all that replaces the MapReduce shuffle.  Received order is (source rank, node,
+    // window), i.e. ascending (node, window): the join relies on it.
+    timer_start(c, "exchange_tuples");
+    int w0 = radix_sort(keys[0].p, keys[1].p, vals[0].p, vals[1].p, Tmax, c->pbit, c->pbit + c->lg_world, s, c->lc,
+                        "partition");
+    DevBuf<u64> dcnt;
+    dcnt.alloc(world, s);
+    CB_CUDA(cudaMemsetAsync(dcnt.p, 0, world * sizeof(u64), s));
+    if (Tmax) {
+      int blocks = div_up(Tmax, 256 * 16);
+      if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+      tuple_dest_hist_kernel<<<blocks, 256, 0, s>>>(keys[w0].p, Tmax, c->pbit, wmask, (ull*)dcnt.p);
+      c->lc.n++;
+    }
+    std::vector<u64> cnt(world), rcnt(world), sb(world), rb(world);
+    CB_CUDA(cudaMemcpyAsync(cnt.data(), dcnt.p, world * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    ex_counts(c, cnt.data(), rcnt.data(), 1);
+    size_t Trecv = 0;
+    for (int r = 0; r < world; r++) Trecv += (size_t)rcnt[r];
+    if (Trecv >= (1ull << 32)) throw Error(CB_E_CAPACITY, "more than 2^32 k-mer tuples per context");
+    DevBuf<u64> rkeys;
+    DevBuf<u32> rvals;
+    rkeys.alloc(Trecv ? Trecv : 1, s);
+    rvals.alloc(Trecv ? Trecv : 1, s);
+    for (int r = 0; r < world; r++) { sb[r] = cnt[r] * 8; rb[r] = rcnt[r] * 8; }
+    ex_alltoallv(c, keys[w0].p, sb.data(), rkeys.p, rb.data());
+    for (int r = 0; r < world; r++) { sb[r] = cnt[r] * 4; rb[r] = rcnt[r] * 4; }
+    ex_alltoallv(c, vals[w0].p, sb.data(), rvals.p, rb.data());
+    Tmax = Trecv;
+    keys[0] = std::move(rkeys);
+    vals[0] = std::move(rvals);
+    keys[1].alloc(Tmax ? Tmax : 1, s);
+    vals[1].alloc(Tmax ? Tmax : 1, s);
+    CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_TUPLES_INVALID, 0, sizeof(u64), s));
+    if (Tmax) {
+      int blocks = div_up(Tmax, 256 * 16);
+      if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+      count_invalid_kernel<<<blocks, 256, 0, s>>>(keys[0].p, Tmax, (ull*)c->dcount.p + DC_TUPLES_INVALID);
+      c->lc.n++;
+    }
+    timer_stop(c, "exchange_tuples");
+  }
   timer_start(c, "sort_tuples");
   int where = radix_sort(keys[0].p, keys[1].p, vals[0].p, vals[1].p, Tmax, 0, 2 * K, s, c->lc, "tuples");
   timer_stop(c, "sort_tuples");
   download_counters(c);
   const u32 T = (u32)(Tmax - c->hcount[DC_TUPLES_INVALID]);
-  c->counters["tuples"] = (int64_t)T;
   keys[where ^ 1].release();
   vals[where ^ 1].release();
 
@@ -537,24 +629,42 @@ void stage_build_overlap(cb_ctx* c) {
     CB_CUDA(cudaGetLastError());
     download_counters(c);
     n_x = c->hcount[DC_EDGES_RAW];
-    if (n_x > xcap) {  // side buffer too small: its exact size is known now
+    u64 x_over = n_x > xcap ? 1 : 0;
+    ex_allreduce(c, &x_over, 1, 1);  // every rank must take the same branch: collectives follow
+    if (x_over) {  // side buffer too small: its exact size is known now
       if (attempt >= 3) throw Error(CB_E_CAPACITY, "side buffer overflow");
-      xcap = n_x;
+      if (n_x > xcap) xcap = n_x;
       continue;
     }
-    // side-buffer records into their lists
+    // side-buffer records into their lists (on the rank that owns the list)
     CB_CUDA(cudaMemcpyAsync(cnt.p, cntM.p, (size_t)n_lists * 4, cudaMemcpyDeviceToDevice, s));
     CB_CUDA(cudaMemsetAsync(extra.p, 0, (size_t)n_lists * 4, s));
-    if (n_x) {
+    const u64* xin = xbuf.p;
+    size_t n_xin = n_x;
+    DevBuf<char> xrecv;
+    if (distributed(c)) {
+      DevBuf<u32> xdest;
+      xdest.alloc(n_x ? n_x : 1, s);
+      if (n_x) {
+        CB_DISPATCH_NW(c->NW, (key_owner_kernel<NW_><<<div_up(n_x, 256), 256, 0, s>>>(
+                                  xbuf.p, n_x, c->lay, c->node_seq.p, L, K, c->pbit, wmask, xdest.p)));
+        c->lc.n++;
+      }
+      route_records(c, xbuf.p, 8, xdest.p, n_x, xrecv, n_xin);
+      xin = (const u64*)xrecv.p;
+    }
+    if (n_xin) {
       c->lc.begin("side_insert");
-      side_insert_kernel<<<div_up(n_x, 256), 256, 0, s>>>(xbuf.p, n_x, c->lay, off1.p, cntM.p, cnt.p, mtmp.p, extra.p,
-                                                         (ull*)c->dcount.p);
+      side_insert_kernel<<<div_up(n_xin, 256), 256, 0, s>>>(xin, n_xin, c->lay, off1.p, cntM.p, cnt.p, mtmp.p, extra.p,
+                                                           (ull*)c->dcount.p);
       c->lc.end("side_insert");
       c->lc.n++;
       CB_CUDA(cudaGetLastError());
     }
     download_counters(c);
-    if (c->hcount[DC_MAX_LIST] == 0) break;
+    u64 slot_over = c->hcount[DC_MAX_LIST];
+    ex_allreduce(c, &slot_over, 1, 0);
+    if (slot_over == 0) break;
     if (attempt >= 3) throw Error(CB_E_CAPACITY, "adjacency slot overflow");
     // enlarge the slot ranges of the lists that overflowed and run the join again
     add_u32_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(slotcnt.p, extra.p, n_lists);
@@ -567,12 +677,13 @@ void stage_build_overlap(cb_ctx* c) {
   vals[where].release();
 
   // BuildHighKmerList's counter (poly-A/T k-mer handled through its global weight)
-  int64_t hkmer = (int64_t)c->hcount[DC_HKMER] + ((long long)c->hcount[DC_POLYA_WEIGHT] > c->cfg.up_kmer ? 1 : 0);
+  reduce_counters(c);
+  int64_t hkmer = (int64_t)c->gcount[DC_HKMER] + ((long long)c->gcount[DC_POLYA_WEIGHT] > c->cfg.up_kmer ? 1 : 0);
   c->counters["hkmer"] = hkmer;
-  c->counters["candidates_verified"] = (int64_t)c->hcount[DC_CAND_VERIFIED];
-  c->counters["side_buffer_edges"] = (int64_t)n_x;
-  c->counters["upkmer_truncated_lists"] = (int64_t)c->hcount[DC_UPKMER_LISTS];
-  c->counters["order_dependent"] = (int64_t)c->hcount[DC_UPKMER_LISTS];
+  c->counters["candidates_verified"] = (int64_t)c->gcount[DC_CAND_VERIFIED];
+  c->counters["side_buffer_edges"] = (int64_t)c->gcount[DC_EDGES_RAW];
+  c->counters["upkmer_truncated_lists"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
+  c->counters["order_dependent"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
   if (hkmer > 0)
     throw Error(CB_E_UNSUPPORTED,
                 "non-empty high-frequency k-mer list: the reference's stopword loader (MatchPrefix.java:81) is "
@@ -583,9 +694,9 @@ void stage_build_overlap(cb_ctx* c) {
   c->slots = slots1;
   c->ckA.keys = std::move(mtmp);
   c->ckA.cnt = std::move(cnt);
-  c->ckA.n = (size_t)(c->hcount[DC_EDGES_M] + c->hcount[DC_EDGES_A]);
+  c->ckA.n = (size_t)(c->hcount[DC_EDGES_M] + c->hcount[DC_EDGES_A]);  // the lists this rank owns
   c->ckA.valid = true;
-  c->counters["edges_overlap"] = (int64_t)c->ckA.n;
+  c->counters["edges_overlap"] = (int64_t)(c->gcount[DC_EDGES_M] + c->gcount[DC_EDGES_A]);
 }
 
 }  // namespace cb

@@ -306,18 +306,89 @@ __global__ void __launch_bounds__(256) build_nodes_kernel(const u32* __restrict_
                                                           const u32* __restrict__ surv_idx, u32 n_lines,
                                                           const u64* __restrict__ reads,
                                                           const IdKey* __restrict__ idkey, const u32* __restrict__ cov,
-                                                          u32* __restrict__ node_line, u64* __restrict__ node_seq,
+                                                          u32 line_base, u32* __restrict__ node_line,
+                                                          u64* __restrict__ node_seq,
                                                           IdKey* __restrict__ node_idkey, u32* __restrict__ node_cov) {
   u32 line = blockIdx.x * blockDim.x + threadIdx.x;
   if (line >= n_lines || !surv_flag[line]) return;
   u32 idx = surv_idx[line];
-  node_line[idx] = line;
+  node_line[idx] = line_base + line;
   node_idkey[idx] = idkey[line];
   node_cov[idx] = cov[line];
   const uint4* src = reinterpret_cast<const uint4*>(reads + (size_t)line * NW);
   uint4* dst = reinterpret_cast<uint4*>(node_seq + (size_t)idx * NW);
 #pragma unroll
   for (int i = 0; i < NW / 2; i++) dst[i] = src[i];
+}
+
+// ---- multi-GPU duplicate detection: reads travel to the rank that owns their canonical hash ----
+// record = [hash][global line][id key hi][id key lo][read words ...] as u64
+template <int NW>
+__global__ void __launch_bounds__(256) dd_pack_kernel(const u64* __restrict__ hkeys, const u64* __restrict__ reads,
+                                                      const IdKey* __restrict__ idkey, u32 n_lines, u32 line_base,
+                                                      int world, u64* __restrict__ recs, u32* __restrict__ dest) {
+  u32 line = blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= n_lines) return;
+  const u64 h = hkeys[line];
+  u64* r = recs + (size_t)line * (4 + NW);
+  r[0] = h;
+  r[1] = (u64)(line_base + line);
+  if (h == ~0ull) {  // not a good read
+    dest[line] = (u32)world;
+    return;
+  }
+  IdKey ik = idkey[line];
+  r[2] = ik.hi;
+  r[3] = ik.lo;
+#pragma unroll
+  for (int w = 0; w < NW; w++) r[4 + w] = reads[(size_t)line * NW + w];
+  dest[line] = (u32)((h >> 32) & (u64)(world - 1));
+}
+
+template <int NW>
+__global__ void __launch_bounds__(256) dd_unpack_kernel(const u64* __restrict__ recs, size_t n,
+                                                        u64* __restrict__ hkeys, u32* __restrict__ hvals,
+                                                        u32* __restrict__ gline, IdKey* __restrict__ idkey,
+                                                        u64* __restrict__ reads) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64* r = recs + i * (4 + NW);
+  hkeys[i] = r[0];
+  hvals[i] = (u32)i;
+  gline[i] = (u32)r[1];
+  IdKey ik;
+  ik.hi = r[2];
+  ik.lo = r[3];
+  idkey[i] = ik;
+#pragma unroll
+  for (int w = 0; w < NW; w++) reads[i * NW + w] = r[4 + w];
+}
+
+// survivors go back to the rank that holds their SFA line: record = (global line, coverage)
+__global__ void __launch_bounds__(256) dd_return_kernel(const u32* __restrict__ surv, const u32* __restrict__ cov,
+                                                        const u32* __restrict__ gline, size_t n,
+                                                        const u64* __restrict__ line_bases, int world,
+                                                        u32* __restrict__ recs, u32* __restrict__ dest) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u32 g = gline[i];
+  recs[2 * i] = g;
+  recs[2 * i + 1] = cov[i];
+  u32 d = (u32)world;
+  if (surv[i]) {
+    d = 0;
+    while ((int)d + 1 < world && (u64)g >= line_bases[d + 1]) d++;
+  }
+  dest[i] = d;
+}
+
+__global__ void __launch_bounds__(256) dd_scatter_kernel(const u32* __restrict__ recs, size_t n, u32 line_base,
+                                                         u32* __restrict__ surv_flag, u32* __restrict__ cov) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 line = recs[2 * i] - line_base;
+  surv_flag[line] = 1;
+  cov[line] = recs[2 * i + 1];
 }
 
 #define CB_DISPATCH_NW(nw, CALL)                                             \
@@ -332,7 +403,8 @@ __global__ void __launch_bounds__(256) build_nodes_kernel(const u32* __restrict_
 void stage_parse_and_pack(cb_ctx* c) {
   cudaStream_t s = c->stream;
   const size_t n = c->text_n;
-  if (n == 0) throw Error(CB_E_NOREADS, "No good reads");
+  const int world = c->cfg.world;
+  if (n == 0 && !distributed(c)) throw Error(CB_E_NOREADS, "No good reads");
   if (n >= (1ull << 32)) throw Error(CB_E_CAPACITY, "SFA input of 4 GiB or more per context");
   c->K = c->cfg.k;
   c->L = c->cfg.readlen;
@@ -340,43 +412,64 @@ void stage_parse_and_pack(cb_ctx* c) {
     throw Error(CB_E_UNSUPPORTED, "k must be odd and <= 31 (even k lets palindromic k-mers drop nodes; SURVEY 8c)");
   if (c->L <= c->K) throw Error(CB_E_INVALID, "readlen must exceed k");
   if (c->L > 255) throw Error(CB_E_UNSUPPORTED, "readlen above 255");
+  if (world < 1 || (world & (world - 1)) || world > 256) throw Error(CB_E_UNSUPPORTED, "world must be a power of two <= 256");
+  if (distributed(c) && !c->has_ex) throw Error(CB_E_INVALID, "cfg.world > 1 needs cb_set_exchange before cb_preprocess");
+  c->lg_world = 0;
+  while ((1 << c->lg_world) < world) c->lg_world++;
+  c->pbit = c->K;  // owner of a k-mer group: bits [K, K + lg_world) of the canonical key (its middle bases)
   c->NW = ((c->L + 31) / 32 + 1) & ~1;
   c->W = c->L - c->K + 1;
   c->dcount.alloc(DC_COUNT, s);
   CB_CUDA(cudaMemsetAsync(c->dcount.p, 0, DC_COUNT * sizeof(u64), s));
 
   timer_start(c, "parse");
-  unsigned nb = (unsigned)div_up(n, PT_BLOCK);
+  c->n_lines = 0;
   DevBuf<u32> bcnt, boff;
-  bcnt.alloc(nb, s);
-  boff.alloc(nb, s);
-  count_terms_kernel<<<nb, PT_THREADS, 0, s>>>(c->text_ptr, n, bcnt.p);
-  c->lc.n++;
-  exclusive_scan_u32(bcnt.p, boff.p, nb, s, c->lc);
-  u32 last_cnt = 0, last_off = 0;
-  char last_byte = 0;
-  CB_CUDA(cudaMemcpyAsync(&last_cnt, bcnt.p + nb - 1, 4, cudaMemcpyDeviceToHost, s));
-  CB_CUDA(cudaMemcpyAsync(&last_off, boff.p + nb - 1, 4, cudaMemcpyDeviceToHost, s));
-  CB_CUDA(cudaMemcpyAsync(&last_byte, c->text_ptr + n - 1, 1, cudaMemcpyDeviceToHost, s));
-  CB_CUDA(cudaStreamSynchronize(s));
-  u32 terms = last_cnt + last_off;
-  bool last_is_term = (last_byte == '\n' || last_byte == '\r');
-  c->n_lines = terms + (last_is_term ? 0 : 1);
+  unsigned nb = (unsigned)div_up(n, PT_BLOCK);
+  if (n) {
+    bcnt.alloc(nb, s);
+    boff.alloc(nb, s);
+    count_terms_kernel<<<nb, PT_THREADS, 0, s>>>(c->text_ptr, n, bcnt.p);
+    c->lc.n++;
+    exclusive_scan_u32(bcnt.p, boff.p, nb, s, c->lc);
+    u32 last_cnt = 0, last_off = 0;
+    char last_byte = 0;
+    CB_CUDA(cudaMemcpyAsync(&last_cnt, bcnt.p + nb - 1, 4, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaMemcpyAsync(&last_off, boff.p + nb - 1, 4, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaMemcpyAsync(&last_byte, c->text_ptr + n - 1, 1, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    u32 terms = last_cnt + last_off;
+    bool last_is_term = (last_byte == '\n' || last_byte == '\r');
+    c->n_lines = terms + (last_is_term ? 0 : 1);
+  }
   c->line_start.alloc((size_t)c->n_lines + 1, s);
   set_u32_kernel<<<1, 1, 0, s>>>(c->line_start.p, 0u);
-  fill_line_starts_kernel<<<nb, PT_THREADS, 0, s>>>(c->text_ptr, n, boff.p, c->line_start.p);
+  if (n) fill_line_starts_kernel<<<nb, PT_THREADS, 0, s>>>(c->text_ptr, n, boff.p, c->line_start.p);
   set_u32_kernel<<<1, 1, 0, s>>>(c->line_start.p + c->n_lines, (u32)n);
   c->lc.n += 3;
 
+  // global line numbering: shards are consecutive line ranges in rank order
+  c->line_bases.assign(world + 1, 0);
+  c->line_base = 0;
+  if (distributed(c)) {
+    std::vector<u64> snd(world, (u64)c->n_lines), rcv(world, 0);
+    ex_counts(c, snd.data(), rcv.data(), 1);
+    for (int r = 0; r < world; r++) c->line_bases[r + 1] = c->line_bases[r] + rcv[r];
+    if (c->line_bases[world] >= (1ull << 32)) throw Error(CB_E_CAPACITY, "more than 2^32 SFA lines");
+    c->line_base = (u32)c->line_bases[c->cfg.rank];
+  } else {
+    c->line_bases[1] = c->n_lines;
+  }
+
   const u32 nl = c->n_lines;
-  c->status.alloc(nl, s);
-  c->reads.alloc((size_t)nl * c->NW, s);
-  c->idkey.alloc(nl, s);
-  // the hash keys / values of the duplicate detection live until stage_dedupe
+  const size_t nl1 = nl ? nl : 1;
+  c->status.alloc(nl1, s);
+  c->reads.alloc(nl1 * c->NW, s);
+  c->idkey.alloc(nl1, s);
   DevBuf<u64> hk[2];
   DevBuf<u32> hv[2];
-  {
-    for (int i = 0; i < 2; i++) { hk[i].alloc(nl, s); hv[i].alloc(nl, s); }
+  for (int i = 0; i < 2; i++) { hk[i].alloc(nl1, s); hv[i].alloc(nl1, s); }
+  if (nl) {
     c->lc.begin("parse_lines");
     CB_DISPATCH_NW(c->NW, (parse_lines_kernel<NW_><<<min(div_up(nl, 128), kNumSMs * 16), 128, 0, s>>>(
                               c->text_ptr, n, c->line_start.p, nl, c->K, c->L, c->status.p, c->reads.p, c->idkey.p,
@@ -384,59 +477,156 @@ void stage_parse_and_pack(cb_ctx* c) {
     c->lc.end("parse_lines");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
-    timer_stop(c, "parse");
-    download_counters(c);
-    if (c->hcount[DC_READS_GOOD] == 0) throw Error(CB_E_NOREADS, "No good reads");
-    if (c->hcount[DC_LEN_MISMATCH])
-      throw Error(CB_E_UNSUPPORTED, "reads of mixed length: " + std::to_string(c->hcount[DC_LEN_MISMATCH]) +
-                                        " good reads differ from -readlen " + std::to_string(c->L));
-    if (c->hcount[DC_LONG_ID]) throw Error(CB_E_UNSUPPORTED, "read ids longer than 16 bytes");
+  }
+  timer_stop(c, "parse");
+  download_counters(c);
+  reduce_counters(c);
+  // decisions are taken on the global counters so that every rank takes the same branch
+  if (c->gcount[DC_READS_GOOD] == 0) throw Error(CB_E_NOREADS, "No good reads");
+  if (c->gcount[DC_LEN_MISMATCH])
+    throw Error(CB_E_UNSUPPORTED, "reads of mixed length: " + std::to_string(c->gcount[DC_LEN_MISMATCH]) +
+                                      " good reads differ from -readlen " + std::to_string(c->L));
+  if (c->gcount[DC_LONG_ID]) throw Error(CB_E_UNSUPPORTED, "read ids longer than 16 bytes");
 
-    // ---- duplicate detection ----
-    timer_start(c, "dedupe");
+  // ---- duplicate detection ----
+  timer_start(c, "dedupe");
+  int bits = 0;
+  while ((1ull << bits) < c->gcount[DC_READS_GOOD]) bits++;
+  int hb = ((bits + 16 + 7) / 8) * 8;
+  if (hb > 64) hb = 64;
+  const u64 keymask = hb == 64 ? ~0ull : ((1ull << hb) - 1);
+  DevBuf<u32> surv_flag, surv_idx, cov;
+  surv_flag.alloc(nl1, s);
+  surv_idx.alloc(nl1, s);
+  cov.alloc(nl1, s);
+  CB_CUDA(cudaMemsetAsync(surv_flag.p, 0, nl1 * 4, s));
+  u32 n_local_nodes = 0;
+  if (!distributed(c)) {
     const u32 n_good = (u32)c->hcount[DC_READS_GOOD];
-    int bits = 0;
-    while ((1ull << bits) < (u64)n_good) bits++;
-    int hb = ((bits + 16 + 7) / 8) * 8;
-    if (hb > 64) hb = 64;
-    const u64 keymask = hb == 64 ? ~0ull : ((1ull << hb) - 1);
     int where = radix_sort(hk[0].p, hk[1].p, hv[0].p, hv[1].p, nl, 0, hb, s, c->lc, "dedupe");
-    DevBuf<u32> surv_flag, surv_idx, cov;
-    surv_flag.alloc(nl, s);
-    surv_idx.alloc(nl, s);
-    cov.alloc(nl, s);
-    CB_CUDA(cudaMemsetAsync(surv_flag.p, 0, (size_t)nl * 4, s));
     c->lc.begin("dedupe_runs");
     CB_DISPATCH_NW(c->NW, (dedupe_runs_kernel<NW_><<<min(div_up(n_good, 128), kNumSMs * 16), 128, 0, s>>>(
                               hk[where].p, hv[where].p, n_good, keymask, c->reads.p, c->idkey.p, c->L, surv_flag.p,
                               cov.p, (ull*)c->dcount.p)));
     c->lc.end("dedupe_runs");
     c->lc.n++;
-    exclusive_scan_u32(surv_flag.p, surv_idx.p, nl, s, c->lc);
     download_counters(c);
-    c->n_nodes = (u32)c->hcount[DC_SURVIVORS];
-    const u32 nn = c->n_nodes;
-    c->node_line.alloc(nn, s);
-    c->node_seq.alloc((size_t)nn * c->NW, s);
-    c->node_idkey.alloc(nn, s);
-    c->node_cov.alloc(nn, s);
+    n_local_nodes = (u32)c->hcount[DC_SURVIVORS];
+  } else {
+    // reads -> owner of their canonical hash -> (survivor, coverage) -> back to the line's rank
+    const int NW = c->NW;
+    const size_t rec_words = 4 + NW;
+    DevBuf<u64> recs;
+    DevBuf<u32> dest;
+    recs.alloc(nl1 * rec_words, s);
+    dest.alloc(nl1, s);
+    if (nl) {
+      CB_DISPATCH_NW(NW, (dd_pack_kernel<NW_><<<div_up(nl, 256), 256, 0, s>>>(hk[0].p, c->reads.p, c->idkey.p, nl,
+                                                                              c->line_base, world, recs.p, dest.p)));
+      c->lc.n++;
+    }
+    DevBuf<char> got;
+    size_t n_got = 0;
+    route_records(c, recs.p, rec_words * 8, dest.p, nl, got, n_got);
+    recs.release();
+    const size_t g1 = n_got ? n_got : 1;
+    DevBuf<u64> rk[2], rreads;
+    DevBuf<u32> rv[2], rline, rsurv, rcov;
+    DevBuf<IdKey> rid;
+    for (int i = 0; i < 2; i++) { rk[i].alloc(g1, s); rv[i].alloc(g1, s); }
+    rline.alloc(g1, s); rsurv.alloc(g1, s); rcov.alloc(g1, s); rid.alloc(g1, s); rreads.alloc(g1 * NW, s);
+    CB_CUDA(cudaMemsetAsync(rsurv.p, 0, g1 * 4, s));
+    CB_CUDA(cudaMemsetAsync(rcov.p, 0, g1 * 4, s));
+    if (n_got) {
+      CB_DISPATCH_NW(NW, (dd_unpack_kernel<NW_><<<div_up(n_got, 256), 256, 0, s>>>((const u64*)got.p, n_got, rk[0].p,
+                                                                                  rv[0].p, rline.p, rid.p, rreads.p)));
+      int where = radix_sort(rk[0].p, rk[1].p, rv[0].p, rv[1].p, n_got, 0, hb, s, c->lc, "dedupe");
+      c->lc.begin("dedupe_runs");
+      CB_DISPATCH_NW(NW, (dedupe_runs_kernel<NW_><<<min(div_up(n_got, 128), kNumSMs * 16), 128, 0, s>>>(
+                             rk[where].p, rv[where].p, (u32)n_got, keymask, rreads.p, rid.p, c->L, rsurv.p, rcov.p,
+                             (ull*)c->dcount.p)));
+      c->lc.end("dedupe_runs");
+      c->lc.n += 2;
+    }
+    DevBuf<u64> dbases;
+    dbases.alloc(world + 1, s);
+    CB_CUDA(cudaMemcpyAsync(dbases.p, c->line_bases.data(), (world + 1) * sizeof(u64), cudaMemcpyHostToDevice, s));
+    DevBuf<u32> ret, rdest;
+    ret.alloc(g1 * 2, s);
+    rdest.alloc(g1, s);
+    if (n_got) {
+      dd_return_kernel<<<div_up(n_got, 256), 256, 0, s>>>(rsurv.p, rcov.p, rline.p, n_got, dbases.p, world, ret.p,
+                                                         rdest.p);
+      c->lc.n++;
+    }
+    DevBuf<char> back;
+    size_t n_back = 0;
+    route_records(c, ret.p, 8, rdest.p, n_got, back, n_back);
+    if (n_back) {
+      dd_scatter_kernel<<<div_up(n_back, 256), 256, 0, s>>>((const u32*)back.p, n_back, c->line_base, surv_flag.p,
+                                                           cov.p);
+      c->lc.n++;
+    }
+    CB_CUDA(cudaGetLastError());
+    download_counters(c);
+    n_local_nodes = (u32)n_back;
+  }
+  reduce_counters(c);
+
+  // ---- nodes of this shard, in line order ----
+  exclusive_scan_u32(surv_flag.p, surv_idx.p, nl1, s, c->lc);
+  const size_t nloc1 = n_local_nodes ? n_local_nodes : 1;
+  DevBuf<u32> l_line, l_cov;
+  DevBuf<u64> l_seq;
+  DevBuf<IdKey> l_id;
+  l_line.alloc(nloc1, s); l_cov.alloc(nloc1, s); l_seq.alloc(nloc1 * c->NW, s); l_id.alloc(nloc1, s);
+  if (nl) {
     CB_DISPATCH_NW(c->NW, (build_nodes_kernel<NW_><<<div_up(nl, 256), 256, 0, s>>>(
-                              surv_flag.p, surv_idx.p, nl, c->reads.p, c->idkey.p, cov.p, c->node_line.p,
-                              c->node_seq.p, c->node_idkey.p, c->node_cov.p)));
+                              surv_flag.p, surv_idx.p, nl, c->reads.p, c->idkey.p, cov.p, c->line_base, l_line.p,
+                              l_seq.p, l_id.p, l_cov.p)));
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
-    timer_stop(c, "dedupe");
   }
+  if (!distributed(c)) {
+    c->n_nodes = n_local_nodes;
+    c->node_lo = 0;
+    c->node_hi = n_local_nodes;
+    c->node_line = std::move(l_line);
+    c->node_cov = std::move(l_cov);
+    c->node_seq = std::move(l_seq);
+    c->node_idkey = std::move(l_id);
+  } else {
+    // the node table (packed reads, id keys, coverage) is small and replicated on every rank, so
+    // every later gather of a neighbour's sequence is a local HBM read
+    std::vector<u64> snd(world, (u64)n_local_nodes), counts(world, 0);
+    ex_counts(c, snd.data(), counts.data(), 1);
+    u64 total = 0, lo = 0;
+    for (int r = 0; r < world; r++) {
+      if (r == c->cfg.rank) lo = total;
+      total += counts[r];
+    }
+    if (total >= (1ull << 27)) throw Error(CB_E_CAPACITY, "more than 2^27 nodes");
+    c->n_nodes = (u32)total;
+    c->node_lo = (u32)lo;
+    c->node_hi = (u32)(lo + n_local_nodes);
+    const size_t t1 = total ? total : 1;
+    c->node_line.alloc(t1, s); c->node_cov.alloc(t1, s); c->node_seq.alloc(t1 * c->NW, s); c->node_idkey.alloc(t1, s);
+    gather_all(c, l_line.p, 4, n_local_nodes, counts, c->node_line.p);
+    gather_all(c, l_cov.p, 4, n_local_nodes, counts, c->node_cov.p);
+    gather_all(c, l_seq.p, (size_t)c->NW * 8, n_local_nodes, counts, c->node_seq.p);
+    gather_all(c, l_id.p, sizeof(IdKey), n_local_nodes, counts, c->node_idkey.p);
+  }
+  timer_stop(c, "dedupe");
 
-  // counters with the reference's names (BrushAssembler.java:266-289)
+  // counters with the reference's names (BrushAssembler.java:266-289); global over the ranks
   auto& C = c->counters;
-  C["reads_good"] = (int64_t)c->hcount[DC_READS_GOOD];
-  C["reads_goodbp"] = (int64_t)c->hcount[DC_READS_GOODBP];
-  C["reads_short"] = (int64_t)c->hcount[DC_READS_SHORT];
-  C["reads_skipped"] = (int64_t)c->hcount[DC_READS_SKIPPED];
-  C["input_lines_invalid"] = (int64_t)c->hcount[DC_LINES_INVALID];
-  C["nodecount"] = (int64_t)c->hcount[DC_READS_GOOD];
-  C["contained"] = (int64_t)(c->hcount[DC_READS_GOOD] - c->hcount[DC_SURVIVORS]);
+  C["reads_good"] = (int64_t)c->gcount[DC_READS_GOOD];
+  C["reads_goodbp"] = (int64_t)c->gcount[DC_READS_GOODBP];
+  C["reads_short"] = (int64_t)c->gcount[DC_READS_SHORT];
+  C["reads_skipped"] = (int64_t)c->gcount[DC_READS_SKIPPED];
+  C["input_lines_invalid"] = (int64_t)c->gcount[DC_LINES_INVALID];
+  C["nodecount"] = (int64_t)c->gcount[DC_READS_GOOD];
+  C["contained"] = (int64_t)(c->gcount[DC_READS_GOOD] - c->n_nodes);
   C["redundant"] = C["contained"];
   C["nodes"] = (int64_t)c->n_nodes;
   // free what later stages do not need (node arrays carry everything forward)
@@ -444,7 +634,5 @@ void stage_parse_and_pack(cb_ctx* c) {
   c->idkey.release();
   c->status.release();
 }
-
-void stage_dedupe(cb_ctx*) {}
 
 }  // namespace cb

@@ -56,6 +56,9 @@ struct StringParams {
   u32* n_work_out;
   int check_consistency;  // literal kernels: re-test the list first
   int dirty_bit;          // 2 in the first cut round, 4 in the second
+  u64* req;               // multi-GPU: keys of mirror records to act on at their owner rank
+  u32* n_req;
+  u32 req_cap;
   ull* dcount;
 };
 
@@ -286,8 +289,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
           P.removed[t] = 1;
           mark_dirty(P, list);
           u64 mk = P.lay.mirror(k);
-          long long mi = find_edge(P, mk);
-          if (mi >= 0) { P.removed[mi] = 1; mark_dirty(P, P.lay.list(mk)); }
+          if (P.req) {  // the mirror's list may live on another rank: request its removal there
+            u32 ri = atomicAdd(P.n_req, 1u);
+            if (ri < P.req_cap) P.req[ri] = mk;
+          } else {
+            long long mi = find_edge(P, mk);
+            if (mi >= 0) { P.removed[mi] = 1; mark_dirty(P, P.lay.list(mk)); }
+          }
           atomicAdd(&P.dcount[DC_EDGE_REMOVAL], 1ull);
         }
       }
@@ -500,6 +508,69 @@ __global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __re
   if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&P.dcount[DC_EDGES_B], (ull)tot);
 }
 
+// ---- multi-GPU helpers: act on routed mirror keys at the rank that owns their list ----
+__global__ void __launch_bounds__(256) apply_removal_requests_kernel(StringParams P, const u64* __restrict__ keys,
+                                                                     size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long mi = find_edge(P, keys[i]);
+  if (mi >= 0) { P.removed[mi] = 1; mark_dirty(P, P.lay.list(keys[i])); }
+}
+
+// one thread per list: the mirror key of every kept record is a "kept" vote for the other end
+__global__ void __launch_bounds__(256) tr_votes_kernel(StringParams P) {
+  for (u32 lid = blockIdx.x * blockDim.x + threadIdx.x; lid < P.n_lists; lid += gridDim.x * blockDim.x) {
+    const u32 n = P.cnt[lid], lo = P.adj_off[lid];
+    for (u32 t = 0; t < n; t++)
+      if (P.kept[lo + t] & 1) {
+        u32 ri = atomicAdd(P.n_req, 1u);
+        if (ri < P.req_cap) P.req[ri] = P.lay.mirror(P.edges[lo + t]);
+      }
+  }
+}
+
+__global__ void __launch_bounds__(256) apply_votes_kernel(StringParams P, const u64* __restrict__ keys, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long mi = find_edge(P, keys[i]);
+  if (mi >= 0) P.kept[mi] |= 2;  // one vote per record at most: no other thread writes this byte
+}
+
+__global__ void __launch_bounds__(256) tr_final_voted_kernel(StringParams P, u64* __restrict__ out,
+                                                             u32* __restrict__ cnt_out) {
+  u32 tot = 0;
+  for (u32 lid = blockIdx.x * blockDim.x + threadIdx.x; lid < P.n_lists; lid += gridDim.x * blockDim.x) {
+    u32 w = 0;
+    const u32 n = P.cnt[lid], lo = P.adj_off[lid];
+    for (u32 t = 0; t < n; t++)
+      if (P.kept[lo + t] == 3) out[lo + w++] = P.edges[lo + t];
+    cnt_out[lid] = w;
+    tot += w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&P.dcount[DC_EDGES_B], (ull)tot);
+}
+
+template <int NW>
+__device__ __forceinline__ u32 list_owner_s(const u64* __restrict__ node_seq, u32 lid, int L, int K, int pbit,
+                                            u32 wmask) {
+  u64 r[NW];
+  load_read_c<NW>(node_seq, lid >> 1, r);
+  u64 km = extract_kmer<NW>(r, (lid & 1u) ? 0 : L - K, K);
+  u64 rk = revcomp_kmer(km, K);
+  u64 canon = km < rk ? km : rk;
+  return (u32)(canon >> pbit) & wmask;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(256) key_owner_s_kernel(const u64* __restrict__ keys, size_t n, EdgeLayout lay,
+                                                          const u64* __restrict__ node_seq, int L, int K, int pbit,
+                                                          u32 wmask, u32* __restrict__ dest) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dest[i] = list_owner_s<NW>(node_seq, lay.list(keys[i]), L, K, pbit, wmask);
+}
+
 #define CB_DISPATCH_NW(nw, CALL)                                             \
   switch (nw) {                                                              \
     case 2: { constexpr int NW_ = 2; CALL; } break;                          \
@@ -533,6 +604,9 @@ static StringParams make_params(cb_ctx* c, const u64* keys, const u32* cnt) {
   P.n_work_out = nullptr;
   P.check_consistency = 0;
   P.dirty_bit = 2;
+  P.req = nullptr;
+  P.n_req = nullptr;
+  P.req_cap = 0;
   P.dcount = (ull*)c->dcount.p;
   return P;
 }
@@ -551,22 +625,40 @@ static u32 read_u32s(cb_ctx* c, const u32* p) {
   return v;
 }
 
+// routes device keys to the owner rank of their adjacency list; returns the received keys
+static size_t route_keys(cb_ctx* c, const u64* keys, size_t n, DevBuf<char>& out) {
+  cudaStream_t s = c->stream;
+  DevBuf<u32> dest;
+  dest.alloc(n ? n : 1, s);
+  if (n) {
+    CB_DISPATCH_NW(c->NW, (key_owner_s_kernel<NW_><<<div_up(n, 256), 256, 0, s>>>(
+                              keys, n, c->lay, c->node_seq.p, c->L, c->K, c->pbit, (u32)c->cfg.world - 1, dest.p)));
+    c->lc.n++;
+  }
+  size_t n_out = 0;
+  route_records(c, keys, 8, dest.p, n, out, n_out);
+  return n_out;
+}
+
 void stage_string_graph(cb_ctx* c) {
   cudaStream_t s = c->stream;
   const u32 n_lists = 2 * c->n_nodes;
   const size_t nl = n_lists ? n_lists : 1;
   const size_t slots = c->slots ? c->slots : 1;
+  const bool dist = distributed(c);
   CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGE_REMOVAL, 0, (DC_COUNT - DC_EDGE_REMOVAL) * sizeof(u64), s));
   c->list_flag.alloc((nl + 3) & ~(size_t)3, s);
   CB_CUDA(cudaMemsetAsync(c->list_flag.p, 1, (nl + 3) & ~(size_t)3, s));
   DevBuf<u32> workA, workB, nwork;  // work lists: inconsistent lists / lists that lost an entry
   workA.alloc(nl, s);
   workB.alloc(nl, s);
-  nwork.alloc(4, s);
-  CB_CUDA(cudaMemsetAsync(nwork.p, 0, 16, s));
+  nwork.alloc(8, s);
+  CB_CUDA(cudaMemsetAsync(nwork.p, 0, 32, s));
   DevBuf<uint8_t> flags;  // per slot: "removed" during the cut rounds, then "kept" for TR
   flags.alloc(slots, s);
   CB_CUDA(cudaMemsetAsync(flags.p, 0, slots, s));
+  DevBuf<u64> req;  // multi-GPU: mirror keys to act on at their owner
+  if (dist) req.alloc(slots, s);
 
   // ---- CutChimericLinks x <= 2 (BrushAssembler.java:347-367) ----
   timer_start(c, "cut");
@@ -575,18 +667,23 @@ void stage_string_graph(cb_ctx* c) {
   size_t cur_n = c->ckA.n;
   c->ckC_is_A = true;
   int64_t e1 = 0, e2 = 0;
-  if (c->ckA.n) {
+  {
     StringParams P = make_params(c, cur_keys, cur_cnt);
-    c->lc.begin("consistency");
-    CB_DISPATCH_NW(c->NW, (consistency_kernel<NW_><<<div_up(c->slots, 256), 256, 0, s>>>(
-                              P, workA.p, nwork.p + 0, c->cfg.majority < 1.0f ? 0 : 1)));
-    c->lc.end("consistency");
-    c->lc.n++;
-    CB_CUDA(cudaGetLastError());
+    if (c->ckA.n) {
+      c->lc.begin("consistency");
+      CB_DISPATCH_NW(c->NW, (consistency_kernel<NW_><<<div_up(c->slots, 256), 256, 0, s>>>(
+                                P, workA.p, nwork.p + 0, c->cfg.majority < 1.0f ? 0 : 1)));
+      c->lc.end("consistency");
+      c->lc.n++;
+      CB_CUDA(cudaGetLastError());
+    }
     u32 n_bad = read_u32s(c, nwork.p + 0);
     const u32* work = workA.p;
     u32 n_work = n_bad;
-    for (int round = 1; round <= 2 && n_work > 0; round++) {
+    for (int round = 1; round <= 2; round++) {
+      u64 any_work = n_work;
+      ex_allreduce(c, &any_work, 1, 0);  // every rank must take the same branches (collectives below)
+      if (any_work == 0) break;
       u32* dirty = (round == 1) ? workB.p : workA.p;  // round 2 reuses A's storage: its list is consumed
       u32* n_dirty = nwork.p + round;
       P = make_params(c, cur_keys, cur_cnt);
@@ -597,15 +694,35 @@ void stage_string_graph(cb_ctx* c) {
       P.n_work_out = n_dirty;
       P.check_consistency = round == 2;
       P.dirty_bit = round == 1 ? 2 : 4;
+      if (dist) {
+        P.req = req.p;
+        P.n_req = nwork.p + 4;
+        P.req_cap = (u32)(slots > 0xffffffffu ? 0xffffffffu : slots);
+        CB_CUDA(cudaMemsetAsync(nwork.p + 4, 0, 4, s));
+      }
       CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGE_REMOVAL, 0, sizeof(u64), s));
-      c->lc.begin("cut");
-      CB_DISPATCH_NW(c->NW, (cut_kernel<NW_><<<warp_grid(n_work), ST_WARPS * 32, 0, s>>>(P)));
-      c->lc.end("cut");
-      c->lc.n++;
-      CB_CUDA(cudaGetLastError());
+      if (n_work) {
+        c->lc.begin("cut");
+        CB_DISPATCH_NW(c->NW, (cut_kernel<NW_><<<warp_grid(n_work), ST_WARPS * 32, 0, s>>>(P)));
+        c->lc.end("cut");
+        c->lc.n++;
+        CB_CUDA(cudaGetLastError());
+      }
+      if (dist) {  // removal requests for mirrors -> owner rank of the mirror's list
+        u32 nr = read_u32s(c, nwork.p + 4);
+        if (nr > P.req_cap) throw Error(CB_E_CAPACITY, "removal request buffer overflow");
+        DevBuf<char> got;
+        size_t n_got = route_keys(c, req.p, nr, got);
+        if (n_got) {
+          apply_removal_requests_kernel<<<div_up(n_got, 256), 256, 0, s>>>(P, (const u64*)got.p, n_got);
+          c->lc.n++;
+          CB_CUDA(cudaGetLastError());
+        }
+      }
       download_counters(c);
-      int64_t cuts = (int64_t)c->hcount[DC_EDGE_REMOVAL];
-      (round == 1 ? e1 : e2) = cuts;
+      u64 cuts = c->hcount[DC_EDGE_REMOVAL];
+      ex_allreduce(c, &cuts, 1, 0);
+      (round == 1 ? e1 : e2) = (int64_t)cuts;
       if (cuts == 0) break;
       // EdgeRemoval: checkpoint chl2 becomes a private copy of A that the dirty lists rewrite
       if (c->ckC_is_A) {
@@ -618,10 +735,12 @@ void stage_string_graph(cb_ctx* c) {
       }
       u32 nd = read_u32s(c, n_dirty);
       CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGES_C, 0, sizeof(u64), s));
-      remove_flagged_kernel<<<warp_grid(nd), ST_WARPS * 32, 0, s>>>(c->ckC.keys.p, c->adj_off.p, c->ckC.cnt.p,
-                                                                   flags.p, dirty, nd, (ull*)c->dcount.p);
-      c->lc.n++;
-      CB_CUDA(cudaGetLastError());
+      if (nd) {
+        remove_flagged_kernel<<<warp_grid(nd), ST_WARPS * 32, 0, s>>>(c->ckC.keys.p, c->adj_off.p, c->ckC.cnt.p,
+                                                                     flags.p, dirty, nd, (ull*)c->dcount.p);
+        c->lc.n++;
+        CB_CUDA(cudaGetLastError());
+      }
       download_counters(c);
       cur_n -= (size_t)c->hcount[DC_EDGES_C];
       c->ckC.n = cur_n;
@@ -636,51 +755,83 @@ void stage_string_graph(cb_ctx* c) {
   c->counters["edge_removal_2"] = e2;
   c->counters["edge_removal"] = e1 > 0 ? e2 : e1;
   timer_stop(c, "cut");
-  c->counters["edges_chl2"] = (int64_t)cur_n;
+  {
+    u64 g = cur_n;
+    ex_allreduce(c, &g, 1, 0);
+    c->counters["edges_chl2"] = (int64_t)g;
+  }
 
   // ---- TransitiveReduction + EdgeRemoval (BrushAssembler.java:370-379) ----
   timer_start(c, "tr");
   c->ckB.keys.alloc(slots, s);
   c->ckB.cnt.alloc(nl, s);
-  if (cur_n == 0) {
-    CB_CUDA(cudaMemsetAsync(c->ckB.cnt.p, 0, nl * 4, s));
-  } else {
+  CB_CUDA(cudaMemsetAsync(c->ckB.cnt.p, 0, nl * 4, s));
+  {
     // `flags` is all zero again here (remove_flagged_kernel clears what it consumed)
     StringParams P = make_params(c, cur_keys, cur_cnt);
     P.kept = flags.p;
-    c->lc.begin("tr_fast");
-    tr_fast_kernel<<<min(div_up(c->slots, 256), kNumSMs * 8), 256, 0, s>>>(P);
-    c->lc.end("tr_fast");
-    CB_CUDA(cudaMemsetAsync(nwork.p + 3, 0, 4, s));
-    tr_worklist_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(c->list_flag.p, cur_cnt, n_lists, workA.p,
-                                                                   nwork.p + 3);
-    c->lc.n += 2;
-    u32 n_slow = read_u32s(c, nwork.p + 3);
-    if (n_slow) {
-      P.work = workA.p;
-      P.n_work = n_slow;
-      c->lc.begin("tr");
-      CB_DISPATCH_NW(c->NW, (tr_kernel<NW_><<<warp_grid(n_slow), ST_WARPS * 32, 0, s>>>(P)));
-      c->lc.end("tr");
-      c->lc.n++;
+    if (cur_n) {
+      c->lc.begin("tr_fast");
+      tr_fast_kernel<<<min(div_up(c->slots, 256), kNumSMs * 8), 256, 0, s>>>(P);
+      c->lc.end("tr_fast");
+      CB_CUDA(cudaMemsetAsync(nwork.p + 3, 0, 4, s));
+      tr_worklist_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(c->list_flag.p, cur_cnt, n_lists, workA.p,
+                                                                     nwork.p + 3);
+      c->lc.n += 2;
+      u32 n_slow = read_u32s(c, nwork.p + 3);
+      if (n_slow) {
+        P.work = workA.p;
+        P.n_work = n_slow;
+        c->lc.begin("tr");
+        CB_DISPATCH_NW(c->NW, (tr_kernel<NW_><<<warp_grid(n_slow), ST_WARPS * 32, 0, s>>>(P)));
+        c->lc.end("tr");
+        c->lc.n++;
+      }
+      CB_CUDA(cudaGetLastError());
     }
-    CB_CUDA(cudaGetLastError());
     CB_CUDA(cudaMemsetAsync(c->ckB.keys.p, 0xff, slots * sizeof(u64), s));
-    c->lc.begin("tr_final");
-    tr_final_kernel<<<min(div_up((size_t)n_lists, 256), kNumSMs * 8), 256, 0, s>>>(P, c->ckB.keys.p, c->ckB.cnt.p);
-    c->lc.end("tr_final");
-    c->lc.n++;
+    const int fgrid = min(div_up((size_t)nl, 256), kNumSMs * 8);
+    if (!dist) {
+      if (cur_n) {
+        c->lc.begin("tr_final");
+        tr_final_kernel<<<fgrid, 256, 0, s>>>(P, c->ckB.keys.p, c->ckB.cnt.p);
+        c->lc.end("tr_final");
+        c->lc.n++;
+      }
+    } else {
+      // the mirror of a kept record may live on another rank: kept records vote for their mirrors
+      P.req = req.p;
+      P.n_req = nwork.p + 5;
+      P.req_cap = (u32)(slots > 0xffffffffu ? 0xffffffffu : slots);
+      CB_CUDA(cudaMemsetAsync(nwork.p + 5, 0, 4, s));
+      if (cur_n) {
+        tr_votes_kernel<<<fgrid, 256, 0, s>>>(P);
+        c->lc.n++;
+      }
+      u32 nv = read_u32s(c, nwork.p + 5);
+      DevBuf<char> got;
+      size_t n_got = route_keys(c, req.p, nv, got);
+      if (n_got) {
+        apply_votes_kernel<<<div_up(n_got, 256), 256, 0, s>>>(P, (const u64*)got.p, n_got);
+        c->lc.n++;
+      }
+      if (cur_n) {
+        tr_final_voted_kernel<<<fgrid, 256, 0, s>>>(P, c->ckB.keys.p, c->ckB.cnt.p);
+        c->lc.n++;
+      }
+    }
     CB_CUDA(cudaGetLastError());
   }
   timer_stop(c, "tr");
   download_counters(c);
+  reduce_counters(c);
   c->ckB.n = (size_t)c->hcount[DC_EDGES_B];
   c->ckB.valid = true;
-  if (c->hcount[DC_TR_OVERFLOW]) throw Error(CB_E_CAPACITY, "TransitiveReduction kept-list capacity exceeded");
-  c->counters["trans_edge"] = (int64_t)c->hcount[DC_TRANS_EDGE];
-  c->counters["contained_edge"] = (int64_t)c->hcount[DC_CONTAINED_EDGE];
-  c->counters["edges_re"] = (int64_t)c->ckB.n;
-  c->counters["slow_lists"] = (int64_t)c->hcount[DC_SLOW_LISTS];
+  if (c->gcount[DC_TR_OVERFLOW]) throw Error(CB_E_CAPACITY, "TransitiveReduction kept-list capacity exceeded");
+  c->counters["trans_edge"] = (int64_t)c->gcount[DC_TRANS_EDGE];
+  c->counters["contained_edge"] = (int64_t)c->gcount[DC_CONTAINED_EDGE];
+  c->counters["edges_re"] = (int64_t)c->gcount[DC_EDGES_B];
+  c->counters["slow_lists"] = (int64_t)c->gcount[DC_SLOW_LISTS];
 }
 
 }  // namespace cb

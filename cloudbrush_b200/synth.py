@@ -22,19 +22,33 @@ CONFIGS = {
 }
 
 
-def synth_reads(genome_len, read_len, coverage, both_strands, seed, n_reads=None, first_id=1):
-    """Returns (codes uint8[N, L] in 0..3, N)."""
-    rng = np.random.Generator(np.random.Philox(seed))
-    genome = rng.integers(0, 4, size=genome_len, dtype=np.uint8)
+N_PARTS = 8  # the read set is always drawn as 8 independent streams, so it does not depend on the GPU count
+
+
+def part_sizes(n_reads):
+    base, rem = divmod(n_reads, N_PARTS)
+    return [base + (1 if p < rem else 0) for p in range(N_PARTS)]
+
+
+def synth_reads(genome_len, read_len, coverage, both_strands, seed, n_reads=None, parts=None):
+    """codes uint8[n, L] in 0..3 of the requested parts (default: all 8, i.e. the whole read set).
+
+    Part p uses its own Philox stream (jumped p+1 times), so rank r of W ranks can generate parts
+    [r*8/W, (r+1)*8/W) on its own and the union over the ranks is the single-GPU read set."""
+    genome = np.random.Generator(np.random.Philox(seed)).integers(0, 4, size=genome_len, dtype=np.uint8)
     n = int(round(genome_len * coverage / read_len)) if n_reads is None else n_reads
-    starts = rng.integers(0, genome_len - read_len + 1, size=n, dtype=np.int64)
-    flip = rng.integers(0, 2, size=n, dtype=np.uint8).astype(bool) if both_strands else None
-    idx = starts[:, None] + np.arange(read_len, dtype=np.int64)[None, :]
-    reads = genome[idx]
-    if both_strands:
-        rc = (3 - reads[:, ::-1])
-        reads = np.where(flip[:, None], rc, reads)
-    return np.ascontiguousarray(reads, dtype=np.uint8)
+    sizes = part_sizes(n)
+    out = []
+    for p in (range(N_PARTS) if parts is None else parts):
+        rng = np.random.Generator(np.random.Philox(seed).jumped(p + 1))
+        starts = rng.integers(0, genome_len - read_len + 1, size=sizes[p], dtype=np.int64)
+        idx = starts[:, None] + np.arange(read_len, dtype=np.int64)[None, :]
+        reads = genome[idx]
+        if both_strands:
+            flip = rng.integers(0, 2, size=sizes[p], dtype=np.uint8).astype(bool)
+            reads = np.where(flip[:, None], 3 - reads[:, ::-1], reads)
+        out.append(np.ascontiguousarray(reads, dtype=np.uint8))
+    return np.concatenate(out, axis=0) if out else np.zeros((0, read_len), np.uint8)
 
 
 def sfa_bytes(codes, first_id=1):
@@ -65,10 +79,17 @@ def sfa_bytes(codes, first_id=1):
     return out
 
 
-def make_config(name, scale_genome=None):
+def make_config(name, scale_genome=None, rank=0, world=1):
+    """SFA bytes of rank's shard (consecutive lines of the whole read set) and the workload's description."""
     G, L, cov, both, k, seed = CONFIGS[name]
     if scale_genome is not None:
         G = scale_genome
-    codes = synth_reads(G, L, cov, both, seed)
-    return sfa_bytes(codes), dict(genome=G, readlen=L, coverage=cov, both_strands=both, k=k, seed=seed,
-                                  n_reads=codes.shape[0])
+    n_total = int(round(G * cov / L))
+    per = N_PARTS // world
+    if per * world != N_PARTS:
+        raise ValueError("world must divide 8")
+    parts = list(range(rank * per, (rank + 1) * per))
+    codes = synth_reads(G, L, cov, both, seed, parts=parts)
+    first_id = 1 + sum(part_sizes(n_total)[:rank * per])
+    return sfa_bytes(codes, first_id=first_id), dict(genome=G, readlen=L, coverage=cov, both_strands=both, k=k,
+                                                     seed=seed, n_reads=codes.shape[0], n_reads_total=n_total)

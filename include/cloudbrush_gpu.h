@@ -146,6 +146,37 @@ int cb_get_launch_count(cb_ctx* ctx, int64_t* n);
 int cb_set_profile(cb_ctx* ctx, int on);
 int cb_get_kernel_stat(cb_ctx* ctx, const char* name, double* total_ms, int64_t* launches);
 
+/* ---- multi-GPU: one process (and one context) per GPU -------------------------------------
+ * The MapReduce shuffle of the reference (HashPartitioner on the Text key inside every
+ * JobClient.runJob, e.g. MatchPrefix.java:468) becomes an all-to-all of k-mer tuples between the
+ * contexts: context `rank` of `world` (cb_config) loads ITS shard of the SFA lines (shards are
+ * consecutive line ranges in rank order) and owns the k-mer groups whose key hashes to it.  The
+ * library does the partitioning on the device and calls back into the host program for the
+ * actual transfers, so the transport (torch.distributed over NCCL in cloudbrush_b200/dist.py, or
+ * NCCL/MPI directly from a Java launcher) stays outside the ABI.  world must be a power of two.
+ *
+ * Every callback returns 0 on success.  Device buffers are complete when a callback is entered
+ * (the library synchronises its stream first) and the callback must have finished the transfer
+ * when it returns.  Counts are in BYTES. */
+typedef struct cb_exchange {
+  void* user;
+  /* recv[i] = what rank i sent to this rank; arrays of world * n_per_rank values (host) */
+  int (*exchange_counts)(void* user, const uint64_t* send, uint64_t* recv, int32_t n_per_rank);
+  /* send_dev holds world consecutive blocks of send_bytes[i]; recv_dev receives world blocks */
+  int (*alltoallv)(void* user, const void* send_dev, const uint64_t* send_bytes, void* recv_dev,
+                   const uint64_t* recv_bytes);
+  /* every rank contributes send_bytes; recv_dev receives the world blocks in rank order */
+  int (*allgatherv)(void* user, const void* send_dev, uint64_t send_bytes, void* recv_dev,
+                    const uint64_t* recv_bytes);
+  /* in-place all-reduce of n host values; op 0 = sum, 1 = max */
+  int (*allreduce_u64)(void* user, uint64_t* vals, int32_t n, int32_t op);
+} cb_exchange;
+
+/* Must be called before cb_preprocess when cfg.world > 1.  With an exchange set, counters are
+ * global sums, cb_export_nodes returns the global node table (replicated) and cb_export_edges the
+ * adjacency lists this rank owns (their union over the ranks is the checkpoint). */
+int cb_set_exchange(cb_ctx* ctx, const cb_exchange* ex);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,71 @@
+"""-m gpu: the sharded (multi-rank) pipeline gives exactly the single-GPU checkpoints.
+
+Two ranks share cuda:0 here (gloo transport staged through the host, because NCCL refuses two ranks
+on one device); on a multi-GPU box bench.py runs the same code over NCCL."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from dist_util import ROOT, run_ranks
+
+pytestmark = pytest.mark.gpu
+
+
+def _sharded_worker(rank, world, sfa_path, k, L, outdir):
+    import torch
+    from cloudbrush_b200 import BrushConfig, BrushGpu
+    from cloudbrush_b200.dist import TorchExchange, shard_lines
+    sfa = open(sfa_path, "rb").read()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    g = BrushGpu(BrushConfig(k=k, readlen=L, device=0, rank=rank, world=world))
+    g.set_exchange(TorchExchange(device=dev))
+    g.load_sfa_buffer(shard_lines(sfa, rank, world))
+    g.run()
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), a=g.edge_rows(1), c=g.edge_rows(2), b=g.edge_rows(3),
+             nodes=g.nodes(), counters=np.array([g.counter(x) for x in COUNTERS]))
+    g.close()
+
+
+COUNTERS = ["reads_good", "nodes", "contained", "tuples", "edges_overlap", "edges_chl2", "edges_re", "trans_edge",
+            "edge_removal_1", "edge_removal_2"]
+
+
+def _check(sfa, k, L, tmp_path, world=2):
+    from cloudbrush_b200 import BrushConfig, BrushGpu
+    p = tmp_path / "in.sfa"
+    p.write_bytes(sfa)
+    run_ranks(_sharded_worker, world, args=(str(p), k, L, str(tmp_path)), tmpdir=tmp_path)
+    g = BrushGpu(BrushConfig(k=k, readlen=L))
+    g.load_sfa_buffer(sfa)
+    g.run()
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    for key, ck in (("a", 1), ("c", 2), ("b", 3)):
+        got = np.concatenate([q[key] for q in parts])
+        got = got[np.lexsort((got[:, 3], got[:, 2], got[:, 1], got[:, 0]))]
+        assert np.array_equal(got, g.edge_rows(ck)), f"checkpoint {key} differs between 1 and {world} ranks"
+    for q in parts:  # the node table is replicated, the counters are global
+        assert np.array_equal(q["nodes"], g.nodes())
+        assert q["counters"].tolist() == [g.counter(x) for x in COUNTERS]
+    g.close()
+
+
+def test_two_ranks_ec10k(tmp_path, ec10k_sfa):
+    _check(ec10k_sfa, 21, 36, tmp_path)
+
+
+def test_two_ranks_synthetic_both_strands(tmp_path):
+    from cloudbrush_b200 import synth
+    buf, m = synth.make_config("cfg3_50k", scale_genome=20_000)
+    _check(bytes(buf), m["k"], m["readlen"], tmp_path)
+
+
+def test_four_ranks_micro_cases(tmp_path):
+    from cases import all_cases
+    for name in ("tiling_both_strands", "branch", "rc_duplicates"):
+        buf, k, L = all_cases()[name]
+        d = tmp_path / name
+        d.mkdir()
+        _check(buf, k, L, d, world=4)
