@@ -568,6 +568,11 @@ void stage_build_overlap(cb_ctx* c) {
   timer_stop(c, "sort_tuples");
   download_counters(c);
   const u32 T = (u32)(Tmax - c->hcount[DC_TUPLES_INVALID]);
+  {
+    u64 tg = T;
+    ex_allreduce(c, &tg, 1, 0);
+    c->counters["tuples"] = (int64_t)tg;
+  }
   keys[where ^ 1].release();
   vals[where ^ 1].release();
 
