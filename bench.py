@@ -96,14 +96,20 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # workload
 # --------------------------------------------------------------------------------------------
-def make_workload(name, genome=None, seed_shift=0):
+def make_workload(name, genome=None, seed_shift=0, rank=0, world=1):
+    """SFA shard of `rank` (weak scaling: the genome grows with the GPU count, reads per GPU stay fixed)."""
     from cloudbrush_b200 import synth
     G, L, cov, both, k, seed = synth.CONFIGS[name]
     if genome:
         G = genome
-    codes = synth.synth_reads(G, L, cov, both, seed + seed_shift)
-    sfa = synth.sfa_bytes(codes)
-    return sfa, dict(genome=G, readlen=L, coverage=cov, both_strands=both, k=k, n_reads=int(codes.shape[0]))
+    G *= world
+    n_total = int(round(G * cov / L))
+    per = synth.N_PARTS // world
+    codes = synth.synth_reads(G, L, cov, both, seed + seed_shift, parts=list(range(rank * per, (rank + 1) * per)))
+    first_id = 1 + sum(synth.part_sizes(n_total)[:rank * per])
+    sfa = synth.sfa_bytes(codes, first_id=first_id)
+    return sfa, dict(genome=G, readlen=L, coverage=cov, both_strands=both, k=k, n_reads=int(codes.shape[0]),
+                     n_reads_total=n_total)
 
 
 def cpu_sample_genome(meta, target_reads=250_000):
@@ -182,7 +188,7 @@ def bench_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -210,7 +216,7 @@ def bench_ours(args):
 
     name = args.config
     t0 = time.time()
-    sfa_np, meta = make_workload(name, genome=args.genome)
+    sfa_np, meta = make_workload(name, genome=args.genome, rank=rank, world=world)
     log(f"[rank {rank}] workload {name}: {meta} ({len(sfa_np)/1e6:.1f} MB SFA) generated in {time.time()-t0:.1f}s")
     k, L = meta["k"], meta["readlen"]
     n_reads = meta["n_reads"]
@@ -218,6 +224,10 @@ def bench_ours(args):
     host = torch.from_numpy(sfa_np).pin_memory()
     dev = host.cuda(non_blocking=False)
     g = BrushGpu(BrushConfig(k=k, readlen=L, device=local_rank, rank=rank, world=world))
+    if world > 1:
+        from cloudbrush_b200.dist import TorchExchange
+        exch = TorchExchange(device=torch.device("cuda", local_rank))
+        g.set_exchange(exch)
 
     def step_resident():
         g.borrow_sfa_device(dev.data_ptr(), dev.numel())
@@ -251,7 +261,7 @@ def bench_ours(args):
     counters = {c: g.counter(c) for c in ["reads_good", "nodes", "tuples", "candidates_verified", "edges_overlap",
                                           "edges_chl2", "edges_re", "trans_edge", "edge_removal_1", "slow_lists"]}
     stage_ms = {t: g.time_ms(t) for t in ["parse", "dedupe", "keygen", "sort_tuples", "join_verify",
-                                          "cut", "tr"]}
+                                          "cut", "tr"] + (["exchange_tuples"] if world > 1 else [])}
 
     # ---- e2e through the C ABI with host buffers ----
     e2e_t = []
@@ -273,9 +283,9 @@ def bench_ours(args):
         t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1]) / 1e3
-        tot = torch.tensor([n_reads, counters["edges_overlap"]], device="cuda", dtype=torch.float64)
+        tot = torch.tensor([n_reads], device="cuda", dtype=torch.float64)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        total_reads, total_edges = float(tot[0]), float(tot[1])
+        total_reads, total_edges = float(tot[0]), float(counters["edges_overlap"])  # counters are global already
     else:
         total_reads, total_edges = float(n_reads), float(counters["edges_overlap"])
 
@@ -289,7 +299,7 @@ def bench_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         # dominant kernel
         W = L - k + 1
-        T_slots = counters["nodes"] * W
+        T_slots = counters["nodes"] * W / world  # tuple slots sorted per GPU (even shards)
         st = stats.get("rs_scatter:tuples")
         roof = None
         if st and st[1] > 0:
@@ -327,7 +337,8 @@ def bench_ours(args):
                                    f"{n_reads} reads per GPU",
                        "l2": "inputs larger than L2 (SFA text and tuple arrays exceed 126 MB)" if len(sfa_np) > 126e6
                              else "input smaller than L2 (reduced run)",
-                       "sharding": "one shard per GPU" if world > 1 else "single GPU"},
+                       "sharding": (f"weak scaling: {world} shards of consecutive SFA lines, k-mer groups hash-partitioned, "
+                                    f"tuple all-to-all over NCCL, packed reads replicated") if world > 1 else "single GPU"},
             "edges_per_sec": total_edges / (ms * 1e-3),
             "wall_ms_per_step": wall * 1e3,
             "e2e": {"value": total_reads / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(len(sfa_np)),
@@ -340,13 +351,31 @@ def bench_ours(args):
             "stage_ms": stage_ms,
             "kernels": kern,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     g.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process' original stdout; everything else (NCCL banners, library
+    chatter written to fd 1) has been redirected to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
