@@ -395,6 +395,10 @@ int cb_write_nodes(cb_ctx* c, int checkpoint, const char* out_dir) {
   CB_API_BEGIN(c)
   if (!out_dir) throw Error(CB_E_INVALID, "null path");
   if (!c->preprocessed) throw Error(CB_E_INVALID, "nodes not available");
+  if (distributed(c))
+    throw Error(CB_E_UNSUPPORTED,
+                "cb_write_nodes on a sharded context: the two adjacency lists of a node may be owned by different "
+                "ranks and the ids live in the line's shard; export edges/nodes per rank and merge by node");
   const EdgeSet* es = nullptr;
   if (checkpoint != CB_CK_PREPROCESS) {
     es = edge_set(c, checkpoint);
