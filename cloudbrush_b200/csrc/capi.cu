@@ -31,25 +31,22 @@ void download_counters(cb_ctx* c) {
   CB_CUDA(cudaStreamSynchronize(c->stream));
 }
 
-// canonical export order (node, type, nbr, ov): gather the lists, re-encode, sort, decode
-__global__ void __launch_bounds__(256) export_gather_kernel(const u64* __restrict__ keys,
-                                                            const u32* __restrict__ adj_off,
-                                                            const u32* __restrict__ cnt,
-                                                            const u32* __restrict__ coff, u32 n_lists, EdgeLayout lay,
+// canonical export order (node, type, nbr, ov): compact the occupied slots, re-encode, sort, decode
+__global__ void __launch_bounds__(256) export_flags_kernel(const u64* __restrict__ keys, size_t n,
+                                                           u32* __restrict__ flag) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = keys[i] != ~0ull ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) export_gather_kernel(const u64* __restrict__ keys, const u32* __restrict__ flag,
+                                                            const u32* __restrict__ idx, size_t n, EdgeLayout lay,
                                                             int K, u64* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (u32 lid = warp_global; lid < n_lists; lid += nwarps) {
-    const u32 n = cnt[lid], src = adj_off[lid], dst = coff[lid];
-    for (u32 t = lane; t < n; t += 32) {
-      u64 k = keys[src + t];
-      u64 type = (u64)lay.x(k) * 2 + lay.y(k);
-      u64 ovf = (u64)(lay.ov(k) - (u32)K);  // K <= ov <= L, so ov - K fits ob bits
-      out[dst + t] = ((u64)lay.node(k) << (lay.nb + lay.ob + 2)) | (type << (lay.nb + lay.ob)) |
-                     ((u64)lay.nbr(k) << lay.ob) | ovf;
-    }
-  }
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  u64 k = keys[i];
+  u64 type = (u64)lay.x(k) * 2 + lay.y(k);
+  u64 ovf = (u64)(lay.ov(k) - (u32)K);  // K <= ov <= L, so ov - K fits ob bits
+  out[idx[i]] = ((u64)lay.node(k) << (lay.nb + lay.ob + 2)) | (type << (lay.nb + lay.ob)) |
+                ((u64)lay.nbr(k) << lay.ob) | ovf;
 }
 __global__ void __launch_bounds__(256) export_decode_kernel(const u64* __restrict__ in, size_t n, EdgeLayout lay,
                                                             int K, const u32* __restrict__ node_line,
@@ -90,23 +87,21 @@ static void export_edges_host(cb_ctx* c, const EdgeSet& es, std::vector<cb_edge>
   cudaStream_t s = c->stream;
   out.resize(es.n);
   if (es.n == 0) return;
-  const u32 n_lists = 2 * c->n_nodes;
-  DevBuf<u32> coff;
-  coff.alloc((size_t)n_lists + 1, s);
-  CB_CUDA(cudaMemcpyAsync(coff.p, es.cnt.p, (size_t)n_lists * 4, cudaMemcpyDeviceToDevice, s));
-  CB_CUDA(cudaMemsetAsync(coff.p + n_lists, 0, 4, s));
-  exclusive_scan_u32(coff.p, coff.p, (size_t)n_lists + 1, s, c->lc);
+  const size_t slots = c->slots;
+  DevBuf<u32> flag, idx;
+  flag.alloc(slots, s);
+  idx.alloc(slots, s);
+  export_flags_kernel<<<div_up(slots, 256), 256, 0, s>>>(es.keys.p, slots, flag.p);
+  exclusive_scan_u32(flag.p, idx.p, slots, s, c->lc);
   DevBuf<u64> a, b;
   a.alloc(es.n, s);
   b.alloc(es.n, s);
-  int blocks = div_up((size_t)n_lists, 8);
-  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  export_gather_kernel<<<blocks, 256, 0, s>>>(es.keys.p, c->adj_off.p, es.cnt.p, coff.p, n_lists, c->lay, c->K, a.p);
+  export_gather_kernel<<<div_up(slots, 256), 256, 0, s>>>(es.keys.p, flag.p, idx.p, slots, c->lay, c->K, a.p);
   int w = radix_sort(a.p, b.p, nullptr, nullptr, es.n, 0, c->lay.total_bits(), s, c->lc, "export");
   DevBuf<cb_edge> d;
   d.alloc(es.n, s);
   export_decode_kernel<<<div_up(es.n, 256), 256, 0, s>>>(w ? b.p : a.p, es.n, c->lay, c->K, c->node_line.p, d.p);
-  c->lc.n += 2;
+  c->lc.n += 3;
   CB_CUDA(cudaMemcpyAsync(out.data(), d.p, es.n * sizeof(cb_edge), cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
 }

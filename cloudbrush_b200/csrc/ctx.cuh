@@ -69,13 +69,13 @@ struct Timer {
   bool done = false;
 };
 
-// One checkpoint of the graph as a gapped CSR: adjacency list `lid` = node*2 + x occupies
-// keys[adj_off[lid] .. adj_off[lid] + cnt[lid]), ordered by overlap descending (ties in any
-// order).  All checkpoints share cb_ctx::adj_off, so "removing edges" is a per-list rewrite.
+// One checkpoint of the graph: adjacency list `lid` = node*2 + x owns the slot range
+// keys[adj_off[lid] .. adj_off[lid+1]); a slot holds a record or ~0 (empty), in no particular
+// order.  All checkpoints share cb_ctx::adj_off and the slot positions, so removing an edge is
+// writing ~0 into its slot.
 struct EdgeSet {
-  DevBuf<u64> keys;  // [slots]
-  DevBuf<u32> cnt;   // [n_lists]
-  size_t n = 0;      // sum of cnt
+  DevBuf<u64> keys;  // [slots], ~0 = empty slot
+  size_t n = 0;      // records
   bool valid = false;
 };
 

@@ -76,18 +76,18 @@ __global__ void __launch_bounds__(256) keygen_kernel(const u64* __restrict__ nod
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6+K7+K8+K9: segmented join fused with the packed-word overlap check and with the
-// GenReverseEdge mirror.
+// K6+K7+K8+K9: per-k-mer join fused with the packed-word overlap check and with the
+// GenReverseEdge mirror -- flat: one thread per k-mer tuple.
 //
 // Node entry (b, y) -- the window-0 tuple of b for y = f, the window-(L-K) tuple for y = r --
 // lives in exactly one k-mer group, and every verified edge (a,x,ov) -> (b,y) of that group has
-// its mirror (b, flip y) -> (a, flip x) in the SAME adjacency list (b, flip y).  The join
-// therefore writes the mirror records straight into that list's slot range (sized by
-// slot_count_kernel: one slot per tuple of the group).  The edge itself belongs to list (a, x);
-// that list is produced by a's own node entry (a, flip x) iff the mirror is proposed and kept
-// there, which is decided locally (see `certain` below).  Only edges for which that is not
-// certain go through the small side buffer X; duplicates are dropped when the lists are
-// assembled.
+// its mirror (b, flip y) -> (a, flip x) in the SAME adjacency list (b, flip y).  That list gets
+// one slot per tuple of the group: the record of the pair (node entry, tuple j) has the fixed
+// position  off[list] + (j - first tuple of the group), so the join needs no ranking and no
+// atomics, and a pair that does not verify simply leaves its slot empty (~0).
+// The edge itself belongs to list (a, x); that list is produced by a's own node entry (a, flip x)
+// iff the mirror is proposed and kept there, which is decided locally (see `certain`).  Only the
+// other edges (~3 %) go through the side buffer and are inserted into a free slot of their list.
 // ---------------------------------------------------------------------------------------------
 struct JoinParams {
   const u64* keys;
@@ -100,17 +100,17 @@ struct JoinParams {
   u32 max_cov;
   long long low_kmer, up_kmer;
   EdgeLayout lay;
-  u32* slotcnt;        // slot_count_kernel output [n_lists]
-  const u32* off1;     // slot offsets of the temporary list storage
-  u64* mtmp;           // temporary list storage
-  u32* cntM;           // records written per list
+  u32* slotcnt;        // group_walk output [n_lists]: slots of the list (= tuples of the group)
+  u32* seg_head;       // [T] first tuple of the tuple's group
+  u32* ne_list;        // [T+1] positions s.. of a group: (list id | entry's dir bit << 31) of its node entries, ~0 ends
+  const u32* off1;     // slot offsets of the lists
+  u64* slots;          // list storage
   u64* xbuf;           // side buffer
   u64 xcap;
   ull* dcount;
 };
 
 constexpr int JN_WARPS = 8;
-constexpr int JN_EB = 256;  // staged side-buffer records per warp
 
 __device__ __forceinline__ u64 tuple_meta(const JoinParams& P, u32 j) {
   return ((P.keys[j] >> (2 * P.K)) << 32) | (u64)P.vals[j];
@@ -150,62 +150,22 @@ __device__ __forceinline__ void entry_of(int L, int K, int pos, int d, int sel, 
           if (b_) { e += __ffs(b_) - 1; break; }                                             \
           e += 32;                                                                           \
         }                                                                                    \
-        __VA_ARGS__                                                                               \
+        __VA_ARGS__                                                                          \
       }                                                                                      \
     }                                                                                        \
   }
 
-// one slot per tuple of the group for every node entry of a group the reducer processes
-__global__ void __launch_bounds__(JN_WARPS * 32) slot_count_kernel(JoinParams P) {
+// One walk over the k-mer groups: every tuple learns the first tuple of its group, the node
+// entries of a group the reducer processes (MatchPrefix.java:366) are listed at the head of the
+// group's index range, and the adjacency list each node entry produces is sized (one slot per
+// tuple of the group).  Also BuildHighKmerList's counter and the UP_KMER flag, which are per group.
+__global__ void __launch_bounds__(JN_WARPS * 32) group_walk_kernel(JoinParams P) {
   const int lane = threadIdx.x & 31;
-  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-  const u32 posmask = (1u << P.pb) - 1;
-  CB_FOR_EACH_SEGMENT(P, {
-    (void)kseg;
-    const u32 g = e - s;
-    if ((long long)g > P.low_kmer) {
-      for (u32 j = s + lane; j < e; j += 32) {
-        u64 m = tuple_meta(P, j);
-        int pos = (int)((m >> 1) & posmask);
-        if (pos == 0 || pos == P.L - P.K) {
-          u32 b = (u32)(m >> (P.pb + 1));
-          u32 y = pos == 0 ? 0u : 1u;
-          P.slotcnt[2 * b + (y ^ 1u)] = g;
-        }
-      }
-    }
-  })
-}
-
-template <int NW>
-__global__ void __launch_bounds__(JN_WARPS * 32) join_verify_kernel(JoinParams P) {
-  __shared__ u64 s_B[JN_WARPS][32][NW];
-  __shared__ u32 s_Bmeta[JN_WARPS][32];
-  __shared__ u32 s_Bbase[JN_WARPS][32];
-  __shared__ u32 s_Bcnt[JN_WARPS][32];
-  __shared__ u64 s_edges[JN_WARPS][JN_EB];
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const u32 lt_mask = (1u << lane) - 1;
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int L = P.L, K = P.K;
   const u32 posmask = (1u << P.pb) - 1;
-  u32 ebuf = 0;        // staged side-buffer records (warp uniform)
-  u32 n_verified = 0;  // lane-local count of maximal verified candidates
-
-  auto flush = [&]() {
-    if (ebuf == 0) return;
-    ull base = 0;
-    if (lane == 0) base = atomicAdd(&P.dcount[DC_EDGES_RAW], (ull)ebuf);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    for (u32 t = lane; t < ebuf; t += 32)
-      if (base + t < P.xcap) P.xbuf[base + t] = s_edges[warp][t];
-    __syncwarp();
-    ebuf = 0;
-  };
-
+  const int L = P.L, K = P.K;
   CB_FOR_EACH_SEGMENT(P, {
     const u32 g = e - s;
     // BuildHighKmerList.java:96-117: weighted count over windows [0, L-K) above UP_KMER
@@ -220,192 +180,210 @@ __global__ void __launch_bounds__(JN_WARPS * 32) join_verify_kernel(JoinParams P
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       if (lane == 0 && (long long)sum > P.up_kmer) atomicAdd(&P.dcount[DC_HKMER], 1ull);
     }
-    if ((long long)g <= P.low_kmer) continue;  // MatchPrefix.java:366
-    if ((long long)g > P.up_kmer && lane == 0) atomicAdd(&P.dcount[DC_UPKMER_LISTS], 1ull);
-
-    u32 scan_pos = s;
-    for (;;) {
-      // ---- collect the next batch of <= 32 node entries (tuples of window 0 / L-K) ----
-      u32 nB = 0;
-      while (scan_pos < e && nB < 32) {
-        u32 j = scan_pos + lane;
-        u64 m = (j < e) ? tuple_meta(P, j) : 0;
+    const bool live = (long long)g > P.low_kmer;
+    if (live && (long long)g > P.up_kmer && lane == 0) atomicAdd(&P.dcount[DC_UPKMER_LISTS], 1ull);
+    u32 nB = 0;
+    for (u32 j0 = s; j0 < e; j0 += 32) {
+      const u32 j = j0 + lane;
+      u64 m = 0;
+      bool isn = false;
+      if (j < e) {
+        P.seg_head[j] = s;
+        m = tuple_meta(P, j);
         int pos = (int)((m >> 1) & posmask);
-        bool isn = (j < e) && (pos == 0 || pos == L - K);
-        u32 bal = __ballot_sync(0xffffffffu, isn);
-        u32 cnt = __popc(bal);
-        u32 advance = 32;
-        if (nB + cnt > 32) {
-          u32 need = 32 - nB, tb = bal;
-          int last = 0;
-          for (u32 t = 0; t < need; t++) { last = __ffs(tb) - 1; tb &= tb - 1; }
-          bal &= (last == 31) ? 0xffffffffu : ((2u << last) - 1);
-          cnt = need;
-          advance = (u32)last + 1;
-        }
-        if (isn && ((bal >> lane) & 1u)) {
-          u32 slot = nB + __popc(bal & lt_mask);
-          u32 b = (u32)(m >> (P.pb + 1));
-          int d = (int)(m & 1);
-          int y = pos == 0 ? 0 : 1;          // prefix entry: b^f starts with X; suffix entry: b^r
-          int sel = pos == 0 ? d : (d ^ 1);  // MatchPrefix.java:275-296
-          u64 r[NW], rcw[NW];
-          load_read_b<NW>(P.node_seq, b, r);
-          if (y) revcomp_read<NW>(r, rcw, L);
-#pragma unroll
-          for (int w = 0; w < NW; w++) s_B[warp][slot][w] = y ? rcw[w] : r[w];
-          s_Bmeta[warp][slot] = b | ((u32)y << 28) | ((u32)sel << 29);
-          s_Bbase[warp][slot] = P.off1[2 * b + (u32)(y ^ 1)];
-          s_Bcnt[warp][slot] = 0;
-        }
-        nB += cnt;
-        scan_pos += advance;
+        isn = live && (pos == 0 || pos == L - K);
       }
-      if (nB == 0) break;
-      __syncwarp();
-      // ---- every tuple of the group against the batch ----
-      for (u32 j0 = s; j0 < e; j0 += 32) {
-        u32 j = j0 + lane;
-        bool act = j < e;
-        u64 m = act ? tuple_meta(P, j) : 0;
-        u32 a = (u32)(m >> (P.pb + 1));
-        int pos = (int)((m >> 1) & posmask);
-        int d = (int)(m & 1);
-        u64 R[NW], Rc[NW];
-        if (act) load_read_b<NW>(P.node_seq, a, R);
-        else {
-#pragma unroll
-          for (int w = 0; w < NW; w++) R[w] = 0;
-        }
-        revcomp_read<NW>(R, Rc, L);
-        // last k-mers of a^f and a^r: the group of the mirror candidate is keyed by their rc
-        const u64 ksuf_f = extract_kmer<NW>(R, L - K, K), ksuf_r = extract_kmer<NW>(Rc, L - K, K);
-        // does a neighbouring tuple of the group belong to the same read?  (tuples of one read
-        // are contiguous: the sort is stable and keygen emits in (node, window) order)
-        bool same_l = act && j > s && (u32)(tuple_meta(P, j - 1) >> (P.pb + 1)) == a;
-        bool same_r = act && j + 1 < e && (u32)(tuple_meta(P, j + 1) >> (P.pb + 1)) == a;
-        for (u32 n = 0; n < nB; n++) {
-          u32 bm = s_Bmeta[warp][n];
-          u32 b = bm & 0x0fffffffu;
-          int y = (bm >> 28) & 1, sel = (bm >> 29) & 1;
-          int x, ov;
-          entry_of(L, K, pos, d, sel, x, ov);
-          u64 A[NW], B[NW];
-#pragma unroll
-          for (int w = 0; w < NW; w++) { A[w] = x ? Rc[w] : R[w]; B[w] = s_B[warp][n][w]; }
-          shl_bases<NW>(A, L - ov);
-          // VerifyOverlap.java:295-309: a^x[L-ov:] == b^y[0:ov]; self candidates skipped at
-          // MatchPrefix.java:405-407
-          bool ok = act && a != b && prefix_equal<NW>(A, B, ov);
-          if (ok && (same_l || same_r)) {
-            // maximal-overlap filter, VerifyOverlap.java:275-283: a larger verified overlap of
-            // the same (a, x) with the same (b, y) wins; an identical entry of an earlier tuple
-            // (MatchPrefix.java:409 hasEdge) is emitted only once
-            for (int dirn = -1; dirn <= 1 && ok; dirn += 2) {
-              long long jj = (long long)j + dirn;
-              while (jj >= (long long)s && jj < (long long)e) {
-                u64 m2 = tuple_meta(P, (u32)jj);
-                if ((u32)(m2 >> (P.pb + 1)) != a) break;
-                int x2, ov2;
-                entry_of(L, K, (int)((m2 >> 1) & posmask), (int)(m2 & 1), sel, x2, ov2);
-                if (x2 == x && ov2 == ov && dirn < 0) { ok = false; break; }
-                if (x2 == x && ov2 > ov) {
-                  u64 A2[NW];
-#pragma unroll
-                  for (int w = 0; w < NW; w++) A2[w] = x ? Rc[w] : R[w];
-                  shl_bases<NW>(A2, L - ov2);
-                  if (prefix_equal<NW>(A2, B, ov2)) { ok = false; break; }
-                }
-                jj += dirn;
-              }
-            }
-          }
-          u32 bal = __ballot_sync(0xffffffffu, ok);
-          if (bal) {
-            u32 cnt = __popc(bal);
-            u32 rank = __popc(bal & lt_mask);
-            u32 mbase = s_Bbase[warp][n] + s_Bcnt[warp][n];
-            // Is the mirror candidate (b, flip y, ov) -> (a, flip x) certain to be proposed and
-            // kept in the group of X' = a^(flip x)[0:K]?  Then a's own node entry writes this
-            // edge into list (a, x) and it need not travel.  (SURVEY.md 8a': proposed iff
-            // ov > K and X' not poly-A/T, or ov == K and X' > rc(X'); kept iff no larger TRUE
-            // overlap, which would show as another tuple of a in this group.)
-            bool certain = false;
-            if (ok) {
-              const u64 ksuf = x ? ksuf_r : ksuf_f;
-              const u64 xp = revcomp_kmer(ksuf, K);
-              const bool proposed = (ov > K) ? ((xp < ksuf ? xp : ksuf) != 0) : (xp > ksuf);
-              certain = proposed && kseg != 0 && !same_l && !same_r && P.low_kmer == 1;
-            }
-            u32 xbal = __ballot_sync(0xffffffffu, ok && !certain);
-            u32 xcnt = __popc(xbal);
-            if (xcnt && ebuf + xcnt > JN_EB) flush();
-            if (ok) {
-              P.mtmp[mbase + rank] = P.lay.encode(b, (u32)(y ^ 1), (u32)ov, (u32)(x ^ 1), a);  // GenReverseEdge
-              if (!certain) s_edges[warp][ebuf + __popc(xbal & lt_mask)] = P.lay.encode(a, (u32)x, (u32)ov, (u32)y, b);
-              n_verified++;
-            }
-            ebuf += xcnt;
-            __syncwarp();
-            if (lane == 0) s_Bcnt[warp][n] += cnt;
-            __syncwarp();
-          }
-        }
+      const u32 bal = __ballot_sync(0xffffffffu, isn);
+      if (isn) {
+        const int pos = (int)((m >> 1) & posmask);
+        const u32 lid = 2 * (u32)(m >> (P.pb + 1)) + (pos == 0 ? 1u : 0u);  // list (b, flip y)
+        P.ne_list[s + nB + __popc(bal & lt_mask)] = lid | ((u32)(m & 1) << 31);
+        P.slotcnt[lid] = g;
       }
-      __syncwarp();
-      if ((u32)lane < nB) {
-        u32 bm = s_Bmeta[warp][lane];
-        u32 b = bm & 0x0fffffffu, y = (bm >> 28) & 1;
-        P.cntM[2 * b + (y ^ 1u)] = s_Bcnt[warp][lane];
-      }
-      __syncwarp();
-      if (scan_pos >= e) break;
+      nB += __popc(bal);
     }
+    // (all ne_list writes of this group are below s + nB <= e, the terminator is inside or right
+    // after the group's own range; the next group starts at e and never reads it as its own)
+    if (lane == 0 && nB < g) P.ne_list[s + nB] = 0xffffffffu;
   })
-  flush();
+}
+
+constexpr int JN_XB = 1024;  // block-staged side-buffer records
+
+template <int NW>
+__global__ void __launch_bounds__(256) join_verify_kernel(JoinParams P) {
+  __shared__ u64 s_x[JN_XB];
+  __shared__ u32 s_nx;
+  __shared__ ull s_base;
+  const int L = P.L, K = P.K;
+  const u32 posmask = (1u << P.pb) - 1;
+  u32 n_verified = 0;
+  if (threadIdx.x == 0) s_nx = 0;
+  __syncthreads();
+  const u32 stride = gridDim.x * blockDim.x;
+  const u32 rounds = (P.T + stride - 1) / stride;
+  for (u32 rnd = 0; rnd < rounds; rnd++) {
+    const u32 j = rnd * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < P.T) {
+      const u32 s = P.seg_head[j];
+      const u64 m = tuple_meta(P, j);
+      const u32 a = (u32)(m >> (P.pb + 1));
+      const int pos = (int)((m >> 1) & posmask);
+      const int d = (int)(m & 1);
+      const u64 kseg = P.keys[j] & P.kmask;
+      u64 R[NW], Rc[NW];
+      load_read_b<NW>(P.node_seq, a, R);
+      revcomp_read<NW>(R, Rc, L);
+      // Everything that depends on the tuple only, for both lists it feeds (sel 0: list of the
+      // canonical key c, sel 1: list of rc(c)): orientation x, overlap ov, the oriented read
+      // shifted so that its last ov bases lead, and whether the mirror candidate is proposed in
+      // the group of X' = a^(flip x)[0:K] (SURVEY.md 8a': ov > K and X' not poly-A/T, or ov == K
+      // and X' > rc(X')).
+      int x0, ov0, x1, ov1;
+      entry_of(L, K, pos, d, 0, x0, ov0);
+      entry_of(L, K, pos, d, 1, x1, ov1);
+      u64 A0[NW], A1[NW];
+#pragma unroll
+      for (int w = 0; w < NW; w++) { A0[w] = x0 ? Rc[w] : R[w]; A1[w] = x1 ? Rc[w] : R[w]; }
+      shl_bases<NW>(A0, L - ov0);
+      shl_bases<NW>(A1, L - ov1);
+      const u64 ksuf_f = extract_kmer<NW>(R, L - K, K), ksuf_r = extract_kmer<NW>(Rc, L - K, K);
+      const u64 xp_f = revcomp_kmer(ksuf_f, K), xp_r = revcomp_kmer(ksuf_r, K);
+      const bool pf_gt = (xp_f < ksuf_f ? xp_f : ksuf_f) != 0, pf_eq = xp_f > ksuf_f;
+      const bool pr_gt = (xp_r < ksuf_r ? xp_r : ksuf_r) != 0, pr_eq = xp_r > ksuf_r;
+      const bool prop0 = x0 ? (ov0 > K ? pr_gt : pr_eq) : (ov0 > K ? pf_gt : pf_eq);
+      const bool prop1 = x1 ? (ov1 > K ? pr_gt : pr_eq) : (ov1 > K ? pf_gt : pf_eq);
+      // does a neighbouring tuple of the group belong to the same read?  (tuples of one read are
+      // contiguous: the sort is stable and keygen emits in (node, window) order)
+      const bool same_l = j > s && (u32)(tuple_meta(P, j - 1) >> (P.pb + 1)) == a;
+      const bool same_r = j + 1 < P.T && P.seg_head[j + 1] == s && (u32)(tuple_meta(P, j + 1) >> (P.pb + 1)) == a;
+      const bool lone = !same_l && !same_r && kseg != 0 && P.low_kmer == 1;
+      for (u32 t = 0;; t++) {
+        const u32 idx = s + t;
+        if (idx >= P.T || (t > 0 && P.seg_head[idx] != s)) break;
+        const u32 v = P.ne_list[idx];
+        if (v == 0xffffffffu) break;
+        const u32 lid = v & 0x7fffffffu;
+        const u32 b = lid >> 1;
+        const int y = (int)((lid & 1u) ^ 1u);          // list (b, flip y) belongs to node entry (b, y)
+        const int dn = (int)(v >> 31);
+        const int sel = y == 0 ? dn : (dn ^ 1);        // MatchPrefix.java:275-296 (y == 0: window-0 entry)
+        const int x = sel ? x1 : x0, ov = sel ? ov1 : ov0;
+        u64 A[NW], B[NW];
+        {
+          u64 r[NW];
+          load_read_b<NW>(P.node_seq, b, r);
+          if (y) revcomp_read<NW>(r, B, L);
+          else {
+#pragma unroll
+            for (int w = 0; w < NW; w++) B[w] = r[w];
+          }
+        }
+#pragma unroll
+        for (int w = 0; w < NW; w++) A[w] = sel ? A1[w] : A0[w];
+        // VerifyOverlap.java:295-309: a^x[L-ov:] == b^y[0:ov]; self candidates skipped at
+        // MatchPrefix.java:405-407
+        bool ok = a != b && prefix_equal<NW>(A, B, ov);
+        if (ok && (same_l || same_r)) {
+          // maximal-overlap filter, VerifyOverlap.java:275-283: a larger verified overlap of the
+          // same (a, x) with the same (b, y) wins; an identical entry of an earlier tuple
+          // (MatchPrefix.java:409 hasEdge) is emitted only once
+          for (int dirn = -1; dirn <= 1 && ok; dirn += 2) {
+            long long jj = (long long)j + dirn;
+            while (jj >= (long long)s && jj < (long long)P.T && P.seg_head[jj] == s) {
+              u64 m2 = tuple_meta(P, (u32)jj);
+              if ((u32)(m2 >> (P.pb + 1)) != a) break;
+              int x2, ov2;
+              entry_of(L, K, (int)((m2 >> 1) & posmask), (int)(m2 & 1), sel, x2, ov2);
+              if (x2 == x && ov2 == ov && dirn < 0) { ok = false; break; }
+              if (x2 == x && ov2 > ov) {
+                u64 A2[NW];
+#pragma unroll
+                for (int w = 0; w < NW; w++) A2[w] = x ? Rc[w] : R[w];
+                shl_bases<NW>(A2, L - ov2);
+                if (prefix_equal<NW>(A2, B, ov2)) { ok = false; break; }
+              }
+              jj += dirn;
+            }
+          }
+        }
+        if (ok) {
+          P.slots[P.off1[lid] + (j - s)] = P.lay.encode(b, (u32)(y ^ 1), (u32)ov, (u32)(x ^ 1), a);  // GenReverseEdge
+          n_verified++;
+          // Is the mirror candidate (b, flip y, ov) -> (a, flip x) certain to be proposed and
+          // kept at a's own node entry?  Then that entry writes this edge into list (a, x) and it
+          // need not travel.  (kept iff no larger TRUE overlap, which would show as another tuple
+          // of a in this group.)
+          const bool certain = lone && (sel ? prop1 : prop0);
+          if (!certain) {
+            const u64 rec = P.lay.encode(a, (u32)x, (u32)ov, (u32)y, b);
+            const u32 pos_x = atomicAdd(&s_nx, 1u);
+            if (pos_x < JN_XB) s_x[pos_x] = rec;
+            else {  // staging full: straight to the side buffer
+              ull gp = atomicAdd(&P.dcount[DC_EDGES_RAW], 1ull);
+              if (gp < P.xcap) P.xbuf[gp] = rec;
+            }
+          }
+        }
+      }
+    }
+    // flush the staged side-buffer records once they fill half of the staging area
+    __syncthreads();
+    const u32 nx = s_nx < (u32)JN_XB ? s_nx : (u32)JN_XB;
+    if (nx >= JN_XB / 2 || (rnd + 1 == rounds && nx > 0)) {
+      if (threadIdx.x == 0) s_base = atomicAdd(&P.dcount[DC_EDGES_RAW], (ull)nx);
+      __syncthreads();
+      for (u32 t = threadIdx.x; t < nx; t += blockDim.x)
+        if (s_base + t < P.xcap) P.xbuf[s_base + t] = s_x[t];
+      __syncthreads();
+      if (threadIdx.x == 0) s_nx = 0;
+    }
+    __syncthreads();
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_verified += __shfl_xor_sync(0xffffffffu, n_verified, o);
-  if (lane == 0 && n_verified) {
+  if ((threadIdx.x & 31) == 0 && n_verified) {
     atomicAdd(&P.dcount[DC_CAND_VERIFIED], (ull)n_verified);
     atomicAdd(&P.dcount[DC_EDGES_M], (ull)n_verified);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Side-buffer records: edge (a,x,ov,y,b) goes into list (a,x) unless a's own node entry already
-// wrote it.  One thread per record: scan the list's own records, then claim a free slot.  A
-// record that does not fit (only possible around poly-A/T k-mers, whose interior windows have no
-// tuple and therefore no slot) is counted in extra[list]; the host then re-runs the join with
-// enlarged slot ranges.
+// Side-buffer records: edge (a,x,ov,y,b) goes into a free slot of list (a,x) unless a's own node
+// entry already wrote it.  One thread per record.  A record that finds no free slot (only
+// possible around poly-A/T k-mers, whose interior windows have no tuple and therefore no slot)
+// is counted in extra[list]; the host then re-runs the join with enlarged slot ranges.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) side_insert_kernel(const u64* __restrict__ xs, size_t n, EdgeLayout lay,
-                                                          const u32* __restrict__ off, const u32* __restrict__ cntM,
-                                                          u32* __restrict__ cnt, u64* __restrict__ keys,
+                                                          const u32* __restrict__ off, u64* __restrict__ slots,
                                                           u32* __restrict__ extra, ull* __restrict__ dcount) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool inserted = false, overflow = false;
-  if (i < n) {
+  u32 inserted = 0, overflow = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const u64 key = xs[i];
     const u32 lid = lay.list(key);
-    const u32 base = off[lid], m = cntM[lid], cap = off[lid + 1] - base;
+    const u32 lo = off[lid], hi = off[lid + 1];
     bool dup = false;
-    for (u32 t = 0; t < m; t++)
-      if (keys[base + t] == key) { dup = true; break; }
-    if (!dup) {
-      u32 pos = atomicAdd(&cnt[lid], 1u);
-      if (pos < cap) {
-        keys[base + pos] = key;
-        inserted = true;
-      } else {
-        atomicAdd(&extra[lid], 1u);
-        overflow = true;
+    for (u32 t = lo; t < hi; t++)
+      if (slots[t] == key) { dup = true; break; }
+    if (dup) continue;
+    bool placed = false;
+    for (u32 t = lo; t < hi && !placed; t++) {
+      if (slots[t] == ~0ull) {
+        ull old = atomicCAS((ull*)&slots[t], ~0ull, (ull)key);
+        placed = old == ~0ull;
       }
     }
+    if (placed) inserted++;
+    else { atomicAdd(&extra[lid], 1u); overflow++; }
   }
-  u32 ni = __popc(__ballot_sync(0xffffffffu, inserted)), no = __popc(__ballot_sync(0xffffffffu, overflow));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    inserted += __shfl_xor_sync(0xffffffffu, inserted, o);
+    overflow += __shfl_xor_sync(0xffffffffu, overflow, o);
+  }
   if ((threadIdx.x & 31) == 0) {
-    if (ni) atomicAdd(&dcount[DC_EDGES_A], (ull)ni);
-    if (no) atomicAdd(&dcount[DC_MAX_LIST], (ull)no);  // reused as the overflow count of this attempt
+    if (inserted) atomicAdd(&dcount[DC_EDGES_A], (ull)inserted);
+    if (overflow) atomicAdd(&dcount[DC_MAX_LIST], (ull)overflow);  // reused as the overflow count of this attempt
   }
 }
 
@@ -586,49 +564,51 @@ void stage_build_overlap(cb_ctx* c) {
   P.kmask = (2 * K == 64) ? ~0ull : ((1ull << (2 * K)) - 1);
   P.node_seq = c->node_seq.p;
   P.node_cov = c->node_cov.p;
-  P.max_cov = (u32)c->hcount[DC_MAX_COV];
+  P.max_cov = (u32)c->gcount[DC_MAX_COV];
   P.low_kmer = c->cfg.low_kmer;
   P.up_kmer = c->cfg.up_kmer;
   P.lay = c->lay;
   P.dcount = (ull*)c->dcount.p;
-  int jblocks = kNumSMs * 8;
+  int wblocks = kNumSMs * 8;
   {
     int need = div_up(((size_t)T + 31) / 32, JN_WARPS);
-    if (need < jblocks) jblocks = need > 0 ? need : 1;
+    if (need < wblocks) wblocks = need > 0 ? need : 1;
   }
-  // slots: one per tuple of the group for every node entry
-  DevBuf<u32> slotcnt, off1, cntM;
+  DevBuf<u32> slotcnt, off1, seg_head, ne_list, extra;
   slotcnt.alloc((size_t)n_lists + 1, s);
   off1.alloc((size_t)n_lists + 1, s);
-  cntM.alloc(n_lists, s);
+  seg_head.alloc(T ? T : 1, s);
+  ne_list.alloc((size_t)T + 1, s);
+  extra.alloc(n_lists ? n_lists : 1, s);
   CB_CUDA(cudaMemsetAsync(slotcnt.p, 0, ((size_t)n_lists + 1) * 4, s));
-  CB_CUDA(cudaMemsetAsync(cntM.p, 0, (size_t)n_lists * 4, s));
   P.slotcnt = slotcnt.p;
-  c->lc.begin("slot_count");
-  slot_count_kernel<<<jblocks, JN_WARPS * 32, 0, s>>>(P);
-  c->lc.end("slot_count");
+  P.seg_head = seg_head.p;
+  P.ne_list = ne_list.p;
+  c->lc.begin("group_walk");
+  group_walk_kernel<<<wblocks, JN_WARPS * 32, 0, s>>>(P);
+  c->lc.end("group_walk");
   c->lc.n++;
   exclusive_scan_u32(slotcnt.p, off1.p, (size_t)n_lists + 1, s, c->lc);
   size_t slots1 = read_u32(c, off1.p + n_lists);
-  DevBuf<u64> mtmp, xbuf;
-  DevBuf<u32> cnt, extra;
-  cnt.alloc(n_lists ? n_lists : 1, s);
-  extra.alloc(n_lists ? n_lists : 1, s);
-  P.cntM = cntM.p;
+  int jgrid = div_up((size_t)T, 256);
+  if (jgrid > kNumSMs * 8) jgrid = kNumSMs * 8;
+  if (jgrid < 1) jgrid = 1;
+  DevBuf<u64> slots, xbuf;
   u64 xcap = (u64)T / 4 + 4096;
   u64 n_x = 0;
   for (int attempt = 0;; attempt++) {
-    mtmp.alloc(slots1 ? slots1 : 1, s);
-    CB_CUDA(cudaMemsetAsync(mtmp.p, 0xff, (slots1 ? slots1 : 1) * sizeof(u64), s));  // free slots read as ~0
+    slots.alloc(slots1 ? slots1 : 1, s);
+    CB_CUDA(cudaMemsetAsync(slots.p, 0xff, (slots1 ? slots1 : 1) * sizeof(u64), s));  // empty slots read as ~0
     xbuf.alloc(xcap, s);
     P.off1 = off1.p;
-    P.mtmp = mtmp.p;
+    P.slots = slots.p;
     P.xbuf = xbuf.p;
     P.xcap = xcap;
-    CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_HKMER, 0, (DC_EDGE_REMOVAL - DC_HKMER) * sizeof(u64), s));
+    // (DC_HKMER and DC_UPKMER_LISTS were counted by group_walk_kernel and stay)
+    CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGES_RAW, 0, (DC_UPKMER_LISTS - DC_EDGES_RAW) * sizeof(u64), s));
     CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_MAX_LIST, 0, sizeof(u64), s));
     c->lc.begin("join_verify");
-    CB_DISPATCH_NW(c->NW, (join_verify_kernel<NW_><<<jblocks, JN_WARPS * 32, 0, s>>>(P)));
+    CB_DISPATCH_NW(c->NW, (join_verify_kernel<NW_><<<jgrid, 256, 0, s>>>(P)));
     c->lc.end("join_verify");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
@@ -642,8 +622,7 @@ void stage_build_overlap(cb_ctx* c) {
       continue;
     }
     // side-buffer records into their lists (on the rank that owns the list)
-    CB_CUDA(cudaMemcpyAsync(cnt.p, cntM.p, (size_t)n_lists * 4, cudaMemcpyDeviceToDevice, s));
-    CB_CUDA(cudaMemsetAsync(extra.p, 0, (size_t)n_lists * 4, s));
+    CB_CUDA(cudaMemsetAsync(extra.p, 0, (size_t)(n_lists ? n_lists : 1) * 4, s));
     const u64* xin = xbuf.p;
     size_t n_xin = n_x;
     DevBuf<char> xrecv;
@@ -659,9 +638,10 @@ void stage_build_overlap(cb_ctx* c) {
       xin = (const u64*)xrecv.p;
     }
     if (n_xin) {
+      int blocks = div_up(n_xin, 256);
+      if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
       c->lc.begin("side_insert");
-      side_insert_kernel<<<div_up(n_xin, 256), 256, 0, s>>>(xin, n_xin, c->lay, off1.p, cntM.p, cnt.p, mtmp.p, extra.p,
-                                                           (ull*)c->dcount.p);
+      side_insert_kernel<<<blocks, 256, 0, s>>>(xin, n_xin, c->lay, off1.p, slots.p, extra.p, (ull*)c->dcount.p);
       c->lc.end("side_insert");
       c->lc.n++;
       CB_CUDA(cudaGetLastError());
@@ -697,8 +677,7 @@ void stage_build_overlap(cb_ctx* c) {
   // checkpoint A: the slot array is the adjacency structure
   c->adj_off = std::move(off1);
   c->slots = slots1;
-  c->ckA.keys = std::move(mtmp);
-  c->ckA.cnt = std::move(cnt);
+  c->ckA.keys = std::move(slots);
   c->ckA.n = (size_t)(c->hcount[DC_EDGES_M] + c->hcount[DC_EDGES_A]);  // the lists this rank owns
   c->ckA.valid = true;
   c->counters["edges_overlap"] = (int64_t)(c->gcount[DC_EDGES_M] + c->gcount[DC_EDGES_A]);

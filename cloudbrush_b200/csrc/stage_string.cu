@@ -36,9 +36,8 @@ __device__ __forceinline__ void load_read_c(const u64* __restrict__ reads, u32 i
 }
 
 struct StringParams {
-  const u64* edges;    // gapped CSR keys (free slots hold ~0)
+  const u64* edges;    // slot array; list lid owns [adj_off[lid], adj_off[lid+1]); ~0 = empty slot
   const u32* adj_off;  // [n_lists + 1]
-  const u32* cnt;      // [n_lists]
   u32 n_lists;         // 2 * n_nodes
   size_t slots;
   EdgeLayout lay;
@@ -49,7 +48,9 @@ struct StringParams {
   float majority, pwm_n;
   uint8_t* removed;    // cut output, per slot
   uint8_t* kept;       // tr output, per slot
-  uint8_t* list_flag;  // per list: 1 consistent, 0 not, 2 dirty (lost an entry)
+  uint8_t* list_flag;  // per list: 1 consistent, 0 not, dirty bits 2 / 4 (lost an entry in cut round 1 / 2)
+  uint8_t* pre;        // per slot, from consistency_kernel: bit0 maximal overlap of its list, bit1 counts as
+                       // transitive if the list is consistent, bit2 ov == L
   const u32* work;     // work list of list ids (literal kernels)
   u32 n_work;
   u32* work_out;       // lists that lost an entry in this round
@@ -89,9 +90,9 @@ __device__ __forceinline__ int base_at(const u64 (&h)[NW], int j) {
 // slot index of `key` in its (unordered) list or -1
 __device__ __forceinline__ long long find_edge(const StringParams& P, u64 key) {
   const u32 list = P.lay.list(key);
-  const u32 base = P.adj_off[list], n = P.cnt[list];
-  for (u32 t = 0; t < n; t++)
-    if (P.edges[base + t] == key) return (long long)(base + t);
+  const u32 lo = P.adj_off[list], hi = P.adj_off[list + 1];
+  for (u32 t = lo; t < hi; t++)
+    if (P.edges[t] == key) return (long long)t;
   return -1;
 }
 
@@ -109,17 +110,28 @@ __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* _
   const u64 k = P.edges[slot];
   if (k == ~0ull) return;
   const u32 lid = P.lay.list(k);
-  const u32 lo = P.adj_off[lid], n = P.cnt[lid];
+  const u32 lo = P.adj_off[lid], hi = P.adj_off[lid + 1];
+  const u32 ov = P.lay.ov(k), nbr = P.lay.nbr(k), y = P.lay.y(k);
+  // one scan of the list gives the longest overhang (minimal overlap, first such record), the
+  // maximal overlap, and the largest overlap among the records of my (type, neighbour) -- what
+  // the fast path of TransitiveReduction needs (tr_fast_kernel)
+  u32 hidx = lo, hov = 0xffffffffu, ovmax = 0, same_max = 0, n = 0;
+  for (u32 t = lo; t < hi; t++) {
+    const u64 q = P.edges[t];
+    if (q == ~0ull) continue;
+    n++;
+    const u32 o = P.lay.ov(q);
+    if (o < hov) { hov = o; hidx = t; }
+    ovmax = max(ovmax, o);
+    if (P.lay.nbr(q) == nbr && P.lay.y(q) == y) same_max = max(same_max, o);
+  }
+  // TransitiveReduction on a consistent list: keep the maximal overlap (:341-343); anything else
+  // is dropped, counted as transitive unless a kept record has my type and neighbour (:325-334)
+  P.pre[slot] = (uint8_t)((ov == ovmax ? 1u : 0u) | ((ov != ovmax && same_max != ovmax) ? 2u : 0u) |
+                          ((int)ov == P.L ? 4u : 0u));
   if (n <= 1) return;  // flag stays 1
   bool bad = force_slow != 0;
   if (!bad) {
-    // the longest overhang: minimal overlap, first such record
-    u32 hidx = lo;
-    u32 hov = P.lay.ov(P.edges[lo]);
-    for (u32 t = 1; t < n; t++) {
-      u32 o = P.lay.ov(P.edges[lo + t]);
-      if (o < hov) { hov = o; hidx = lo + t; }
-    }
     u64 H[NW], h[NW];
     int lenH, len;
     load_overhang<NW>(P, P.edges[hidx], H, lenH);
@@ -162,27 +174,36 @@ __device__ __forceinline__ TopKey warp_top_min(TopKey v) {
   return v;
 }
 
-// warp version of the consistency test (lists that changed since consistency_kernel ran)
+// warp version of the consistency test (lists that changed since consistency_kernel ran);
+// also returns the number of records
 template <int NW>
-__device__ __forceinline__ bool list_consistent_warp(const StringParams& P, u32 lo, u32 n, int lane) {
-  u32 hov = 0xffffffffu, hidx = 0xffffffffu;
-  for (u32 t = lane; t < n; t += 32) {
-    u32 o = P.lay.ov(P.edges[lo + t]);
-    if (o < hov) { hov = o; hidx = lo + t; }
+__device__ __forceinline__ bool list_consistent_warp(const StringParams& P, u32 lo, u32 hi, int lane, u32& n_out) {
+  u32 hov = 0xffffffffu, hidx = 0xffffffffu, n = 0;
+  for (u32 t = lo + lane; t < hi; t += 32) {
+    const u64 q = P.edges[t];
+    if (q == ~0ull) continue;
+    n++;
+    u32 o = P.lay.ov(q);
+    if (o < hov) { hov = o; hidx = t; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     u32 ov2 = __shfl_xor_sync(0xffffffffu, hov, o), ix2 = __shfl_xor_sync(0xffffffffu, hidx, o);
     if (ov2 < hov || (ov2 == hov && ix2 < hidx)) { hov = ov2; hidx = ix2; }
+    n += __shfl_xor_sync(0xffffffffu, n, o);
   }
+  n_out = n;
+  if (n <= 1) return true;
   u64 H[NW];
   int lenH;
   load_overhang<NW>(P, P.edges[hidx], H, lenH);
   bool good = true;
-  for (u32 t = lane; t < n; t += 32) {
+  for (u32 t = lo + lane; t < hi; t += 32) {
+    const u64 q = P.edges[t];
+    if (q == ~0ull) continue;
     u64 h[NW];
     int len;
-    load_overhang<NW>(P, P.edges[lo + t], h, len);
+    load_overhang<NW>(P, q, h, len);
     good = good && prefix_equal<NW>(h, H, len);
   }
   return __all_sync(0xffffffffu, good);
@@ -207,21 +228,31 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
   const int L = P.L;
   for (u32 wi = warp_global; wi < P.n_work; wi += nwarps) {
     const u32 list = P.work[wi];
-    const u32 n = P.cnt[list];
-    const u32 lo = P.adj_off[list];
-    if (n <= 1) continue;  // CutChimericLinks.java:306 "flist.size() > 1"
-    if (P.check_consistency && P.majority < 1.0f && list_consistent_warp<NW>(P, lo, n, lane)) continue;
+    const u32 lo = P.adj_off[list], hi = P.adj_off[list + 1];
+    u32 n = 0;
+    if (P.check_consistency) {
+      const bool cons = list_consistent_warp<NW>(P, lo, hi, lane, n);
+      if (n <= 1) continue;  // CutChimericLinks.java:306 "flist.size() > 1"
+      if (cons && P.majority < 1.0f) continue;
+    } else {
+      for (u32 t = lo + lane; t < hi; t += 32) n += P.edges[t] != ~0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+      if (n <= 1) continue;
+    }
     if (lane == 0) atomicAdd(&P.dcount[DC_SLOW_LISTS], 1ull);
     const u32 x = list & 1;
     // ---- entries 0, 1 of the Consensus order and the overlap of entry 2 (Node.java:1295-1320) ----
     TopKey best[3];
+#pragma unroll
     for (int r = 0; r < 3; r++) {
       TopKey mine;
       mine.ov = 0xffffffffu; mine.hi = ~0ull; mine.lo = ~0ull; mine.idx = 0xffffffffu;
-      for (u32 t = lo + lane; t < lo + n; t += 32) {
+      for (u32 t = lo + lane; t < hi; t += 32) {
         if (r >= 1 && t == best[0].idx) continue;
         if (r >= 2 && t == best[1].idx) continue;
         u64 k = P.edges[t];
+        if (k == ~0ull) continue;
         IdKey ik = P.node_idkey[P.lay.nbr(k)];
         TopKey c;
         c.ov = P.lay.ov(k);
@@ -243,8 +274,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
       int j = j0 + lane;
       int cnt[4] = {0, 0, 0, 0};
       int sum = 0;
-      for (u32 t = lo; t < lo + n; t++) {
+      for (u32 t = lo; t < hi; t++) {
         u64 k = P.edges[t];
+        if (k == ~0ull) continue;
         u64 h[NW];
         int len;
         load_overhang<NW>(P, k, h, len);
@@ -272,10 +304,10 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
     // Node.java:1369-1371 (0/0 = NaN compares false, as in Java)
     if (__fdiv_rn((float)ncount, (float)clen) > P.pwm_n) continue;
     // ---- entries that disagree with the consensus (CutChimericLinks.java:337-381) ----
-    for (u32 t0 = lo; t0 < lo + n; t0 += 32) {
+    for (u32 t0 = lo; t0 < hi; t0 += 32) {
       u32 t = t0 + lane;
-      if (t < lo + n) {
-        u64 k = P.edges[t];
+      u64 k = t < hi ? P.edges[t] : ~0ull;
+      if (k != ~0ull) {
         u64 h[NW];
         int len;
         load_overhang<NW>(P, k, h, len);
@@ -304,69 +336,37 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
   }
 }
 
-// EdgeRemoval (EdgeRemoval.java:121-202) on the lists that lost an entry: in-place compaction.
-__global__ void __launch_bounds__(ST_WARPS * 32) remove_flagged_kernel(u64* __restrict__ keys,
-                                                                       const u32* __restrict__ adj_off,
-                                                                       u32* __restrict__ cnt,
-                                                                       uint8_t* __restrict__ drop,
-                                                                       const u32* __restrict__ work, u32 n_work,
-                                                                       ull* __restrict__ dcount) {
-  const int lane = threadIdx.x & 31;
-  const u32 lt_mask = (1u << lane) - 1;
-  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-  ull removed_total = 0;
-  for (u32 wi = warp_global; wi < n_work; wi += nwarps) {
-    const u32 list = work[wi];
-    const u32 n = cnt[list], lo = adj_off[list];
-    u32 w = 0;
-    for (u32 t0 = 0; t0 < n; t0 += 32) {
-      u32 t = t0 + lane;
-      bool keep = t < n && !drop[lo + t];
-      u64 k = t < n ? keys[lo + t] : 0;
-      __syncwarp();
-      u32 bal = __ballot_sync(0xffffffffu, keep);
-      if (keep) keys[lo + w + __popc(bal & lt_mask)] = k;  // w <= t0: never overtakes the reads
-      if (t < n) drop[lo + t] = 0;
-      w += __popc(bal);
-      __syncwarp();
+// EdgeRemoval (EdgeRemoval.java:121-202): a flagged record's slot becomes empty.  One thread per
+// slot; clears the flags it consumes.
+__global__ void __launch_bounds__(256) remove_flagged_kernel(u64* __restrict__ keys, uint8_t* __restrict__ drop,
+                                                             size_t slots, ull* __restrict__ dcount) {
+  u32 removed = 0;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < slots; t += (size_t)gridDim.x * blockDim.x)
+    if (drop[t]) {
+      keys[t] = ~0ull;
+      drop[t] = 0;
+      removed++;
     }
-    for (u32 t = w + lane; t < n; t += 32) keys[lo + t] = ~0ull;
-    if (lane == 0) { cnt[list] = w; removed_total += n - w; }
-  }
-  if (lane == 0 && removed_total) atomicAdd(&dcount[DC_EDGES_C], removed_total);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+  if ((threadIdx.x & 31) == 0 && removed) atomicAdd(&dcount[DC_EDGES_C], (ull)removed);
 }
 
 // ---------------------------------------------------------------------------------------------
 // K11: TransitiveReduction
 // ---------------------------------------------------------------------------------------------
-// consistent lists, one thread per record: keep the records of maximal overlap
+// consistent lists, one thread per record: apply what consistency_kernel precomputed
 __global__ void __launch_bounds__(256) tr_fast_kernel(StringParams P) {
   u32 trans = 0, contained = 0;
   for (size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x; slot < P.slots;
        slot += (size_t)gridDim.x * blockDim.x) {
     const u64 k = P.edges[slot];
-    if (k != ~0ull) {
-      const u32 lid = P.lay.list(k);
-      if (P.list_flag[lid] == 1) {
-        const u32 lo = P.adj_off[lid], n = P.cnt[lid];
-        const u32 ov = P.lay.ov(k);
-        u32 ovmax = 0;
-        for (u32 t = 0; t < n; t++) ovmax = max(ovmax, P.lay.ov(P.edges[lo + t]));
-        if ((int)ov == P.L) contained++;  // TransitiveReduction.java:319-323 (equal-length reads)
-        if (ov == ovmax) P.kept[slot] = 1;
-        else {
-          // :325-334 an entry of the same type to the same neighbour already kept -> dropped
-          // without counting as transitive
-          bool step2 = false;
-          for (u32 t = 0; t < n; t++) {
-            u64 kq = P.edges[lo + t];
-            if (P.lay.ov(kq) == ovmax && P.lay.nbr(kq) == P.lay.nbr(k) && P.lay.y(kq) == P.lay.y(k)) { step2 = true; break; }
-          }
-          if (!step2) trans++;
-        }
-      }
-    }
+    if (k == ~0ull) continue;
+    if (P.list_flag[P.lay.list(k)] != 1) continue;  // literal kernel
+    const uint8_t f = P.pre[slot];
+    if (f & 1) P.kept[slot] = 1;
+    trans += (f >> 1) & 1;
+    contained += (f >> 2) & 1;  // TransitiveReduction.java:319-323 (equal-length reads)
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -381,10 +381,10 @@ __global__ void __launch_bounds__(256) tr_fast_kernel(StringParams P) {
 
 // lists whose flag is not "consistent" -> work list for the literal kernel
 __global__ void __launch_bounds__(256) tr_worklist_kernel(const uint8_t* __restrict__ list_flag,
-                                                          const u32* __restrict__ cnt, u32 n_lists,
+                                                          const u32* __restrict__ adj_off, u32 n_lists,
                                                           u32* __restrict__ work, u32* __restrict__ n_work) {
   u32 lid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lid < n_lists && list_flag[lid] != 1 && cnt[lid] > 0) work[atomicAdd(n_work, 1u)] = lid;
+  if (lid < n_lists && list_flag[lid] != 1 && adj_off[lid + 1] > adj_off[lid]) work[atomicAdd(n_work, 1u)] = lid;
 }
 
 constexpr int TR_KC = 64;  // kept entries per list in the literal scan
@@ -405,16 +405,17 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
   u32 trans = 0, contained = 0;
   for (u32 wi = warp_global; wi < P.n_work; wi += nwarps) {
     const u32 list = P.work[wi];
-    const u32 n = P.cnt[list], lo = P.adj_off[list];
-    if (n == 0) continue;
+    const u32 lo = P.adj_off[list], hi = P.adj_off[list + 1];
     if (lane == 0) atomicAdd(&P.dcount[DC_SLOW_LISTS], 1ull);
     u32 nk = 0;
     int level = L + 1;  // overlap levels strictly below `level` are still to do
     for (;;) {
       // next level: the largest overlap below `level`
       int nxt = -1;
-      for (u32 t = lane; t < n; t += 32) {
-        int o = (int)P.lay.ov(P.edges[lo + t]);
+      for (u32 t = lo + lane; t < hi; t += 32) {
+        const u64 q = P.edges[t];
+        if (q == ~0ull) continue;
+        int o = (int)P.lay.ov(q);
         if (o < level && o > nxt) nxt = o;
       }
 #pragma unroll
@@ -422,10 +423,10 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
       if (nxt < 0) break;
       level = nxt;
       const u32 nk_level = nk;  // entries of this level are compared with earlier levels only
-      for (u32 t0 = 0; t0 < n; t0 += 32) {
+      for (u32 t0 = lo; t0 < hi; t0 += 32) {
         u32 t = t0 + lane;
-        u64 k = t < n ? P.edges[lo + t] : ~0ull;
-        bool mine = t < n && (int)P.lay.ov(k) == level;
+        u64 k = t < hi ? P.edges[t] : ~0ull;
+        bool mine = k != ~0ull && (int)P.lay.ov(k) == level;
         bool keep = false;
         u64 h[NW];
         if (mine) {
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
 #pragma unroll
               for (int w = 0; w < NW; w++) s_kh[warp][pos][w] = h[w];
               s_kkey[warp][pos] = k;
-              P.kept[lo + t] = 1;
+              P.kept[t] = 1;
             } else {
               atomicAdd(&P.dcount[DC_TR_OVERFLOW], 1ull);
             }
@@ -480,28 +481,20 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
 }
 
 // EdgeRemoval after TransitiveReduction: an edge survives iff both endpoints kept it.
-// One thread per list writes the surviving records (checkpoint B) at the list's own offset.
-__global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __restrict__ out,
-                                                       u32* __restrict__ cnt_out) {
+// One thread per kept record looks its mirror up; the survivor keeps its slot in checkpoint B
+// (`out` pre-filled with ~0).
+__global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __restrict__ out) {
   u32 tot = 0;
-  for (u32 lid = blockIdx.x * blockDim.x + threadIdx.x; lid < P.n_lists; lid += gridDim.x * blockDim.x) {
-    u32 w = 0;
-    const u32 n = P.cnt[lid], lo = P.adj_off[lid];
-    for (u32 t = 0; t < n; t++) {
-      if (!P.kept[lo + t]) continue;
-      const u64 k = P.edges[lo + t];
-      const u64 mk = P.lay.mirror(k);
-      const u32 ml = P.lay.list(mk);
-      const u32 mlo = P.adj_off[ml], mn = P.cnt[ml];
-      bool found = false, keep = false;
-      for (u32 q = 0; q < mn; q++) {
-        if (P.edges[mlo + q] == mk) { found = true; keep = P.kept[mlo + q] != 0; break; }
-      }
-      if (!found) keep = true;  // no mirror: nobody can ask for the removal
-      if (keep) out[lo + w++] = k;
+  for (size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x; slot < P.slots;
+       slot += (size_t)gridDim.x * blockDim.x) {
+    if (!P.kept[slot]) continue;
+    const u64 k = P.edges[slot];
+    long long mi = find_edge(P, P.lay.mirror(k));
+    const bool keep = mi < 0 ? true : (P.kept[mi] != 0);  // no mirror: nobody can ask for the removal
+    if (keep) {
+      out[slot] = k;
+      tot++;
     }
-    cnt_out[lid] = w;
-    tot += w;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
@@ -517,16 +510,14 @@ __global__ void __launch_bounds__(256) apply_removal_requests_kernel(StringParam
   if (mi >= 0) { P.removed[mi] = 1; mark_dirty(P, P.lay.list(keys[i])); }
 }
 
-// one thread per list: the mirror key of every kept record is a "kept" vote for the other end
+// the mirror key of every kept record is a "kept" vote for the other end
 __global__ void __launch_bounds__(256) tr_votes_kernel(StringParams P) {
-  for (u32 lid = blockIdx.x * blockDim.x + threadIdx.x; lid < P.n_lists; lid += gridDim.x * blockDim.x) {
-    const u32 n = P.cnt[lid], lo = P.adj_off[lid];
-    for (u32 t = 0; t < n; t++)
-      if (P.kept[lo + t] & 1) {
-        u32 ri = atomicAdd(P.n_req, 1u);
-        if (ri < P.req_cap) P.req[ri] = P.lay.mirror(P.edges[lo + t]);
-      }
-  }
+  for (size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x; slot < P.slots;
+       slot += (size_t)gridDim.x * blockDim.x)
+    if (P.kept[slot] & 1) {
+      u32 ri = atomicAdd(P.n_req, 1u);
+      if (ri < P.req_cap) P.req[ri] = P.lay.mirror(P.edges[slot]);
+    }
 }
 
 __global__ void __launch_bounds__(256) apply_votes_kernel(StringParams P, const u64* __restrict__ keys, size_t n) {
@@ -536,17 +527,14 @@ __global__ void __launch_bounds__(256) apply_votes_kernel(StringParams P, const 
   if (mi >= 0) P.kept[mi] |= 2;  // one vote per record at most: no other thread writes this byte
 }
 
-__global__ void __launch_bounds__(256) tr_final_voted_kernel(StringParams P, u64* __restrict__ out,
-                                                             u32* __restrict__ cnt_out) {
+__global__ void __launch_bounds__(256) tr_final_voted_kernel(StringParams P, u64* __restrict__ out) {
   u32 tot = 0;
-  for (u32 lid = blockIdx.x * blockDim.x + threadIdx.x; lid < P.n_lists; lid += gridDim.x * blockDim.x) {
-    u32 w = 0;
-    const u32 n = P.cnt[lid], lo = P.adj_off[lid];
-    for (u32 t = 0; t < n; t++)
-      if (P.kept[lo + t] == 3) out[lo + w++] = P.edges[lo + t];
-    cnt_out[lid] = w;
-    tot += w;
-  }
+  for (size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x; slot < P.slots;
+       slot += (size_t)gridDim.x * blockDim.x)
+    if (P.kept[slot] == 3) {
+      out[slot] = P.edges[slot];
+      tot++;
+    }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
   if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&P.dcount[DC_EDGES_B], (ull)tot);
@@ -580,11 +568,10 @@ __global__ void __launch_bounds__(256) key_owner_s_kernel(const u64* __restrict_
     default: throw Error(CB_E_UNSUPPORTED, "read length above 256 bases");   \
   }
 
-static StringParams make_params(cb_ctx* c, const u64* keys, const u32* cnt) {
+static StringParams make_params(cb_ctx* c, const u64* keys) {
   StringParams P;
   P.edges = keys;
   P.adj_off = c->adj_off.p;
-  P.cnt = cnt;
   P.n_lists = 2 * c->n_nodes;
   P.slots = c->slots;
   P.lay = c->lay;
@@ -598,6 +585,7 @@ static StringParams make_params(cb_ctx* c, const u64* keys, const u32* cnt) {
   P.removed = nullptr;
   P.kept = nullptr;
   P.list_flag = c->list_flag.p;
+  P.pre = nullptr;
   P.work = nullptr;
   P.n_work = 0;
   P.work_out = nullptr;
@@ -613,6 +601,13 @@ static StringParams make_params(cb_ctx* c, const u64* keys, const u32* cnt) {
 
 static int warp_grid(size_t n_items) {
   int blocks = div_up(n_items, ST_WARPS);
+  int cap = kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  return blocks > 0 ? blocks : 1;
+}
+
+static int slot_grid(size_t slots) {
+  int blocks = div_up(slots, 256);
   int cap = kNumSMs * 8;
   if (blocks > cap) blocks = cap;
   return blocks > 0 ? blocks : 1;
@@ -657,18 +652,20 @@ void stage_string_graph(cb_ctx* c) {
   DevBuf<uint8_t> flags;  // per slot: "removed" during the cut rounds, then "kept" for TR
   flags.alloc(slots, s);
   CB_CUDA(cudaMemsetAsync(flags.p, 0, slots, s));
+  DevBuf<uint8_t> pre;  // per slot: TransitiveReduction's fast-path decision (consistency_kernel)
+  pre.alloc(slots, s);
   DevBuf<u64> req;  // multi-GPU: mirror keys to act on at their owner
   if (dist) req.alloc(slots, s);
 
   // ---- CutChimericLinks x <= 2 (BrushAssembler.java:347-367) ----
   timer_start(c, "cut");
   const u64* cur_keys = c->ckA.keys.p;
-  const u32* cur_cnt = c->ckA.cnt.p;
   size_t cur_n = c->ckA.n;
   c->ckC_is_A = true;
   int64_t e1 = 0, e2 = 0;
   {
-    StringParams P = make_params(c, cur_keys, cur_cnt);
+    StringParams P = make_params(c, cur_keys);
+    P.pre = pre.p;
     if (c->ckA.n) {
       c->lc.begin("consistency");
       CB_DISPATCH_NW(c->NW, (consistency_kernel<NW_><<<div_up(c->slots, 256), 256, 0, s>>>(
@@ -686,7 +683,7 @@ void stage_string_graph(cb_ctx* c) {
       if (any_work == 0) break;
       u32* dirty = (round == 1) ? workB.p : workA.p;  // round 2 reuses A's storage: its list is consumed
       u32* n_dirty = nwork.p + round;
-      P = make_params(c, cur_keys, cur_cnt);
+      P = make_params(c, cur_keys);
       P.removed = flags.p;
       P.work = work;
       P.n_work = n_work;
@@ -724,28 +721,22 @@ void stage_string_graph(cb_ctx* c) {
       ex_allreduce(c, &cuts, 1, 0);
       (round == 1 ? e1 : e2) = (int64_t)cuts;
       if (cuts == 0) break;
-      // EdgeRemoval: checkpoint chl2 becomes a private copy of A that the dirty lists rewrite
+      // EdgeRemoval: checkpoint chl2 becomes a private copy of A in which the flagged slots are emptied
       if (c->ckC_is_A) {
         c->ckC.keys.alloc(slots, s);
-        c->ckC.cnt.alloc(nl, s);
         CB_CUDA(cudaMemcpyAsync(c->ckC.keys.p, c->ckA.keys.p, slots * sizeof(u64), cudaMemcpyDeviceToDevice, s));
-        CB_CUDA(cudaMemcpyAsync(c->ckC.cnt.p, c->ckA.cnt.p, nl * 4, cudaMemcpyDeviceToDevice, s));
         c->ckC_is_A = false;
         c->ckC.valid = true;
       }
-      u32 nd = read_u32s(c, n_dirty);
       CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGES_C, 0, sizeof(u64), s));
-      if (nd) {
-        remove_flagged_kernel<<<warp_grid(nd), ST_WARPS * 32, 0, s>>>(c->ckC.keys.p, c->adj_off.p, c->ckC.cnt.p,
-                                                                     flags.p, dirty, nd, (ull*)c->dcount.p);
-        c->lc.n++;
-        CB_CUDA(cudaGetLastError());
-      }
+      remove_flagged_kernel<<<slot_grid(slots), 256, 0, s>>>(c->ckC.keys.p, flags.p, slots, (ull*)c->dcount.p);
+      c->lc.n++;
+      CB_CUDA(cudaGetLastError());
+      u32 nd = read_u32s(c, n_dirty);
       download_counters(c);
       cur_n -= (size_t)c->hcount[DC_EDGES_C];
       c->ckC.n = cur_n;
       cur_keys = c->ckC.keys.p;
-      cur_cnt = c->ckC.cnt.p;
       // round 2 only has to look at the lists that changed: an unchanged list cuts nothing again
       work = dirty;
       n_work = nd;
@@ -764,19 +755,19 @@ void stage_string_graph(cb_ctx* c) {
   // ---- TransitiveReduction + EdgeRemoval (BrushAssembler.java:370-379) ----
   timer_start(c, "tr");
   c->ckB.keys.alloc(slots, s);
-  c->ckB.cnt.alloc(nl, s);
-  CB_CUDA(cudaMemsetAsync(c->ckB.cnt.p, 0, nl * 4, s));
+  CB_CUDA(cudaMemsetAsync(c->ckB.keys.p, 0xff, slots * sizeof(u64), s));
   {
     // `flags` is all zero again here (remove_flagged_kernel clears what it consumed)
-    StringParams P = make_params(c, cur_keys, cur_cnt);
+    StringParams P = make_params(c, cur_keys);
     P.kept = flags.p;
+    P.pre = pre.p;
     if (cur_n) {
       c->lc.begin("tr_fast");
-      tr_fast_kernel<<<min(div_up(c->slots, 256), kNumSMs * 8), 256, 0, s>>>(P);
+      tr_fast_kernel<<<slot_grid(slots), 256, 0, s>>>(P);
       c->lc.end("tr_fast");
       CB_CUDA(cudaMemsetAsync(nwork.p + 3, 0, 4, s));
-      tr_worklist_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(c->list_flag.p, cur_cnt, n_lists, workA.p,
-                                                                     nwork.p + 3);
+      tr_worklist_kernel<<<div_up((size_t)nl, 256), 256, 0, s>>>(c->list_flag.p, c->adj_off.p, n_lists, workA.p,
+                                                                nwork.p + 3);
       c->lc.n += 2;
       u32 n_slow = read_u32s(c, nwork.p + 3);
       if (n_slow) {
@@ -789,12 +780,10 @@ void stage_string_graph(cb_ctx* c) {
       }
       CB_CUDA(cudaGetLastError());
     }
-    CB_CUDA(cudaMemsetAsync(c->ckB.keys.p, 0xff, slots * sizeof(u64), s));
-    const int fgrid = min(div_up((size_t)nl, 256), kNumSMs * 8);
     if (!dist) {
       if (cur_n) {
         c->lc.begin("tr_final");
-        tr_final_kernel<<<fgrid, 256, 0, s>>>(P, c->ckB.keys.p, c->ckB.cnt.p);
+        tr_final_kernel<<<slot_grid(slots), 256, 0, s>>>(P, c->ckB.keys.p);
         c->lc.end("tr_final");
         c->lc.n++;
       }
@@ -805,7 +794,7 @@ void stage_string_graph(cb_ctx* c) {
       P.req_cap = (u32)(slots > 0xffffffffu ? 0xffffffffu : slots);
       CB_CUDA(cudaMemsetAsync(nwork.p + 5, 0, 4, s));
       if (cur_n) {
-        tr_votes_kernel<<<fgrid, 256, 0, s>>>(P);
+        tr_votes_kernel<<<slot_grid(slots), 256, 0, s>>>(P);
         c->lc.n++;
       }
       u32 nv = read_u32s(c, nwork.p + 5);
@@ -816,7 +805,7 @@ void stage_string_graph(cb_ctx* c) {
         c->lc.n++;
       }
       if (cur_n) {
-        tr_final_voted_kernel<<<fgrid, 256, 0, s>>>(P, c->ckB.keys.p, c->ckB.cnt.p);
+        tr_final_voted_kernel<<<slot_grid(slots), 256, 0, s>>>(P, c->ckB.keys.p);
         c->lc.n++;
       }
     }
