@@ -264,20 +264,30 @@ def bench_ours(args):
                                           "cut", "tr"] + (["exchange_tuples"] if world > 1 else [])}
 
     # ---- e2e through the C ABI with host buffers ----
-    e2e_t = []
+    from cloudbrush_b200.api import EDGE_DTYPE, NODE_DTYPE
+    # the caller's result buffers are pinned host memory (sized from the resident run)
+    pin_e = torch.empty((g.num_edges(L_.CK_RE) + 1024) * EDGE_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    pin_n = torch.empty((counters["nodes"] + 1024) * NODE_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    out_e = pin_e.numpy().view(EDGE_DTYPE)
+    out_n = pin_n.numpy().view(NODE_DTYPE)
+    e2e_t, e2e_parts = [], []
     d2h = 0
     for i in range(max(1, min(args.steps, 3)) + 1):
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         g.load_sfa_buffer(host)
+        t2 = time.perf_counter()
         g.run()
-        eb = g.edges(L_.CK_RE)
-        nd = g.nodes()
-        dt = time.perf_counter() - t1
+        t3 = time.perf_counter()
+        eb = g.edges(L_.CK_RE, out=out_e)
+        nd = g.nodes(out=out_n)
+        t4 = time.perf_counter()
         d2h = eb.nbytes + nd.nbytes
         if i > 0:  # first one warms the export path
-            e2e_t.append(dt)
+            e2e_t.append(t4 - t1)
+            e2e_parts.append((t2 - t1, t3 - t2, t4 - t3))
     e2e_s = float(np.mean(e2e_t))
+    e2e_split = [float(np.mean([p[k] for p in e2e_parts])) * 1e3 for k in range(3)]
 
     if world > 1:
         t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
@@ -342,7 +352,8 @@ def bench_ours(args):
             "edges_per_sec": total_edges / (ms * 1e-3),
             "wall_ms_per_step": wall * 1e3,
             "e2e": {"value": total_reads / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(len(sfa_np)),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+                    "ms_h2d_load": e2e_split[0], "ms_stages": e2e_split[1], "ms_export_d2h": e2e_split[2]},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

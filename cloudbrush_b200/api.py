@@ -131,14 +131,18 @@ class BrushGpu:
         self._check(self._L.cb_get_counter(self._h, name.encode(), C.byref(v)))
         return v.value
 
-    def edges(self, checkpoint):
-        """structured array (node, nbr, ov, type) sorted by (node, type, nbr, ov)."""
+    def edges(self, checkpoint, out=None):
+        """structured array (node, nbr, ov, type) sorted by (node, type, nbr, ov).
+
+        `out`: optional preallocated EDGE_DTYPE array (e.g. a view of pinned host memory, which makes
+        the device-to-host copy run at PCIe speed); a slice of it is returned."""
         n = C.c_size_t()
         self._check(self._L.cb_export_edges(self._h, checkpoint, None, 0, C.byref(n)))
-        out = np.zeros(n.value, EDGE_DTYPE)
+        if out is None or len(out) < n.value:
+            out = np.empty(n.value, EDGE_DTYPE)
         if n.value:
-            self._check(self._L.cb_export_edges(self._h, checkpoint, out.ctypes.data, n.value, C.byref(n)))
-        return out
+            self._check(self._L.cb_export_edges(self._h, checkpoint, out.ctypes.data, len(out), C.byref(n)))
+        return out[:n.value]
 
     def edge_rows(self, checkpoint):
         """int64[n,4] rows (node line, type, nbr line, ov) -- the oracle's canonical form."""
@@ -151,13 +155,14 @@ class BrushGpu:
         self._check(self._L.cb_export_edges(self._h, checkpoint, None, 0, C.byref(n)))
         return n.value
 
-    def nodes(self):
+    def nodes(self, out=None):
         n = C.c_size_t()
         self._check(self._L.cb_export_nodes(self._h, None, 0, C.byref(n)))
-        out = np.zeros(n.value, NODE_DTYPE)
+        if out is None or len(out) < n.value:
+            out = np.empty(n.value, NODE_DTYPE)
         if n.value:
-            self._check(self._L.cb_export_nodes(self._h, out.ctypes.data, n.value, C.byref(n)))
-        return out
+            self._check(self._L.cb_export_nodes(self._h, out.ctypes.data, len(out), C.byref(n)))
+        return out[:n.value]
 
     def write_nodes(self, checkpoint, out_dir):
         self._check(self._L.cb_write_nodes(self._h, checkpoint, str(out_dir).encode()))

@@ -83,9 +83,10 @@ static const EdgeSet* edge_set(cb_ctx* c, int ck) {
   return nullptr;
 }
 
-static void export_edges_host(cb_ctx* c, const EdgeSet& es, std::vector<cb_edge>& out) {
+// sorted cb_edge records of a checkpoint straight into caller memory (pinned memory makes the
+// device-to-host copy run at PCIe speed)
+static void export_edges_to(cb_ctx* c, const EdgeSet& es, cb_edge* out) {
   cudaStream_t s = c->stream;
-  out.resize(es.n);
   if (es.n == 0) return;
   const size_t slots = c->slots;
   DevBuf<u32> flag, idx;
@@ -102,8 +103,13 @@ static void export_edges_host(cb_ctx* c, const EdgeSet& es, std::vector<cb_edge>
   d.alloc(es.n, s);
   export_decode_kernel<<<div_up(es.n, 256), 256, 0, s>>>(w ? b.p : a.p, es.n, c->lay, c->K, c->node_line.p, d.p);
   c->lc.n += 3;
-  CB_CUDA(cudaMemcpyAsync(out.data(), d.p, es.n * sizeof(cb_edge), cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaMemcpyAsync(out, d.p, es.n * sizeof(cb_edge), cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
+}
+
+static void export_edges_host(cb_ctx* c, const EdgeSet& es, std::vector<cb_edge>& out) {
+  out.resize(es.n);
+  export_edges_to(c, es, out.data());
 }
 
 static void read_file(const std::string& path, std::vector<char>& out) {
@@ -362,11 +368,7 @@ int cb_export_edges(cb_ctx* c, int checkpoint, cb_edge* out, size_t cap, size_t*
   const EdgeSet* es = edge_set(c, checkpoint);
   if (!es) throw Error(CB_E_INVALID, "checkpoint not available");
   *n = es->n;
-  if (out && cap >= es->n && es->n) {
-    std::vector<cb_edge> tmp;
-    export_edges_host(c, *es, tmp);
-    memcpy(out, tmp.data(), tmp.size() * sizeof(cb_edge));
-  }
+  if (out && cap >= es->n && es->n) export_edges_to(c, *es, out);
   CB_API_END(c)
 }
 

@@ -102,14 +102,15 @@ void exclusive_scan_u32(const u32* in, u32* out, size_t n, cudaStream_t s, Launc
 // ------------------------------------------------------------------------------------------
 // radix sort
 // ------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256;
-constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_SUB = RS_THREADS * RS_ITEMS;  // 4096 elements ranked at a time
+constexpr int RS_UP_THREADS = 256;               // upsweep: one thread per digit bin
+constexpr int RS_THREADS = 512;                  // scatter: 512 threads x 8 keys = 4096 elements ranked at a time
+constexpr int RS_WARPS = RS_THREADS / 32;        // (ncu on 256 x 16: 128 registers, 25 % occupancy, long
+constexpr int RS_ITEMS = 8;                      //  smem dependency chains; this shape halves the chain and
+constexpr int RS_SUB = RS_THREADS * RS_ITEMS;    //  doubles the resident warps)
 constexpr int RS_SUBTILES = 4;
 constexpr int RS_TILE = RS_SUB * RS_SUBTILES;  // 16384 elements per block
 
-__global__ void __launch_bounds__(RS_THREADS) rs_upsweep(const u64* __restrict__ kin, u32* __restrict__ hist, size_t n,
+__global__ void __launch_bounds__(RS_UP_THREADS) rs_upsweep(const u64* __restrict__ kin, u32* __restrict__ hist, size_t n,
                                                          int shift, u32 mask) {
   __shared__ u32 h[256];
   h[threadIdx.x] = 0;
@@ -117,8 +118,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_upsweep(const u64* __restrict__
   size_t base = (size_t)blockIdx.x * RS_TILE;
   int lane = threadIdx.x & 31;
 #pragma unroll 4
-  for (int i = 0; i < RS_TILE / RS_THREADS; i++) {
-    size_t idx = base + (size_t)i * RS_THREADS + threadIdx.x;
+  for (int i = 0; i < RS_TILE / RS_UP_THREADS; i++) {
+    size_t idx = base + (size_t)i * RS_UP_THREADS + threadIdx.x;
     bool valid = idx < n;
     u32 d = valid ? (u32)((kin[valid ? idx : 0] >> shift) & mask) : 0xffffffffu;
     u32 peers = __match_any_sync(0xffffffffu, d);
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const u64* __restrict__
                                                          const u32* __restrict__ vin, u32* __restrict__ vout,
                                                          const u32* __restrict__ offsets, size_t n, int shift,
                                                          u32 mask) {
-  __shared__ u32 warp_hist[RS_WARPS][256];
+  __shared__ unsigned short warp_hist[RS_WARPS][256];  // <= 8 x 32 per warp and digit, <= 4096 after the scan
   __shared__ u32 digit_base[256];
   __shared__ u32 sub_start[256];
   __shared__ u32 scan_tmp[RS_WARPS + 1];
@@ -176,14 +177,13 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const u64* __restrict__
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt_mask = (1u << lane) - 1;
-  digit_base[tid] = offsets[(size_t)blockIdx.x * 256 + tid];
+  if (tid < 256) digit_base[tid] = offsets[(size_t)blockIdx.x * 256 + tid];
 
   for (int sub = 0; sub < RS_SUBTILES; sub++) {
     size_t base = (size_t)blockIdx.x * RS_TILE + (size_t)sub * RS_SUB;
     if (base >= n) break;  // uniform across the block
     int nvalid = (int)min((size_t)RS_SUB, n - base);
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; w++) warp_hist[w][tid] = 0;
+    for (int t = tid; t < RS_WARPS * 256; t += RS_THREADS) (&warp_hist[0][0])[t] = 0;
     __syncthreads();
 
     u64 key[RS_ITEMS];
@@ -201,22 +201,24 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const u64* __restrict__
       u32 peers = __match_any_sync(0xffffffffu, d);
       u32 prev = warp_hist[warp][d];
       __syncwarp();
-      if (lane == __ffs(peers) - 1) warp_hist[warp][d] = prev + __popc(peers);
+      if (lane == __ffs(peers) - 1) warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
       __syncwarp();
       pos[i] = prev + __popc(peers & lt_mask);
     }
     __syncthreads();
     // per digit (thread tid): exclusive scan over the warps, then over the digits
     u32 run = 0;
+    if (tid < 256) {
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; w++) {
-      u32 c = warp_hist[w][tid];
-      warp_hist[w][tid] = run;
-      run += c;
+      for (int w = 0; w < RS_WARPS; w++) {
+        u32 c = warp_hist[w][tid];
+        warp_hist[w][tid] = (unsigned short)run;
+        run += c;
+      }
     }
     u32 total;
-    u32 dstart = block_excl_scan(run, scan_tmp, total);
-    sub_start[tid] = dstart;
+    u32 dstart = block_excl_scan(run, scan_tmp, total);  // threads >= 256 contribute 0
+    if (tid < 256) sub_start[tid] = dstart;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const u64* __restrict__
       }
     }
     __syncthreads();
-    digit_base[tid] += run;  // padding only inflates digit 255 of the very last sub-tile
+    if (tid < 256) digit_base[tid] += run;  // padding only inflates digit 255 of the very last sub-tile
     __syncthreads();
   }
 }
@@ -282,7 +284,7 @@ int radix_sort(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int
     int nbits = end_bit - bit < 8 ? end_bit - bit : 8;
     u32 mask = (1u << nbits) - 1;
     lc.begin(nm_up);
-    rs_upsweep<<<tiles, RS_THREADS, 0, s>>>(kin, hist.p, n, bit, mask);
+    rs_upsweep<<<tiles, RS_UP_THREADS, 0, s>>>(kin, hist.p, n, bit, mask);
     lc.end(nm_up);
     rs_chunk_sums<<<chunks, 256, 0, s>>>(hist.p, chunk.p, tiles, rows_per_chunk);
     rs_chunk_scan<<<1, 256, 0, s>>>(chunk.p, chunks);
