@@ -8,6 +8,8 @@
 //   rs_scatter   stable in-tile ranking with __match_any_sync, shared-memory staged so that each
 //                digit run leaves the SM as one contiguous, coalesced store
 // HBM traffic per pass: 8 B (keys, histogram) + 12 B read + 12 B write per tuple.
+#include <cstdlib>
+
 #include "primitives.cuh"
 
 namespace cb {
@@ -110,20 +112,28 @@ constexpr int RS_SUB = RS_THREADS * RS_ITEMS;    //  doubles the resident warps)
 constexpr int RS_SUBTILES = 4;
 constexpr int RS_TILE = RS_SUB * RS_SUBTILES;  // 16384 elements per block
 
+// MATCH: aggregate equal digits of a warp with __match_any_sync before the shared atomic (narrow,
+// skewed digits, e.g. the 2-bit top digit of a 42-bit key); otherwise plain shared atomics, whose
+// rare bank conflicts the hardware serialises at a few cycles each.
+template <bool MATCH>
 __global__ void __launch_bounds__(RS_UP_THREADS) rs_upsweep(const u64* __restrict__ kin, u32* __restrict__ hist, size_t n,
-                                                         int shift, u32 mask) {
+                                                            int shift, u32 mask) {
   __shared__ u32 h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
   size_t base = (size_t)blockIdx.x * RS_TILE;
   int lane = threadIdx.x & 31;
-#pragma unroll 4
+#pragma unroll 8
   for (int i = 0; i < RS_TILE / RS_UP_THREADS; i++) {
     size_t idx = base + (size_t)i * RS_UP_THREADS + threadIdx.x;
     bool valid = idx < n;
     u32 d = valid ? (u32)((kin[valid ? idx : 0] >> shift) & mask) : 0xffffffffu;
-    u32 peers = __match_any_sync(0xffffffffu, d);
-    if (valid && lane == __ffs(peers) - 1) atomicAdd(&h[d], __popc(peers));
+    if (MATCH) {
+      u32 peers = __match_any_sync(0xffffffffu, d);
+      if (valid && lane == __ffs(peers) - 1) atomicAdd(&h[d], __popc(peers));
+    } else {
+      if (valid) atomicAdd(&h[d], 1u);
+    }
   }
   __syncthreads();
   hist[(size_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
@@ -261,10 +271,238 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const u64* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// onesweep: one histogram read of the keys per SORT (all digit positions at once), then ONE
+// kernel per digit pass.  The per-tile digit offsets come from a chained scan with decoupled
+// look-back: tile t publishes its digit counts (flag 1), adds up the published values of the
+// tiles before it until it meets an inclusive prefix (flag 2), then publishes its own inclusive
+// prefix.  Flag and value share one 32-bit word, so a single store publishes both.  Tile ids are
+// handed out by an atomic counter in start order, so a tile only ever waits for tiles that are
+// already running.  HBM traffic per pass: 12 B read + 12 B written per tuple.
+// ------------------------------------------------------------------------------------------
+constexpr int RS_MAXPASS = 8;
+constexpr u32 ST_FLAG_LOCAL = 1u << 30, ST_FLAG_INCL = 2u << 30, ST_VALUE = (1u << 30) - 1;
+constexpr u32 SPIN_LIMIT = 1u << 22;
+
+__global__ void __launch_bounds__(256) rs_hist_all_kernel(const u64* __restrict__ kin, size_t n, int begin_bit,
+                                                          int end_bit, u32* __restrict__ ghist) {
+  __shared__ u32 h[RS_MAXPASS][256];
+  for (int t = threadIdx.x; t < RS_MAXPASS * 256; t += blockDim.x) (&h[0][0])[t] = 0;
+  __syncthreads();
+  const int npass = (end_bit - begin_bit + 7) / 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u64 k = kin[i];
+#pragma unroll
+    for (int p = 0; p < RS_MAXPASS; p++) {
+      if (p < npass) {
+        const int bit = begin_bit + 8 * p;
+        const int nb = end_bit - bit < 8 ? end_bit - bit : 8;
+        atomicAdd(&h[p][(u32)(k >> bit) & ((1u << nb) - 1)], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < npass * 256; t += blockDim.x) {
+    u32 v = (&h[0][0])[t];
+    if (v) atomicAdd(&ghist[t], v);
+  }
+}
+
+// one block: exclusive scan of every pass' 256 digit totals (in place)
+__global__ void __launch_bounds__(256) rs_scan_hist_kernel(u32* __restrict__ ghist, int npass) {
+  __shared__ u32 tmp[256 / 32 + 1];
+  for (int p = 0; p < npass; p++) {
+    u32 v = ghist[p * 256 + threadIdx.x];
+    u32 total;
+    u32 ex = block_excl_scan(v, tmp, total);
+    ghist[p * 256 + threadIdx.x] = ex;
+  }
+}
+
+template <bool HAS_VALS>
+__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u64* __restrict__ kin, u64* __restrict__ kout,
+                                                                 const u32* __restrict__ vin, u32* __restrict__ vout,
+                                                                 volatile u32* status, u32* tile_ctr,
+                                                                 const u32* __restrict__ gbase, u32* err, size_t n,
+                                                                 int shift, u32 mask) {
+  __shared__ unsigned short warp_hist[RS_WARPS][256];
+  __shared__ u32 digit_base[256];
+  __shared__ u32 sub_start[256];
+  __shared__ u32 scan_tmp[RS_WARPS + 1];
+  __shared__ u64 stage[RS_SUB];
+  __shared__ unsigned char sorted_digit[RS_SUB];
+  __shared__ u32 s_tile;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt_mask = (1u << lane) - 1;
+  if (tid == 0) s_tile = atomicAdd(tile_ctr, 1u);
+  for (int t = tid; t < RS_WARPS * 256; t += RS_THREADS) (&warp_hist[0][0])[t] = 0;
+  __syncthreads();
+  const u32 tile = s_tile;
+  const size_t base = (size_t)tile * RS_SUB;
+  if (base >= n) return;  // uniform
+  const int nvalid = (int)min((size_t)RS_SUB, n - base);
+
+  u64 key[RS_ITEMS];
+  u32 pos[RS_ITEMS];
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; i++) {
+    int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
+    key[i] = (e < nvalid) ? kin[base + e] : ~0ull;
+  }
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; i++) {
+    int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
+    u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;  // padding ranks last
+    u32 peers = __match_any_sync(0xffffffffu, d);
+    u32 prev = warp_hist[warp][d];
+    __syncwarp();
+    if (lane == __ffs(peers) - 1) warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
+    __syncwarp();
+    pos[i] = prev + __popc(peers & lt_mask);
+  }
+  __syncthreads();
+  u32 run = 0;
+  if (tid < 256) {
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) {
+      u32 c = warp_hist[w][tid];
+      warp_hist[w][tid] = (unsigned short)run;
+      run += c;
+    }
+    // padding was ranked as digit 255 (last sub-tile only): it must not be published
+    u32 cnt = run;
+    if (tid == 255) cnt -= (u32)(RS_SUB - nvalid);
+    volatile u32* st = status + (size_t)tile * 256 + tid;
+    u32 excl = 0;
+    if (tile == 0) {
+      *st = cnt | ST_FLAG_INCL;
+    } else {
+      *st = cnt | ST_FLAG_LOCAL;
+      long long p = (long long)tile - 1;
+      u32 spins = 0;
+      while (p >= 0) {
+        u32 v = status[(size_t)p * 256 + tid];
+        if ((v >> 30) == 0) {
+          if (++spins > SPIN_LIMIT) { *err = 1; break; }  // never hang the GPU on a bug
+          continue;
+        }
+        excl += v & ST_VALUE;
+        if ((v >> 30) == 2) break;
+        p--;
+      }
+      *st = (excl + cnt) | ST_FLAG_INCL;
+    }
+    digit_base[tid] = gbase[tid] + excl;
+  }
+  u32 total;
+  u32 dstart = block_excl_scan(run, scan_tmp, total);  // threads >= 256 contribute 0
+  if (tid < 256) sub_start[tid] = dstart;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; i++) {
+    int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
+    u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;
+    pos[i] += sub_start[d] + warp_hist[warp][d];
+    stage[pos[i]] = key[i];
+    sorted_digit[pos[i]] = (unsigned char)d;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; j++) {
+    int p = j * RS_THREADS + tid;
+    if (p < nvalid) {
+      u32 d = sorted_digit[p];
+      kout[digit_base[d] + (p - sub_start[d])] = stage[p];
+    }
+  }
+  if (HAS_VALS) {
+    __syncthreads();
+    u32* vstage = reinterpret_cast<u32*>(stage);
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+      int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
+      vstage[pos[i]] = (e < nvalid) ? vin[base + e] : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+      int p = j * RS_THREADS + tid;
+      if (p < nvalid) {
+        u32 d = sorted_digit[p];
+        vout[digit_base[d] + (p - sub_start[d])] = vstage[p];
+      }
+    }
+  }
+}
+
+static int radix_sort_onesweep(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int begin_bit,
+                               int end_bit, cudaStream_t s, LaunchCounter& lc, const char* tag) {
+  const int npass = (end_bit - begin_bit + 7) / 8;
+  const u32 tiles = (u32)((n + RS_SUB - 1) / RS_SUB);
+  DevBuf<u32> ghist, status, ctl;
+  ghist.alloc((size_t)npass * 256, s);
+  status.alloc((size_t)tiles * 256, s);
+  ctl.alloc(2, s);  // [0] tile counter, [1] error flag
+  CB_CUDA(cudaMemsetAsync(ghist.p, 0, (size_t)npass * 256 * 4, s));
+  CB_CUDA(cudaMemsetAsync(ctl.p, 0, 8, s));
+  const std::string nm_up_s = std::string("rs_upsweep:") + tag, nm_sc_s = std::string("rs_scatter:") + tag;
+  lc.begin(nm_up_s.c_str());
+  {
+    int blocks = div_up(n, 256 * 16);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    rs_hist_all_kernel<<<blocks, 256, 0, s>>>(keys_a, n, begin_bit, end_bit, ghist.p);
+    rs_scan_hist_kernel<<<1, 256, 0, s>>>(ghist.p, npass);
+  }
+  lc.end(nm_up_s.c_str());
+  lc.n += 2;
+  u64* kin = keys_a;
+  u64* kout = keys_b;
+  u32* vin = vals_a;
+  u32* vout = vals_b;
+  int where = 0;
+  for (int p = 0; p < npass; p++) {
+    const int bit = begin_bit + 8 * p;
+    const int nbits = end_bit - bit < 8 ? end_bit - bit : 8;
+    const u32 mask = (1u << nbits) - 1;
+    CB_CUDA(cudaMemsetAsync(status.p, 0, (size_t)tiles * 256 * 4, s));
+    CB_CUDA(cudaMemsetAsync(ctl.p, 0, 4, s));
+    lc.begin(nm_sc_s.c_str());
+    if (vin)
+      rs_onesweep_kernel<true><<<tiles, RS_THREADS, 0, s>>>(kin, kout, vin, vout, status.p, ctl.p, ghist.p + p * 256,
+                                                           ctl.p + 1, n, bit, mask);
+    else
+      rs_onesweep_kernel<false><<<tiles, RS_THREADS, 0, s>>>(kin, kout, nullptr, nullptr, status.p, ctl.p,
+                                                            ghist.p + p * 256, ctl.p + 1, n, bit, mask);
+    lc.end(nm_sc_s.c_str());
+    lc.n++;
+    CB_CUDA(cudaGetLastError());
+    u64* tk = kin; kin = kout; kout = tk;
+    u32* tv = vin; vin = vout; vout = tv;
+    where ^= 1;
+  }
+  u32 err = 0;
+  CB_CUDA(cudaMemcpyAsync(&err, ctl.p + 1, 4, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  if (err) throw Error(CB_E_CUDA, "radix sort: look-back spin limit exceeded");
+  return where;
+}
+
+static bool use_onesweep() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CB_SORT");
+    v = (e && std::string(e) == "classic") ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int radix_sort(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int begin_bit, int end_bit,
                cudaStream_t s, LaunchCounter& lc, const char* tag) {
   if (n == 0 || end_bit <= begin_bit) return 0;
   if (n >= (1ull << 32)) throw Error(CB_E_CAPACITY, "radix_sort: more than 2^32-1 elements");
+  if (n < (1ull << 30) && (end_bit - begin_bit + 7) / 8 <= RS_MAXPASS && use_onesweep())
+    return radix_sort_onesweep(keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, s, lc, tag);
   int tiles = (int)((n + RS_TILE - 1) / RS_TILE);
   int chunks = tiles < 4 * kNumSMs ? tiles : 4 * kNumSMs;
   int rows_per_chunk = (tiles + chunks - 1) / chunks;
@@ -284,7 +522,8 @@ int radix_sort(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int
     int nbits = end_bit - bit < 8 ? end_bit - bit : 8;
     u32 mask = (1u << nbits) - 1;
     lc.begin(nm_up);
-    rs_upsweep<<<tiles, RS_UP_THREADS, 0, s>>>(kin, hist.p, n, bit, mask);
+    if (nbits < 6) rs_upsweep<true><<<tiles, RS_UP_THREADS, 0, s>>>(kin, hist.p, n, bit, mask);
+    else rs_upsweep<false><<<tiles, RS_UP_THREADS, 0, s>>>(kin, hist.p, n, bit, mask);
     lc.end(nm_up);
     rs_chunk_sums<<<chunks, 256, 0, s>>>(hist.p, chunk.p, tiles, rows_per_chunk);
     rs_chunk_scan<<<1, 256, 0, s>>>(chunk.p, chunks);
