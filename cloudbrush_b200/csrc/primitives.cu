@@ -330,7 +330,6 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u64* __re
   __shared__ u32 sub_start[256];
   __shared__ u32 scan_tmp[RS_WARPS + 1];
   __shared__ u64 stage[RS_SUB];
-  __shared__ unsigned char sorted_digit[RS_SUB];
   __shared__ u32 s_tile;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -362,7 +361,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u64* __re
     pos[i] = prev + __popc(peers & lt_mask);
   }
   __syncthreads();
-  u32 run = 0;
+  u32 run = 0, cnt_pub = 0;
   if (tid < 256) {
 #pragma unroll
     for (int w = 0; w < RS_WARPS; w++) {
@@ -370,15 +369,37 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u64* __re
       warp_hist[w][tid] = (unsigned short)run;
       run += c;
     }
-    // padding was ranked as digit 255 (last sub-tile only): it must not be published
-    u32 cnt = run;
-    if (tid == 255) cnt -= (u32)(RS_SUB - nvalid);
-    volatile u32* st = status + (size_t)tile * 256 + tid;
+    // publish this tile's digit counts right away (padding was ranked as digit 255 in the last
+    // tile only and must not be published); the look-back itself waits until the keys are staged
+    // in shared memory, which gives the tiles before this one time to publish
+    cnt_pub = run;
+    if (tid == 255) cnt_pub -= (u32)(RS_SUB - nvalid);
+    status[(size_t)tile * 256 + tid] = cnt_pub | (tile == 0 ? ST_FLAG_INCL : ST_FLAG_LOCAL);
+  }
+  u32 total;
+  u32 dstart = block_excl_scan(run, scan_tmp, total);  // threads >= 256 contribute 0
+  if (tid < 256) sub_start[tid] = dstart;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; i++) {
+    int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
+    u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;
+    pos[i] += sub_start[d] + warp_hist[warp][d];
+    stage[pos[i]] = key[i];
+  }
+  // the key registers are dead now: issue the payload loads so that their latency overlaps the
+  // look-back and the key write-out
+  u32 val[RS_ITEMS];
+  if (HAS_VALS) {
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+      int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
+      val[i] = (e < nvalid) ? vin[base + e] : 0u;
+    }
+  }
+  if (tid < 256) {
     u32 excl = 0;
-    if (tile == 0) {
-      *st = cnt | ST_FLAG_INCL;
-    } else {
-      *st = cnt | ST_FLAG_LOCAL;
+    if (tile != 0) {
       long long p = (long long)tile - 1;
       u32 spins = 0;
       while (p >= 0) {
@@ -391,47 +412,33 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u64* __re
         if ((v >> 30) == 2) break;
         p--;
       }
-      *st = (excl + cnt) | ST_FLAG_INCL;
+      status[(size_t)tile * 256 + tid] = (excl + cnt_pub) | ST_FLAG_INCL;
     }
     digit_base[tid] = gbase[tid] + excl;
   }
-  u32 total;
-  u32 dstart = block_excl_scan(run, scan_tmp, total);  // threads >= 256 contribute 0
-  if (tid < 256) sub_start[tid] = dstart;
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++) {
-    int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
-    u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;
-    pos[i] += sub_start[d] + warp_hist[warp][d];
-    stage[pos[i]] = key[i];
-    sorted_digit[pos[i]] = (unsigned char)d;
-  }
-  __syncthreads();
+  u32 gpos[RS_ITEMS];  // global position of sorted element j * RS_THREADS + tid (keys and payload alike)
 #pragma unroll
   for (int j = 0; j < RS_ITEMS; j++) {
     int p = j * RS_THREADS + tid;
+    gpos[j] = 0;
     if (p < nvalid) {
-      u32 d = sorted_digit[p];
-      kout[digit_base[d] + (p - sub_start[d])] = stage[p];
+      u64 k = stage[p];
+      u32 d = (u32)((k >> shift) & mask);
+      gpos[j] = digit_base[d] + (p - sub_start[d]);
+      kout[gpos[j]] = k;
     }
   }
   if (HAS_VALS) {
     __syncthreads();
     u32* vstage = reinterpret_cast<u32*>(stage);
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; i++) {
-      int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
-      vstage[pos[i]] = (e < nvalid) ? vin[base + e] : 0u;
-    }
+    for (int i = 0; i < RS_ITEMS; i++) vstage[pos[i]] = val[i];
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
       int p = j * RS_THREADS + tid;
-      if (p < nvalid) {
-        u32 d = sorted_digit[p];
-        vout[digit_base[d] + (p - sub_start[d])] = vstage[p];
-      }
+      if (p < nvalid) vout[gpos[j]] = vstage[p];
     }
   }
 }
