@@ -99,51 +99,65 @@ __device__ __forceinline__ long long find_edge(const StringParams& P, u64 key) {
 constexpr int ST_WARPS = 8;
 
 // ---------------------------------------------------------------------------------------------
-// consistency of every list, one thread per record.  Threads of one list run in lock step over
-// the same addresses (broadcast loads), so the per-record list scan is cheap.
+// consistency of every list, one thread per list: one scan finds the longest overhang (minimal
+// overlap, first such record) and the maximal overlap, a second pass compares every overhang
+// with the longest one and precomputes what the fast path of TransitiveReduction needs
+// (tr_fast_kernel): bit0 maximal overlap, bit1 counts as transitive, bit2 ov == L.
 // ---------------------------------------------------------------------------------------------
 template <int NW>
 __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* __restrict__ work_out,
                                                           u32* __restrict__ n_work_out, int force_slow) {
-  size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= P.slots) return;
-  const u64 k = P.edges[slot];
-  if (k == ~0ull) return;
-  const u32 lid = P.lay.list(k);
-  const u32 lo = P.adj_off[lid], hi = P.adj_off[lid + 1];
-  const u32 ov = P.lay.ov(k), nbr = P.lay.nbr(k), y = P.lay.y(k);
-  // one scan of the list gives the longest overhang (minimal overlap, first such record), the
-  // maximal overlap, and the largest overlap among the records of my (type, neighbour) -- what
-  // the fast path of TransitiveReduction needs (tr_fast_kernel)
-  u32 hidx = lo, hov = 0xffffffffu, ovmax = 0, same_max = 0, n = 0;
-  for (u32 t = lo; t < hi; t++) {
-    const u64 q = P.edges[t];
-    if (q == ~0ull) continue;
-    n++;
-    const u32 o = P.lay.ov(q);
-    if (o < hov) { hov = o; hidx = t; }
-    ovmax = max(ovmax, o);
-    if (P.lay.nbr(q) == nbr && P.lay.y(q) == y) same_max = max(same_max, o);
-  }
-  // TransitiveReduction on a consistent list: keep the maximal overlap (:341-343); anything else
-  // is dropped, counted as transitive unless a kept record has my type and neighbour (:325-334)
-  P.pre[slot] = (uint8_t)((ov == ovmax ? 1u : 0u) | ((ov != ovmax && same_max != ovmax) ? 2u : 0u) |
-                          ((int)ov == P.L ? 4u : 0u));
-  if (n <= 1) return;  // flag stays 1
-  bool bad = force_slow != 0;
-  if (!bad) {
-    u64 H[NW], h[NW];
-    int lenH, len;
-    load_overhang<NW>(P, P.edges[hidx], H, lenH);
-    load_overhang<NW>(P, k, h, len);
-    bad = !prefix_equal<NW>(h, H, len);
-  }
-  if (bad) {
-    // first thread to clear the flag queues the list for the literal kernel
-    unsigned int* word = reinterpret_cast<unsigned int*>(P.list_flag + (lid & ~3u));
-    unsigned int bit = 0xffu << (8 * (lid & 3u));
-    unsigned int old = atomicAnd(word, ~bit);
-    if (old & bit) work_out[atomicAdd(n_work_out, 1u)] = lid;
+  for (u32 lid = blockIdx.x * blockDim.x + threadIdx.x; lid < P.n_lists; lid += gridDim.x * blockDim.x) {
+    const u32 lo = P.adj_off[lid], hi = P.adj_off[lid + 1];
+    u32 hidx = lo, hov = 0xffffffffu, ovmax = 0, n = 0, nmax = 0;
+    u64 m0 = ~0ull, m1 = ~0ull;  // the first two records of maximal overlap
+    for (u32 t = lo; t < hi; t++) {
+      const u64 q = P.edges[t];
+      if (q == ~0ull) continue;
+      n++;
+      const u32 o = P.lay.ov(q);
+      if (o < hov) { hov = o; hidx = t; }
+      if (o > ovmax) { ovmax = o; nmax = 1; m0 = q; m1 = ~0ull; }
+      else if (o == ovmax) { if (nmax == 1) m1 = q; nmax++; }
+    }
+    if (n == 0) continue;
+    u64 H[NW];
+    int lenH = 0;
+    const bool test = n > 1 && !force_slow;
+    if (test) load_overhang<NW>(P, P.edges[hidx], H, lenH);
+    bool bad = n > 1 && force_slow;
+    for (u32 t = lo; t < hi; t++) {
+      const u64 k = P.edges[t];
+      if (k == ~0ull) continue;
+      const u32 ov = P.lay.ov(k);
+      if (test && t != hidx) {
+        u64 h[NW];
+        int len;
+        load_overhang<NW>(P, k, h, len);
+        bad = bad || !prefix_equal<NW>(h, H, len);
+      }
+      // TransitiveReduction on a consistent list: keep the maximal overlap (:341-343); anything
+      // else is dropped, counted as transitive unless a kept record has my type and neighbour
+      // (:325-334)
+      uint8_t f = (int)ov == P.L ? 4u : 0u;
+      if (ov == ovmax) f |= 1u;
+      else {
+        const u32 nbr = P.lay.nbr(k), y = P.lay.y(k);
+        bool step2 = (P.lay.nbr(m0) == nbr && P.lay.y(m0) == y) ||
+                     (m1 != ~0ull && P.lay.nbr(m1) == nbr && P.lay.y(m1) == y);
+        if (!step2 && nmax > 2)
+          for (u32 q = lo; q < hi && !step2; q++) {
+            const u64 kq = P.edges[q];
+            if (kq != ~0ull && P.lay.ov(kq) == ovmax && P.lay.nbr(kq) == nbr && P.lay.y(kq) == y) step2 = true;
+          }
+        if (!step2) f |= 2u;
+      }
+      P.pre[t] = f;
+    }
+    if (bad) {  // only this thread writes the list's flag here
+      P.list_flag[lid] = 0;
+      work_out[atomicAdd(n_work_out, 1u)] = lid;
+    }
   }
 }
 
@@ -668,7 +682,7 @@ void stage_string_graph(cb_ctx* c) {
     P.pre = pre.p;
     if (c->ckA.n) {
       c->lc.begin("consistency");
-      CB_DISPATCH_NW(c->NW, (consistency_kernel<NW_><<<div_up(c->slots, 256), 256, 0, s>>>(
+      CB_DISPATCH_NW(c->NW, (consistency_kernel<NW_><<<min(div_up((size_t)nl, 256), kNumSMs * 16), 256, 0, s>>>(
                                 P, workA.p, nwork.p + 0, c->cfg.majority < 1.0f ? 0 : 1)));
       c->lc.end("consistency");
       c->lc.n++;
