@@ -362,12 +362,22 @@ __global__ void __launch_bounds__(256) side_insert_kernel(const u64* __restrict_
     const u64 key = xs[i];
     const u32 lid = lay.list(key);
     const u32 lo = off[lid], hi = off[lid + 1];
+    // one pass over the list's slots, eight loads in flight: duplicate? first free slot?
     bool dup = false;
-    for (u32 t = lo; t < hi; t++)
-      if (slots[t] == key) { dup = true; break; }
+    u32 hole = 0xffffffffu;
+    for (u32 t = lo; t < hi && !dup; t += 8) {
+      u64 k[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) k[i] = (t + i < hi) ? slots[t + i] : 0ull;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (k[i] == key) dup = true;
+        if (k[i] == ~0ull && hole == 0xffffffffu && t + i < hi) hole = t + i;
+      }
+    }
     if (dup) continue;
     bool placed = false;
-    for (u32 t = lo; t < hi && !placed; t++) {
+    for (u32 t = hole; t < hi && !placed; t++) {  // another record may claim the slot first: move on
       if (slots[t] == ~0ull) {
         ull old = atomicCAS((ull*)&slots[t], ~0ull, (ull)key);
         placed = old == ~0ull;
@@ -627,6 +637,7 @@ void stage_build_overlap(cb_ctx* c) {
     size_t n_xin = n_x;
     DevBuf<char> xrecv;
     if (distributed(c)) {
+      timer_start(c, "side_route");
       DevBuf<u32> xdest;
       xdest.alloc(n_x ? n_x : 1, s);
       if (n_x) {
@@ -636,6 +647,7 @@ void stage_build_overlap(cb_ctx* c) {
       }
       route_records(c, xbuf.p, 8, xdest.p, n_x, xrecv, n_xin);
       xin = (const u64*)xrecv.p;
+      timer_stop(c, "side_route");
     }
     if (n_xin) {
       int blocks = div_up(n_xin, 256);

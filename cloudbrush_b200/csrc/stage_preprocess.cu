@@ -516,6 +516,7 @@ void stage_parse_and_pack(cb_ctx* c) {
     // reads -> owner of their canonical hash -> (survivor, coverage) -> back to the line's rank
     const int NW = c->NW;
     const size_t rec_words = 4 + NW;
+    timer_start(c, "dd_route");
     DevBuf<u64> recs;
     DevBuf<u32> dest;
     recs.alloc(nl1 * rec_words, s);
@@ -529,6 +530,7 @@ void stage_parse_and_pack(cb_ctx* c) {
     size_t n_got = 0;
     route_records(c, recs.p, rec_words * 8, dest.p, nl, got, n_got);
     recs.release();
+    timer_stop(c, "dd_route");
     const size_t g1 = n_got ? n_got : 1;
     DevBuf<u64> rk[2], rreads;
     DevBuf<u32> rv[2], rline, rsurv, rcov;
@@ -548,6 +550,7 @@ void stage_parse_and_pack(cb_ctx* c) {
       c->lc.end("dedupe_runs");
       c->lc.n += 2;
     }
+    timer_start(c, "dd_return");
     DevBuf<u64> dbases;
     dbases.alloc(world + 1, s);
     CB_CUDA(cudaMemcpyAsync(dbases.p, c->line_bases.data(), (world + 1) * sizeof(u64), cudaMemcpyHostToDevice, s));
@@ -568,6 +571,7 @@ void stage_parse_and_pack(cb_ctx* c) {
       c->lc.n++;
     }
     CB_CUDA(cudaGetLastError());
+    timer_stop(c, "dd_return");
     download_counters(c);
     n_local_nodes = (u32)n_back;
   }
@@ -610,11 +614,13 @@ void stage_parse_and_pack(cb_ctx* c) {
     c->node_lo = (u32)lo;
     c->node_hi = (u32)(lo + n_local_nodes);
     const size_t t1 = total ? total : 1;
+    timer_start(c, "node_gather");
     c->node_line.alloc(t1, s); c->node_cov.alloc(t1, s); c->node_seq.alloc(t1 * c->NW, s); c->node_idkey.alloc(t1, s);
     gather_all(c, l_line.p, 4, n_local_nodes, counts, c->node_line.p);
     gather_all(c, l_cov.p, 4, n_local_nodes, counts, c->node_cov.p);
     gather_all(c, l_seq.p, (size_t)c->NW * 8, n_local_nodes, counts, c->node_seq.p);
     gather_all(c, l_id.p, sizeof(IdKey), n_local_nodes, counts, c->node_idkey.p);
+    timer_stop(c, "node_gather");
   }
   timer_stop(c, "dedupe");
 
