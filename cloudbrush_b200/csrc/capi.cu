@@ -249,7 +249,8 @@ int cb_borrow_sfa_device(cb_ctx* c, const void* dev_buf, size_t n) {
 }
 
 int cb_set_exchange(cb_ctx* c, const cb_exchange* ex) {
-  if (!c || !ex || !ex->exchange_counts || !ex->alltoallv || !ex->allgatherv || !ex->allreduce_u64) return CB_E_INVALID;
+  if (!c || !ex || !ex->exchange_counts || !ex->alltoallv || !ex->allgatherv || !ex->allreduce_u64 ||
+      !ex->allreduce_max_u8_dev) return CB_E_INVALID;
   c->ex = *ex;
   c->has_ex = true;
   return CB_OK;

@@ -142,6 +142,8 @@ void download_counters(cb_ctx* c);
 // dist.cu -- routing helpers of the multi-GPU path
 inline bool distributed(const cb_ctx* c) { return c->cfg.world > 1; }
 void ex_allreduce(cb_ctx* c, u64* vals, int n, int op);
+// in-place max over the ranks of a DEVICE byte array
+void ex_allreduce_max_u8(cb_ctx* c, uint8_t* dev, size_t n);
 void ex_counts(cb_ctx* c, const u64* send, u64* recv, int n_per_rank);
 void ex_alltoallv(cb_ctx* c, const void* send, const u64* send_bytes, void* recv, const u64* recv_bytes);
 void ex_allgatherv(cb_ctx* c, const void* send, u64 send_bytes, void* recv, const u64* recv_bytes);

@@ -22,6 +22,15 @@ void ex_allreduce(cb_ctx* c, u64* vals, int n, int op) {
   if (rc) ex_fail("allreduce_u64", rc);
 }
 
+void ex_allreduce_max_u8(cb_ctx* c, uint8_t* dev, size_t n) {
+  if (!distributed(c)) return;
+  need_ex(c);
+  if (!c->ex.allreduce_max_u8_dev) throw Error(CB_E_INVALID, "cb_exchange.allreduce_max_u8_dev is not set");
+  CB_CUDA(cudaStreamSynchronize(c->stream));
+  int rc = c->ex.allreduce_max_u8_dev(c->ex.user, dev, (uint64_t)n);
+  if (rc) ex_fail("allreduce_max_u8_dev", rc);
+}
+
 void ex_counts(cb_ctx* c, const u64* send, u64* recv, int n_per_rank) {
   need_ex(c);
   int rc = c->ex.exchange_counts(c->ex.user, (const uint64_t*)send, (uint64_t*)recv, n_per_rank);

@@ -18,7 +18,7 @@
 // (one thread per record, consistency_kernel).  For a consistent list (a) the PWM consensus of
 // CutChimericLinks equals the longest overhang wherever it is defined, has no N and cuts nothing
 // (needs MAJORITY < 1); (b) the greedy scan of TransitiveReduction keeps exactly the entries of
-// maximal overlap (tr_fast_kernel, one thread per record).  Lists that are not consistent
+// maximal overlap (tr_final_kernel, one thread per record).  Lists that are not consistent
 // (sequencing errors, repeats) go through work lists to the literal warp-per-list kernels.
 #include "ctx.cuh"
 
@@ -51,6 +51,9 @@ struct StringParams {
   uint8_t* list_flag;  // per list: 1 consistent, 0 not, dirty bits 2 / 4 (lost an entry in cut round 1 / 2)
   uint8_t* pre;        // per slot, from consistency_kernel: bit0 maximal overlap of its list, bit1 counts as
                        // transitive if the list is consistent, bit2 ov == L
+  uint8_t* ovmax;      // per list, from consistency_kernel: the maximal overlap of the list (0: empty list)
+  const uint8_t* lsum; // per list, all ranks: ovmax if the list is consistent and untouched by the cut rounds
+                       // (TransitiveReduction keeps exactly its records of that overlap), else 0
   const u32* work;     // work list of list ids (literal kernels)
   u32 n_work;
   u32* work_out;       // lists that lost an entry in this round
@@ -103,7 +106,7 @@ constexpr int ST_WARPS = 8;
 // consistency of every list, one thread per list: one scan finds the longest overhang (minimal
 // overlap, first such record) and the maximal overlap, a second pass compares every overhang
 // with the longest one and precomputes what the fast path of TransitiveReduction needs
-// (tr_fast_kernel): bit0 maximal overlap, bit1 counts as transitive, bit2 ov == L.
+// (tr_final_kernel): bit0 maximal overlap, bit1 counts as transitive, bit2 ov == L.
 // ---------------------------------------------------------------------------------------------
 template <int NW>
 __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* __restrict__ work_out,
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* _
       else if (o == ovmax) { if (nmax == 1) m1 = q; nmax++; }
     }
     if (n == 0) continue;
+    P.ovmax[lid] = (uint8_t)ovmax;
     u64 H[NW];
     int lenH = 0;
     const bool test = n > 1 && !force_slow;
@@ -370,36 +374,19 @@ __global__ void __launch_bounds__(256) remove_flagged_kernel(u64* __restrict__ k
 // ---------------------------------------------------------------------------------------------
 // K11: TransitiveReduction
 // ---------------------------------------------------------------------------------------------
-// consistent lists, one thread per record: apply what consistency_kernel precomputed
-__global__ void __launch_bounds__(256) tr_fast_kernel(StringParams P) {
-  u32 trans = 0, contained = 0;
-  for (size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x; slot < P.slots;
-       slot += (size_t)gridDim.x * blockDim.x) {
-    const u64 k = P.edges[slot];
-    if (k == ~0ull) continue;
-    if (P.list_flag[P.lay.list(k)] != 1) continue;  // literal kernel
-    const uint8_t f = P.pre[slot];
-    if (f & 1) P.kept[slot] = 1;
-    trans += (f >> 1) & 1;
-    contained += (f >> 2) & 1;  // TransitiveReduction.java:319-323 (equal-length reads)
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    trans += __shfl_xor_sync(0xffffffffu, trans, o);
-    contained += __shfl_xor_sync(0xffffffffu, contained, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    if (trans) atomicAdd(&P.dcount[DC_TRANS_EDGE], (ull)trans);
-    if (contained) atomicAdd(&P.dcount[DC_CONTAINED_EDGE], (ull)contained);
-  }
-}
-
-// lists whose flag is not "consistent" -> work list for the literal kernel
+// lists whose flag is not "consistent" -> work list for the literal kernel; every list's summary
+// byte for the final pass (lsum)
 __global__ void __launch_bounds__(256) tr_worklist_kernel(const uint8_t* __restrict__ list_flag,
-                                                          const u32* __restrict__ adj_off, u32 n_lists,
-                                                          u32* __restrict__ work, u32* __restrict__ n_work) {
+                                                          const u32* __restrict__ adj_off,
+                                                          const uint8_t* __restrict__ ovmax, u32 n_lists,
+                                                          u32* __restrict__ work, u32* __restrict__ n_work,
+                                                          uint8_t* __restrict__ lsum) {
   u32 lid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lid < n_lists && list_flag[lid] != 1 && adj_off[lid + 1] > adj_off[lid]) work[atomicAdd(n_work, 1u)] = lid;
+  if (lid >= n_lists) return;
+  const bool nonempty = adj_off[lid + 1] > adj_off[lid];
+  const bool fast = list_flag[lid] == 1;
+  lsum[lid] = (nonempty && fast) ? ovmax[lid] : (uint8_t)0;
+  if (nonempty && !fast) work[atomicAdd(n_work, 1u)] = lid;
 }
 
 constexpr int TR_KC = 64;  // kept entries per list in the literal scan
@@ -495,25 +482,56 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
   }
 }
 
-// EdgeRemoval after TransitiveReduction: an edge survives iff both endpoints kept it.
-// One thread per kept record looks its mirror up; the survivor keeps its slot in checkpoint B
-// (`out` pre-filled with ~0).
+// TransitiveReduction on the consistent lists fused with the EdgeRemoval that follows it
+// (TransitiveReduction.java:300-409 + EdgeRemoval.java:121-202): an edge survives iff both
+// endpoints kept it.  One thread per slot.  A record of a consistent list is kept iff its overlap
+// is the list's maximum (precomputed by consistency_kernel: `pre`); whether the MIRROR was kept is
+// read off the mirror list's summary byte -- lsum[list] = that list's maximal overlap if it is
+// consistent -- so no list is searched and, on several GPUs, nothing is exchanged per edge.  Only a
+// mirror in an inconsistent list (literal tr_kernel) is looked up (one GPU) or was voted for by its
+// owner (VOTED, several GPUs: bit 1 of kept[slot]).
+template <bool VOTED>
 __global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __restrict__ out) {
-  u32 tot = 0;
+  u32 tot = 0, trans = 0, contained = 0;
   for (size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x; slot < P.slots;
        slot += (size_t)gridDim.x * blockDim.x) {
-    if (!P.kept[slot]) continue;
     const u64 k = P.edges[slot];
-    long long mi = find_edge(P, P.lay.mirror(k));
-    const bool keep = mi < 0 ? true : (P.kept[mi] != 0);  // no mirror: nobody can ask for the removal
+    if (k == ~0ull) continue;
+    bool kept_here;
+    if (P.list_flag[P.lay.list(k)] == 1) {
+      const uint8_t f = P.pre[slot];
+      kept_here = f & 1;
+      trans += (f >> 1) & 1;
+      contained += (f >> 2) & 1;  // TransitiveReduction.java:319-323 (equal-length reads)
+    } else {
+      kept_here = (P.kept[slot] & 1) != 0;  // literal kernel
+    }
+    if (!kept_here) continue;
+    const u64 mk = P.lay.mirror(k);
+    const uint8_t ms = P.lsum[P.lay.list(mk)];
+    bool keep;
+    if (ms) keep = P.lay.ov(k) == (u32)ms;
+    else if (VOTED) keep = (P.kept[slot] & 2) != 0;
+    else {
+      long long mi = find_edge(P, mk);
+      keep = mi < 0 ? true : (P.kept[mi] != 0);  // no mirror: nobody can ask for the removal
+    }
     if (keep) {
       out[slot] = k;
       tot++;
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&P.dcount[DC_EDGES_B], (ull)tot);
+  for (int o = 16; o > 0; o >>= 1) {
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    trans += __shfl_xor_sync(0xffffffffu, trans, o);
+    contained += __shfl_xor_sync(0xffffffffu, contained, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (tot) atomicAdd(&P.dcount[DC_EDGES_B], (ull)tot);
+    if (trans) atomicAdd(&P.dcount[DC_TRANS_EDGE], (ull)trans);
+    if (contained) atomicAdd(&P.dcount[DC_CONTAINED_EDGE], (ull)contained);
+  }
 }
 
 // ---- multi-GPU helpers: act on routed mirror keys at the rank that owns their list ----
@@ -525,14 +543,21 @@ __global__ void __launch_bounds__(256) apply_removal_requests_kernel(StringParam
   if (mi >= 0) { P.removed[mi] = 1; mark_dirty(P, P.lay.list(keys[i])); }
 }
 
-// the mirror key of every kept record is a "kept" vote for the other end
+// several GPUs: every record the literal kernel kept (inconsistent lists only, a handful) votes
+// "kept" for its mirror at the rank that owns the mirror's list.  One warp per queued list.
 __global__ void __launch_bounds__(256) tr_votes_kernel(StringParams P) {
-  for (size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x; slot < P.slots;
-       slot += (size_t)gridDim.x * blockDim.x)
-    if (P.kept[slot] & 1) {
-      u32 ri = atomicAdd(P.n_req, 1u);
-      if (ri < P.req_cap) P.req[ri] = P.lay.mirror(P.edges[slot]);
-    }
+  const int lane = threadIdx.x & 31;
+  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 wi = warp_global; wi < P.n_work; wi += nwarps) {
+    const u32 list = P.work[wi];
+    const u32 lo = P.adj_off[list], hi = P.adj_off[list + 1];
+    for (u32 t = lo + lane; t < hi; t += 32)
+      if (P.kept[t] & 1) {
+        u32 ri = atomicAdd(P.n_req, 1u);
+        if (ri < P.req_cap) P.req[ri] = P.lay.mirror(P.edges[t]);
+      }
+  }
 }
 
 __global__ void __launch_bounds__(256) apply_votes_kernel(StringParams P, const u64* __restrict__ keys, size_t n) {
@@ -540,19 +565,6 @@ __global__ void __launch_bounds__(256) apply_votes_kernel(StringParams P, const 
   if (i >= n) return;
   long long mi = find_edge(P, keys[i]);
   if (mi >= 0) P.kept[mi] |= 2;  // one vote per record at most: no other thread writes this byte
-}
-
-__global__ void __launch_bounds__(256) tr_final_voted_kernel(StringParams P, u64* __restrict__ out) {
-  u32 tot = 0;
-  for (size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x; slot < P.slots;
-       slot += (size_t)gridDim.x * blockDim.x)
-    if (P.kept[slot] == 3) {
-      out[slot] = P.edges[slot];
-      tot++;
-    }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&P.dcount[DC_EDGES_B], (ull)tot);
 }
 
 template <int NW>
@@ -601,6 +613,8 @@ static StringParams make_params(cb_ctx* c, const u64* keys) {
   P.kept = nullptr;
   P.list_flag = c->list_flag.p;
   P.pre = nullptr;
+  P.ovmax = nullptr;
+  P.lsum = nullptr;
   P.work = nullptr;
   P.n_work = 0;
   P.work_out = nullptr;
@@ -669,6 +683,10 @@ void stage_string_graph(cb_ctx* c) {
   CB_CUDA(cudaMemsetAsync(flags.p, 0, slots, s));
   DevBuf<uint8_t> pre;  // per slot: TransitiveReduction's fast-path decision (consistency_kernel)
   pre.alloc(slots, s);
+  DevBuf<uint8_t> ovmax, lsum;  // per list: maximal overlap / summary byte of the final pass
+  ovmax.alloc(nl, s);
+  lsum.alloc(nl, s);
+  CB_CUDA(cudaMemsetAsync(ovmax.p, 0, nl, s));
   DevBuf<u64> req;  // multi-GPU: mirror keys to act on at their owner
   if (dist) req.alloc(slots, s);
 
@@ -681,6 +699,7 @@ void stage_string_graph(cb_ctx* c) {
   {
     StringParams P = make_params(c, cur_keys);
     P.pre = pre.p;
+    P.ovmax = ovmax.p;
     if (c->ckA.n) {
       c->lc.begin("consistency");
       CB_DISPATCH_NW(c->NW, (consistency_kernel<NW_><<<min(div_up((size_t)nl, 256), kNumSMs * 16), 256, 0, s>>>(
@@ -776,55 +795,56 @@ void stage_string_graph(cb_ctx* c) {
     StringParams P = make_params(c, cur_keys);
     P.kept = flags.p;
     P.pre = pre.p;
-    if (cur_n) {
-      c->lc.begin("tr_fast");
-      tr_fast_kernel<<<slot_grid(slots), 256, 0, s>>>(P);
-      c->lc.end("tr_fast");
-      CB_CUDA(cudaMemsetAsync(nwork.p + 3, 0, 4, s));
-      tr_worklist_kernel<<<div_up((size_t)nl, 256), 256, 0, s>>>(c->list_flag.p, c->adj_off.p, n_lists, workA.p,
-                                                                nwork.p + 3);
-      c->lc.n += 2;
-      u32 n_slow = read_u32s(c, nwork.p + 3);
-      if (n_slow) {
-        P.work = workA.p;
-        P.n_work = n_slow;
-        c->lc.begin("tr");
-        CB_DISPATCH_NW(c->NW, (tr_kernel<NW_><<<warp_grid(n_slow), ST_WARPS * 32, 0, s>>>(P)));
-        c->lc.end("tr");
-        c->lc.n++;
-      }
-      CB_CUDA(cudaGetLastError());
+    P.ovmax = ovmax.p;
+    P.lsum = lsum.p;
+    // literal path first: lists that are inconsistent or lost an entry in a cut round
+    CB_CUDA(cudaMemsetAsync(nwork.p + 3, 0, 4, s));
+    tr_worklist_kernel<<<div_up((size_t)nl, 256), 256, 0, s>>>(c->list_flag.p, c->adj_off.p, ovmax.p, n_lists,
+                                                              workA.p, nwork.p + 3, lsum.p);
+    c->lc.n++;
+    u32 n_slow = read_u32s(c, nwork.p + 3);
+    if (n_slow) {
+      P.work = workA.p;
+      P.n_work = n_slow;
+      c->lc.begin("tr");
+      CB_DISPATCH_NW(c->NW, (tr_kernel<NW_><<<warp_grid(n_slow), ST_WARPS * 32, 0, s>>>(P)));
+      c->lc.end("tr");
+      c->lc.n++;
     }
-    if (!dist) {
-      if (cur_n) {
-        c->lc.begin("tr_final");
-        tr_final_kernel<<<slot_grid(slots), 256, 0, s>>>(P, c->ckB.keys.p);
-        c->lc.end("tr_final");
-        c->lc.n++;
-      }
-    } else {
-      // the mirror of a kept record may live on another rank: kept records vote for their mirrors
+    CB_CUDA(cudaGetLastError());
+    if (dist) {
+      // every rank needs the summary byte of every list (each list has one owner; the others hold 0)
       timer_start(c, "tr_votes");
+      ex_allreduce_max_u8(c, lsum.p, nl);
+      // mirrors that live in an inconsistent list: its owner votes for the records it kept
       P.req = req.p;
       P.n_req = nwork.p + 5;
       P.req_cap = (u32)(slots > 0xffffffffu ? 0xffffffffu : slots);
       CB_CUDA(cudaMemsetAsync(nwork.p + 5, 0, 4, s));
-      if (cur_n) {
-        tr_votes_kernel<<<slot_grid(slots), 256, 0, s>>>(P);
+      if (n_slow) {
+        tr_votes_kernel<<<warp_grid(n_slow), ST_WARPS * 32, 0, s>>>(P);
         c->lc.n++;
       }
       u32 nv = read_u32s(c, nwork.p + 5);
-      DevBuf<char> got;
-      size_t n_got = route_keys(c, req.p, nv, got);
-      if (n_got) {
-        apply_votes_kernel<<<div_up(n_got, 256), 256, 0, s>>>(P, (const u64*)got.p, n_got);
-        c->lc.n++;
-      }
-      if (cur_n) {
-        tr_final_voted_kernel<<<slot_grid(slots), 256, 0, s>>>(P, c->ckB.keys.p);
-        c->lc.n++;
+      if (nv > P.req_cap) throw Error(CB_E_CAPACITY, "vote buffer overflow");
+      u64 any_votes = nv;
+      ex_allreduce(c, &any_votes, 1, 0);
+      if (any_votes) {
+        DevBuf<char> got;
+        size_t n_got = route_keys(c, req.p, nv, got);
+        if (n_got) {
+          apply_votes_kernel<<<div_up(n_got, 256), 256, 0, s>>>(P, (const u64*)got.p, n_got);
+          c->lc.n++;
+        }
       }
       timer_stop(c, "tr_votes");
+    }
+    if (cur_n) {
+      c->lc.begin("tr_final");
+      if (dist) tr_final_kernel<true><<<slot_grid(slots), 256, 0, s>>>(P, c->ckB.keys.p);
+      else tr_final_kernel<false><<<slot_grid(slots), 256, 0, s>>>(P, c->ckB.keys.p);
+      c->lc.end("tr_final");
+      c->lc.n++;
     }
     CB_CUDA(cudaGetLastError());
   }

@@ -23,11 +23,12 @@ CB_COUNTS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.
 CB_A2A = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64))
 CB_AGV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64))
 CB_ARED = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_int32, C.c_int32)
+CB_AMAX8 = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
 
 
 class cb_exchange(C.Structure):
     _fields_ = [("user", C.c_void_p), ("exchange_counts", CB_COUNTS), ("alltoallv", CB_A2A),
-                ("allgatherv", CB_AGV), ("allreduce_u64", CB_ARED)]
+                ("allgatherv", CB_AGV), ("allreduce_u64", CB_ARED), ("allreduce_max_u8_dev", CB_AMAX8)]
 
 
 class _DevMem:
@@ -125,6 +126,17 @@ class TorchExchange:
         dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX, group=self.group)
         return t.cpu()
 
+    def allreduce_max_u8(self, t):
+        """in-place element-wise max of a uint8 tensor (device tensor on nccl, any tensor on gloo)."""
+        if self.on_device:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            return t
+        h = t.cpu() if t.is_cuda else t
+        dist.all_reduce(h, op=dist.ReduceOp.MAX, group=self.group)
+        if h is not t:
+            t.copy_(h)
+        return t
+
     def _global(self, r):
         return dist.get_global_rank(self.group, r) if self.group is not None else r
 
@@ -166,8 +178,11 @@ class TorchExchange:
             for i in range(n):
                 vals[i] = int(out[i])
 
+        def amax8(user, dev, n):
+            self.allreduce_max_u8(_dev_tensor(dev, int(n), self.device))
+
         self._cbs = (CB_COUNTS(self._guard(counts)), CB_A2A(self._guard(a2a)), CB_AGV(self._guard(agv)),
-                     CB_ARED(self._guard(ared)))
+                     CB_ARED(self._guard(ared)), CB_AMAX8(self._guard(amax8)))
         self._struct = cb_exchange(None, *self._cbs)
         return self._struct
 

@@ -170,6 +170,8 @@ typedef struct cb_exchange {
                     const uint64_t* recv_bytes);
   /* in-place all-reduce of n host values; op 0 = sum, 1 = max */
   int (*allreduce_u64)(void* user, uint64_t* vals, int32_t n, int32_t op);
+  /* in-place element-wise MAX over the ranks of a DEVICE array of n bytes */
+  int (*allreduce_max_u8_dev)(void* user, void* dev, uint64_t n);
 } cb_exchange;
 
 /* Must be called before cb_preprocess when cfg.world > 1.  With an exchange set, counters are

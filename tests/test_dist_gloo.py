@@ -33,9 +33,15 @@ def _exchange_worker(rank, world):
     # allreduce sum / max
     assert ex.allreduce([rank + 1, 7], 0).tolist() == [sum(range(1, world + 1)), 7 * world]
     assert ex.allreduce([rank + 1, 7 - rank], 1).tolist() == [world, 7]
+    # element-wise max of a byte array (list summaries of the TransitiveReduction final pass)
+    b = torch.zeros(8, dtype=torch.uint8)
+    b[rank] = 10 + rank
+    b[7] = 3 * rank
+    ex.allreduce_max_u8(b)
+    assert b.tolist() == [10 + r if r < world else 0 for r in range(7)] + [3 * (world - 1)]
     # the C callback structure can be built without a device
     st = ex.as_struct()
-    assert st.exchange_counts and st.alltoallv and st.allgatherv and st.allreduce_u64
+    assert st.exchange_counts and st.alltoallv and st.allgatherv and st.allreduce_u64 and st.allreduce_max_u8_dev
 
 
 def test_torch_exchange_world2_gloo(tmp_path):
