@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const u64* __restrict__
 constexpr int RS_MAXPASS = 8;
 constexpr u32 ST_FLAG_LOCAL = 1u << 30, ST_FLAG_INCL = 2u << 30, ST_VALUE = (1u << 30) - 1;
 constexpr u32 SPIN_LIMIT = 1u << 22;
+constexpr int RS_LB = 8;  // look-back loads in flight
 
 __global__ void __launch_bounds__(256) rs_hist_all_kernel(const u64* __restrict__ kin, size_t n, int begin_bit,
                                                           int end_bit, u32* __restrict__ ghist) {
@@ -400,17 +401,31 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u64* __re
   if (tid < 256) {
     u32 excl = 0;
     if (tile != 0) {
+      // decoupled look-back, RS_LB predecessors per round trip: the status words of tiles
+      // p, p-1, ..., p-RS_LB+1 are loaded together (independent L2 loads in flight) and consumed in
+      // order up to the first one that is not published yet.  (One dependent load per predecessor
+      // made the walk -- ~30 tiles deep with 296 tiles in flight -- the longest phase of the kernel.)
       long long p = (long long)tile - 1;
       u32 spins = 0;
-      while (p >= 0) {
-        u32 v = status[(size_t)p * 256 + tid];
-        if ((v >> 30) == 0) {
-          if (++spins > SPIN_LIMIT) { *err = 1; break; }  // never hang the GPU on a bug
-          continue;
+      bool done = false;
+      while (!done) {
+        u32 v[RS_LB];
+#pragma unroll
+        for (int i = 0; i < RS_LB; i++) {
+          const long long q = p - i;
+          v[i] = q >= 0 ? status[(size_t)q * 256 + tid] : (2u << 30);  // before tile 0: inclusive 0
         }
-        excl += v & ST_VALUE;
-        if ((v >> 30) == 2) break;
-        p--;
+        int consumed = 0;
+#pragma unroll
+        for (int i = 0; i < RS_LB; i++) {
+          if (!done && consumed == i && (v[i] >> 30) != 0) {
+            excl += v[i] & ST_VALUE;
+            consumed = i + 1;
+            done = (v[i] >> 30) == 2;
+          }
+        }
+        p -= consumed;
+        if (!done && consumed == 0 && ++spins > SPIN_LIMIT) { *err = 1; break; }  // never hang the GPU on a bug
       }
       status[(size_t)tile * 256 + tid] = (excl + cnt_pub) | ST_FLAG_INCL;
     }

@@ -13,6 +13,8 @@
 // group of b^y[0:K]), so the maximal-overlap filter of VerifyOverlap (:275-283) can be applied
 // inside the group and candidates never have to be materialised: the join emits verified edges
 // and their GenReverseEdge mirrors directly (SURVEY.md 8a').
+#include <cstdlib>
+
 #include "ctx.cuh"
 
 namespace cb {
@@ -29,12 +31,14 @@ __device__ __forceinline__ void load_read_b(const u64* __restrict__ reads, u32 i
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: warp-cooperative canonical k-mer key generator.  One warp per node, one lane per window:
-// the packed read is loaded once (broadcast), every lane funnel-shifts its window out of the
-// words, reverse-complements it in registers, and the warp stores 32 consecutive 8-byte keys
-// and 4-byte payloads (fully coalesced).  Slot of (node, window i) is node*W + i; windows that
-// emit nothing (MatchPrefix.java:163,170: canonical all-A interior windows) get the all-ones key
-// and sort to the end.
+// K3: warp-cooperative canonical k-mer key generator.  One thread per (node, window) slot in
+// slot order, so a warp covers 32 consecutive windows -- of one read or of several short ones
+// (36 bp, k=21: two reads per warp; a lane-per-window-of-one-read layout left half the lanes
+// idle).  The lanes of one read load the same 16..64-byte packed row (one broadcast request),
+// funnel-shift their window out of the words, reverse-complement it in registers, and the warp
+// stores 32 consecutive 8-byte keys and 4-byte payloads (fully coalesced).  Slot of (node,
+// window i) is node*W + i; windows that emit nothing (MatchPrefix.java:163,170: canonical all-A
+// interior windows) get the all-ones key and sort to the end.
 //   payload meta = node << (pb+1) | i << 1 | dir      dir 0: window < rc(window) ('f'), 1: 'r'
 //   key = canonical k-mer | (meta >> 32) << 2K        (bits above 2K are not sorted on)
 // ---------------------------------------------------------------------------------------------
@@ -44,30 +48,33 @@ __global__ void __launch_bounds__(256) keygen_kernel(const u64* __restrict__ nod
                                                      int L, int K, int W, int pb, u64* __restrict__ keys,
                                                      u32* __restrict__ vals, ull* __restrict__ dcount) {
   const int lane = threadIdx.x & 31;
-  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  const u32 total = n_nodes * (u32)W;  // < 2^32 (checked by the host)
+  const u32 stride = gridDim.x * blockDim.x;
   u32 invalid = 0;
   // nodes [node_lo, node_lo + n_nodes) are this rank's (all of them on a single GPU)
-  for (u32 loc = warp_global; loc < n_nodes; loc += nwarps) {
-    const u32 node = node_lo + loc;
-    u64 r[NW];
-    load_read_b<NW>(node_seq, node, r);
-    for (int w0 = 0; w0 < W; w0 += 32) {
-      int i = w0 + lane;
-      if (i < W) {
-        u64 km = extract_kmer<NW>(r, i, K);
-        u64 rk = revcomp_kmer(km, K);
-        bool fwd = km < rk;
-        u64 canon = fwd ? km : rk;
-        bool interior = (i >= 1) && (i <= L - K - 1);
-        bool emit = (km != rk) && !(interior && canon == 0);
-        if (canon == 0 && i < L - K) atomicAdd(&dcount[DC_POLYA_WEIGHT], (ull)node_cov[node]);
-        u64 meta = ((u64)node << (pb + 1)) | ((u64)i << 1) | (fwd ? 0ull : 1ull);
-        size_t slot = (size_t)loc * W + i;
-        keys[slot] = emit ? (canon | ((meta >> 32) << (2 * K))) : ~0ull;
-        vals[slot] = emit ? (u32)meta : ~0u;
-        if (!emit) invalid++;
-      }
+  for (u32 slot0 = blockIdx.x * blockDim.x; slot0 < total; slot0 += stride) {
+    const u32 slot = slot0 + threadIdx.x;
+    if (slot < total) {
+      const u32 loc = slot / (u32)W;
+      const int i = (int)(slot - loc * (u32)W);
+      const u32 node = node_lo + loc;
+      // the two words the window straddles, straight from the row (L1-resident: the lanes of a
+      // read share it; indexing a register copy of the row dynamically would put it in local memory)
+      const u64* row = node_seq + (size_t)node * NW;
+      const int w = i >> 5, off = (i & 31) * 2;
+      const u64 hi = __ldg(row + w), lo = (w + 1 < NW) ? __ldg(row + w + 1) : 0ull;
+      const u64 top = off ? ((hi << off) | (lo >> (64 - off))) : hi;
+      u64 km = top >> (64 - 2 * K);
+      u64 rk = revcomp_kmer(km, K);
+      bool fwd = km < rk;
+      u64 canon = fwd ? km : rk;
+      bool interior = (i >= 1) && (i <= L - K - 1);
+      bool emit = (km != rk) && !(interior && canon == 0);
+      if (canon == 0 && i < L - K) atomicAdd(&dcount[DC_POLYA_WEIGHT], (ull)node_cov[node]);
+      u64 meta = ((u64)node << (pb + 1)) | ((u64)i << 1) | (fwd ? 0ull : 1ull);
+      keys[slot] = emit ? (canon | ((meta >> 32) << (2 * K))) : ~0ull;
+      vals[slot] = emit ? (u32)meta : ~0u;
+      if (!emit) invalid++;
     }
   }
 #pragma unroll
@@ -208,31 +215,84 @@ __global__ void __launch_bounds__(JN_WARPS * 32) group_walk_kernel(JoinParams P)
   })
 }
 
-constexpr int JN_XB = 1024;  // block-staged side-buffer records
+constexpr int JN_XW = 64;  // side-buffer records staged per warp (flushed once 32 are waiting)
 
 template <int NW>
-__global__ void __launch_bounds__(256) join_verify_kernel(JoinParams P) {
-  __shared__ u64 s_x[JN_XB];
-  __shared__ u32 s_nx;
-  __shared__ ull s_base;
+__device__ __forceinline__ void unpack_row(const uint4 (&q)[NW / 2], u64 (&r)[NW]) {
+#pragma unroll
+  for (int i = 0; i < NW / 2; i++) {
+    r[2 * i] = (u64)q[i].x | ((u64)q[i].y << 32);
+    r[2 * i + 1] = (u64)q[i].z | ((u64)q[i].w << 32);
+  }
+}
+template <int NW>
+__device__ __forceinline__ void load_row(const u64* __restrict__ reads, u32 idx, uint4 (&q)[NW / 2]) {
+  const uint4* row = reinterpret_cast<const uint4*>(reads + (size_t)idx * NW);
+#pragma unroll
+  for (int i = 0; i < NW / 2; i++) q[i] = __ldg(row + i);
+}
+
+// The kernel is bound by load latency, not bandwidth (ncu: one dependent chain seg_head -> tuple
+// -> read a -> ne_list -> read b -> off1 -> store, six DRAM round trips deep), so everything a
+// thread will need is requested as early as its address is known: level 1 the tuple and its
+// group head, level 2 the read, both neighbour tuples and the first two node entries of the
+// group (most groups have at most two: one window-0 and one last-window tuple), level 3 the rows
+// and slot offsets of those entries.  Side-buffer records are staged per WARP in shared memory
+// and flushed warp-synchronously, so the tuple loop has no block barrier.
+template <int NW, int MINB>
+__global__ void __launch_bounds__(256, MINB) join_verify_kernel(JoinParams P) {
+  __shared__ u64 s_x[8][JN_XW];
   const int L = P.L, K = P.K;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 lt_mask = (1u << lane) - 1;
   const u32 posmask = (1u << P.pb) - 1;
   u32 n_verified = 0;
-  if (threadIdx.x == 0) s_nx = 0;
-  __syncthreads();
+  u32 wn = 0;  // records staged by this warp (warp-uniform)
   const u32 stride = gridDim.x * blockDim.x;
   const u32 rounds = (P.T + stride - 1) / stride;
   for (u32 rnd = 0; rnd < rounds; rnd++) {
     const u32 j = rnd * stride + blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < P.T) {
+    const bool active = j < P.T;
+    u64 xrec[4];  // side-buffer records of this tuple in this round (beyond 4: straight to global)
+    int nx = 0;
+    if (active) {
+      // ---- level 1 ----
       const u32 s = P.seg_head[j];
-      const u64 m = tuple_meta(P, j);
+      const u64 kj = P.keys[j];
+      const u32 vj = P.vals[j];
+      const u64 m = ((kj >> (2 * K)) << 32) | (u64)vj;
       const u32 a = (u32)(m >> (P.pb + 1));
+      // ---- level 2: everything addressed by (j, s, a) ----
+      uint4 qa[NW / 2];
+      load_row<NW>(P.node_seq, a, qa);
+      const bool has_l = j > s, has_r = j + 1 < P.T;
+      const u64 k_l = has_l ? P.keys[j - 1] : 0ull;
+      const u32 v_l = has_l ? P.vals[j - 1] : 0u;
+      const u64 k_r = has_r ? P.keys[j + 1] : 0ull;
+      const u32 v_r = has_r ? P.vals[j + 1] : 0u;
+      const u32 sh_r = has_r ? P.seg_head[j + 1] : 0xffffffffu;
+      u32 ne[2];
+      ne[0] = P.ne_list[s];
+      const u32 sh_1 = s + 1 < P.T ? P.seg_head[s + 1] : 0xffffffffu;
+      ne[1] = s + 1 < P.T ? P.ne_list[s + 1] : 0xffffffffu;
+      if (ne[0] == 0xffffffffu || sh_1 != s) ne[1] = 0xffffffffu;
+      // ---- level 3: rows and slot offsets of the first two node entries ----
+      uint4 qb0[NW / 2], qb1[NW / 2];
+      u32 offv0 = 0, offv1 = 0;
+      if (ne[0] != 0xffffffffu) {
+        load_row<NW>(P.node_seq, (ne[0] & 0x7fffffffu) >> 1, qb0);
+        offv0 = P.off1[ne[0] & 0x7fffffffu];
+      }
+      if (ne[1] != 0xffffffffu) {
+        load_row<NW>(P.node_seq, (ne[1] & 0x7fffffffu) >> 1, qb1);
+        offv1 = P.off1[ne[1] & 0x7fffffffu];
+      }
+
       const int pos = (int)((m >> 1) & posmask);
       const int d = (int)(m & 1);
-      const u64 kseg = P.keys[j] & P.kmask;
+      const u64 kseg = kj & P.kmask;
       u64 R[NW], Rc[NW];
-      load_read_b<NW>(P.node_seq, a, R);
+      unpack_row<NW>(qa, R);
       revcomp_read<NW>(R, Rc, L);
       // Everything that depends on the tuple only, for both lists it feeds (sel 0: list of the
       // canonical key c, sel 1: list of rc(c)): orientation x, overlap ov, the oriented read
@@ -255,30 +315,26 @@ __global__ void __launch_bounds__(256) join_verify_kernel(JoinParams P) {
       const bool prop1 = x1 ? (ov1 > K ? pr_gt : pr_eq) : (ov1 > K ? pf_gt : pf_eq);
       // does a neighbouring tuple of the group belong to the same read?  (tuples of one read are
       // contiguous: the sort is stable and keygen emits in (node, window) order)
-      const bool same_l = j > s && (u32)(tuple_meta(P, j - 1) >> (P.pb + 1)) == a;
-      const bool same_r = j + 1 < P.T && P.seg_head[j + 1] == s && (u32)(tuple_meta(P, j + 1) >> (P.pb + 1)) == a;
+      const u64 m_l = ((k_l >> (2 * K)) << 32) | (u64)v_l, m_r = ((k_r >> (2 * K)) << 32) | (u64)v_r;
+      const bool same_l = has_l && (u32)(m_l >> (P.pb + 1)) == a;
+      const bool same_r = has_r && sh_r == s && (u32)(m_r >> (P.pb + 1)) == a;
       const bool lone = !same_l && !same_r && kseg != 0 && P.low_kmer == 1;
-      for (u32 t = 0;; t++) {
-        const u32 idx = s + t;
-        if (idx >= P.T || (t > 0 && P.seg_head[idx] != s)) break;
-        const u32 v = P.ne_list[idx];
-        if (v == 0xffffffffu) break;
+      // one node entry of the group against this tuple (inlined for the two prefetched entries
+      // and for the rare further ones)
+      auto process = [&](const u32 v, const u32 off_l, u64 (&B)[NW]) {
         const u32 lid = v & 0x7fffffffu;
         const u32 b = lid >> 1;
         const int y = (int)((lid & 1u) ^ 1u);          // list (b, flip y) belongs to node entry (b, y)
         const int dn = (int)(v >> 31);
         const int sel = y == 0 ? dn : (dn ^ 1);        // MatchPrefix.java:275-296 (y == 0: window-0 entry)
         const int x = sel ? x1 : x0, ov = sel ? ov1 : ov0;
-        u64 A[NW], B[NW];
-        {
+        if (y) {
           u64 r[NW];
-          load_read_b<NW>(P.node_seq, b, r);
-          if (y) revcomp_read<NW>(r, B, L);
-          else {
 #pragma unroll
-            for (int w = 0; w < NW; w++) B[w] = r[w];
-          }
+          for (int w = 0; w < NW; w++) r[w] = B[w];
+          revcomp_read<NW>(r, B, L);
         }
+        u64 A[NW];
 #pragma unroll
         for (int w = 0; w < NW; w++) A[w] = sel ? A1[w] : A0[w];
         // VerifyOverlap.java:295-309: a^x[L-ov:] == b^y[0:ov]; self candidates skipped at
@@ -308,7 +364,7 @@ __global__ void __launch_bounds__(256) join_verify_kernel(JoinParams P) {
           }
         }
         if (ok) {
-          P.slots[P.off1[lid] + (j - s)] = P.lay.encode(b, (u32)(y ^ 1), (u32)ov, (u32)(x ^ 1), a);  // GenReverseEdge
+          P.slots[off_l + (j - s)] = P.lay.encode(b, (u32)(y ^ 1), (u32)ov, (u32)(x ^ 1), a);  // GenReverseEdge
           n_verified++;
           // Is the mirror candidate (b, flip y, ov) -> (a, flip x) certain to be proposed and
           // kept at a's own node entry?  Then that entry writes this edge into list (a, x) and it
@@ -317,32 +373,66 @@ __global__ void __launch_bounds__(256) join_verify_kernel(JoinParams P) {
           const bool certain = lone && (sel ? prop1 : prop0);
           if (!certain) {
             const u64 rec = P.lay.encode(a, (u32)x, (u32)ov, (u32)y, b);
-            const u32 pos_x = atomicAdd(&s_nx, 1u);
-            if (pos_x < JN_XB) s_x[pos_x] = rec;
-            else {  // staging full: straight to the side buffer
+            if (nx < 4) {
+#pragma unroll
+              for (int q = 0; q < 4; q++)
+                if (q == nx) xrec[q] = rec;
+              nx++;
+            } else {  // more than four per tuple: straight to the side buffer
               ull gp = atomicAdd(&P.dcount[DC_EDGES_RAW], 1ull);
               if (gp < P.xcap) P.xbuf[gp] = rec;
             }
           }
         }
+      };
+      if (ne[0] != 0xffffffffu) {
+        u64 B[NW];
+        unpack_row<NW>(qb0, B);
+        process(ne[0], offv0, B);
+        if (ne[1] != 0xffffffffu) {
+          unpack_row<NW>(qb1, B);
+          process(ne[1], offv1, B);
+          for (u32 t = 2;; t++) {
+            const u32 idx = s + t;
+            if (idx >= P.T || P.seg_head[idx] != s) break;
+            const u32 v = P.ne_list[idx];
+            if (v == 0xffffffffu) break;
+            load_read_b<NW>(P.node_seq, (v & 0x7fffffffu) >> 1, B);
+            process(v, P.off1[v & 0x7fffffffu], B);
+          }
+        }
       }
     }
-    // flush the staged side-buffer records once they fill half of the staging area
-    __syncthreads();
-    const u32 nx = s_nx < (u32)JN_XB ? s_nx : (u32)JN_XB;
-    if (nx >= JN_XB / 2 || (rnd + 1 == rounds && nx > 0)) {
-      if (threadIdx.x == 0) s_base = atomicAdd(&P.dcount[DC_EDGES_RAW], (ull)nx);
-      __syncthreads();
-      for (u32 t = threadIdx.x; t < nx; t += blockDim.x)
-        if (s_base + t < P.xcap) P.xbuf[s_base + t] = s_x[t];
-      __syncthreads();
-      if (threadIdx.x == 0) s_nx = 0;
+    // ---- stage this round's side-buffer records per warp; flush once 32 are waiting ----
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const bool have = q < nx;
+      const u32 bal = __ballot_sync(0xffffffffu, have);
+      if (bal == 0) break;  // warp-uniform
+      if (have) s_x[warp][wn + __popc(bal & lt_mask)] = xrec[q];
+      wn += __popc(bal);
+      __syncwarp();
+      if (wn >= 32) {
+        ull base = 0;
+        if (lane == 0) base = atomicAdd(&P.dcount[DC_EDGES_RAW], (ull)wn);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (u32 t = lane; t < wn; t += 32)
+          if (base + t < P.xcap) P.xbuf[base + t] = s_x[warp][t];
+        wn = 0;
+        __syncwarp();
+      }
     }
-    __syncthreads();
+  }
+  if (wn) {
+    ull base = 0;
+    if (lane == 0) base = atomicAdd(&P.dcount[DC_EDGES_RAW], (ull)wn);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (u32 t = lane; t < wn; t += 32)
+      if (base + t < P.xcap) P.xbuf[base + t] = s_x[warp][t];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_verified += __shfl_xor_sync(0xffffffffu, n_verified, o);
-  if ((threadIdx.x & 31) == 0 && n_verified) {
+  if (lane == 0 && n_verified) {
     atomicAdd(&P.dcount[DC_CAND_VERIFIED], (ull)n_verified);
     atomicAdd(&P.dcount[DC_EDGES_M], (ull)n_verified);
   }
@@ -492,7 +582,7 @@ void stage_build_overlap(cb_ctx* c) {
   for (int i = 0; i < 2; i++) { keys[i].alloc(Tmax ? Tmax : 1, s); vals[i].alloc(Tmax ? Tmax : 1, s); }
   CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_TUPLES_INVALID, 0, (DC_COUNT - DC_TUPLES_INVALID) * sizeof(u64), s));
   if (n_own) {
-    int blocks = div_up((size_t)n_own * 32, 256);
+    int blocks = div_up(Tmax, 256);
     int cap = kNumSMs * 8 * 4;
     if (blocks > cap) blocks = cap;
     c->lc.begin("keygen");
@@ -618,7 +708,12 @@ void stage_build_overlap(cb_ctx* c) {
     CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGES_RAW, 0, (DC_UPKMER_LISTS - DC_EDGES_RAW) * sizeof(u64), s));
     CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_MAX_LIST, 0, sizeof(u64), s));
     c->lc.begin("join_verify");
-    CB_DISPATCH_NW(c->NW, (join_verify_kernel<NW_><<<jgrid, 256, 0, s>>>(P)));
+    {
+      static const int minb = getenv("CB_JOIN_MINB") ? atoi(getenv("CB_JOIN_MINB")) : 4;
+      if (c->NW == 2 && minb == 4) join_verify_kernel<2, 4><<<jgrid, 256, 0, s>>>(P);
+      else if (c->NW == 2 && minb == 3) join_verify_kernel<2, 3><<<jgrid, 256, 0, s>>>(P);
+      else CB_DISPATCH_NW(c->NW, (join_verify_kernel<NW_, 2><<<jgrid, 256, 0, s>>>(P)));
+    }
     c->lc.end("join_verify");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
