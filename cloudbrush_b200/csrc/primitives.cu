@@ -283,14 +283,48 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const u64* __restrict__
 constexpr int RS_MAXPASS = 8;
 constexpr u32 ST_FLAG_LOCAL = 1u << 30, ST_FLAG_INCL = 2u << 30, ST_VALUE = (1u << 30) - 1;
 constexpr u32 SPIN_LIMIT = 1u << 22;
-constexpr int RS_LB = 8;  // look-back loads in flight
+constexpr int RS_LB = 8;  // look-back loads in flight (16 and 32 measured slower: registers, L2 traffic)
+
+// peers of this lane's digit within the warp.  MATCH.ANY's latency grows with the number of
+// distinct values among the lanes (ncu: on random 8-bit digits the instructions consuming its
+// result collect 23 % of the kernel's stall samples, on clustered digits 1 %); eight ballots, one
+// per digit bit, cost the same whatever the values are.  `ballot` is uniform over the grid: every
+// pass measures how many distinct digits of the NEXT pass a warp will see (its write-out order is
+// the next pass' input order) and the next pass picks the cheaper ranking from that.
+__device__ __forceinline__ u32 digit_peers(u32 d, bool ballot) {
+  if (!ballot) return __match_any_sync(0xffffffffu, d);
+  u32 peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 8; b++) {
+    const bool bit = (d >> b) & 1u;
+    const u32 bal = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
+}
+constexpr u32 RS_BALLOT_ABOVE = 12;  // distinct digits per warp above which the ballots win
+
+// one sample of the digit diversity a warp sees: adds (#distinct digits, 1) to ent[0], ent[1]
+__device__ __forceinline__ void sample_diversity(u32 d, int lane, u32* ent) {
+  const u32 peers = __match_any_sync(0xffffffffu, d);
+  const u32 leaders = __ballot_sync(0xffffffffu, lane == __ffs(peers) - 1);
+  if (lane == 0) {
+    atomicAdd(&ent[0], (u32)__popc(leaders));
+    atomicAdd(&ent[1], 1u);
+  }
+}
 
 __global__ void __launch_bounds__(256) rs_hist_all_kernel(const u64* __restrict__ kin, size_t n, int begin_bit,
-                                                          int end_bit, u32* __restrict__ ghist) {
+                                                          int end_bit, u32* __restrict__ ghist, u32* __restrict__ ent0) {
   __shared__ u32 h[RS_MAXPASS][256];
   for (int t = threadIdx.x; t < RS_MAXPASS * 256; t += blockDim.x) (&h[0][0])[t] = 0;
   __syncthreads();
   const int npass = (end_bit - begin_bit + 7) / 8;
+  if (threadIdx.x < 32 && (size_t)blockIdx.x * blockDim.x + 32 <= n) {  // first warp: digit diversity of pass 0
+    const int nb0 = end_bit - begin_bit < 8 ? end_bit - begin_bit : 8;
+    sample_diversity((u32)(kin[(size_t)blockIdx.x * blockDim.x + threadIdx.x] >> begin_bit) & ((1u << nb0) - 1),
+                     (int)threadIdx.x, ent0);
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const u64 k = kin[i];
 #pragma unroll
@@ -320,91 +354,156 @@ __global__ void __launch_bounds__(256) rs_scan_hist_kernel(u32* __restrict__ ghi
   }
 }
 
-template <bool HAS_VALS>
-__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u64* __restrict__ kin, u64* __restrict__ kout,
-                                                                 const u32* __restrict__ vin, u32* __restrict__ vout,
-                                                                 volatile u32* status, u32* tile_ctr,
-                                                                 const u32* __restrict__ gbase, u32* err, size_t n,
-                                                                 int shift, u32 mask) {
-  __shared__ unsigned short warp_hist[RS_WARPS][256];
-  __shared__ u32 digit_base[256];
-  __shared__ u32 sub_start[256];
+// status words are read and written with gpu-scope relaxed accesses (flag and value share the
+// word, so no ordering with other data is needed); `volatile` compiles to system-scope accesses
+__device__ __forceinline__ u32 ld_status(const volatile u32* p) {
+  u32 v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(volatile u32* p, u32 v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// -DCB_OS_TIMING: clock64 phase breakdown of the onesweep kernel (thread 0 of every CTA), read
+// with cb_debug_os_prof (tools/os_timing.py).  Not part of the product build.
+#ifdef CB_OS_TIMING
+__device__ unsigned long long g_os_prof[16];
+#define OS_T(i) { if (tid == 0) { long long now_ = clock64(); atomicAdd(&g_os_prof[i], (unsigned long long)(now_ - t_prev_)); t_prev_ = now_; } }
+extern "C" void cb_debug_os_prof(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_os_prof, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_os_prof, z, sizeof(z)); }
+}
+#else
+#define OS_T(i)
+#endif
+
+template <bool HAS_VALS, int S>
+constexpr size_t os_smem_bytes() {
+  return (size_t)S * RS_SUB * (HAS_VALS ? 12 : 8) + RS_WARPS * 256 * 2 + 3 * S * 256 * 4;
+}
+
+// One logical tile = S sub-tiles of RS_SUB keys processed back to back by one CTA and staged in
+// shared memory side by side; the digit counts of the sub-tiles are published together and ONE
+// look-back serves them all.  (clock64 phase timing of the S = 1 shape on 69 M pairs: 37 % of a
+// tile's 22.9 k cycles were the look-back -- 4.5 dependent round trips of ~1900 cycles each, the
+// status loads queue behind the SM's bulk traffic -- over a window of 31 predecessor tiles.  With
+// S = 2 the window halves, because tiles start half as often, and its cost is shared by twice the
+// keys.)  Payloads are staged in their own buffer and leave in the same loop as the keys.
+template <bool HAS_VALS, int S>
+__global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64* __restrict__ kin, u64* __restrict__ kout,
+                                                                    const u32* __restrict__ vin, u32* __restrict__ vout,
+                                                                    u32* status, u32* tile_ctr,
+                                                                    const u32* __restrict__ gbase, u32* err, u32 n,
+                                                                    int shift, u32 mask, const u32* __restrict__ ent_in,
+                                                                    u32* __restrict__ ent_out, int next_shift,
+                                                                    u32 next_mask, int force_rank) {
+  extern __shared__ __align__(16) unsigned char os_smem[];
+  u64* stage = reinterpret_cast<u64*>(os_smem);                                       // [S][RS_SUB]
+  u32* vstage = reinterpret_cast<u32*>(os_smem + (size_t)S * RS_SUB * 8);             // [S][RS_SUB] (pairs only)
+  unsigned short(*warp_hist)[256] =
+      reinterpret_cast<unsigned short(*)[256]>(os_smem + (size_t)S * RS_SUB * (HAS_VALS ? 12 : 8));
+  u32* cnt = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(warp_hist) + RS_WARPS * 256 * 2);  // [S][256]
+  u32* sub_start = cnt + S * 256;                                                      // [S][256]
+  u32* digit_base = sub_start + S * 256;                                               // [S][256]
   __shared__ u32 scan_tmp[RS_WARPS + 1];
-  __shared__ u64 stage[RS_SUB];
   __shared__ u32 s_tile;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt_mask = (1u << lane) - 1;
+#ifdef CB_OS_TIMING
+  long long t_prev_ = clock64();
+#endif
   if (tid == 0) s_tile = atomicAdd(tile_ctr, 1u);
-  for (int t = tid; t < RS_WARPS * 256; t += RS_THREADS) (&warp_hist[0][0])[t] = 0;
   __syncthreads();
   const u32 tile = s_tile;
-  const size_t base = (size_t)tile * RS_SUB;
-  if (base >= n) return;  // uniform
-  const int nvalid = (int)min((size_t)RS_SUB, n - base);
+  const u32 base0 = tile * (u32)(S * RS_SUB);
+  if (base0 >= n) return;  // uniform
+  // grid-uniform choice of the ranking primitive from the diversity the previous pass measured
+  const bool ballot = force_rank ? force_rank == 2 : ent_in[0] > RS_BALLOT_ABOVE * ent_in[1];
+  const int e0 = warp * (RS_ITEMS * 32) + lane;  // warp-striped: element order is (warp, item, lane) == ascending index
+  u32 cnt_pub = 0;
 
-  u64 key[RS_ITEMS];
-  u32 pos[RS_ITEMS];
-#pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++) {
-    int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
-    key[i] = (e < nvalid) ? kin[base + e] : ~0ull;
-  }
-#pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++) {
-    int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
-    u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;  // padding ranks last
-    u32 peers = __match_any_sync(0xffffffffu, d);
-    u32 prev = warp_hist[warp][d];
-    __syncwarp();
-    if (lane == __ffs(peers) - 1) warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
-    __syncwarp();
-    pos[i] = prev + __popc(peers & lt_mask);
-  }
-  __syncthreads();
-  u32 run = 0, cnt_pub = 0;
-  if (tid < 256) {
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; w++) {
-      u32 c = warp_hist[w][tid];
-      warp_hist[w][tid] = (unsigned short)run;
-      run += c;
-    }
-    // publish this tile's digit counts right away (padding was ranked as digit 255 in the last
-    // tile only and must not be published); the look-back itself waits until the keys are staged
-    // in shared memory, which gives the tiles before this one time to publish
-    cnt_pub = run;
-    if (tid == 255) cnt_pub -= (u32)(RS_SUB - nvalid);
-    status[(size_t)tile * 256 + tid] = cnt_pub | (tile == 0 ? ST_FLAG_INCL : ST_FLAG_LOCAL);
-  }
-  u32 total;
-  u32 dstart = block_excl_scan(run, scan_tmp, total);  // threads >= 256 contribute 0
-  if (tid < 256) sub_start[tid] = dstart;
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++) {
-    int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
-    u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;
-    pos[i] += sub_start[d] + warp_hist[warp][d];
-    stage[pos[i]] = key[i];
-  }
-  // the key registers are dead now: issue the payload loads so that their latency overlaps the
-  // look-back and the key write-out
-  u32 val[RS_ITEMS];
-  if (HAS_VALS) {
+#pragma unroll 1
+  for (int sub = 0; sub < S; sub++) {
+    const u32 base = base0 + (u32)sub * RS_SUB;
+    const int nvalid = base < n ? (int)min((u32)RS_SUB, n - base) : 0;
+    for (int t = tid; t < RS_WARPS * 256 / 2; t += RS_THREADS) reinterpret_cast<u32*>(&warp_hist[0][0])[t] = 0;
+    u64 key[RS_ITEMS];
+    u32 pos[RS_ITEMS];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
-      int e = warp * (RS_ITEMS * 32) + i * 32 + lane;
-      val[i] = (e < nvalid) ? vin[base + e] : 0u;
+      const int e = e0 + i * 32;
+      key[i] = (e < nvalid) ? kin[base + e] : ~0ull;
     }
+    __syncthreads();  // histograms are zero (and the previous sub-tile is done with them)
+    OS_T(0)  // tile id / zeroing / load issue
+#ifdef CB_OS_TIMING
+    if (tid == 0 && key[0] == 0x123456789abcdefull && key[7] == 1) atomicAdd(&g_os_prof[15], 1ull);  // wait for the loads
+    OS_T(1)
+#endif
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+      const int e = e0 + i * 32;
+      const u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;  // padding ranks last
+      const u32 peers = digit_peers(d, ballot);
+      const u32 prev = warp_hist[warp][d];
+      __syncwarp();
+      if (lane == __ffs(peers) - 1) warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
+      __syncwarp();
+      pos[i] = prev + __popc(peers & lt_mask);
+    }
+    OS_T(2)  // ranking
+    __syncthreads();
+    OS_T(3)  // barrier after ranking
+    u32 run = 0;
+    if (tid < 256) {
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; w++) {
+        const u32 c = warp_hist[w][tid];
+        warp_hist[w][tid] = (unsigned short)run;
+        run += c;
+      }
+      cnt[sub * 256 + tid] = run;
+      // padding was ranked as digit 255 (in the last logical tile only) and must not be published
+      cnt_pub += run - (tid == 255 ? (u32)(RS_SUB - nvalid) : 0u);
+      // publish the logical tile's digit counts as soon as the last sub-tile is counted; the
+      // look-back itself waits until that sub-tile is staged
+      if (sub == S - 1) st_status(&status[(size_t)tile * 256 + tid], cnt_pub | (tile == 0 ? ST_FLAG_INCL : ST_FLAG_LOCAL));
+    }
+    OS_T(4)  // per-digit scan over the warps + publish
+    u32 total;
+    const u32 dstart = block_excl_scan(run, scan_tmp, total);  // threads >= 256 contribute 0
+    if (tid < 256) sub_start[sub * 256 + tid] = dstart;
+    __syncthreads();
+    OS_T(5)  // block scan
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+      const int e = e0 + i * 32;
+      const u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;
+      pos[i] += sub_start[sub * 256 + d] + warp_hist[warp][d];
+      stage[sub * RS_SUB + pos[i]] = key[i];
+    }
+    if (HAS_VALS) {  // the key registers are dead now
+      u32 val[RS_ITEMS];
+#pragma unroll
+      for (int i = 0; i < RS_ITEMS; i++) {
+        const int e = e0 + i * 32;
+        val[i] = (e < nvalid) ? vin[base + e] : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < RS_ITEMS; i++) vstage[sub * RS_SUB + pos[i]] = val[i];
+    }
+    if (sub + 1 < S) __syncthreads();  // the next sub-tile zeroes the histograms this one's staging still reads
+    OS_T(6)  // staging keys + payloads
   }
   if (tid < 256) {
     u32 excl = 0;
     if (tile != 0) {
       // decoupled look-back, RS_LB predecessors per round trip: the status words of tiles
-      // p, p-1, ..., p-RS_LB+1 are loaded together (independent L2 loads in flight) and consumed in
-      // order up to the first one that is not published yet.  (One dependent load per predecessor
-      // made the walk -- ~30 tiles deep with 296 tiles in flight -- the longest phase of the kernel.)
+      // p, p-1, ..., p-RS_LB+1 are loaded together (independent loads in flight) and consumed in
+      // order up to the first one that is not published yet
       long long p = (long long)tile - 1;
       u32 spins = 0;
       bool done = false;
@@ -413,7 +512,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u64* __re
 #pragma unroll
         for (int i = 0; i < RS_LB; i++) {
           const long long q = p - i;
-          v[i] = q >= 0 ? status[(size_t)q * 256 + tid] : (2u << 30);  // before tile 0: inclusive 0
+          v[i] = q >= 0 ? ld_status(&status[(size_t)q * 256 + tid]) : (2u << 30);  // before tile 0: inclusive 0
         }
         int consumed = 0;
 #pragma unroll
@@ -425,55 +524,81 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u64* __re
           }
         }
         p -= consumed;
+#ifdef CB_OS_TIMING
+        if (tid == 0) { atomicAdd(&g_os_prof[11], 1ull); if (consumed == 0) atomicAdd(&g_os_prof[12], 1ull); atomicAdd(&g_os_prof[13], (unsigned long long)consumed); }
+#endif
         if (!done && consumed == 0 && ++spins > SPIN_LIMIT) { *err = 1; break; }  // never hang the GPU on a bug
       }
-      status[(size_t)tile * 256 + tid] = (excl + cnt_pub) | ST_FLAG_INCL;
+      st_status(&status[(size_t)tile * 256 + tid], (excl + cnt_pub) | ST_FLAG_INCL);
     }
-    digit_base[tid] = gbase[tid] + excl;
+    // global position of the element at sorted position p of sub-tile s: digit_base[s][d] + p
+    u32 before = gbase[tid] + excl;
+#pragma unroll
+    for (int sub = 0; sub < S; sub++) {
+      digit_base[sub * 256 + tid] = before - sub_start[sub * 256 + tid];
+      before += cnt[sub * 256 + tid];
+    }
   }
+  OS_T(7)  // look-back (digit 0)
   __syncthreads();
-  u32 gpos[RS_ITEMS];  // global position of sorted element j * RS_THREADS + tid (keys and payload alike)
-#pragma unroll
-  for (int j = 0; j < RS_ITEMS; j++) {
-    int p = j * RS_THREADS + tid;
-    gpos[j] = 0;
-    if (p < nvalid) {
-      u64 k = stage[p];
-      u32 d = (u32)((k >> shift) & mask);
-      gpos[j] = digit_base[d] + (p - sub_start[d]);
-      kout[gpos[j]] = k;
-    }
-  }
-  if (HAS_VALS) {
-    __syncthreads();
-    u32* vstage = reinterpret_cast<u32*>(stage);
-#pragma unroll
-    for (int i = 0; i < RS_ITEMS; i++) vstage[pos[i]] = val[i];
-    __syncthreads();
+  OS_T(8)  // barrier after look-back
+#pragma unroll 1
+  for (int sub = 0; sub < S; sub++) {
+    const u32 base = base0 + (u32)sub * RS_SUB;
+    const int nvalid = base < n ? (int)min((u32)RS_SUB, n - base) : 0;
+    if (ent_out && sub == 0 && warp == 0 && nvalid == RS_SUB)  // what the next pass will see in one warp
+      sample_diversity((u32)((stage[tid] >> next_shift) & next_mask), lane, ent_out);
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
-      int p = j * RS_THREADS + tid;
-      if (p < nvalid) vout[gpos[j]] = vstage[p];
+      const int p = j * RS_THREADS + tid;
+      if (p < nvalid) {
+        const u64 k = stage[sub * RS_SUB + p];
+        const u32 g = digit_base[sub * 256 + (u32)((k >> shift) & mask)] + (u32)p;
+        kout[g] = k;
+        if (HAS_VALS) vout[g] = vstage[sub * RS_SUB + p];
+      }
     }
   }
+  OS_T(9)  // write-out
+#ifdef CB_OS_TIMING
+  if (tid == 0) atomicAdd(&g_os_prof[14], 1ull);
+#endif
+}
+
+template <bool HAS_VALS, int S>
+static void launch_onesweep(u32 tiles, cudaStream_t s, const u64* kin, u64* kout, const u32* vin, u32* vout, u32* status,
+                            u32* ctl, const u32* gbase, u32 n, int bit, u32 mask, const u32* ent_in, u32* ent_out,
+                            int next_shift, u32 next_mask, int force_rank) {
+  constexpr size_t dyn = os_smem_bytes<HAS_VALS, S>();
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    CB_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<HAS_VALS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    configured = true;
+  }
+  rs_onesweep_kernel<HAS_VALS, S><<<tiles, RS_THREADS, dyn, s>>>(kin, kout, vin, vout, status, ctl, gbase, ctl + 1, n, bit,
+                                                                mask, ent_in, ent_out, next_shift, next_mask, force_rank);
 }
 
 static int radix_sort_onesweep(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int begin_bit,
                                int end_bit, cudaStream_t s, LaunchCounter& lc, const char* tag) {
+  static const int subs = getenv("CB_OS_SUB") ? atoi(getenv("CB_OS_SUB")) : 1;      // sub-tiles per CTA; 2 measured slower (3.64 vs 3.27 ms): 225 KB of shared memory per SM leave no L1 for loads in flight
+  static const int force_rank = getenv("CB_RANK") ? atoi(getenv("CB_RANK")) : 0;   // experiment: 1 match, 2 ballots
+  const int S = subs == 1 ? 1 : 2;
   const int npass = (end_bit - begin_bit + 7) / 8;
-  const u32 tiles = (u32)((n + RS_SUB - 1) / RS_SUB);
+  const u32 tiles = (u32)((n + (size_t)S * RS_SUB - 1) / ((size_t)S * RS_SUB));
   DevBuf<u32> ghist, status, ctl;
   ghist.alloc((size_t)npass * 256, s);
   status.alloc((size_t)tiles * 256, s);
-  ctl.alloc(2, s);  // [0] tile counter, [1] error flag
+  ctl.alloc(2 + 2 * (RS_MAXPASS + 1), s);  // [0] tile counter, [1] error flag, then (distinct, samples) per pass
+  u32* ent = ctl.p + 2;
   CB_CUDA(cudaMemsetAsync(ghist.p, 0, (size_t)npass * 256 * 4, s));
-  CB_CUDA(cudaMemsetAsync(ctl.p, 0, 8, s));
+  CB_CUDA(cudaMemsetAsync(ctl.p, 0, (2 + 2 * (RS_MAXPASS + 1)) * 4, s));
   const std::string nm_up_s = std::string("rs_upsweep:") + tag, nm_sc_s = std::string("rs_scatter:") + tag;
   lc.begin(nm_up_s.c_str());
   {
     int blocks = div_up(n, 256 * 16);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    rs_hist_all_kernel<<<blocks, 256, 0, s>>>(keys_a, n, begin_bit, end_bit, ghist.p);
+    rs_hist_all_kernel<<<blocks, 256, 0, s>>>(keys_a, n, begin_bit, end_bit, ghist.p, ent);
     rs_scan_hist_kernel<<<1, 256, 0, s>>>(ghist.p, npass);
   }
   lc.end(nm_up_s.c_str());
@@ -487,15 +612,19 @@ static int radix_sort_onesweep(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_
     const int bit = begin_bit + 8 * p;
     const int nbits = end_bit - bit < 8 ? end_bit - bit : 8;
     const u32 mask = (1u << nbits) - 1;
+    const int nbit = bit + 8;
+    const int nnbits = p + 1 < npass ? (end_bit - nbit < 8 ? end_bit - nbit : 8) : 0;
+    const u32 nmask = (1u << nnbits) - 1;
+    u32* ent_out = p + 1 < npass ? ent + 2 * (p + 1) : nullptr;
     CB_CUDA(cudaMemsetAsync(status.p, 0, (size_t)tiles * 256 * 4, s));
     CB_CUDA(cudaMemsetAsync(ctl.p, 0, 4, s));
+    const u32* gb = ghist.p + p * 256;
     lc.begin(nm_sc_s.c_str());
-    if (vin)
-      rs_onesweep_kernel<true><<<tiles, RS_THREADS, 0, s>>>(kin, kout, vin, vout, status.p, ctl.p, ghist.p + p * 256,
-                                                           ctl.p + 1, n, bit, mask);
-    else
-      rs_onesweep_kernel<false><<<tiles, RS_THREADS, 0, s>>>(kin, kout, nullptr, nullptr, status.p, ctl.p,
-                                                            ghist.p + p * 256, ctl.p + 1, n, bit, mask);
+#define CB_OS_GO(HV, SS) \
+  launch_onesweep<HV, SS>(tiles, s, kin, kout, vin, vout, status.p, ctl.p, gb, (u32)n, bit, mask, ent + 2 * p, ent_out, nbit, nmask, force_rank)
+    if (S == 2) { if (vin) CB_OS_GO(true, 2); else CB_OS_GO(false, 2); }
+    else { if (vin) CB_OS_GO(true, 1); else CB_OS_GO(false, 1); }
+#undef CB_OS_GO
     lc.end(nm_sc_s.c_str());
     lc.n++;
     CB_CUDA(cudaGetLastError());
