@@ -273,9 +273,12 @@ def bench_ours(args):
     dev = host.cuda(non_blocking=False)
     g = BrushGpu(BrushConfig(k=k, readlen=L, device=local_rank, rank=rank, world=world))
     if world > 1:
-        from cloudbrush_b200.dist import TorchExchange
-        exch = TorchExchange(device=torch.device("cuda", local_rank))
-        g.set_exchange(exch)
+        if args.transport == "nccl":  # the library drives NCCL itself (ncclSend/ncclRecv on its own stream)
+            g.init_nccl()
+        else:  # the cb_exchange callbacks implemented with torch.distributed (cloudbrush_b200/dist.py)
+            from cloudbrush_b200.dist import TorchExchange
+            exch = TorchExchange(device=torch.device("cuda", local_rank))
+            g.set_exchange(exch)
 
     def step_resident():
         g.borrow_sfa_device(dev.data_ptr(), dev.numel())
@@ -397,7 +400,7 @@ def bench_ours(args):
                        "l2": "inputs larger than L2 (SFA text and tuple arrays exceed 126 MB)" if len(sfa_np) > 126e6
                              else "input smaller than L2 (reduced run)",
                        "sharding": (f"weak scaling: {world} shards of consecutive SFA lines, k-mer groups hash-partitioned, "
-                                    f"tuple all-to-all over NCCL, packed reads replicated") if world > 1 else "single GPU"},
+                                    f"tuple all-to-all over NCCL ({args.transport} transport), packed reads replicated") if world > 1 else "single GPU"},
             "edges_per_sec": total_edges / (ms * 1e-3),
             "wall_ms_per_step": wall * 1e3,
             "e2e": {"value": total_reads / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(len(sfa_np)),
@@ -447,6 +450,8 @@ def main():
     ap.add_argument("--ref-sample-reads", type=int, default=120_000)
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "torch"],
+                    help="N>1: native NCCL inside the library (default) or the torch.distributed callbacks")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)

@@ -101,6 +101,25 @@ class BrushGpu:
         st = exchange.as_struct()
         self._check(self._L.cb_set_exchange(self._h, C.cast(C.byref(st), C.c_void_p)))
 
+    def init_nccl(self, group=None):
+        """Native transport (cfg.world > 1): the library drives NCCL itself on its own stream.
+
+        torch.distributed (any backend) is only used to hand rank 0's NCCL unique id to the ranks."""
+        import torch
+        import torch.distributed as dist
+        buf = (C.c_uint8 * 128)()
+        if dist.get_rank(group) == 0:
+            rc = self._L.cb_nccl_get_unique_id(buf)
+            if rc != 0:
+                raise BrushGpuError(rc, "cb_nccl_get_unique_id failed (libnccl.so.2 not loadable?)")
+        t = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda(self.cfg.device)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(t, src=src, group=group)
+        ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+        self._check(self._L.cb_init_nccl(self._h, ident))
+
     def set_profile(self, on=True):
         self._check(self._L.cb_set_profile(self._h, 1 if on else 0))
 

@@ -219,6 +219,7 @@ void cb_destroy(cb_ctx* c) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
     if (kv.second.b) cudaEventDestroy(kv.second.b);
   }
+  cb::nccl_shutdown(c);
   cudaStream_t s = c->stream;
   delete c;  // DevBufs return to the arena, the arena returns everything to the driver
   cudaStreamDestroy(s);
@@ -254,6 +255,19 @@ int cb_set_exchange(cb_ctx* c, const cb_exchange* ex) {
   c->ex = *ex;
   c->has_ex = true;
   return CB_OK;
+}
+
+int cb_nccl_get_unique_id(void* id128) {
+  if (!id128) return CB_E_INVALID;
+  std::string err;
+  return cb::nccl_unique_id(id128, err);
+}
+
+int cb_init_nccl(cb_ctx* c, const void* id128) {
+  CB_API_BEGIN(c)
+  if (!id128) throw Error(CB_E_INVALID, "null id");
+  nccl_init(c, id128);
+  CB_API_END(c)
 }
 
 int cb_set_profile(cb_ctx* c, int on) {

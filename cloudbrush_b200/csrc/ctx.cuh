@@ -93,6 +93,9 @@ struct cb_ctx {
   // multi-GPU (cfg.world > 1): transport callbacks and the global numbering
   cb_exchange ex = {};
   bool has_ex = false;
+  void* nccl_comm = nullptr;      // native transport (cb_init_nccl); takes precedence over the callbacks
+  u64* ex_scratch = nullptr;      // small device scratch of the native transport
+  size_t ex_scratch_words = 0;
   int lg_world = 0;               // log2(world)
   int pbit = 0;                   // k-mer groups are owned by rank (key >> pbit) & (world - 1)
   u32 line_base = 0;              // global index of this shard's first SFA line
@@ -141,6 +144,9 @@ void download_counters(cb_ctx* c);
 
 // dist.cu -- routing helpers of the multi-GPU path
 inline bool distributed(const cb_ctx* c) { return c->cfg.world > 1; }
+int nccl_unique_id(void* id128, std::string& err);
+void nccl_init(cb_ctx* c, const void* id128);
+void nccl_shutdown(cb_ctx* c);
 void ex_allreduce(cb_ctx* c, u64* vals, int n, int op);
 // in-place max over the ranks of a DEVICE byte array
 void ex_allreduce_max_u8(cb_ctx* c, uint8_t* dev, size_t n);

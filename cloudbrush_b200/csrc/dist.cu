@@ -3,6 +3,12 @@
 //
 // This replaces Hadoop's HashPartitioner + shuffle (every JobClient.runJob of the path, e.g.
 // MatchPrefix.java:468) with: partition on the device -> exchange byte counts -> one all-to-all.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdlib>
+#include <cstring>
+
 #include "ctx.cuh"
 
 namespace cb {
@@ -11,13 +17,116 @@ static void ex_fail(const char* what, int rc) {
   throw Error(CB_E_CUDA, std::string("exchange callback ") + what + " failed with " + std::to_string(rc));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Native transport: NCCL, located at run time (the library has no link-time dependency on it, so
+// the single-GPU path and the CPU-side symbol tests load without NCCL).  Every transfer is
+// enqueued on the context's stream: no host round trip per exchange.
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string why;
+};
+
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.lib ? &api : nullptr;
+  tried = true;
+  const char* names[] = {getenv("CB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    if (!nm || !*nm) continue;
+    api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+    api.why = dlerror();
+  }
+  if (!api.lib) return nullptr;
+#define CB_NCCL_SYM(field, name)                                          \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name)); \
+  if (!api.field) { api.why = std::string("missing symbol ") + name; api.lib = nullptr; return nullptr; }
+  CB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  CB_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  CB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  CB_NCCL_SYM(GroupStart, "ncclGroupStart")
+  CB_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+  CB_NCCL_SYM(Send, "ncclSend")
+  CB_NCCL_SYM(Recv, "ncclRecv")
+  CB_NCCL_SYM(AllReduce, "ncclAllReduce")
+  CB_NCCL_SYM(AllGather, "ncclAllGather")
+  CB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef CB_NCCL_SYM
+  return &api;
+}
+
+#define CB_NCCL(expr)                                                                                  \
+  do {                                                                                                 \
+    ncclResult_t r_ = (expr);                                                                          \
+    if (r_ != ncclSuccess)                                                                             \
+      throw Error(CB_E_CUDA, std::string(#expr) + ": " + nccl_api()->GetErrorString(r_));             \
+  } while (0)
+
+int nccl_unique_id(void* id128, std::string& err) {
+  NcclApi* A = nccl_api();
+  if (!A) { err = "NCCL is not available: " + (nccl_api() ? std::string() : std::string("dlopen failed")); return CB_E_UNSUPPORTED; }
+  ncclUniqueId id;
+  ncclResult_t r = A->GetUniqueId(&id);
+  if (r != ncclSuccess) { err = A->GetErrorString(r); return CB_E_CUDA; }
+  memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES);
+  return CB_OK;
+}
+
+void nccl_init(cb_ctx* c, const void* id128) {
+  NcclApi* A = nccl_api();
+  if (!A) throw Error(CB_E_UNSUPPORTED, "NCCL is not available (libnccl.so.2 could not be loaded)");
+  if (c->cfg.world < 2) throw Error(CB_E_INVALID, "cb_init_nccl needs cfg.world > 1");
+  if (c->nccl_comm) nccl_shutdown(c);
+  ncclUniqueId id;
+  memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+  ncclComm_t comm = nullptr;
+  CB_NCCL(A->CommInitRank(&comm, c->cfg.world, id, c->cfg.rank));
+  c->nccl_comm = comm;
+  const size_t W = (size_t)c->cfg.world;
+  const size_t words = W * W * 4 + 4 * W + (size_t)DC_COUNT + 64;
+  CB_CUDA(cudaMalloc(&c->ex_scratch, words * sizeof(u64)));
+  c->ex_scratch_words = words;
+}
+
+void nccl_shutdown(cb_ctx* c) {
+  if (c->nccl_comm && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)c->nccl_comm);
+  c->nccl_comm = nullptr;
+  if (c->ex_scratch) cudaFree(c->ex_scratch);
+  c->ex_scratch = nullptr;
+}
+
+static inline ncclComm_t comm_of(cb_ctx* c) { return (ncclComm_t)c->nccl_comm; }
+
 static void need_ex(cb_ctx* c) {
-  if (!c->has_ex) throw Error(CB_E_INVALID, "cfg.world > 1 but no cb_exchange was set (cb_set_exchange)");
+  if (!c->has_ex && !c->nccl_comm)
+    throw Error(CB_E_INVALID, "cfg.world > 1 but no transport was set (cb_init_nccl or cb_set_exchange)");
 }
 
 void ex_allreduce(cb_ctx* c, u64* vals, int n, int op) {
   if (!distributed(c)) return;
   need_ex(c);
+  if (c->nccl_comm) {
+    if ((size_t)n > c->ex_scratch_words) throw Error(CB_E_INVALID, "ex_allreduce: too many values");
+    NcclApi* A = nccl_api();
+    CB_CUDA(cudaMemcpyAsync(c->ex_scratch, vals, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CB_NCCL(A->AllReduce(c->ex_scratch, c->ex_scratch, (size_t)n, ncclUint64, op == 0 ? ncclSum : ncclMax, comm_of(c),
+                         c->stream));
+    CB_CUDA(cudaMemcpyAsync(vals, c->ex_scratch, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    return;
+  }
   int rc = c->ex.allreduce_u64(c->ex.user, (uint64_t*)vals, n, op);
   if (rc) ex_fail("allreduce_u64", rc);
 }
@@ -25,6 +134,10 @@ void ex_allreduce(cb_ctx* c, u64* vals, int n, int op) {
 void ex_allreduce_max_u8(cb_ctx* c, uint8_t* dev, size_t n) {
   if (!distributed(c)) return;
   need_ex(c);
+  if (c->nccl_comm) {
+    CB_NCCL(nccl_api()->AllReduce(dev, dev, n, ncclUint8, ncclMax, comm_of(c), c->stream));
+    return;
+  }
   if (!c->ex.allreduce_max_u8_dev) throw Error(CB_E_INVALID, "cb_exchange.allreduce_max_u8_dev is not set");
   CB_CUDA(cudaStreamSynchronize(c->stream));
   int rc = c->ex.allreduce_max_u8_dev(c->ex.user, dev, (uint64_t)n);
@@ -33,12 +146,48 @@ void ex_allreduce_max_u8(cb_ctx* c, uint8_t* dev, size_t n) {
 
 void ex_counts(cb_ctx* c, const u64* send, u64* recv, int n_per_rank) {
   need_ex(c);
+  if (c->nccl_comm) {
+    // every rank's whole send vector is gathered; this rank's column is picked out on the host
+    const size_t W = (size_t)c->cfg.world, m = W * (size_t)n_per_rank;
+    if (m + W * m > c->ex_scratch_words) throw Error(CB_E_INVALID, "ex_counts: too many values");
+    u64* d_send = c->ex_scratch;
+    u64* d_all = c->ex_scratch + m;
+    CB_CUDA(cudaMemcpyAsync(d_send, send, m * 8, cudaMemcpyHostToDevice, c->stream));
+    CB_NCCL(nccl_api()->AllGather(d_send, d_all, m, ncclUint64, comm_of(c), c->stream));
+    std::vector<u64> all(W * m);
+    CB_CUDA(cudaMemcpyAsync(all.data(), d_all, W * m * 8, cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t r = 0; r < W; r++)
+      for (int j = 0; j < n_per_rank; j++)
+        recv[r * n_per_rank + j] = all[r * m + (size_t)c->cfg.rank * n_per_rank + j];
+    return;
+  }
   int rc = c->ex.exchange_counts(c->ex.user, (const uint64_t*)send, (uint64_t*)recv, n_per_rank);
   if (rc) ex_fail("exchange_counts", rc);
 }
 
 void ex_alltoallv(cb_ctx* c, const void* send, const u64* send_bytes, void* recv, const u64* recv_bytes) {
   need_ex(c);
+  if (c->nccl_comm) {
+    NcclApi* A = nccl_api();
+    const int W = c->cfg.world, me = c->cfg.rank;
+    size_t so = 0, ro = 0;
+    CB_NCCL(A->GroupStart());
+    for (int r = 0; r < W; r++) {
+      const char* sp = (const char*)send + so;
+      char* rp = (char*)recv + ro;
+      if (r == me) {
+        if (send_bytes[r]) CB_CUDA(cudaMemcpyAsync(rp, sp, send_bytes[r], cudaMemcpyDeviceToDevice, c->stream));
+      } else {
+        if (send_bytes[r]) CB_NCCL(A->Send(sp, send_bytes[r], ncclUint8, r, comm_of(c), c->stream));
+        if (recv_bytes[r]) CB_NCCL(A->Recv(rp, recv_bytes[r], ncclUint8, r, comm_of(c), c->stream));
+      }
+      so += send_bytes[r];
+      ro += recv_bytes[r];
+    }
+    CB_NCCL(A->GroupEnd());
+    return;
+  }
   CB_CUDA(cudaStreamSynchronize(c->stream));
   int rc = c->ex.alltoallv(c->ex.user, send, (const uint64_t*)send_bytes, recv, (const uint64_t*)recv_bytes);
   if (rc) ex_fail("alltoallv", rc);
@@ -46,6 +195,24 @@ void ex_alltoallv(cb_ctx* c, const void* send, const u64* send_bytes, void* recv
 
 void ex_allgatherv(cb_ctx* c, const void* send, u64 send_bytes, void* recv, const u64* recv_bytes) {
   need_ex(c);
+  if (c->nccl_comm) {
+    NcclApi* A = nccl_api();
+    const int W = c->cfg.world, me = c->cfg.rank;
+    size_t ro = 0;
+    CB_NCCL(A->GroupStart());
+    for (int r = 0; r < W; r++) {
+      char* rp = (char*)recv + ro;
+      if (r == me) {
+        if (send_bytes) CB_CUDA(cudaMemcpyAsync(rp, send, send_bytes, cudaMemcpyDeviceToDevice, c->stream));
+      } else {
+        if (send_bytes) CB_NCCL(A->Send(send, send_bytes, ncclUint8, r, comm_of(c), c->stream));
+        if (recv_bytes[r]) CB_NCCL(A->Recv(rp, recv_bytes[r], ncclUint8, r, comm_of(c), c->stream));
+      }
+      ro += recv_bytes[r];
+    }
+    CB_NCCL(A->GroupEnd());
+    return;
+  }
   CB_CUDA(cudaStreamSynchronize(c->stream));
   int rc = c->ex.allgatherv(c->ex.user, send, send_bytes, recv, (const uint64_t*)recv_bytes);
   if (rc) ex_fail("allgatherv", rc);

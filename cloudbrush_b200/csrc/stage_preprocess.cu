@@ -413,7 +413,8 @@ void stage_parse_and_pack(cb_ctx* c) {
   if (c->L <= c->K) throw Error(CB_E_INVALID, "readlen must exceed k");
   if (c->L > 255) throw Error(CB_E_UNSUPPORTED, "readlen above 255");
   if (world < 1 || (world & (world - 1)) || world > 256) throw Error(CB_E_UNSUPPORTED, "world must be a power of two <= 256");
-  if (distributed(c) && !c->has_ex) throw Error(CB_E_INVALID, "cfg.world > 1 needs cb_set_exchange before cb_preprocess");
+  if (distributed(c) && !c->has_ex && !c->nccl_comm)
+    throw Error(CB_E_INVALID, "cfg.world > 1 needs cb_init_nccl or cb_set_exchange before cb_preprocess");
   c->lg_world = 0;
   while ((1 << c->lg_world) < world) c->lg_world++;
   c->pbit = c->K;  // owner of a k-mer group: bits [K, K + lg_world) of the canonical key (its middle bases)

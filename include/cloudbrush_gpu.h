@@ -179,6 +179,17 @@ typedef struct cb_exchange {
  * adjacency lists this rank owns (their union over the ranks is the checkpoint). */
 int cb_set_exchange(cb_ctx* ctx, const cb_exchange* ex);
 
+/* Native transport: NCCL over NVLink / NVSwitch, driven by the library on its own stream (no host
+ * round trip per transfer; replaces the cb_exchange callbacks, which stay available for hosts
+ * that bring their own transport).  Rank 0 obtains the 128-byte id with cb_nccl_get_unique_id and
+ * the host program hands it to every rank by any channel (torch.distributed broadcast in
+ * cloudbrush_b200/api.py; a socket or MPI_Bcast from a Java launcher); then every rank calls
+ * cb_init_nccl before cb_preprocess.  libnccl.so.2 is located at run time (dlopen; the
+ * environment variable CB_NCCL_LIB overrides the name); CB_E_UNSUPPORTED if it cannot be loaded. */
+#define CB_NCCL_ID_BYTES 128
+int cb_nccl_get_unique_id(void* id128);
+int cb_init_nccl(cb_ctx* ctx, const void* id128);
+
 #ifdef __cplusplus
 }
 #endif
