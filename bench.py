@@ -313,7 +313,7 @@ def bench_ours(args):
                                           "edges_chl2", "edges_re", "trans_edge", "edge_removal_1", "slow_lists"]}
     stage_ms = {t: g.time_ms(t) for t in ["parse", "dedupe", "keygen", "sort_tuples", "join_verify",
                                           "cut", "tr"] + (["exchange_tuples", "dd_route", "dd_return", "node_gather",
-                                                           "side_route", "tr_votes"] if world > 1 else [])}
+                                                           "side_route", "tr_votes", "a2a_tuples"] if world > 1 else [])}
 
     # ---- e2e through the C ABI with host buffers ----
     from cloudbrush_b200.api import EDGE_DTYPE, NODE_DTYPE

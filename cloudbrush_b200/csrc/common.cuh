@@ -230,6 +230,24 @@ __host__ __device__ __forceinline__ int cmp_words(const u64 (&a)[NW], const u64 
   return 0;
 }
 
+// Overhang storage: the first NWO 32-bit words (16 bases each, MSB first) of a left-aligned
+// NW-word base string.  NWO <= 2*NW.
+template <int NW>
+__device__ __forceinline__ void store_overhang(u32* __restrict__ dst, const u64 (&h)[NW], int nwo) {
+#pragma unroll
+  for (int i = 0; i < 2 * NW; i++)
+    if (i < nwo) dst[i] = (i & 1) ? (u32)h[i >> 1] : (u32)(h[i >> 1] >> 32);
+}
+template <int NW>
+__device__ __forceinline__ void fetch_overhang(const u32* __restrict__ src, u64 (&h)[NW], int nwo) {
+#pragma unroll
+  for (int i = 0; i < NW; i++) {
+    const u32 hi = (2 * i < nwo) ? src[2 * i] : 0u;
+    const u32 lo = (2 * i + 1 < nwo) ? src[2 * i + 1] : 0u;
+    h[i] = ((u64)hi << 32) | (u64)lo;
+  }
+}
+
 __host__ __device__ __forceinline__ u64 mix64(u64 x) {  // splitmix64 finaliser
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
   x ^= x >> 27; x *= 0x94d049bb133111ebull;

@@ -132,6 +132,8 @@ struct cb_ctx {
   cb::DevBuf<u32> adj_off;          // [2*n_nodes + 1] slot offset of list node*2 + x
   size_t slots = 0;
   cb::DevBuf<uint8_t> list_flag;    // [2*n_nodes] 1: all overhangs nest (consistent), 0: not, 2: unknown
+  cb::DevBuf<u32> ovh;              // [slots][NWo] overhang nbr^y[ov:] of the record in the slot (any checkpoint),
+  int NWo = 0;                      //   2-bit packed, left aligned, 16 bases per word; NWo = ceil((L-K)/16)
   cb::EdgeSet ckA, ckC, ckB;        // 01-overlap, 01-overlap.chl2, 01-overlap.re
   bool ckC_is_A = false;
 };

@@ -112,6 +112,8 @@ struct JoinParams {
   u32* ne_list;        // [T+1] positions s.. of a group: (list id | entry's dir bit << 31) of its node entries, ~0 ends
   const u32* off1;     // slot offsets of the lists
   u64* slots;          // list storage
+  u32* ovh;            // [slots][nwo] overhang of the record in the slot
+  int nwo;
   u64* xbuf;           // side buffer
   u64 xcap;
   ull* dcount;
@@ -364,7 +366,15 @@ __global__ void __launch_bounds__(256, MINB) join_verify_kernel(JoinParams P) {
           }
         }
         if (ok) {
-          P.slots[off_l + (j - s)] = P.lay.encode(b, (u32)(y ^ 1), (u32)ov, (u32)(x ^ 1), a);  // GenReverseEdge
+          const size_t slot = (size_t)off_l + (j - s);
+          P.slots[slot] = P.lay.encode(b, (u32)(y ^ 1), (u32)ov, (u32)(x ^ 1), a);  // GenReverseEdge
+          {  // the record's overhang as seen from b: a^(flip x)[ov:]
+            u64 H[NW];
+#pragma unroll
+            for (int w = 0; w < NW; w++) H[w] = x ? R[w] : Rc[w];
+            shl_bases<NW>(H, ov);
+            store_overhang<NW>(P.ovh + slot * (size_t)P.nwo, H, P.nwo);
+          }
           n_verified++;
           // Is the mirror candidate (b, flip y, ov) -> (a, flip x) certain to be proposed and
           // kept at a's own node entry?  Then that entry writes this edge into list (a, x) and it
@@ -444,14 +454,20 @@ __global__ void __launch_bounds__(256, MINB) join_verify_kernel(JoinParams P) {
 // possible around poly-A/T k-mers, whose interior windows have no tuple and therefore no slot)
 // is counted in extra[list]; the host then re-runs the join with enlarged slot ranges.
 // ---------------------------------------------------------------------------------------------
+template <int NW>
 __global__ void __launch_bounds__(256) side_insert_kernel(const u64* __restrict__ xs, size_t n, EdgeLayout lay,
                                                           const u32* __restrict__ off, u64* __restrict__ slots,
-                                                          u32* __restrict__ extra, ull* __restrict__ dcount) {
+                                                          u32* __restrict__ extra, ull* __restrict__ dcount,
+                                                          const u64* __restrict__ node_seq, u32* __restrict__ ovh,
+                                                          int nwo, int L) {
   u32 inserted = 0, overflow = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const u64 key = xs[i];
     const u32 lid = lay.list(key);
     const u32 lo = off[lid], hi = off[lid + 1];
+    // the record's overhang b^y[ov:] (requested before the list is scanned)
+    u64 H[NW];
+    load_read_b<NW>(node_seq, lay.nbr(key), H);
     // one pass over the list's slots, eight loads in flight: duplicate? first free slot?
     bool dup = false;
     u32 hole = 0xffffffffu;
@@ -467,14 +483,25 @@ __global__ void __launch_bounds__(256) side_insert_kernel(const u64* __restrict_
     }
     if (dup) continue;
     bool placed = false;
+    u32 at = 0;
     for (u32 t = hole; t < hi && !placed; t++) {  // another record may claim the slot first: move on
       if (slots[t] == ~0ull) {
         ull old = atomicCAS((ull*)&slots[t], ~0ull, (ull)key);
         placed = old == ~0ull;
+        at = t;
       }
     }
-    if (placed) inserted++;
-    else { atomicAdd(&extra[lid], 1u); overflow++; }
+    if (placed) {
+      inserted++;
+      if (lay.y(key)) {
+        u64 r[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) r[w] = H[w];
+        revcomp_read<NW>(r, H, L);
+      }
+      shl_bases<NW>(H, (int)lay.ov(key));
+      store_overhang<NW>(ovh + (size_t)at * nwo, H, nwo);
+    } else { atomicAdd(&extra[lid], 1u); overflow++; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -623,10 +650,12 @@ void stage_build_overlap(cb_ctx* c) {
     DevBuf<u32> rvals;
     rkeys.alloc(Trecv ? Trecv : 1, s);
     rvals.alloc(Trecv ? Trecv : 1, s);
+    timer_start(c, "a2a_tuples");
     for (int r = 0; r < world; r++) { sb[r] = cnt[r] * 8; rb[r] = rcnt[r] * 8; }
     ex_alltoallv(c, keys[w0].p, sb.data(), rkeys.p, rb.data());
     for (int r = 0; r < world; r++) { sb[r] = cnt[r] * 4; rb[r] = rcnt[r] * 4; }
     ex_alltoallv(c, vals[w0].p, sb.data(), rvals.p, rb.data());
+    timer_stop(c, "a2a_tuples");
     Tmax = Trecv;
     keys[0] = std::move(rkeys);
     vals[0] = std::move(rvals);
@@ -694,14 +723,19 @@ void stage_build_overlap(cb_ctx* c) {
   if (jgrid > kNumSMs * 8) jgrid = kNumSMs * 8;
   if (jgrid < 1) jgrid = 1;
   DevBuf<u64> slots, xbuf;
+  DevBuf<u32> ovh;
+  c->NWo = (L - K + 15) / 16;
   u64 xcap = (u64)T / 4 + 4096;
   u64 n_x = 0;
   for (int attempt = 0;; attempt++) {
     slots.alloc(slots1 ? slots1 : 1, s);
     CB_CUDA(cudaMemsetAsync(slots.p, 0xff, (slots1 ? slots1 : 1) * sizeof(u64), s));  // empty slots read as ~0
     xbuf.alloc(xcap, s);
+    ovh.alloc((slots1 ? slots1 : 1) * (size_t)c->NWo, s);
     P.off1 = off1.p;
     P.slots = slots.p;
+    P.ovh = ovh.p;
+    P.nwo = c->NWo;
     P.xbuf = xbuf.p;
     P.xcap = xcap;
     // (DC_HKMER and DC_UPKMER_LISTS were counted by group_walk_kernel and stay)
@@ -748,7 +782,9 @@ void stage_build_overlap(cb_ctx* c) {
       int blocks = div_up(n_xin, 256);
       if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
       c->lc.begin("side_insert");
-      side_insert_kernel<<<blocks, 256, 0, s>>>(xin, n_xin, c->lay, off1.p, slots.p, extra.p, (ull*)c->dcount.p);
+      CB_DISPATCH_NW(c->NW, (side_insert_kernel<NW_><<<blocks, 256, 0, s>>>(xin, n_xin, c->lay, off1.p, slots.p, extra.p,
+                                                                           (ull*)c->dcount.p, c->node_seq.p, ovh.p,
+                                                                           c->NWo, L)));
       c->lc.end("side_insert");
       c->lc.n++;
       CB_CUDA(cudaGetLastError());
@@ -785,6 +821,7 @@ void stage_build_overlap(cb_ctx* c) {
   c->adj_off = std::move(off1);
   c->slots = slots1;
   c->ckA.keys = std::move(slots);
+  c->ovh = std::move(ovh);
   c->ckA.n = (size_t)(c->hcount[DC_EDGES_M] + c->hcount[DC_EDGES_A]);  // the lists this rank owns
   c->ckA.valid = true;
   c->counters["edges_overlap"] = (int64_t)(c->gcount[DC_EDGES_M] + c->gcount[DC_EDGES_A]);

@@ -42,6 +42,8 @@ struct StringParams {
   size_t slots;
   EdgeLayout lay;
   const u64* node_seq;
+  const u32* ovh;      // [slots][nwo] stored overhang of the record in the slot
+  int nwo;
   const IdKey* node_idkey;
   const u32* node_cov;
   int L, K;
@@ -66,19 +68,14 @@ struct StringParams {
   ull* dcount;
 };
 
-// overhang b^y[ov:], left aligned, of an adjacency record
+// overhang b^y[ov:], left aligned, of the adjacency record in slot `slot`.  The join stored it next
+// to the record, so the lists are read sequentially here and no neighbour read is gathered (with the
+// node table replicated over several GPUs those gathers missed the L2: 1.5 ms of consistency_kernel
+// on one GPU became 5.0 ms on four).
 template <int NW>
-__device__ __forceinline__ void load_overhang(const StringParams& P, u64 key, u64 (&h)[NW], int& len) {
-  u64 r[NW];
-  load_read_c<NW>(P.node_seq, P.lay.nbr(key), r);
-  if (P.lay.y(key)) revcomp_read<NW>(r, h, P.L);
-  else {
-#pragma unroll
-    for (int w = 0; w < NW; w++) h[w] = r[w];
-  }
-  int ov = (int)P.lay.ov(key);
-  shl_bases<NW>(h, ov);
-  len = P.L - ov;
+__device__ __forceinline__ void load_overhang(const StringParams& P, size_t slot, u64 key, u64 (&h)[NW], int& len) {
+  fetch_overhang<NW>(P.ovh + slot * (size_t)P.nwo, h, P.nwo);
+  len = P.L - (int)P.lay.ov(key);
 }
 
 template <int NW>
@@ -129,7 +126,7 @@ __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* _
     u64 H[NW];
     int lenH = 0;
     const bool test = n > 1 && !force_slow;
-    if (test) load_overhang<NW>(P, P.edges[hidx], H, lenH);
+    if (test) load_overhang<NW>(P, hidx, P.edges[hidx], H, lenH);
     bool bad = n > 1 && force_slow;
     for (u32 t = lo; t < hi; t++) {
       const u64 k = P.edges[t];
@@ -138,7 +135,7 @@ __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* _
       if (test && t != hidx) {
         u64 h[NW];
         int len;
-        load_overhang<NW>(P, k, h, len);
+        load_overhang<NW>(P, t, k, h, len);
         bad = bad || !prefix_equal<NW>(h, H, len);
       }
       // TransitiveReduction on a consistent list: keep the maximal overlap (:341-343); anything
@@ -215,14 +212,14 @@ __device__ __forceinline__ bool list_consistent_warp(const StringParams& P, u32 
   if (n <= 1) return true;
   u64 H[NW];
   int lenH;
-  load_overhang<NW>(P, P.edges[hidx], H, lenH);
+  load_overhang<NW>(P, hidx, P.edges[hidx], H, lenH);
   bool good = true;
   for (u32 t = lo + lane; t < hi; t += 32) {
     const u64 q = P.edges[t];
     if (q == ~0ull) continue;
     u64 h[NW];
     int len;
-    load_overhang<NW>(P, q, h, len);
+    load_overhang<NW>(P, t, q, h, len);
     good = good && prefix_equal<NW>(h, H, len);
   }
   return __all_sync(0xffffffffu, good);
@@ -298,7 +295,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
         if (k == ~0ull) continue;
         u64 h[NW];
         int len;
-        load_overhang<NW>(P, k, h, len);
+        load_overhang<NW>(P, t, k, h, len);
         int w = (int)P.node_cov[P.lay.nbr(k)];
         if (j < len && j < clen) {
           int b = base_at<NW>(h, j);
@@ -329,7 +326,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
       if (k != ~0ull) {
         u64 h[NW];
         int len;
-        load_overhang<NW>(P, k, h, len);
+        load_overhang<NW>(P, t, k, h, len);
         int m = len < clen ? len : clen;
         bool miss = false;
         for (int j = 0; j < m; j++) {
@@ -433,7 +430,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
         u64 h[NW];
         if (mine) {
           int len;
-          load_overhang<NW>(P, k, h, len);
+          load_overhang<NW>(P, t, k, h, len);
           if (level == L) contained++;
           bool step2 = false, step3 = false;
           for (u32 q = 0; q < nk_level; q++) {  // :325-334 comes before the transitive test
@@ -603,6 +600,8 @@ static StringParams make_params(cb_ctx* c, const u64* keys) {
   P.slots = c->slots;
   P.lay = c->lay;
   P.node_seq = c->node_seq.p;
+  P.ovh = c->ovh.p;
+  P.nwo = c->NWo;
   P.node_idkey = c->node_idkey.p;
   P.node_cov = c->node_cov.p;
   P.L = c->L;
