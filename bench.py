@@ -260,6 +260,9 @@ def bench_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL reads these when it is first initialised in the process (see cloudbrush_b200/csrc/dist.cu)
+        for k_, v_ in (("NCCL_MIN_P2P_NCHANNELS", "64"), ("NCCL_MAX_P2P_NCHANNELS", "64"), ("NCCL_MAX_NCHANNELS", "64")):
+            os.environ.setdefault(k_, v_)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     name = args.config

@@ -74,42 +74,68 @@ __global__ void __launch_bounds__(256) export_nodes_kernel(const u32* __restrict
   out[i] = v;
 }
 
-static const EdgeSet* edge_set(cb_ctx* c, int ck) {
+// records of a checkpoint, or -1 if it is not available yet
+static long long edge_count(cb_ctx* c, int ck) {
   switch (ck) {
-    case CB_CK_OVERLAP: return c->overlapped ? &c->ckA : nullptr;
-    case CB_CK_CHL2: return c->reduced ? (c->ckC_is_A ? &c->ckA : &c->ckC) : nullptr;
-    case CB_CK_RE: return c->reduced ? &c->ckB : nullptr;
+    case CB_CK_OVERLAP: return c->overlapped ? (long long)c->ckA.n : -1;
+    case CB_CK_CHL2: return c->reduced ? (long long)c->n_edges_c : -1;
+    case CB_CK_RE: return c->reduced ? (long long)c->ckB.n : -1;
   }
-  return nullptr;
+  return -1;
+}
+
+__global__ void __launch_bounds__(256) export_recode_kernel(const u64* __restrict__ keys, size_t n, EdgeLayout lay,
+                                                            int K, u64* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 k = keys[i];
+  u64 type = (u64)lay.x(k) * 2 + lay.y(k);
+  u64 ovf = (u64)(lay.ov(k) - (u32)K);
+  out[i] = ((u64)lay.node(k) << (lay.nb + lay.ob + 2)) | (type << (lay.nb + lay.ob)) | ((u64)lay.nbr(k) << lay.ob) | ovf;
 }
 
 // sorted cb_edge records of a checkpoint straight into caller memory (pinned memory makes the
-// device-to-host copy run at PCIe speed)
-static void export_edges_to(cb_ctx* c, const EdgeSet& es, cb_edge* out) {
+// device-to-host copy run at PCIe speed).  01-overlap.re is a compact record list; 01-overlap and
+// 01-overlap.chl2 share the slot array (ctx.cuh): once CutChimericLinks has removed records in
+// place, 01-overlap is exported from a restored private copy.
+static void export_edges_to(cb_ctx* c, int ck, cb_edge* out) {
   cudaStream_t s = c->stream;
-  if (es.n == 0) return;
-  const size_t slots = c->slots;
-  DevBuf<u32> flag, idx;
-  flag.alloc(slots, s);
-  idx.alloc(slots, s);
-  export_flags_kernel<<<div_up(slots, 256), 256, 0, s>>>(es.keys.p, slots, flag.p);
-  exclusive_scan_u32(flag.p, idx.p, slots, s, c->lc);
+  const size_t n = (size_t)edge_count(c, ck);
+  if (n == 0) return;
   DevBuf<u64> a, b;
-  a.alloc(es.n, s);
-  b.alloc(es.n, s);
-  export_gather_kernel<<<div_up(slots, 256), 256, 0, s>>>(es.keys.p, flag.p, idx.p, slots, c->lay, c->K, a.p);
-  int w = radix_sort(a.p, b.p, nullptr, nullptr, es.n, 0, c->lay.total_bits(), s, c->lc, "export");
+  a.alloc(n, s);
+  b.alloc(n, s);
+  if (ck == CB_CK_RE) {
+    export_recode_kernel<<<div_up(n, 256), 256, 0, s>>>(c->ckB.keys.p, n, c->lay, c->K, a.p);
+    c->lc.n++;
+  } else {
+    const size_t slots = c->slots;
+    DevBuf<u64> restored;
+    const u64* keys = c->ckA.keys.p;
+    if (ck == CB_CK_OVERLAP && c->n_cut_log) {
+      restore_overlap_copy(c, restored);
+      keys = restored.p;
+    }
+    DevBuf<u32> flag, idx;
+    flag.alloc(slots, s);
+    idx.alloc(slots, s);
+    export_flags_kernel<<<div_up(slots, 256), 256, 0, s>>>(keys, slots, flag.p);
+    exclusive_scan_u32(flag.p, idx.p, slots, s, c->lc);
+    export_gather_kernel<<<div_up(slots, 256), 256, 0, s>>>(keys, flag.p, idx.p, slots, c->lay, c->K, a.p);
+    c->lc.n += 2;
+  }
+  int w = radix_sort(a.p, b.p, nullptr, nullptr, n, 0, c->lay.total_bits(), s, c->lc, "export");
   DevBuf<cb_edge> d;
-  d.alloc(es.n, s);
-  export_decode_kernel<<<div_up(es.n, 256), 256, 0, s>>>(w ? b.p : a.p, es.n, c->lay, c->K, c->node_line.p, d.p);
-  c->lc.n += 3;
-  CB_CUDA(cudaMemcpyAsync(out, d.p, es.n * sizeof(cb_edge), cudaMemcpyDeviceToHost, s));
+  d.alloc(n, s);
+  export_decode_kernel<<<div_up(n, 256), 256, 0, s>>>(w ? b.p : a.p, n, c->lay, c->K, c->node_line.p, d.p);
+  c->lc.n++;
+  CB_CUDA(cudaMemcpyAsync(out, d.p, n * sizeof(cb_edge), cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
 }
 
-static void export_edges_host(cb_ctx* c, const EdgeSet& es, std::vector<cb_edge>& out) {
-  out.resize(es.n);
-  export_edges_to(c, es, out.data());
+static void export_edges_host(cb_ctx* c, int ck, std::vector<cb_edge>& out) {
+  out.resize((size_t)edge_count(c, ck));
+  export_edges_to(c, ck, out.data());
 }
 
 static void read_file(const std::string& path, std::vector<char>& out) {
@@ -143,8 +169,9 @@ static void reset_after_load(cb_ctx* c) {
   c->host_text.clear();
   c->counters.clear();
   c->ckA = EdgeSet();
-  c->ckC = EdgeSet();
   c->ckB = EdgeSet();
+  c->n_cut_log = 0;
+  c->n_edges_c = 0;
 }
 
 }  // namespace cb
@@ -380,10 +407,10 @@ int cb_get_counter(cb_ctx* c, const char* name, int64_t* value) {
 int cb_export_edges(cb_ctx* c, int checkpoint, cb_edge* out, size_t cap, size_t* n) {
   CB_API_BEGIN(c)
   if (!n) throw Error(CB_E_INVALID, "null size pointer");
-  const EdgeSet* es = edge_set(c, checkpoint);
-  if (!es) throw Error(CB_E_INVALID, "checkpoint not available");
-  *n = es->n;
-  if (out && cap >= es->n && es->n) export_edges_to(c, *es, out);
+  const long long cnt = edge_count(c, checkpoint);
+  if (cnt < 0) throw Error(CB_E_INVALID, "checkpoint not available");
+  *n = (size_t)cnt;
+  if (out && cap >= (size_t)cnt && cnt) export_edges_to(c, checkpoint, out);
   CB_API_END(c)
 }
 
@@ -411,11 +438,8 @@ int cb_write_nodes(cb_ctx* c, int checkpoint, const char* out_dir) {
     throw Error(CB_E_UNSUPPORTED,
                 "cb_write_nodes on a sharded context: the two adjacency lists of a node may be owned by different "
                 "ranks and the ids live in the line's shard; export edges/nodes per rank and merge by node");
-  const EdgeSet* es = nullptr;
-  if (checkpoint != CB_CK_PREPROCESS) {
-    es = edge_set(c, checkpoint);
-    if (!es) throw Error(CB_E_INVALID, "checkpoint not available");
-  }
+  const bool with_edges = checkpoint != CB_CK_PREPROCESS;
+  if (with_edges && edge_count(c, checkpoint) < 0) throw Error(CB_E_INVALID, "checkpoint not available");
   cudaStream_t s = c->stream;
   if (c->host_text.empty() && c->text_n) {
     c->host_text.resize(c->text_n);
@@ -430,7 +454,7 @@ int cb_write_nodes(cb_ctx* c, int checkpoint, const char* out_dir) {
   CB_CUDA(cudaMemcpyAsync(seq.data(), c->node_seq.p, seq.size() * 8, cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
   std::vector<cb_edge> edges;
-  if (es) export_edges_host(c, *es, edges);
+  if (with_edges) export_edges_host(c, checkpoint, edges);
   auto id_of = [&](u32 line) {
     const char* p = c->host_text.data() + line_start[line];
     const char* e = c->host_text.data() + line_start[line + 1];

@@ -74,9 +74,10 @@ struct Timer {
 // order.  All checkpoints share cb_ctx::adj_off and the slot positions, so removing an edge is
 // writing ~0 into its slot.
 struct EdgeSet {
-  DevBuf<u64> keys;  // [slots], ~0 = empty slot
+  DevBuf<u64> keys;  // [slots], ~0 = empty slot; or, if compact, the n records back to back in no order
   size_t n = 0;      // records
   bool valid = false;
+  bool compact = false;
 };
 
 }  // namespace cb
@@ -134,8 +135,13 @@ struct cb_ctx {
   cb::DevBuf<uint8_t> list_flag;    // [2*n_nodes] 1: all overhangs nest (consistent), 0: not, 2: unknown
   cb::DevBuf<u32> ovh;              // [slots][NWo] overhang nbr^y[ov:] of the record in the slot (any checkpoint),
   int NWo = 0;                      //   2-bit packed, left aligned, 16 bases per word; NWo = ceil((L-K)/16)
-  cb::EdgeSet ckA, ckC, ckB;        // 01-overlap, 01-overlap.chl2, 01-overlap.re
-  bool ckC_is_A = false;
+  // 01-overlap lives in ckA.keys until CutChimericLinks removes records IN PLACE: from then on the
+  // array is 01-overlap.chl2 and (slot, record) of everything removed is in cut_log, from which an
+  // export of 01-overlap restores a private copy.  01-overlap.re (ckB) is a compact record list.
+  cb::EdgeSet ckA, ckB;
+  cb::DevBuf<u64> cut_log;          // [2 * n_cut_log]: slot, record
+  size_t n_cut_log = 0;
+  size_t n_edges_c = 0;             // records of 01-overlap.chl2
 };
 
 namespace cb {
@@ -172,5 +178,6 @@ void stage_parse_and_pack(cb_ctx* c);
 void stage_build_overlap(cb_ctx* c);
 // stage_string.cu
 void stage_string_graph(cb_ctx* c);
+void restore_overlap_copy(cb_ctx* c, DevBuf<u64>& out);
 
 }  // namespace cb

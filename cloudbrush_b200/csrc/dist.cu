@@ -89,6 +89,11 @@ void nccl_init(cb_ctx* c, const void* id128) {
   if (!A) throw Error(CB_E_UNSUPPORTED, "NCCL is not available (libnccl.so.2 could not be loaded)");
   if (c->cfg.world < 2) throw Error(CB_E_INVALID, "cb_init_nccl needs cfg.world > 1");
   if (c->nccl_comm) nccl_shutdown(c);
+  // the all-to-alls are grouped ncclSend/ncclRecv: with NCCL's default channel count per peer they
+  // reach ~200 GB/s per GPU on 4 B200s, with 64 channels ~300 GB/s (measured; existing settings win)
+  setenv("NCCL_MIN_P2P_NCHANNELS", "64", 0);
+  setenv("NCCL_MAX_P2P_NCHANNELS", "64", 0);
+  setenv("NCCL_MAX_NCHANNELS", "64", 0);
   ncclUniqueId id;
   memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
   ncclComm_t comm = nullptr;

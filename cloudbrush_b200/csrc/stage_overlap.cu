@@ -824,6 +824,8 @@ void stage_build_overlap(cb_ctx* c) {
   c->ovh = std::move(ovh);
   c->ckA.n = (size_t)(c->hcount[DC_EDGES_M] + c->hcount[DC_EDGES_A]);  // the lists this rank owns
   c->ckA.valid = true;
+  c->ckA.compact = false;
+  c->n_cut_log = 0;
   c->counters["edges_overlap"] = (int64_t)(c->gcount[DC_EDGES_M] + c->gcount[DC_EDGES_A]);
 }
 

@@ -246,11 +246,28 @@ __device__ __forceinline__ void load_canon(const u64* __restrict__ reads, u32 id
   for (int i = 0; i < NW; i++) canon[i] = c <= 0 ? r[i] : rc[i];
 }
 
+template <int NW>
+__device__ __forceinline__ void canon_of(const uint4 (&q)[NW / 2], int L, u64 (&canon)[NW], bool& selfrc) {
+  u64 r[NW], rc[NW];
+#pragma unroll
+  for (int i = 0; i < NW / 2; i++) {
+    r[2 * i] = (u64)q[i].x | ((u64)q[i].y << 32);
+    r[2 * i + 1] = (u64)q[i].z | ((u64)q[i].w << 32);
+  }
+  revcomp_read<NW>(r, rc, L);
+  int c = cmp_words<NW>(r, rc);
+  selfrc = (c == 0);
+#pragma unroll
+  for (int i = 0; i < NW; i++) canon[i] = c <= 0 ? r[i] : rc[i];
+}
+
 // Sorted by canonical-read hash: every read scans the run of equal (masked) hashes it lies in,
 // compares the canonical reads exactly wherever the full 64-bit hashes agree, and decides on its
 // own whether it is the survivor of its duplicate class (smallest id key) and what the class
 // size is.  Runs are as long as the duplicate classes (a few reads), so the scans are short and
-// every thread is busy.
+// every thread is busy.  The two nearest entries on either side are fetched up front together
+// with the read's own row (the serial scan was a chain of dependent gathers: entry -> line ->
+// row -> id key, once per neighbour); only longer runs continue one entry at a time.
 template <int NW>
 __global__ void __launch_bounds__(128) dedupe_runs_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals,
                                                           u32 n_good, u64 keymask, const u64* __restrict__ reads,
@@ -259,18 +276,62 @@ __global__ void __launch_bounds__(128) dedupe_runs_kernel(const u64* __restrict_
                                                           ull* __restrict__ dcount) {
   u32 ns = 0, mx = 0;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_good; i += gridDim.x * blockDim.x) {
-    bool survivor = false;
-    u32 cv = 0;
     const u64 ki = keys[i], km = ki & keymask;
     const u32 li = vals[i];
+    // offsets -2, -1, +1, +2 (index 0..3)
+    u64 kn[4];
+    u32 ln[4];
+    bool hit[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const long long j = (long long)i + (q < 2 ? q - 2 : q - 1);
+      const bool in = j >= 0 && j < (long long)n_good;
+      kn[q] = in ? keys[j] : ~ki;
+      ln[q] = in ? vals[j] : 0u;
+    }
+    // an entry takes part iff the masked hashes agree all the way from i to it
+    const bool run_l1 = (kn[1] & keymask) == km, run_l2 = run_l1 && (kn[0] & keymask) == km;
+    const bool run_r1 = (kn[2] & keymask) == km, run_r2 = run_r1 && (kn[3] & keymask) == km;
+    hit[0] = run_l2 && kn[0] == ki;
+    hit[1] = run_l1 && kn[1] == ki;
+    hit[2] = run_r1 && kn[2] == ki;
+    hit[3] = run_r2 && kn[3] == ki;
+    uint4 qi[NW / 2], qn[4][NW / 2];
+    IdKey idn[4];
+    {
+      const uint4* row = reinterpret_cast<const uint4*>(reads + (size_t)li * NW);
+#pragma unroll
+      for (int w = 0; w < NW / 2; w++) qi[w] = __ldg(row + w);
+    }
+    const IdKey mine = idkey[li];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (hit[q]) {
+        const uint4* row = reinterpret_cast<const uint4*>(reads + (size_t)ln[q] * NW);
+#pragma unroll
+        for (int w = 0; w < NW / 2; w++) qn[q][w] = __ldg(row + w);
+        idn[q] = idkey[ln[q]];
+      }
+    }
     u64 ci[NW], cj[NW];
     bool self, self2;
-    load_canon<NW>(reads, li, L, ci, self);
-    const IdKey mine = idkey[li];
+    canon_of<NW>(qi, L, ci, self);
     u32 cnt = 1;
-    survivor = true;
+    bool survivor = true;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (hit[q]) {
+        canon_of<NW>(qn[q], L, cj, self2);
+        if (cmp_words<NW>(ci, cj) == 0) {
+          cnt++;
+          if (idkey_less(idn[q], mine) || (!idkey_less(mine, idn[q]) && ln[q] < li)) survivor = false;
+        }
+      }
+    }
+    // longer runs: continue beyond the prefetched entries
     for (int dirn = -1; dirn <= 1; dirn += 2) {
-      for (long long j = (long long)i + dirn; j >= 0 && j < (long long)n_good; j += dirn) {
+      if (!(dirn < 0 ? run_l2 : run_r2)) continue;
+      for (long long j = (long long)i + 3 * dirn; j >= 0 && j < (long long)n_good; j += dirn) {
         const u64 kj = keys[j];
         if ((kj & keymask) != km) break;
         if (kj != ki) continue;
@@ -283,7 +344,7 @@ __global__ void __launch_bounds__(128) dedupe_runs_kernel(const u64* __restrict_
       }
     }
     if (survivor) {
-      cv = 1 + (cnt - 1) * (self ? 2u : 1u);  // GenNonContainedReads.java:176-201
+      const u32 cv = 1 + (cnt - 1) * (self ? 2u : 1u);  // GenNonContainedReads.java:176-201
       surv_flag[li] = 1;
       cov[li] = cv;
       ns++;

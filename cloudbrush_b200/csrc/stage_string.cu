@@ -105,10 +105,14 @@ constexpr int ST_WARPS = 8;
 // with the longest one and precomputes what the fast path of TransitiveReduction needs
 // (tr_final_kernel): bit0 maximal overlap, bit1 counts as transitive, bit2 ov == L.
 // ---------------------------------------------------------------------------------------------
+// `lists` (several GPUs): the non-empty lists, i.e. the ones this rank owns -- without it three
+// of four lanes of a warp would idle on four GPUs
 template <int NW>
 __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* __restrict__ work_out,
-                                                          u32* __restrict__ n_work_out, int force_slow) {
-  for (u32 lid = blockIdx.x * blockDim.x + threadIdx.x; lid < P.n_lists; lid += gridDim.x * blockDim.x) {
+                                                          u32* __restrict__ n_work_out, int force_slow,
+                                                          const u32* __restrict__ lists, u32 n_iter) {
+  for (u32 it = blockIdx.x * blockDim.x + threadIdx.x; it < n_iter; it += gridDim.x * blockDim.x) {
+    const u32 lid = lists ? lists[it] : it;
     const u32 lo = P.adj_off[lid], hi = P.adj_off[lid + 1];
     u32 hidx = lo, hov = 0xffffffffu, ovmax = 0, n = 0, nmax = 0;
     u64 m0 = ~0ull, m1 = ~0ull;  // the first two records of maximal overlap
@@ -161,6 +165,20 @@ __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* _
       work_out[atomicAdd(n_work_out, 1u)] = lid;
     }
   }
+}
+
+// non-empty lists in ascending order of their id within a warp (warp-aggregated append)
+__global__ void __launch_bounds__(256) own_lists_kernel(const u32* __restrict__ adj_off, u32 n_lists,
+                                                        u32* __restrict__ out, u32* __restrict__ n_out) {
+  const u32 lid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool have = lid < n_lists && adj_off[lid + 1] > adj_off[lid];
+  const u32 bal = __ballot_sync(0xffffffffu, have);
+  if (bal == 0) return;
+  u32 base = 0;
+  if (lane == 0) base = atomicAdd(n_out, (u32)__popc(bal));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (have) out[base + __popc(bal & ((1u << lane) - 1))] = lid;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -352,20 +370,39 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
   }
 }
 
-// EdgeRemoval (EdgeRemoval.java:121-202): a flagged record's slot becomes empty.  One thread per
-// slot; clears the flags it consumes.
+// EdgeRemoval (EdgeRemoval.java:121-202): a flagged record's slot becomes empty.  Only the lists
+// that lost a record in this round are visited (one warp per list); the record and its slot are
+// logged so that 01-overlap can be restored for an export.  Clears the flags it consumes.
 __global__ void __launch_bounds__(256) remove_flagged_kernel(u64* __restrict__ keys, uint8_t* __restrict__ drop,
-                                                             size_t slots, ull* __restrict__ dcount) {
+                                                             const u32* __restrict__ adj_off,
+                                                             const u32* __restrict__ lists, u32 n_lists_dirty,
+                                                             u64* __restrict__ log, u32* __restrict__ n_log, u32 log_cap,
+                                                             ull* __restrict__ dcount) {
+  const int lane = threadIdx.x & 31;
+  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
   u32 removed = 0;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < slots; t += (size_t)gridDim.x * blockDim.x)
-    if (drop[t]) {
-      keys[t] = ~0ull;
-      drop[t] = 0;
-      removed++;
-    }
+  for (u32 wi = warp_global; wi < n_lists_dirty; wi += nwarps) {
+    const u32 lid = lists[wi];
+    const u32 lo = adj_off[lid], hi = adj_off[lid + 1];
+    for (u32 t = lo + lane; t < hi; t += 32)
+      if (drop[t]) {
+        const u32 at = atomicAdd(n_log, 1u);
+        if (at < log_cap) { log[2 * (size_t)at] = t; log[2 * (size_t)at + 1] = keys[t]; }
+        keys[t] = ~0ull;
+        drop[t] = 0;
+        removed++;
+      }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
-  if ((threadIdx.x & 31) == 0 && removed) atomicAdd(&dcount[DC_EDGES_C], (ull)removed);
+  if (lane == 0 && removed) atomicAdd(&dcount[DC_EDGES_C], (ull)removed);
+}
+
+// writes logged records back into their slots (restores 01-overlap)
+__global__ void __launch_bounds__(256) restore_log_kernel(u64* __restrict__ keys, const u64* __restrict__ log, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[log[2 * i]] = log[2 * i + 1];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -489,34 +526,59 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
 // owner (VOTED, several GPUs: bit 1 of kept[slot]).
 template <bool VOTED>
 __global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __restrict__ out) {
+  __shared__ u64 s_out[8][64];
   u32 tot = 0, trans = 0, contained = 0;
-  for (size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x; slot < P.slots;
-       slot += (size_t)gridDim.x * blockDim.x) {
-    const u64 k = P.edges[slot];
-    if (k == ~0ull) continue;
-    bool kept_here;
-    if (P.list_flag[P.lay.list(k)] == 1) {
-      const uint8_t f = P.pre[slot];
-      kept_here = f & 1;
-      trans += (f >> 1) & 1;
-      contained += (f >> 2) & 1;  // TransitiveReduction.java:319-323 (equal-length reads)
-    } else {
-      kept_here = (P.kept[slot] & 1) != 0;  // literal kernel
+  u32 wn = 0;  // survivors staged by this warp (warp-uniform)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 lt_mask = (1u << lane) - 1;
+  // block-uniform trip count: every warp reaches the ballot below with all its lanes
+  for (size_t slot0 = (size_t)blockIdx.x * blockDim.x; slot0 < P.slots; slot0 += (size_t)gridDim.x * blockDim.x) {
+    const size_t slot = slot0 + threadIdx.x;
+    const u64 k = slot < P.slots ? P.edges[slot] : ~0ull;
+    bool keep = false;
+    if (k != ~0ull) {
+      bool kept_here;
+      if (P.list_flag[P.lay.list(k)] == 1) {
+        const uint8_t f = P.pre[slot];
+        kept_here = f & 1;
+        trans += (f >> 1) & 1;
+        contained += (f >> 2) & 1;  // TransitiveReduction.java:319-323 (equal-length reads)
+      } else {
+        kept_here = (P.kept[slot] & 1) != 0;  // literal kernel
+      }
+      if (kept_here) {
+        const u64 mk = P.lay.mirror(k);
+        const uint8_t ms = P.lsum[P.lay.list(mk)];
+        if (ms) keep = P.lay.ov(k) == (u32)ms;
+        else if (VOTED) keep = (P.kept[slot] & 2) != 0;
+        else {
+          long long mi = find_edge(P, mk);
+          keep = mi < 0 ? true : (P.kept[mi] != 0);  // no mirror: nobody can ask for the removal
+        }
+      }
     }
-    if (!kept_here) continue;
-    const u64 mk = P.lay.mirror(k);
-    const uint8_t ms = P.lsum[P.lay.list(mk)];
-    bool keep;
-    if (ms) keep = P.lay.ov(k) == (u32)ms;
-    else if (VOTED) keep = (P.kept[slot] & 2) != 0;
-    else {
-      long long mi = find_edge(P, mk);
-      keep = mi < 0 ? true : (P.kept[mi] != 0);  // no mirror: nobody can ask for the removal
+    // survivors are staged per warp in shared memory and appended back to back once 32 are waiting
+    // (one same-address atomic per warp and round cost 2.2 ms); the export sorts them anyway
+    const u32 bal = __ballot_sync(0xffffffffu, keep);
+    if (bal) {
+      if (keep) s_out[warp][wn + __popc(bal & lt_mask)] = k;
+      wn += __popc(bal);
+      __syncwarp();
+      if (wn >= 32) {
+        ull base = 0;
+        if (lane == 0) base = atomicAdd(&P.dcount[DC_EDGES_B], (ull)wn);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (u32 t = lane; t < wn; t += 32) out[base + t] = s_out[warp][t];
+        wn = 0;
+        __syncwarp();
+      }
     }
-    if (keep) {
-      out[slot] = k;
-      tot++;
-    }
+  }
+  if (wn) {
+    ull base = 0;
+    if (lane == 0) base = atomicAdd(&P.dcount[DC_EDGES_B], (ull)wn);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (u32 t = lane; t < wn; t += 32) out[base + t] = s_out[warp][t];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -525,7 +587,6 @@ __global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __re
     contained += __shfl_xor_sync(0xffffffffu, contained, o);
   }
   if ((threadIdx.x & 31) == 0) {
-    if (tot) atomicAdd(&P.dcount[DC_EDGES_B], (ull)tot);
     if (trans) atomicAdd(&P.dcount[DC_TRANS_EDGE], (ull)trans);
     if (contained) atomicAdd(&P.dcount[DC_CONTAINED_EDGE], (ull)contained);
   }
@@ -663,6 +724,18 @@ static size_t route_keys(cb_ctx* c, const u64* keys, size_t n, DevBuf<char>& out
   return n_out;
 }
 
+// a private copy of the slot array with everything CutChimericLinks removed put back (01-overlap)
+void restore_overlap_copy(cb_ctx* c, DevBuf<u64>& out) {
+  cudaStream_t s = c->stream;
+  const size_t slots = c->slots ? c->slots : 1;
+  out.alloc(slots, s);
+  CB_CUDA(cudaMemcpyAsync(out.p, c->ckA.keys.p, slots * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+  if (c->n_cut_log) {
+    restore_log_kernel<<<div_up(c->n_cut_log, 256), 256, 0, s>>>(out.p, c->cut_log.p, c->n_cut_log);
+    c->lc.n++;
+  }
+}
+
 void stage_string_graph(cb_ctx* c) {
   cudaStream_t s = c->stream;
   const u32 n_lists = 2 * c->n_nodes;
@@ -691,18 +764,33 @@ void stage_string_graph(cb_ctx* c) {
 
   // ---- CutChimericLinks x <= 2 (BrushAssembler.java:347-367) ----
   timer_start(c, "cut");
-  const u64* cur_keys = c->ckA.keys.p;
+  // a previous run of this stage group removed records in place: put them back first
+  if (c->n_cut_log) {
+    restore_log_kernel<<<div_up(c->n_cut_log, 256), 256, 0, s>>>(c->ckA.keys.p, c->cut_log.p, c->n_cut_log);
+    c->lc.n++;
+    c->n_cut_log = 0;
+  }
+  u64* const cur_keys = c->ckA.keys.p;  // 01-overlap, then (in place) 01-overlap.chl2
   size_t cur_n = c->ckA.n;
-  c->ckC_is_A = true;
+  u32 log_cap = 0;
   int64_t e1 = 0, e2 = 0;
   {
     StringParams P = make_params(c, cur_keys);
     P.pre = pre.p;
     P.ovmax = ovmax.p;
     if (c->ckA.n) {
+      const u32* lists = nullptr;
+      u32 n_iter = n_lists;
+      if (dist) {  // workB is free until the first cut round writes its dirty list
+        own_lists_kernel<<<div_up((size_t)nl, 256), 256, 0, s>>>(c->adj_off.p, n_lists, workB.p, nwork.p + 6);
+        c->lc.n++;
+        n_iter = read_u32s(c, nwork.p + 6);
+        lists = workB.p;
+      }
       c->lc.begin("consistency");
-      CB_DISPATCH_NW(c->NW, (consistency_kernel<NW_><<<min(div_up((size_t)nl, 256), kNumSMs * 16), 256, 0, s>>>(
-                                P, workA.p, nwork.p + 0, c->cfg.majority < 1.0f ? 0 : 1)));
+      if (n_iter)
+        CB_DISPATCH_NW(c->NW, (consistency_kernel<NW_><<<min(div_up((size_t)n_iter, 256), kNumSMs * 16), 256, 0, s>>>(
+                                  P, workA.p, nwork.p + 0, c->cfg.majority < 1.0f ? 0 : 1, lists, n_iter)));
       c->lc.end("consistency");
       c->lc.n++;
       CB_CUDA(cudaGetLastError());
@@ -738,11 +826,13 @@ void stage_string_graph(cb_ctx* c) {
         c->lc.n++;
         CB_CUDA(cudaGetLastError());
       }
+      size_t n_req_applied = 0;
       if (dist) {  // removal requests for mirrors -> owner rank of the mirror's list
         u32 nr = read_u32s(c, nwork.p + 4);
         if (nr > P.req_cap) throw Error(CB_E_CAPACITY, "removal request buffer overflow");
         DevBuf<char> got;
         size_t n_got = route_keys(c, req.p, nr, got);
+        n_req_applied = n_got;
         if (n_got) {
           apply_removal_requests_kernel<<<div_up(n_got, 256), 256, 0, s>>>(P, (const u64*)got.p, n_got);
           c->lc.n++;
@@ -754,22 +844,32 @@ void stage_string_graph(cb_ctx* c) {
       ex_allreduce(c, &cuts, 1, 0);
       (round == 1 ? e1 : e2) = (int64_t)cuts;
       if (cuts == 0) break;
-      // EdgeRemoval: checkpoint chl2 becomes a private copy of A in which the flagged slots are emptied
-      if (c->ckC_is_A) {
-        c->ckC.keys.alloc(slots, s);
-        CB_CUDA(cudaMemcpyAsync(c->ckC.keys.p, c->ckA.keys.p, slots * sizeof(u64), cudaMemcpyDeviceToDevice, s));
-        c->ckC_is_A = false;
-        c->ckC.valid = true;
+      // EdgeRemoval: the flagged slots of the lists that lost a record are emptied in place and logged
+      u32 nd = read_u32s(c, n_dirty);
+      {  // room for this round's removals: every local cut flags its record, plus the mirrors flagged here
+        const size_t add = dist ? (size_t)c->hcount[DC_EDGE_REMOVAL] + n_req_applied : 2 * (size_t)c->hcount[DC_EDGE_REMOVAL];
+        const size_t need = c->n_cut_log + add;
+        if (c->cut_log.n < 2 * need) {
+          DevBuf<u64> bigger;
+          bigger.alloc(2 * need + 64, s);
+          if (c->n_cut_log)
+            CB_CUDA(cudaMemcpyAsync(bigger.p, c->cut_log.p, 2 * c->n_cut_log * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+          c->cut_log = std::move(bigger);
+        }
+        log_cap = (u32)(c->cut_log.n / 2);
       }
       CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGES_C, 0, sizeof(u64), s));
-      remove_flagged_kernel<<<slot_grid(slots), 256, 0, s>>>(c->ckC.keys.p, flags.p, slots, (ull*)c->dcount.p);
-      c->lc.n++;
-      CB_CUDA(cudaGetLastError());
-      u32 nd = read_u32s(c, n_dirty);
+      if (nd) {
+        remove_flagged_kernel<<<warp_grid(nd), ST_WARPS * 32, 0, s>>>(cur_keys, flags.p, c->adj_off.p, dirty, nd,
+                                                                     c->cut_log.p, nwork.p + 7, log_cap,
+                                                                     (ull*)c->dcount.p);
+        c->lc.n++;
+        CB_CUDA(cudaGetLastError());
+      }
       download_counters(c);
       cur_n -= (size_t)c->hcount[DC_EDGES_C];
-      c->ckC.n = cur_n;
-      cur_keys = c->ckC.keys.p;
+      c->n_cut_log = read_u32s(c, nwork.p + 7);
+      if (c->n_cut_log > log_cap) throw Error(CB_E_CAPACITY, "cut log overflow");
       // round 2 only has to look at the lists that changed: an unchanged list cuts nothing again
       work = dirty;
       n_work = nd;
@@ -787,8 +887,8 @@ void stage_string_graph(cb_ctx* c) {
 
   // ---- TransitiveReduction + EdgeRemoval (BrushAssembler.java:370-379) ----
   timer_start(c, "tr");
-  c->ckB.keys.alloc(slots, s);
-  CB_CUDA(cudaMemsetAsync(c->ckB.keys.p, 0xff, slots * sizeof(u64), s));
+  c->ckB.keys.alloc(cur_n ? cur_n : 1, s);  // compact: the survivors back to back (no more than what is left)
+  c->ckB.compact = true;
   {
     // `flags` is all zero again here (remove_flagged_kernel clears what it consumed)
     StringParams P = make_params(c, cur_keys);
@@ -852,6 +952,7 @@ void stage_string_graph(cb_ctx* c) {
   reduce_counters(c);
   c->ckB.n = (size_t)c->hcount[DC_EDGES_B];
   c->ckB.valid = true;
+  c->n_edges_c = cur_n;
   if (c->gcount[DC_TR_OVERFLOW]) throw Error(CB_E_CAPACITY, "TransitiveReduction kept-list capacity exceeded");
   c->counters["trans_edge"] = (int64_t)c->gcount[DC_TRANS_EDGE];
   c->counters["contained_edge"] = (int64_t)c->gcount[DC_CONTAINED_EDGE];
