@@ -384,6 +384,20 @@ def bench_ours(args):
                     "share_of_step": st[0] / args.steps / ms}
         kern = {kn: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                 for kn, v in stats.items() if v}
+        # ---- whole-path figure of BASELINE.md / SURVEY.md 8(d): B_alg from the run's measured counts ----
+        # (the byte budget of a sort-based pipeline; this build replaces its edge sort by slot writes and
+        # still reports against it.  C = verified candidates only: rejected ones are never materialised.)
+        N_in, N, T = counters["reads_good"] / world, counters["nodes"] / world, counters["tuples"] / world
+        C, E_A = counters["candidates_verified"] / world, counters["edges_overlap"] / world
+        E_c, E_B = counters["edges_chl2"] / world, counters["edges_re"] / world
+        A_, R_, P_, Pn_ = L + 10, 4 * ((2 * L + 31) // 32), (2 * k + 7) // 8, 4
+        b_alg = (N_in * (A_ + R_) + N_in * (2 * R_ + 24 + 24 * P_) + N * R_ + 12 * T + T * (8 + 24 * P_) + 12 * T + 12 * C
+                 + C * (12 + 2 * R_) + 12 * E_A + 24 * E_A + E_A * (8 + 24 * Pn_) + E_A * (12 + R_) + E_c * (12 + R_)
+                 + 12 * E_B)
+        path = {"alg_bytes_per_gpu": b_alg, "achieved": b_alg / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                "frac_of_measured_peak": b_alg / (ms * 1e-3) / 1e9 / peak,
+                "frac_of_nominal_8TBs": b_alg / (ms * 1e-3) / 1e9 / 8000.0,
+                "formula": "SURVEY.md 8(d) B_alg (pack+dedupe+keygen+sort+join+verify+mirror+cut+tr), per GPU"}
         # ---- CPU baseline (oracle port, 1 core, bounded sample) ----
         cpu = None
         if not args.no_cpu_baseline:
@@ -412,6 +426,7 @@ def bench_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
+            "roofline_path": path,
             "cpu_baseline": cpu,
             "counters": counters,
             "stage_ms": stage_ms,

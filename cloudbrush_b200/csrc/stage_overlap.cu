@@ -136,85 +136,138 @@ __device__ __forceinline__ void entry_of(int L, int K, int pos, int d, int sel, 
   ov = sel ? (L + K - ovc) : ovc;
 }
 
-// walks the k-mer groups whose head lies in this warp's 32-tuple chunks
-#define CB_FOR_EACH_SEGMENT(P, ...)                                                          \
-  {                                                                                          \
-    const u32 nchunks_ = ((P).T + 31) / 32;                                                  \
-    for (u32 chunk_ = warp_global; chunk_ < nchunks_; chunk_ += nwarps) {                    \
-      u32 i_ = chunk_ * 32 + lane;                                                           \
-      bool valid_ = i_ < (P).T;                                                              \
-      u64 ki_ = valid_ ? ((P).keys[i_] & (P).kmask) : 0;                                     \
-      u64 kprev_ = (valid_ && i_ > 0) ? ((P).keys[i_ - 1] & (P).kmask) : ~ki_;               \
-      u32 heads_ = __ballot_sync(0xffffffffu, valid_ && ki_ != kprev_);                      \
-      while (heads_) {                                                                       \
-        int h_ = __ffs(heads_) - 1;                                                          \
-        heads_ &= heads_ - 1;                                                                \
-        const u32 s = chunk_ * 32 + h_;                                                      \
-        const u64 kseg = __shfl_sync(0xffffffffu, ki_, h_);                                  \
-        u32 e = s + 1;                                                                       \
-        for (;;) {                                                                           \
-          u32 j_ = e + lane;                                                                 \
-          bool diff_ = (j_ >= (P).T) || (((P).keys[j_ < (P).T ? j_ : 0] & (P).kmask) != kseg); \
-          u32 b_ = __ballot_sync(0xffffffffu, diff_);                                        \
-          if (b_) { e += __ffs(b_) - 1; break; }                                             \
-          e += 32;                                                                           \
-        }                                                                                    \
-        __VA_ARGS__                                                                          \
-      }                                                                                      \
-    }                                                                                        \
+// first index in [lo, hi) whose masked key is >= (UPPER: >) kseg (keys are sorted on the masked bits)
+template <bool UPPER>
+__device__ __forceinline__ u32 key_bound(const JoinParams& P, u64 kseg, u32 lo, u32 hi) {
+  while (lo < hi) {
+    const u32 mid = lo + ((hi - lo) >> 1);
+    const u64 km = P.keys[mid] & P.kmask;
+    if (UPPER ? km <= kseg : km < kseg) lo = mid + 1;
+    else hi = mid;
   }
+  return lo;
+}
 
-// One walk over the k-mer groups: every tuple learns the first tuple of its group, the node
-// entries of a group the reducer processes (MatchPrefix.java:366) are listed at the head of the
-// group's index range, and the adjacency list each node entry produces is sized (one slot per
-// tuple of the group).  Also BuildHighKmerList's counter and the UP_KMER flag, which are per group.
-__global__ void __launch_bounds__(JN_WARPS * 32) group_walk_kernel(JoinParams P) {
-  const int lane = threadIdx.x & 31;
+// One flat pass over the sorted tuples, one thread per tuple: every tuple learns the first tuple
+// of its k-mer group (block-wide running maximum of the group heads; a group that began before the
+// block is found by binary search), and the node entries of a group the reducer processes
+// (MatchPrefix.java:366) claim the first free positions of the group's own index range in
+// `ne_list` (pre-filled with the terminator ~0) and size the adjacency list they produce: one
+// slot per tuple of the group.  The end of a group is the next head, found the same way from the
+// right (a serial forward scan by the node entries measured 2.3 ms; a group that runs past the
+// block is followed in global memory).  BuildHighKmerList's counter and the
+// UP_KMER flag are per group and are evaluated by the group's head.
+constexpr int GW_THREADS = 256;
+__global__ void __launch_bounds__(GW_THREADS) group_walk_kernel(JoinParams P) {
+  __shared__ u32 s_wmax[GW_THREADS / 32], s_wmin[GW_THREADS / 32], s_wcnt[GW_THREADS / 32], s_first, s_last;
+  __shared__ unsigned short s_pre[GW_THREADS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const u32 lt_mask = (1u << lane) - 1;
-  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
   const u32 posmask = (1u << P.pb) - 1;
   const int L = P.L, K = P.K;
-  CB_FOR_EACH_SEGMENT(P, {
-    const u32 g = e - s;
-    // BuildHighKmerList.java:96-117: weighted count over windows [0, L-K) above UP_KMER
-    if (kseg != 0 && (long long)g * (long long)P.max_cov > P.up_kmer) {
-      ull sum = 0;
-      for (u32 j = s + lane; j < e; j += 32) {
-        u64 m = tuple_meta(P, j);
-        int pos = (int)((m >> 1) & posmask);
-        if (pos < L - K) sum += P.node_cov[(u32)(m >> (P.pb + 1))];
-      }
+  for (u32 j0 = blockIdx.x * GW_THREADS; j0 < P.T; j0 += gridDim.x * GW_THREADS) {  // block-uniform
+    const u32 j = j0 + threadIdx.x;
+    const bool valid = j < P.T;
+    const u64 kj = valid ? P.keys[j] : 0ull;
+    const u32 vj = valid ? P.vals[j] : 0u;
+    const u64 kseg = kj & P.kmask;
+    const u64 kprev = (valid && j > 0) ? (P.keys[j - 1] & P.kmask) : ~kseg;
+    const bool head = valid && kseg != kprev;
+    const u64 m = ((kj >> (2 * K)) << 32) | (u64)vj;
+    const int pos = (int)((m >> 1) & posmask);
+    const bool cand = valid && (pos == 0 || pos == L - K);  // a NODEMSG tuple
+    // running maximum of the head positions (+1; 0 = no head yet in this block)
+    u32 h = head ? j + 1 : 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if (lane == 0 && (long long)sum > P.up_kmer) atomicAdd(&P.dcount[DC_HKMER], 1ull);
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_up_sync(0xffffffffu, h, o);
+      if (lane >= o) h = max(h, t);
     }
+    // ... and the running minimum, from the right, of the head positions: where the next group begins
+    u32 nx = head ? j : 0xffffffffu;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_down_sync(0xffffffffu, nx, o);
+      if (lane + o < 32) nx = min(nx, t);
+    }
+    const u32 cbal = __ballot_sync(0xffffffffu, cand);
+    if (lane == 31) s_wmax[warp] = h;
+    if (lane == 0) { s_wmin[warp] = nx; s_wcnt[warp] = (u32)__popc(cbal); }
+    // the two groups that may extend beyond the block are followed by one warp each, 32 keys per
+    // (coalesced) load: a per-thread binary search here cost 1.2 ms in dependent L2 round trips
+    if (warp == 0) {  // where does the group of the block's first tuple begin?
+      const u64 kf = __shfl_sync(0xffffffffu, kseg, 0);
+      u32 sfirst = 0xffffffffu, hi = j0;  // keys[hi .. j0] all equal kf
+      for (int rounds = 0; sfirst == 0xffffffffu; rounds++) {
+        if (hi == 0) { sfirst = 0; break; }
+        if (rounds == 4) { sfirst = key_bound<false>(P, kf, 0, hi); break; }
+        const u32 base = hi >= 32 ? hi - 32 : 0;
+        const u32 idx = base + lane;
+        const bool differs = idx < hi && (P.keys[idx] & P.kmask) != kf;
+        const u32 bal = __ballot_sync(0xffffffffu, differs);
+        if (bal) sfirst = base + (31 - __clz(bal)) + 1;
+        else hi = base;
+      }
+      if (lane == 0) s_first = sfirst;
+    }
+    if (warp == GW_THREADS / 32 - 1) {  // where does the group of the block's last tuple end?
+      const u32 jl = min(j0 + (u32)GW_THREADS, P.T) - 1;
+      const u64 kl = P.keys[jl] & P.kmask;
+      u32 elast = 0xffffffffu, lo = jl + 1;  // keys[jl .. lo-1] all equal kl
+      for (int rounds = 0; elast == 0xffffffffu; rounds++) {
+        if (lo >= P.T) { elast = P.T; break; }
+        if (rounds == 4) { elast = key_bound<true>(P, kl, lo, P.T); break; }
+        const u32 idx = lo + lane;
+        const bool differs = idx >= P.T || (P.keys[idx] & P.kmask) != kl;
+        const u32 bal = __ballot_sync(0xffffffffu, differs);
+        if (bal) elast = lo + (__ffs(bal) - 1);
+        else lo += 32;
+      }
+      if (lane == 0) s_last = elast;
+    }
+    __syncthreads();
+    const u32 sf = s_first, sl = s_last;  // read before the next barrier: the next round overwrites them
+    u32 before = 0, after = 0xffffffffu, cpre = (u32)__popc(cbal & lt_mask);
+    for (int w = 0; w < warp; w++) { before = max(before, s_wmax[w]); cpre += s_wcnt[w]; }
+    for (int w = warp + 1; w < GW_THREADS / 32; w++) after = min(after, s_wmin[w]);
+    h = max(h, before);
+    u32 e = __shfl_down_sync(0xffffffffu, nx, 1);
+    if (lane == 31) e = 0xffffffffu;
+    e = min(e, after);
+    s_pre[threadIdx.x] = (unsigned short)cpre;  // NODEMSG tuples of the block before this one
+    __syncthreads();
+    if (!valid) continue;
+    const bool inside = h != 0 && e != 0xffffffffu;  // the whole group lies in this block
+    const u32 s = h ? h - 1 : sf;                    // else it began before the block ...
+    if (e == 0xffffffffu) e = sl;                    // ... or runs past it
+    P.seg_head[j] = s;
+    if (!cand && !head) continue;
+    const u32 g = e - s;
     const bool live = (long long)g > P.low_kmer;
-    if (live && (long long)g > P.up_kmer && lane == 0) atomicAdd(&P.dcount[DC_UPKMER_LISTS], 1ull);
-    u32 nB = 0;
-    for (u32 j0 = s; j0 < e; j0 += 32) {
-      const u32 j = j0 + lane;
-      u64 m = 0;
-      bool isn = false;
-      if (j < e) {
-        P.seg_head[j] = s;
-        m = tuple_meta(P, j);
-        int pos = (int)((m >> 1) & posmask);
-        isn = live && (pos == 0 || pos == L - K);
+    if (head) {
+      // BuildHighKmerList.java:96-117: weighted count over windows [0, L-K) above UP_KMER
+      if (kseg != 0 && (long long)g * (long long)P.max_cov > P.up_kmer) {
+        ull sum = 0;
+        for (u32 t = s; t < e; t++) {
+          const u64 m2 = tuple_meta(P, t);
+          if ((int)((m2 >> 1) & posmask) < L - K) sum += P.node_cov[(u32)(m2 >> (P.pb + 1))];
+        }
+        if ((long long)sum > P.up_kmer) atomicAdd(&P.dcount[DC_HKMER], 1ull);
       }
-      const u32 bal = __ballot_sync(0xffffffffu, isn);
-      if (isn) {
-        const int pos = (int)((m >> 1) & posmask);
-        const u32 lid = 2 * (u32)(m >> (P.pb + 1)) + (pos == 0 ? 1u : 0u);  // list (b, flip y)
-        P.ne_list[s + nB + __popc(bal & lt_mask)] = lid | ((u32)(m & 1) << 31);
-        P.slotcnt[lid] = g;
-      }
-      nB += __popc(bal);
+      if (live && (long long)g > P.up_kmer) atomicAdd(&P.dcount[DC_UPKMER_LISTS], 1ull);
     }
-    // (all ne_list writes of this group are below s + nB <= e, the terminator is inside or right
-    // after the group's own range; the next group starts at e and never reads it as its own)
-    if (lane == 0 && nB < g) P.ne_list[s + nB] = 0xffffffffu;
-  })
+    if (cand && live) {
+      const u32 lid = 2 * (u32)(m >> (P.pb + 1)) + (pos == 0 ? 1u : 0u);  // list (b, flip y)
+      const u32 v = lid | ((u32)(m & 1) << 31);
+      if (inside) {  // position = number of NODEMSG tuples of the group before this one: no atomics
+        P.ne_list[s + (cpre - (u32)s_pre[s - j0])] = v;
+      } else {       // the group straddles blocks: claim the first free position of its range
+        for (u32 t = s; t < e; t++)
+          if (atomicCAS(&P.ne_list[t], 0xffffffffu, v) == 0xffffffffu) break;
+      }
+      P.slotcnt[lid] = g;
+    }
+  }
 }
 
 constexpr int JN_XW = 64;  // side-buffer records staged per warp (flushed once 32 are waiting)
@@ -698,11 +751,9 @@ void stage_build_overlap(cb_ctx* c) {
   P.up_kmer = c->cfg.up_kmer;
   P.lay = c->lay;
   P.dcount = (ull*)c->dcount.p;
-  int wblocks = kNumSMs * 8;
-  {
-    int need = div_up(((size_t)T + 31) / 32, JN_WARPS);
-    if (need < wblocks) wblocks = need > 0 ? need : 1;
-  }
+  int wblocks = div_up((size_t)T, GW_THREADS);
+  if (wblocks > kNumSMs * 8) wblocks = kNumSMs * 8;
+  if (wblocks < 1) wblocks = 1;
   DevBuf<u32> slotcnt, off1, seg_head, ne_list, extra;
   slotcnt.alloc((size_t)n_lists + 1, s);
   off1.alloc((size_t)n_lists + 1, s);
@@ -710,11 +761,12 @@ void stage_build_overlap(cb_ctx* c) {
   ne_list.alloc((size_t)T + 1, s);
   extra.alloc(n_lists ? n_lists : 1, s);
   CB_CUDA(cudaMemsetAsync(slotcnt.p, 0, ((size_t)n_lists + 1) * 4, s));
+  CB_CUDA(cudaMemsetAsync(ne_list.p, 0xff, ((size_t)T + 1) * 4, s));  // terminators; node entries claim from the left
   P.slotcnt = slotcnt.p;
   P.seg_head = seg_head.p;
   P.ne_list = ne_list.p;
   c->lc.begin("group_walk");
-  group_walk_kernel<<<wblocks, JN_WARPS * 32, 0, s>>>(P);
+  group_walk_kernel<<<wblocks, GW_THREADS, 0, s>>>(P);
   c->lc.end("group_walk");
   c->lc.n++;
   exclusive_scan_u32(slotcnt.p, off1.p, (size_t)n_lists + 1, s, c->lc);

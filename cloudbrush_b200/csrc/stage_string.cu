@@ -51,9 +51,10 @@ struct StringParams {
   uint8_t* removed;    // cut output, per slot
   uint8_t* kept;       // tr output, per slot
   uint8_t* list_flag;  // per list: 1 consistent, 0 not, dirty bits 2 / 4 (lost an entry in cut round 1 / 2)
-  uint8_t* pre;        // per slot, from consistency_kernel: bit0 maximal overlap of its list, bit1 counts as
-                       // transitive if the list is consistent, bit2 ov == L
   uint8_t* ovmax;      // per list, from consistency_kernel: the maximal overlap of the list (0: empty list)
+  u32* lmax;           // per list: [2*lid], [2*lid+1] = (nbr | y << 31) of the first two records of maximal
+                       // overlap (~0: none); lnmax[lid] = how many there are (saturating at 255)
+  uint8_t* lnmax;
   const uint8_t* lsum; // per list, all ranks: ovmax if the list is consistent and untouched by the cut rounds
                        // (TransitiveReduction keeps exactly its records of that overlap), else 0
   const u32* work;     // work list of list ids (literal kernels)
@@ -114,53 +115,46 @@ __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* _
   for (u32 it = blockIdx.x * blockDim.x + threadIdx.x; it < n_iter; it += gridDim.x * blockDim.x) {
     const u32 lid = lists ? lists[it] : it;
     const u32 lo = P.adj_off[lid], hi = P.adj_off[lid + 1];
-    u32 hidx = lo, hov = 0xffffffffu, ovmax = 0, n = 0, nmax = 0;
-    u64 m0 = ~0ull, m1 = ~0ull;  // the first two records of maximal overlap
-    for (u32 t = lo; t < hi; t++) {
-      const u64 q = P.edges[t];
-      if (q == ~0ull) continue;
-      n++;
-      const u32 o = P.lay.ov(q);
-      if (o < hov) { hov = o; hidx = t; }
-      if (o > ovmax) { ovmax = o; nmax = 1; m0 = q; m1 = ~0ull; }
-      else if (o == ovmax) { if (nmax == 1) m1 = q; nmax++; }
-    }
-    if (n == 0) continue;
-    P.ovmax[lid] = (uint8_t)ovmax;
+    // ONE pass over the list: the overhangs nest iff every record nests with the longest overhang
+    // seen so far (if the new one is longer it must extend that one, and then everything before it
+    // is a prefix of the new one as well)
+    u32 ovmax = 0, n = 0, nmax = 0;
+    u32 m0 = 0xffffffffu, m1 = 0xffffffffu;  // (nbr | y << 31) of the first two records of maximal overlap
     u64 H[NW];
-    int lenH = 0;
-    const bool test = n > 1 && !force_slow;
-    if (test) load_overhang<NW>(P, hidx, P.edges[hidx], H, lenH);
-    bool bad = n > 1 && force_slow;
+    int lenH = -1;
+    bool bad = false;
     for (u32 t = lo; t < hi; t++) {
       const u64 k = P.edges[t];
       if (k == ~0ull) continue;
-      const u32 ov = P.lay.ov(k);
-      if (test && t != hidx) {
+      n++;
+      const u32 o = P.lay.ov(k);
+      const u32 nby = P.lay.nbr(k) | (P.lay.y(k) << 31);
+      if (o > ovmax) { ovmax = o; nmax = 1; m0 = nby; m1 = 0xffffffffu; }
+      else if (o == ovmax) { if (nmax == 1) m1 = nby; nmax++; }
+      if (!force_slow) {
         u64 h[NW];
         int len;
         load_overhang<NW>(P, t, k, h, len);
-        bad = bad || !prefix_equal<NW>(h, H, len);
+        if (lenH < 0) {
+#pragma unroll
+          for (int w = 0; w < NW; w++) H[w] = h[w];
+          lenH = len;
+        } else if (len > lenH) {
+          bad = bad || !prefix_equal<NW>(H, h, lenH);
+#pragma unroll
+          for (int w = 0; w < NW; w++) H[w] = h[w];
+          lenH = len;
+        } else {
+          bad = bad || !prefix_equal<NW>(h, H, len);
+        }
       }
-      // TransitiveReduction on a consistent list: keep the maximal overlap (:341-343); anything
-      // else is dropped, counted as transitive unless a kept record has my type and neighbour
-      // (:325-334)
-      uint8_t f = (int)ov == P.L ? 4u : 0u;
-      if (ov == ovmax) f |= 1u;
-      else {
-        const u32 nbr = P.lay.nbr(k), y = P.lay.y(k);
-        bool step2 = (P.lay.nbr(m0) == nbr && P.lay.y(m0) == y) ||
-                     (m1 != ~0ull && P.lay.nbr(m1) == nbr && P.lay.y(m1) == y);
-        if (!step2 && nmax > 2)
-          for (u32 q = lo; q < hi && !step2; q++) {
-            const u64 kq = P.edges[q];
-            if (kq != ~0ull && P.lay.ov(kq) == ovmax && P.lay.nbr(kq) == nbr && P.lay.y(kq) == y) step2 = true;
-          }
-        if (!step2) f |= 2u;
-      }
-      P.pre[t] = f;
     }
-    if (bad) {  // only this thread writes the list's flag here
+    if (n == 0) continue;
+    P.ovmax[lid] = (uint8_t)ovmax;
+    P.lmax[2 * (size_t)lid] = m0;
+    P.lmax[2 * (size_t)lid + 1] = m1;
+    P.lnmax[lid] = (uint8_t)(nmax > 255 ? 255 : nmax);
+    if (n > 1 && (bad || force_slow)) {  // only this thread writes the list's flag here
       P.list_flag[lid] = 0;
       work_out[atomicAdd(n_work_out, 1u)] = lid;
     }
@@ -538,11 +532,28 @@ __global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __re
     bool keep = false;
     if (k != ~0ull) {
       bool kept_here;
-      if (P.list_flag[P.lay.list(k)] == 1) {
-        const uint8_t f = P.pre[slot];
-        kept_here = f & 1;
-        trans += (f >> 1) & 1;
-        contained += (f >> 2) & 1;  // TransitiveReduction.java:319-323 (equal-length reads)
+      const u32 lid = P.lay.list(k);
+      const u32 om = P.lsum[lid];  // the list's maximal overlap if it is consistent and untouched, else 0
+      if (om) {
+        // TransitiveReduction on a consistent list: keep the maximal overlap (:341-343); anything
+        // else is dropped, counted as transitive unless a kept record has my type and neighbour
+        // (:325-334)
+        const u32 ov = P.lay.ov(k);
+        kept_here = ov == om;
+        contained += (int)ov == P.L;  // TransitiveReduction.java:319-323 (equal-length reads)
+        if (!kept_here) {
+          const u32 nby = P.lay.nbr(k) | (P.lay.y(k) << 31);
+          const uint2 mm = *reinterpret_cast<const uint2*>(P.lmax + 2 * (size_t)lid);
+          bool step2 = mm.x == nby || mm.y == nby;
+          if (!step2 && P.lnmax[lid] > 2) {
+            const u32 lo = P.adj_off[lid], hi = P.adj_off[lid + 1];
+            for (u32 q = lo; q < hi && !step2; q++) {
+              const u64 kq = P.edges[q];
+              if (kq != ~0ull && P.lay.ov(kq) == om && (P.lay.nbr(kq) | (P.lay.y(kq) << 31)) == nby) step2 = true;
+            }
+          }
+          trans += !step2;
+        }
       } else {
         kept_here = (P.kept[slot] & 1) != 0;  // literal kernel
       }
@@ -672,8 +683,9 @@ static StringParams make_params(cb_ctx* c, const u64* keys) {
   P.removed = nullptr;
   P.kept = nullptr;
   P.list_flag = c->list_flag.p;
-  P.pre = nullptr;
   P.ovmax = nullptr;
+  P.lmax = nullptr;
+  P.lnmax = nullptr;
   P.lsum = nullptr;
   P.work = nullptr;
   P.n_work = 0;
@@ -753,11 +765,12 @@ void stage_string_graph(cb_ctx* c) {
   DevBuf<uint8_t> flags;  // per slot: "removed" during the cut rounds, then "kept" for TR
   flags.alloc(slots, s);
   CB_CUDA(cudaMemsetAsync(flags.p, 0, slots, s));
-  DevBuf<uint8_t> pre;  // per slot: TransitiveReduction's fast-path decision (consistency_kernel)
-  pre.alloc(slots, s);
-  DevBuf<uint8_t> ovmax, lsum;  // per list: maximal overlap / summary byte of the final pass
+  DevBuf<uint8_t> ovmax, lsum, lnmax;  // per list: maximal overlap / summary byte of the final pass / #maximal records
+  DevBuf<u32> lmax;                    // per list: the first two records of maximal overlap
   ovmax.alloc(nl, s);
   lsum.alloc(nl, s);
+  lnmax.alloc(nl, s);
+  lmax.alloc(2 * nl, s);
   CB_CUDA(cudaMemsetAsync(ovmax.p, 0, nl, s));
   DevBuf<u64> req;  // multi-GPU: mirror keys to act on at their owner
   if (dist) req.alloc(slots, s);
@@ -776,8 +789,9 @@ void stage_string_graph(cb_ctx* c) {
   int64_t e1 = 0, e2 = 0;
   {
     StringParams P = make_params(c, cur_keys);
-    P.pre = pre.p;
     P.ovmax = ovmax.p;
+    P.lmax = lmax.p;
+    P.lnmax = lnmax.p;
     if (c->ckA.n) {
       const u32* lists = nullptr;
       u32 n_iter = n_lists;
@@ -893,8 +907,9 @@ void stage_string_graph(cb_ctx* c) {
     // `flags` is all zero again here (remove_flagged_kernel clears what it consumed)
     StringParams P = make_params(c, cur_keys);
     P.kept = flags.p;
-    P.pre = pre.p;
     P.ovmax = ovmax.p;
+    P.lmax = lmax.p;
+    P.lnmax = lnmax.p;
     P.lsum = lsum.p;
     // literal path first: lists that are inconsistent or lost an entry in a cut round
     CB_CUDA(cudaMemsetAsync(nwork.p + 3, 0, 4, s));
