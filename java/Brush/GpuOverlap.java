@@ -37,6 +37,8 @@ public class GpuOverlap implements AutoCloseable {
     private static native int nWriteNodes(long ctx, int checkpoint, String outDir);
     private static native long nCounter(long ctx, String name);      // Long.MIN_VALUE if unknown
     private static native double nTimeMs(long ctx, String what);
+    private static native byte[] nNcclUniqueId();                      // multi-GPU launchers: rank 0
+    private static native int nInitNccl(long ctx, byte[] id128);      // every rank, before preprocess
 
     public GpuOverlap() throws IOException {
         // the options the path reads, straight from BrushConfig (BrushConfig.java:55-84)

@@ -59,3 +59,19 @@ JNIEXPORT jdouble JNICALL Java_Brush_GpuOverlap_nTimeMs(JNIEnv* env, jclass cls,
   (*env)->ReleaseStringUTFChars(env, what, p);
   return ms;
 }
+
+/* multi-GPU launchers (one JVM per GPU): rank 0 obtains the NCCL id, the launcher distributes the
+ * 128 bytes over its own channel, every rank initialises the library's native transport */
+JNIEXPORT jbyteArray JNICALL Java_Brush_GpuOverlap_nNcclUniqueId(JNIEnv* env, jclass cls) {
+  jbyte id[CB_NCCL_ID_BYTES];
+  if (cb_nccl_get_unique_id(id) != CB_OK) return NULL;
+  jbyteArray out = (*env)->NewByteArray(env, CB_NCCL_ID_BYTES);
+  (*env)->SetByteArrayRegion(env, out, 0, CB_NCCL_ID_BYTES, id);
+  return out;
+}
+
+JNIEXPORT jint JNICALL Java_Brush_GpuOverlap_nInitNccl(JNIEnv* env, jclass cls, jlong h, jbyteArray id) {
+  jbyte buf[CB_NCCL_ID_BYTES];
+  (*env)->GetByteArrayRegion(env, id, 0, CB_NCCL_ID_BYTES, buf);
+  return cb_init_nccl(CTX(h), buf);
+}

@@ -61,6 +61,16 @@ def test_null_and_bad_arguments_return_codes():
     assert lib.cb_get_counter(None, b"nodes", C.byref(v)) == -1
 
 
+def test_native_nccl_entry_points_reject_bad_arguments():
+    """cb_nccl_get_unique_id / cb_init_nccl validate before touching NCCL (no GPU needed)."""
+    from cloudbrush_b200 import _lib
+    lib = _lib.load()
+    assert lib.cb_nccl_get_unique_id(None) == -1
+    assert lib.cb_init_nccl(None, None) == -1
+    txt = open(os.path.join(ROOT, "include", "cloudbrush_gpu.h")).read()
+    assert "CB_NCCL_ID_BYTES 128" in txt and "allreduce_max_u8_dev" in txt
+
+
 def test_running_job_lookalike():
     from cloudbrush_b200.stages import RunningJob
     j = RunningJob("preprocess", {"nodes": 5, "reads_good": 7}, 0.1)

@@ -69,3 +69,18 @@ def test_four_ranks_micro_cases(tmp_path):
         d = tmp_path / name
         d.mkdir()
         _check(buf, k, L, d, world=4)
+
+
+def test_native_nccl_two_gpus(tmp_path):
+    """Native NCCL transport (cb_init_nccl) on a box with two GPUs: tools/dist_check.py under torchrun."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (the same check runs through `gpurun --gpus 2 tools/dist_check.py`)")
+    from dist_util import free_port
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+                        os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("PARITY OK") == 4
