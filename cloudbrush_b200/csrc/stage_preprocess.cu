@@ -25,17 +25,35 @@ __device__ __forceinline__ bool is_term(const char* __restrict__ text, size_t i,
   return false;
 }
 
+// 0x80 in every byte of w that equals the byte replicated in `pat` (exact, no carry artefacts)
+__device__ __forceinline__ u32 bytes_equal(u32 w, u32 pat) {
+  const u32 t = w ^ pat;
+  return ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t | 0x7f7f7f7fu);
+}
+
+// bit j set: byte j of the thread's 16-byte chunk ends a line.  Four bytes per step (SWAR): a
+// '\n' always ends a line; '\r' (rare) does unless a '\n' follows, which is resolved per byte.
 __device__ __forceinline__ u32 thread_term_mask(const char* __restrict__ text, size_t base, size_t n) {
   u32 m = 0;
   if (base + PT_BYTES < n) {  // whole chunk and the look-ahead byte are in range
     uint4 v = *reinterpret_cast<const uint4*>(text + base);
     u32 w[4] = {v.x, v.y, v.z, v.w};
-    char nxt = text[base + PT_BYTES];
+    u32 any_cr = 0;
 #pragma unroll
-    for (int j = 0; j < PT_BYTES; j++) {
-      char c = (char)((w[j >> 2] >> ((j & 3) * 8)) & 0xff);
-      char c1 = (j + 1 < PT_BYTES) ? (char)((w[(j + 1) >> 2] >> (((j + 1) & 3) * 8)) & 0xff) : nxt;
-      if (c == '\n' || (c == '\r' && c1 != '\n')) m |= 1u << j;
+    for (int q = 0; q < 4; q++) {
+      const u32 nl = bytes_equal(w[q], 0x0a0a0a0au);
+      any_cr |= bytes_equal(w[q], 0x0d0d0d0du);
+      // 0x80 of bytes 0..3 -> bits 0..3
+      m |= (((nl >> 7) * 0x00204081u) >> 21 & 0xfu) << (4 * q);
+    }
+    if (any_cr) {  // a lone '\r' also ends a line (Hadoop LineReader)
+      char nxt = text[base + PT_BYTES];
+#pragma unroll
+      for (int j = 0; j < PT_BYTES; j++) {
+        char c = (char)((w[j >> 2] >> ((j & 3) * 8)) & 0xff);
+        char c1 = (j + 1 < PT_BYTES) ? (char)((w[(j + 1) >> 2] >> (((j + 1) & 3) * 8)) & 0xff) : nxt;
+        if (c == '\r' && c1 != '\n') m |= 1u << j;
+      }
     }
   } else {
     for (int j = 0; j < PT_BYTES; j++)
@@ -133,28 +151,51 @@ __global__ void __launch_bounds__(128) parse_lines_kernel(const char* __restrict
         if ((size_t)chunk + j < text_n) v[j >> 2] |= (u32)(unsigned char)text[chunk + j] << ((j & 3) * 8);
     }
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const u32 p = chunk + j;
-      const u32 c = (v[j >> 2] >> ((j & 3) * 8)) & 0xffu;
-      if (p < s || p >= e || done) continue;
-      if (c == '\n' || c == '\r') { done = true; continue; }  // the terminator is the end of the line
-      if (c == '\t') { field++; continue; }
-      last_nonempty = field;
-      if (field == 0) {
-        if (idlen < 8) ik.hi |= (u64)c << (56 - 8 * idlen);
-        else if (idlen < 16) ik.lo |= (u64)c << (56 - 8 * (idlen - 8));
-        idlen++;
-      } else if (field == 1) {
-        u32 u = (c & 0xdfu) - 'A';
-        bool ok = u < 20u && ((0x80045u >> u) & 1u);
-        bad |= !ok;
-        acc = (acc << 2) | (u64)(((c >> 1) ^ (c >> 2)) & 3u);
-        nb++;
+    for (int q = 0; q < 4; q++) {
+      const u32 p0 = chunk + 4 * q;
+      const u32 wq = v[q];
+      // fast path: four sequence bytes at once (SWAR) -- all inside field 1 and the line, all of
+      // them ACGT in either case (which also rules out a tab or a terminator), and not straddling
+      // a 32-base word of the packed row
+      const u32 cc = ((wq >> 1) ^ (wq >> 2)) & 0x03030303u;  // A,C,G,T -> 0,1,2,3 per byte
+      const u32 hi2 = (cc >> 1) & 0x01010101u, both = cc & hi2;
+      const u32 expect = 0x41414141u + 2u * cc + 2u * hi2 + 11u * both;  // 'A','C','G','T' of the codes
+      if (field == 1 && !done && p0 >= s && p0 + 3 < e && expect == (wq & 0xdfdfdfdfu) && (nb & 31) <= 28) {
+        acc = (acc << 8) | (u64)(((cc * 0x40100401u) >> 24) & 0xffu);  // first byte -> highest pair
+        nb += 4;
+        last_nonempty = 1;
         if ((nb & 31) == 0) {
           int wi = (nb >> 5) - 1;
 #pragma unroll
-          for (int q = 0; q < NW; q++)
-            if (q == wi) w[q] = acc;
+          for (int t = 0; t < NW; t++)
+            if (t == wi) w[t] = acc;
+        }
+        continue;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const u32 p = p0 + jj;
+        const u32 c = (wq >> (jj * 8)) & 0xffu;
+        if (p < s || p >= e || done) continue;
+        if (c == '\n' || c == '\r') { done = true; continue; }  // the terminator is the end of the line
+        if (c == '\t') { field++; continue; }
+        last_nonempty = field;
+        if (field == 0) {
+          if (idlen < 8) ik.hi |= (u64)c << (56 - 8 * idlen);
+          else if (idlen < 16) ik.lo |= (u64)c << (56 - 8 * (idlen - 8));
+          idlen++;
+        } else if (field == 1) {
+          u32 u = (c & 0xdfu) - 'A';
+          bool ok = u < 20u && ((0x80045u >> u) & 1u);
+          bad |= !ok;
+          acc = (acc << 2) | (u64)(((c >> 1) ^ (c >> 2)) & 3u);
+          nb++;
+          if ((nb & 31) == 0) {
+            int wi = (nb >> 5) - 1;
+#pragma unroll
+            for (int t = 0; t < NW; t++)
+              if (t == wi) w[t] = acc;
+          }
         }
       }
     }
