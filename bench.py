@@ -377,7 +377,7 @@ def bench_ours(args):
                 traffic = tj.get("rs_scatter:tuples", {}).get("dram_bytes_per_launch")
             except Exception:
                 pass
-            roof = {"bound": "hbm", "kernel": "rs_scatter<pairs> (k-mer tuple sort, one 8-bit LSD pass)",
+            roof = {"bound": "hbm", "kernel": "rs_onesweep<pairs> (k-mer tuple sort, one 8/9-bit LSD pass)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
                     "ms_per_launch": per_launch_ms, "launches_per_step": st[1] / args.steps,

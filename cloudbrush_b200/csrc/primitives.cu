@@ -291,11 +291,12 @@ constexpr int RS_LB = 8;  // look-back loads in flight (16 and 32 measured slowe
 // per digit bit, cost the same whatever the values are.  `ballot` is uniform over the grid: every
 // pass measures how many distinct digits of the NEXT pass a warp will see (its write-out order is
 // the next pass' input order) and the next pass picks the cheaper ranking from that.
+template <int RB>
 __device__ __forceinline__ u32 digit_peers(u32 d, bool ballot) {
   if (!ballot) return __match_any_sync(0xffffffffu, d);
   u32 peers = 0xffffffffu;
 #pragma unroll
-  for (int b = 0; b < 8; b++) {
+  for (int b = 0; b < RB; b++) {
     const bool bit = (d >> b) & 1u;
     const u32 bal = __ballot_sync(0xffffffffu, bit);
     peers &= bit ? bal : ~bal;
@@ -314,43 +315,58 @@ __device__ __forceinline__ void sample_diversity(u32 d, int lane, u32* ent) {
   }
 }
 
-__global__ void __launch_bounds__(256) rs_hist_all_kernel(const u64* __restrict__ kin, size_t n, int begin_bit,
-                                                          int end_bit, u32* __restrict__ ghist, u32* __restrict__ ent0) {
-  __shared__ u32 h[RS_MAXPASS][256];
-  for (int t = threadIdx.x; t < RS_MAXPASS * 256; t += blockDim.x) (&h[0][0])[t] = 0;
-  __syncthreads();
-  const int npass = (end_bit - begin_bit + 7) / 8;
-  if (threadIdx.x < 32 && (size_t)blockIdx.x * blockDim.x + 32 <= n) {  // first warp: digit diversity of pass 0
-    const int nb0 = end_bit - begin_bit < 8 ? end_bit - begin_bit : 8;
-    sample_diversity((u32)(kin[(size_t)blockIdx.x * blockDim.x + threadIdx.x] >> begin_bit) & ((1u << nb0) - 1),
-                     (int)threadIdx.x, ent0);
+// Pass plan of one sort: key bits [begin, end) are cut into ceil(bits / 9) digits of 8 or 9 bits
+// (42 bits of a k=21 tuple key: 8+8+8+9+9, five passes instead of six; 62 bits for k=31: seven
+// instead of eight).  A 9-bit pass uses 512 bins = one per thread of the scatter kernel.
+constexpr int RS_MAXRADIX = 512;
+struct PassPlan {
+  int npass;
+  int shift[RS_MAXPASS];
+  int bits[RS_MAXPASS];
+};
+static PassPlan make_plan(int begin_bit, int end_bit, int max_digit_bits) {
+  PassPlan pl;
+  const int B = end_bit - begin_bit;
+  pl.npass = (B + max_digit_bits - 1) / max_digit_bits;
+  const int base = B / pl.npass, rem = B % pl.npass;
+  int at = begin_bit;
+  for (int p = 0; p < RS_MAXPASS; p++) {
+    pl.shift[p] = at;
+    pl.bits[p] = p < pl.npass ? base + (p >= pl.npass - rem ? 1 : 0) : 0;  // the wider digits go last: late passes see clustered digits, whose ranking is cheap
+    at += pl.bits[p];
   }
+  return pl;
+}
+
+__global__ void __launch_bounds__(256) rs_hist_all_kernel(const u64* __restrict__ kin, size_t n, PassPlan pl,
+                                                          u32* __restrict__ ghist, u32* __restrict__ ent0) {
+  extern __shared__ u32 hsm[];  // [npass][RS_MAXRADIX]
+  for (int t = threadIdx.x; t < pl.npass * RS_MAXRADIX; t += blockDim.x) hsm[t] = 0;
+  __syncthreads();
+  if (threadIdx.x < 32 && (size_t)blockIdx.x * blockDim.x + 32 <= n)  // first warp: digit diversity of pass 0
+    sample_diversity((u32)(kin[(size_t)blockIdx.x * blockDim.x + threadIdx.x] >> pl.shift[0]) & ((1u << pl.bits[0]) - 1),
+                     (int)threadIdx.x, ent0);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const u64 k = kin[i];
 #pragma unroll
-    for (int p = 0; p < RS_MAXPASS; p++) {
-      if (p < npass) {
-        const int bit = begin_bit + 8 * p;
-        const int nb = end_bit - bit < 8 ? end_bit - bit : 8;
-        atomicAdd(&h[p][(u32)(k >> bit) & ((1u << nb) - 1)], 1u);
-      }
-    }
+    for (int p = 0; p < RS_MAXPASS; p++)
+      if (p < pl.npass) atomicAdd(&hsm[p * RS_MAXRADIX + ((u32)(k >> pl.shift[p]) & ((1u << pl.bits[p]) - 1))], 1u);
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < npass * 256; t += blockDim.x) {
-    u32 v = (&h[0][0])[t];
+  for (int t = threadIdx.x; t < pl.npass * RS_MAXRADIX; t += blockDim.x) {
+    u32 v = hsm[t];
     if (v) atomicAdd(&ghist[t], v);
   }
 }
 
-// one block: exclusive scan of every pass' 256 digit totals (in place)
-__global__ void __launch_bounds__(256) rs_scan_hist_kernel(u32* __restrict__ ghist, int npass) {
-  __shared__ u32 tmp[256 / 32 + 1];
+// one block of RS_MAXRADIX threads: exclusive scan of every pass' digit totals (in place)
+__global__ void __launch_bounds__(RS_MAXRADIX) rs_scan_hist_kernel(u32* __restrict__ ghist, int npass) {
+  __shared__ u32 tmp[RS_MAXRADIX / 32 + 1];
   for (int p = 0; p < npass; p++) {
-    u32 v = ghist[p * 256 + threadIdx.x];
+    u32 v = ghist[p * RS_MAXRADIX + threadIdx.x];
     u32 total;
     u32 ex = block_excl_scan(v, tmp, total);
-    ghist[p * 256 + threadIdx.x] = ex;
+    ghist[p * RS_MAXRADIX + threadIdx.x] = ex;
   }
 }
 
@@ -379,9 +395,9 @@ extern "C" void cb_debug_os_prof(unsigned long long* out, int reset) {
 #define OS_T(i)
 #endif
 
-template <bool HAS_VALS, int S>
+template <bool HAS_VALS, int S, int RB>
 constexpr size_t os_smem_bytes() {
-  return (size_t)S * RS_SUB * (HAS_VALS ? 12 : 8) + RS_WARPS * 256 * 2 + 3 * S * 256 * 4;
+  return (size_t)S * RS_SUB * (HAS_VALS ? 12 : 8) + RS_WARPS * (1 << RB) * 2 + 3 * S * (1 << RB) * 4;
 }
 
 // One logical tile = S sub-tiles of RS_SUB keys processed back to back by one CTA and staged in
@@ -391,7 +407,7 @@ constexpr size_t os_smem_bytes() {
 // status loads queue behind the SM's bulk traffic -- over a window of 31 predecessor tiles.  With
 // S = 2 the window halves, because tiles start half as often, and its cost is shared by twice the
 // keys.)  Payloads are staged in their own buffer and leave in the same loop as the keys.
-template <bool HAS_VALS, int S>
+template <bool HAS_VALS, int S, int RB>
 __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64* __restrict__ kin, u64* __restrict__ kout,
                                                                     const u32* __restrict__ vin, u32* __restrict__ vout,
                                                                     u32* status, u32* tile_ctr,
@@ -399,14 +415,16 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64* _
                                                                     int shift, u32 mask, const u32* __restrict__ ent_in,
                                                                     u32* __restrict__ ent_out, int next_shift,
                                                                     u32 next_mask, int force_rank) {
+  constexpr int RADIX = 1 << RB;  // 256 or 512 (= RS_THREADS) digit bins
+  static_assert(RADIX <= RS_THREADS, "one thread per digit bin");
   extern __shared__ __align__(16) unsigned char os_smem[];
   u64* stage = reinterpret_cast<u64*>(os_smem);                                       // [S][RS_SUB]
   u32* vstage = reinterpret_cast<u32*>(os_smem + (size_t)S * RS_SUB * 8);             // [S][RS_SUB] (pairs only)
-  unsigned short(*warp_hist)[256] =
-      reinterpret_cast<unsigned short(*)[256]>(os_smem + (size_t)S * RS_SUB * (HAS_VALS ? 12 : 8));
-  u32* cnt = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(warp_hist) + RS_WARPS * 256 * 2);  // [S][256]
-  u32* sub_start = cnt + S * 256;                                                      // [S][256]
-  u32* digit_base = sub_start + S * 256;                                               // [S][256]
+  unsigned short(*warp_hist)[RADIX] =
+      reinterpret_cast<unsigned short(*)[RADIX]>(os_smem + (size_t)S * RS_SUB * (HAS_VALS ? 12 : 8));
+  u32* cnt = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(warp_hist) + RS_WARPS * RADIX * 2);  // [S][RADIX]
+  u32* sub_start = cnt + S * RADIX;                                                      // [S][256]
+  u32* digit_base = sub_start + S * RADIX;                                               // [S][256]
   __shared__ u32 scan_tmp[RS_WARPS + 1];
   __shared__ u32 s_tile;
 
@@ -429,7 +447,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64* _
   for (int sub = 0; sub < S; sub++) {
     const u32 base = base0 + (u32)sub * RS_SUB;
     const int nvalid = base < n ? (int)min((u32)RS_SUB, n - base) : 0;
-    for (int t = tid; t < RS_WARPS * 256 / 2; t += RS_THREADS) reinterpret_cast<u32*>(&warp_hist[0][0])[t] = 0;
+    for (int t = tid; t < RS_WARPS * RADIX / 2; t += RS_THREADS) reinterpret_cast<u32*>(&warp_hist[0][0])[t] = 0;
     u64 key[RS_ITEMS];
     u32 pos[RS_ITEMS];
 #pragma unroll
@@ -446,8 +464,8 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64* _
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
       const int e = e0 + i * 32;
-      const u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;  // padding ranks last
-      const u32 peers = digit_peers(d, ballot);
+      const u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : (u32)(RADIX - 1);  // padding ranks last
+      const u32 peers = digit_peers<RB>(d, ballot);
       const u32 prev = warp_hist[warp][d];
       __syncwarp();
       if (lane == __ffs(peers) - 1) warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
@@ -458,31 +476,31 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64* _
     __syncthreads();
     OS_T(3)  // barrier after ranking
     u32 run = 0;
-    if (tid < 256) {
+    if (tid < RADIX) {
 #pragma unroll
       for (int w = 0; w < RS_WARPS; w++) {
         const u32 c = warp_hist[w][tid];
         warp_hist[w][tid] = (unsigned short)run;
         run += c;
       }
-      cnt[sub * 256 + tid] = run;
+      cnt[sub * RADIX + tid] = run;
       // padding was ranked as digit 255 (in the last logical tile only) and must not be published
-      cnt_pub += run - (tid == 255 ? (u32)(RS_SUB - nvalid) : 0u);
+      cnt_pub += run - (tid == RADIX - 1 ? (u32)(RS_SUB - nvalid) : 0u);
       // publish the logical tile's digit counts as soon as the last sub-tile is counted; the
       // look-back itself waits until that sub-tile is staged
-      if (sub == S - 1) st_status(&status[(size_t)tile * 256 + tid], cnt_pub | (tile == 0 ? ST_FLAG_INCL : ST_FLAG_LOCAL));
+      if (sub == S - 1) st_status(&status[(size_t)tile * RADIX + tid], cnt_pub | (tile == 0 ? ST_FLAG_INCL : ST_FLAG_LOCAL));
     }
     OS_T(4)  // per-digit scan over the warps + publish
     u32 total;
-    const u32 dstart = block_excl_scan(run, scan_tmp, total);  // threads >= 256 contribute 0
-    if (tid < 256) sub_start[sub * 256 + tid] = dstart;
+    const u32 dstart = block_excl_scan(run, scan_tmp, total);  // threads >= RADIX contribute 0
+    if (tid < RADIX) sub_start[sub * RADIX + tid] = dstart;
     __syncthreads();
     OS_T(5)  // block scan
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
       const int e = e0 + i * 32;
-      const u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : 255u;
-      pos[i] += sub_start[sub * 256 + d] + warp_hist[warp][d];
+      const u32 d = (e < nvalid) ? (u32)((key[i] >> shift) & mask) : (u32)(RADIX - 1);
+      pos[i] += sub_start[sub * RADIX + d] + warp_hist[warp][d];
       stage[sub * RS_SUB + pos[i]] = key[i];
     }
     if (HAS_VALS) {  // the key registers are dead now
@@ -498,7 +516,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64* _
     if (sub + 1 < S) __syncthreads();  // the next sub-tile zeroes the histograms this one's staging still reads
     OS_T(6)  // staging keys + payloads
   }
-  if (tid < 256) {
+  if (tid < RADIX) {
     u32 excl = 0;
     if (tile != 0) {
       // decoupled look-back, RS_LB predecessors per round trip: the status words of tiles
@@ -512,7 +530,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64* _
 #pragma unroll
         for (int i = 0; i < RS_LB; i++) {
           const long long q = p - i;
-          v[i] = q >= 0 ? ld_status(&status[(size_t)q * 256 + tid]) : (2u << 30);  // before tile 0: inclusive 0
+          v[i] = q >= 0 ? ld_status(&status[(size_t)q * RADIX + tid]) : (2u << 30);  // before tile 0: inclusive 0
         }
         int consumed = 0;
 #pragma unroll
@@ -529,14 +547,14 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64* _
 #endif
         if (!done && consumed == 0 && ++spins > SPIN_LIMIT) { *err = 1; break; }  // never hang the GPU on a bug
       }
-      st_status(&status[(size_t)tile * 256 + tid], (excl + cnt_pub) | ST_FLAG_INCL);
+      st_status(&status[(size_t)tile * RADIX + tid], (excl + cnt_pub) | ST_FLAG_INCL);
     }
     // global position of the element at sorted position p of sub-tile s: digit_base[s][d] + p
     u32 before = gbase[tid] + excl;
 #pragma unroll
     for (int sub = 0; sub < S; sub++) {
-      digit_base[sub * 256 + tid] = before - sub_start[sub * 256 + tid];
-      before += cnt[sub * 256 + tid];
+      digit_base[sub * RADIX + tid] = before - sub_start[sub * RADIX + tid];
+      before += cnt[sub * RADIX + tid];
     }
   }
   OS_T(7)  // look-back (digit 0)
@@ -553,7 +571,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64* _
       const int p = j * RS_THREADS + tid;
       if (p < nvalid) {
         const u64 k = stage[sub * RS_SUB + p];
-        const u32 g = digit_base[sub * 256 + (u32)((k >> shift) & mask)] + (u32)p;
+        const u32 g = digit_base[sub * RADIX + (u32)((k >> shift) & mask)] + (u32)p;
         kout[g] = k;
         if (HAS_VALS) vout[g] = vstage[sub * RS_SUB + p];
       }
@@ -565,41 +583,45 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64* _
 #endif
 }
 
-template <bool HAS_VALS, int S>
+template <bool HAS_VALS, int S, int RB>
 static void launch_onesweep(u32 tiles, cudaStream_t s, const u64* kin, u64* kout, const u32* vin, u32* vout, u32* status,
                             u32* ctl, const u32* gbase, u32 n, int bit, u32 mask, const u32* ent_in, u32* ent_out,
                             int next_shift, u32 next_mask, int force_rank) {
-  constexpr size_t dyn = os_smem_bytes<HAS_VALS, S>();
+  constexpr size_t dyn = os_smem_bytes<HAS_VALS, S, RB>();
   static bool configured = false;  // per instantiation
   if (!configured) {
-    CB_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<HAS_VALS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CB_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<HAS_VALS, S, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)dyn));
     configured = true;
   }
-  rs_onesweep_kernel<HAS_VALS, S><<<tiles, RS_THREADS, dyn, s>>>(kin, kout, vin, vout, status, ctl, gbase, ctl + 1, n, bit,
-                                                                mask, ent_in, ent_out, next_shift, next_mask, force_rank);
+  rs_onesweep_kernel<HAS_VALS, S, RB><<<tiles, RS_THREADS, dyn, s>>>(kin, kout, vin, vout, status, ctl, gbase, ctl + 1, n,
+                                                                    bit, mask, ent_in, ent_out, next_shift, next_mask,
+                                                                    force_rank);
 }
 
 static int radix_sort_onesweep(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int begin_bit,
                                int end_bit, cudaStream_t s, LaunchCounter& lc, const char* tag) {
   static const int subs = getenv("CB_OS_SUB") ? atoi(getenv("CB_OS_SUB")) : 1;      // sub-tiles per CTA; 2 measured slower (3.64 vs 3.27 ms): 225 KB of shared memory per SM leave no L1 for loads in flight
   static const int force_rank = getenv("CB_RANK") ? atoi(getenv("CB_RANK")) : 0;   // experiment: 1 match, 2 ballots
-  const int S = subs == 1 ? 1 : 2;
-  const int npass = (end_bit - begin_bit + 7) / 8;
+  static const int digit_bits = getenv("CB_DIGIT_BITS") ? atoi(getenv("CB_DIGIT_BITS")) : 9;  // experiment: 8
+  const int S = subs == 2 ? 2 : 1;
+  const PassPlan pl = make_plan(begin_bit, end_bit, digit_bits == 8 ? 8 : 9);
+  const int npass = pl.npass;
   const u32 tiles = (u32)((n + (size_t)S * RS_SUB - 1) / ((size_t)S * RS_SUB));
   DevBuf<u32> ghist, status, ctl;
-  ghist.alloc((size_t)npass * 256, s);
-  status.alloc((size_t)tiles * 256, s);
+  ghist.alloc((size_t)npass * RS_MAXRADIX, s);
+  status.alloc((size_t)tiles * RS_MAXRADIX, s);
   ctl.alloc(2 + 2 * (RS_MAXPASS + 1), s);  // [0] tile counter, [1] error flag, then (distinct, samples) per pass
   u32* ent = ctl.p + 2;
-  CB_CUDA(cudaMemsetAsync(ghist.p, 0, (size_t)npass * 256 * 4, s));
+  CB_CUDA(cudaMemsetAsync(ghist.p, 0, (size_t)npass * RS_MAXRADIX * 4, s));
   CB_CUDA(cudaMemsetAsync(ctl.p, 0, (2 + 2 * (RS_MAXPASS + 1)) * 4, s));
   const std::string nm_up_s = std::string("rs_upsweep:") + tag, nm_sc_s = std::string("rs_scatter:") + tag;
   lc.begin(nm_up_s.c_str());
   {
     int blocks = div_up(n, 256 * 16);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    rs_hist_all_kernel<<<blocks, 256, 0, s>>>(keys_a, n, begin_bit, end_bit, ghist.p, ent);
-    rs_scan_hist_kernel<<<1, 256, 0, s>>>(ghist.p, npass);
+    rs_hist_all_kernel<<<blocks, 256, (size_t)npass * RS_MAXRADIX * 4, s>>>(keys_a, n, pl, ghist.p, ent);
+    rs_scan_hist_kernel<<<1, RS_MAXRADIX, 0, s>>>(ghist.p, npass);
   }
   lc.end(nm_up_s.c_str());
   lc.n += 2;
@@ -609,21 +631,23 @@ static int radix_sort_onesweep(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_
   u32* vout = vals_b;
   int where = 0;
   for (int p = 0; p < npass; p++) {
-    const int bit = begin_bit + 8 * p;
-    const int nbits = end_bit - bit < 8 ? end_bit - bit : 8;
-    const u32 mask = (1u << nbits) - 1;
-    const int nbit = bit + 8;
-    const int nnbits = p + 1 < npass ? (end_bit - nbit < 8 ? end_bit - nbit : 8) : 0;
-    const u32 nmask = (1u << nnbits) - 1;
-    u32* ent_out = p + 1 < npass ? ent + 2 * (p + 1) : nullptr;
-    CB_CUDA(cudaMemsetAsync(status.p, 0, (size_t)tiles * 256 * 4, s));
+    const int bit = pl.shift[p];
+    const u32 mask = (1u << pl.bits[p]) - 1;
+    const bool last = p + 1 == npass;
+    const int nbit = last ? 0 : pl.shift[p + 1];
+    const u32 nmask = last ? 0u : (1u << pl.bits[p + 1]) - 1;
+    u32* ent_out = last ? nullptr : ent + 2 * (p + 1);
+    const int radix = pl.bits[p] > 8 ? 512 : 256;
+    CB_CUDA(cudaMemsetAsync(status.p, 0, (size_t)tiles * radix * 4, s));
     CB_CUDA(cudaMemsetAsync(ctl.p, 0, 4, s));
-    const u32* gb = ghist.p + p * 256;
+    const u32* gb = ghist.p + p * RS_MAXRADIX;
     lc.begin(nm_sc_s.c_str());
-#define CB_OS_GO(HV, SS) \
-  launch_onesweep<HV, SS>(tiles, s, kin, kout, vin, vout, status.p, ctl.p, gb, (u32)n, bit, mask, ent + 2 * p, ent_out, nbit, nmask, force_rank)
-    if (S == 2) { if (vin) CB_OS_GO(true, 2); else CB_OS_GO(false, 2); }
-    else { if (vin) CB_OS_GO(true, 1); else CB_OS_GO(false, 1); }
+#define CB_OS_GO(HV, SS, RB) \
+  launch_onesweep<HV, SS, RB>(tiles, s, kin, kout, vin, vout, status.p, ctl.p, gb, (u32)n, bit, mask, ent + 2 * p, ent_out, nbit, nmask, force_rank)
+#define CB_OS_GO_RB(HV, SS) { if (radix == 512) CB_OS_GO(HV, SS, 9); else CB_OS_GO(HV, SS, 8); }
+    if (S == 2) { if (vin) CB_OS_GO_RB(true, 2) else CB_OS_GO_RB(false, 2) }
+    else { if (vin) CB_OS_GO_RB(true, 1) else CB_OS_GO_RB(false, 1) }
+#undef CB_OS_GO_RB
 #undef CB_OS_GO
     lc.end(nm_sc_s.c_str());
     lc.n++;
@@ -652,7 +676,7 @@ int radix_sort(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int
                cudaStream_t s, LaunchCounter& lc, const char* tag) {
   if (n == 0 || end_bit <= begin_bit) return 0;
   if (n >= (1ull << 32)) throw Error(CB_E_CAPACITY, "radix_sort: more than 2^32-1 elements");
-  if (n < (1ull << 30) && (end_bit - begin_bit + 7) / 8 <= RS_MAXPASS && use_onesweep())
+  if (n < (1ull << 30) && end_bit - begin_bit <= 64 && use_onesweep())
     return radix_sort_onesweep(keys_a, keys_b, vals_a, vals_b, n, begin_bit, end_bit, s, lc, tag);
   int tiles = (int)((n + RS_TILE - 1) / RS_TILE);
   int chunks = tiles < 4 * kNumSMs ? tiles : 4 * kNumSMs;
