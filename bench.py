@@ -12,9 +12,9 @@ synthetic reads.  At N=1 the workload is BASELINE.json c
   e2e     reads/s through the public C-ABI call sequence with HOST buffers: pinned-host SFA ->
           cb_load_sfa_buffer (H2D) -> cb_preprocess/cb_build_overlap/cb_string_graph ->
           cb_export_edges(checkpoint B) + cb_export_nodes (D2H), wall clock
-  roofline  the dominant kernel (rs_scatter of the k-mer tuple sort): algorithmic bytes per launch
+  roofline  the dominant kernel (rs_onesweep of the k-mer tuple sort): algorithmic bytes per launch
           (24 B per tuple: 12 B read + 12 B written) / its mean CUDA-event duration, against the
-          measured HBM copy bandwidth of MEASURED_PEAKS.json
+          measured HBM copy bandwidth of MEASURED_PEAKS.json; roofline_path: SURVEY.md 8(d) B_alg / step
   cpu_baseline  the CPU restatement oracle ("port", 1 core) on a bounded sample of the same workload
 
 `--impl reference` times the reference's CPU algorithm (the oracle port -- the reference itself is
@@ -381,7 +381,8 @@ def bench_ours(args):
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
                     "ms_per_launch": per_launch_ms, "launches_per_step": st[1] / args.steps,
-                    "share_of_step": st[0] / args.steps / ms}
+                    "share_of_step": st[0] / args.steps / ms,
+                    "share_of_step_all_sorts": (st[0] + (stats.get("rs_scatter:dedupe") or (0, 0))[0]) / args.steps / ms}
         kern = {kn: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                 for kn, v in stats.items() if v}
         # ---- whole-path figure of BASELINE.md / SURVEY.md 8(d): B_alg from the run's measured counts ----
