@@ -79,4 +79,17 @@ def all_cases():
             + b"tabs\t" + g[15:55].encode() + b"\t\t\n" + b"four\t" + g[18:58].encode() + b"\tx\ty\n"
             + b"\t" + g[21:61].encode() + b"\n" + b"last\t" + g[24:64].encode())
     cases["line_formats"] = (body, 21, 40)
+    # 12. a repeated k-mer in the INTERIOR of 700 reads (one k-mer group of 700+ tuples spanning several
+    #     256-tuple blocks of the group walk) plus reads that start / end with it (node entries of that group)
+    rep = rand_dna(21, 41)
+    reads = [(f"i{n}", rand_dna(7, 1000 + n) + rep + rand_dna(8, 3000 + n)) for n in range(700)]
+    reads += [(f"p{n}", rep + rand_dna(15, 5000 + n)) for n in range(3)]
+    reads += [(f"s{n}", rand_dna(15, 6000 + n) + rep) for n in range(3)]
+    cases["long_group"] = (sfa(reads), 21, 36)
+    # 13. a repeat boundary with many branches: 40 reads end with the k-mer, 40 start with it (exact-K overlaps
+    #     between all of them: 40 node entries in one group, adjacency lists of 40 inconsistent overhangs)
+    rep2 = rand_dna(21, 42)
+    reads = [(f"e{n}", rand_dna(15, 7000 + n) + rep2) for n in range(40)]
+    reads += [(f"b{n}", rep2 + rand_dna(15, 8000 + n)) for n in range(40)]
+    cases["many_branches"] = (sfa(reads), 21, 36)
     return cases

@@ -109,6 +109,26 @@ def test_rerun_is_deterministic_and_context_is_reusable():
     g.close()
 
 
+def test_string_graph_twice_and_checkpoint_a_restored(ec10k_sfa):
+    """CutChimericLinks removes records IN PLACE and logs them: 01-overlap must still export intact after
+    cb_string_graph (restored from the log), and running the stage group again must give the same three
+    checkpoints (the log is played back first)."""
+    r = run_oracle(ec10k_sfa, 21, 36)
+    g = run_gpu(ec10k_sfa, 21, 36)
+    first = [g.edge_rows(ck) for ck in (1, 2, 3)]
+    assert len(first[1]) < len(first[0])  # this input has real cuts (42 600 + 15 removal messages)
+    assert compare(g, r, "first run") == []
+    g.string_graph()
+    again = [g.edge_rows(ck) for ck in (1, 2, 3)]
+    for a, b in zip(first, again):
+        assert np.array_equal(a, b)
+    assert compare(g, r, "second run") == []
+    g.build_overlap()  # and from one stage group earlier
+    g.string_graph()
+    assert compare(g, r, "third run") == []
+    g.close()
+
+
 def test_full_size_properties():
     """Size-independent properties at a size the oracle is not run at: mirror closure of every
     checkpoint, nesting B <= chl2 <= A, coverage sum == reads, two kept edges per direction at most
