@@ -418,13 +418,17 @@ int cb_export_nodes(cb_ctx* c, cb_node* out, size_t cap, size_t* n) {
   CB_API_BEGIN(c)
   if (!n) throw Error(CB_E_INVALID, "null size pointer");
   if (!c->preprocessed) throw Error(CB_E_INVALID, "nodes not available");
-  *n = c->n_nodes;
-  if (out && cap >= c->n_nodes && c->n_nodes) {
+  // a sharded context exports the nodes built from ITS shard of the SFA lines (the union over the
+  // ranks, in rank order, is the node table sorted by line)
+  const u32 lo = distributed(c) ? c->node_lo : 0, hi = distributed(c) ? c->node_hi : c->n_nodes;
+  const u32 cnt = hi - lo;
+  *n = cnt;
+  if (out && cap >= cnt && cnt) {
     DevBuf<cb_node> d;
-    d.alloc(c->n_nodes, c->stream);
-    export_nodes_kernel<<<div_up(c->n_nodes, 256), 256, 0, c->stream>>>(c->node_line.p, c->node_cov.p, c->n_nodes, d.p);
+    d.alloc(cnt, c->stream);
+    export_nodes_kernel<<<div_up(cnt, 256), 256, 0, c->stream>>>(c->node_line.p + lo, c->node_cov.p + lo, cnt, d.p);
     c->lc.n++;
-    CB_CUDA(cudaMemcpyAsync(out, d.p, (size_t)c->n_nodes * sizeof(cb_node), cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaMemcpyAsync(out, d.p, (size_t)cnt * sizeof(cb_node), cudaMemcpyDeviceToHost, c->stream));
     CB_CUDA(cudaStreamSynchronize(c->stream));
   }
   CB_API_END(c)

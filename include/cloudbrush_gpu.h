@@ -174,9 +174,10 @@ typedef struct cb_exchange {
   int (*allreduce_max_u8_dev)(void* user, void* dev, uint64_t n);
 } cb_exchange;
 
-/* Must be called before cb_preprocess when cfg.world > 1.  With an exchange set, counters are
- * global sums, cb_export_nodes returns the global node table (replicated) and cb_export_edges the
- * adjacency lists this rank owns (their union over the ranks is the checkpoint). */
+/* Must be called before cb_preprocess when cfg.world > 1 (or cb_init_nccl, below).  On a sharded
+ * context counters are global sums, cb_export_nodes returns the nodes built from this rank's shard
+ * of the SFA lines (in rank order their union is the node table sorted by line) and
+ * cb_export_edges the adjacency lists this rank owns (their union over the ranks is the checkpoint). */
 int cb_set_exchange(cb_ctx* ctx, const cb_exchange* ex);
 
 /* Native transport: NCCL over NVLink / NVSwitch, driven by the library on its own stream (no host

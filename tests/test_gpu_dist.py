@@ -46,8 +46,9 @@ def _check(sfa, k, L, tmp_path, world=2):
         got = np.concatenate([q[key] for q in parts])
         got = got[np.lexsort((got[:, 3], got[:, 2], got[:, 1], got[:, 0]))]
         assert np.array_equal(got, g.edge_rows(ck)), f"checkpoint {key} differs between 1 and {world} ranks"
-    for q in parts:  # the node table is replicated, the counters are global
-        assert np.array_equal(q["nodes"], g.nodes())
+    # every rank exports the nodes built from its shard of the lines: in rank order, the node table
+    assert np.array_equal(np.concatenate([q["nodes"] for q in parts]), g.nodes())
+    for q in parts:  # the counters are global
         assert q["counters"].tolist() == [g.counter(x) for x in COUNTERS]
     g.close()
 

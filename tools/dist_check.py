@@ -58,9 +58,9 @@ def main():
                 got = got[np.lexsort((got[:, 3], got[:, 2], got[:, 1], got[:, 0]))]
                 if not np.array_equal(got, s.edge_rows(ck)):
                     bad.append(f"checkpoint {key}: {len(got)} vs {len(s.edge_rows(ck))}")
+            if not np.array_equal(np.concatenate([q["nodes"] for q in parts]), s.nodes()):
+                bad.append("node table")
             for q in parts:
-                if not np.array_equal(q["nodes"], s.nodes()):
-                    bad.append("node table")
                 if q["counters"] != [s.counter(x) for x in COUNTERS]:
                     bad.append(f"counters {q['counters']} vs {[s.counter(x) for x in COUNTERS]}")
             print(f"{name}: world={world} transport={args.transport} nodes={s.counter('nodes')} "
