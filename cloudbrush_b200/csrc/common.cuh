@@ -230,6 +230,18 @@ __host__ __device__ __forceinline__ int cmp_words(const u64 (&a)[NW], const u64 
   return 0;
 }
 
+// one packed read row (NW even: NW/2 aligned 16-byte loads through the read-only path)
+template <int NW>
+__device__ __forceinline__ void load_read_row(const u64* __restrict__ reads, u32 idx, u64 (&r)[NW]) {
+  const uint4* row = reinterpret_cast<const uint4*>(reads + (size_t)idx * NW);
+#pragma unroll
+  for (int i = 0; i < NW / 2; i++) {
+    uint4 v = __ldg(row + i);
+    r[2 * i] = (u64)v.x | ((u64)v.y << 32);
+    r[2 * i + 1] = (u64)v.z | ((u64)v.w << 32);
+  }
+}
+
 // Overhang storage: the first NWO 32-bit words (16 bases each, MSB first) of a left-aligned
 // NW-word base string.  NWO <= 2*NW.
 template <int NW>

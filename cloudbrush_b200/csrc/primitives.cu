@@ -2,7 +2,14 @@
 //
 // The Hadoop shuffle of MatchPrefix (reference: JobClient.runJob at MatchPrefix.java:468 --
 // HashPartitioner + sort by Text key + group) is replaced by a stable LSD radix sort of
-// (canonical k-mer key, payload) tuples.  One pass over an 8-bit digit is:
+// (canonical k-mer key, payload) tuples.
+//
+// What ships ("onesweep", second half of this file): ONE histogram read of the keys per sort
+// (rs_hist_all, all digit positions at once), then one kernel per digit pass (rs_onesweep) whose
+// per-tile digit offsets come from a chained scan with decoupled look-back; digits are 8 or 9 bits
+// wide (PassPlan).  HBM traffic per pass: 12 B read + 12 B written per tuple, the algorithmic minimum.
+//
+// Fallback (n >= 2^30 or CB_SORT=classic), one pass over an 8-bit digit is:
 //   rs_upsweep   per-tile digit histogram (shared-memory staged, warp-aggregated atomics)
 //   rs_chunk_sums / rs_chunk_scan / rs_apply   column-wise exclusive scan of the tile histograms
 //   rs_scatter   stable in-tile ranking with __match_any_sync, shared-memory staged so that each

@@ -6,7 +6,7 @@
 //   Hadoop shuffle/sort/group      MatchPrefix.java:468       radix_sort (primitives.cu)
 //   MatchPrefixReducer.reduce      MatchPrefix.java:241-431   join_verify_kernel (candidate part)
 //   VerifyOverlapMapper/Reducer    VerifyOverlap.java:103-133, :203-344   join_verify_kernel (check part)
-//   GenReverseEdgeMapper/Reducer   GenReverseEdge.java:54-81, :149-244    mirror records + sort + unique
+//   GenReverseEdgeMapper/Reducer   GenReverseEdge.java:54-81, :149-244    mirror records written in place (join_verify_kernel), side_insert_kernel
 //   BuildHighKmerList              BuildHighKmerList.java:50-117          "hkmer" counter (by-product)
 //
 // Every candidate (a,x,ov) -> (b,y) of the reference is produced inside ONE k-mer group (the
@@ -18,17 +18,6 @@
 #include "ctx.cuh"
 
 namespace cb {
-
-template <int NW>
-__device__ __forceinline__ void load_read_b(const u64* __restrict__ reads, u32 idx, u64 (&r)[NW]) {
-  const uint4* row = reinterpret_cast<const uint4*>(reads + (size_t)idx * NW);
-#pragma unroll
-  for (int i = 0; i < NW / 2; i++) {
-    uint4 v = __ldg(row + i);
-    r[2 * i] = (u64)v.x | ((u64)v.y << 32);
-    r[2 * i + 1] = (u64)v.z | ((u64)v.w << 32);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // K3: warp-cooperative canonical k-mer key generator.  One thread per (node, window) slot in
@@ -118,8 +107,6 @@ struct JoinParams {
   u64 xcap;
   ull* dcount;
 };
-
-constexpr int JN_WARPS = 8;
 
 __device__ __forceinline__ u64 tuple_meta(const JoinParams& P, u32 j) {
   return ((P.keys[j] >> (2 * P.K)) << 32) | (u64)P.vals[j];
@@ -460,7 +447,7 @@ __global__ void __launch_bounds__(256, MINB) join_verify_kernel(JoinParams P) {
             if (idx >= P.T || P.seg_head[idx] != s) break;
             const u32 v = P.ne_list[idx];
             if (v == 0xffffffffu) break;
-            load_read_b<NW>(P.node_seq, (v & 0x7fffffffu) >> 1, B);
+            load_read_row<NW>(P.node_seq, (v & 0x7fffffffu) >> 1, B);
             process(v, P.off1[v & 0x7fffffffu], B);
           }
         }
@@ -520,7 +507,7 @@ __global__ void __launch_bounds__(256) side_insert_kernel(const u64* __restrict_
     const u32 lo = off[lid], hi = off[lid + 1];
     // the record's overhang b^y[ov:] (requested before the list is scanned)
     u64 H[NW];
-    load_read_b<NW>(node_seq, lay.nbr(key), H);
+    load_read_row<NW>(node_seq, lay.nbr(key), H);
     // one pass over the list's slots, eight loads in flight: duplicate? first free slot?
     bool dup = false;
     u32 hole = 0xffffffffu;
@@ -573,7 +560,7 @@ template <int NW>
 __device__ __forceinline__ u32 list_owner(const u64* __restrict__ node_seq, u32 lid, int L, int K, int pbit,
                                           u32 wmask) {
   u64 r[NW];
-  load_read_b<NW>(node_seq, lid >> 1, r);
+  load_read_row<NW>(node_seq, lid >> 1, r);
   u64 km = extract_kmer<NW>(r, (lid & 1u) ? 0 : L - K, K);
   u64 rk = revcomp_kmer(km, K);
   u64 canon = km < rk ? km : rk;

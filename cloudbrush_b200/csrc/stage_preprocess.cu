@@ -265,21 +265,10 @@ __global__ void __launch_bounds__(128) parse_lines_kernel(const char* __restrict
 }
 
 template <int NW>
-__device__ __forceinline__ void load_read(const u64* __restrict__ reads, u32 idx, u64 (&r)[NW]) {
-  const uint4* row = reinterpret_cast<const uint4*>(reads + (size_t)idx * NW);
-#pragma unroll
-  for (int i = 0; i < NW / 2; i++) {
-    uint4 v = __ldg(row + i);
-    r[2 * i] = (u64)v.x | ((u64)v.y << 32);
-    r[2 * i + 1] = (u64)v.z | ((u64)v.w << 32);
-  }
-}
-
-template <int NW>
 __device__ __forceinline__ void load_canon(const u64* __restrict__ reads, u32 idx, int L, u64 (&canon)[NW],
                                            bool& selfrc) {
   u64 r[NW], rc[NW];
-  load_read<NW>(reads, idx, r);
+  load_read_row<NW>(reads, idx, r);
   revcomp_read<NW>(r, rc, L);
   int c = cmp_words<NW>(r, rc);
   selfrc = (c == 0);

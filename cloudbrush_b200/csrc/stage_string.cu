@@ -1,39 +1,31 @@
 // stage_string.cu -- per-node adjacency pruning: CutChimericLinks, EdgeRemoval and
-// TransitiveReduction on the sorted edge set, one warp per (node, direction) list.
+// TransitiveReduction on the adjacency lists the join left in HBM.
 //
 // Replaces (reference):
-//   CutChimericLinksMapper/Reducer  CutChimericLinks.java:87-114, :258-409  cut_kernel
+//   CutChimericLinksMapper/Reducer  CutChimericLinks.java:87-114, :258-409  consistency_kernel, cut_kernel
 //   Node.Consensus                  Node.java:1293-1377                     cut_kernel (PWM part)
-//   EdgeRemovalMapper/Reducer       EdgeRemoval.java:58-87, :121-202        removed flags + compaction
-//   TransitiveReductionReducer      TransitiveReduction.java:239-547        tr_kernel
+//   EdgeRemovalMapper/Reducer       EdgeRemoval.java:58-87, :121-202        remove_flagged_kernel, tr_final_kernel
+//   TransitiveReductionReducer      TransitiveReduction.java:239-547        tr_kernel, tr_final_kernel
 //   driver loop                     BrushAssembler.java:337-379             stage_string_graph
 //
 // The graph of checkpoint A is symmetric (S u mirror(S)), so the neighbour messages each
 // reducer rebuilds its lists from (DARKMSG / OVALMSG, sent by the mirror edge) are exactly the
-// node's own adjacency list: the cnt[lid] records at keys[adj_off[lid] ...), lid = 2a + x, in no
-// particular order.  The overhang of an entry is b^y[ov:], the bases of the neighbour that extend
-// past the node.
+// node's own adjacency list: the records in keys[adj_off[lid] .. adj_off[lid+1]), lid = 2a + x, in
+// no particular order, empty slots ~0.  The overhang of an entry is b^y[ov:], the bases of the
+// neighbour that extend past the node; the join stored it next to the record (ovh[slot]).
 //
 // First every list is tested for "consistency": is every overhang a prefix of the longest one?
-// (one thread per record, consistency_kernel).  For a consistent list (a) the PWM consensus of
-// CutChimericLinks equals the longest overhang wherever it is defined, has no N and cuts nothing
-// (needs MAJORITY < 1); (b) the greedy scan of TransitiveReduction keeps exactly the entries of
-// maximal overlap (tr_final_kernel, one thread per record).  Lists that are not consistent
-// (sequencing errors, repeats) go through work lists to the literal warp-per-list kernels.
+// (one thread per list, one pass: consistency_kernel).  For a consistent list (a) the PWM
+// consensus of CutChimericLinks equals the longest overhang wherever it is defined, has no N and
+// cuts nothing (needs MAJORITY < 1); (b) the greedy scan of TransitiveReduction keeps exactly the
+// entries of maximal overlap, so the list is summarised by ONE byte (that overlap) and
+// tr_final_kernel decides every record, and the fate of its mirror at the other end, from the
+// summaries alone.  Lists that are not consistent (sequencing errors, repeats) go through work
+// lists to the literal warp-per-list kernels.  CutChimericLinks removes records in place and logs
+// them (ctx.cuh: cut_log), checkpoint B is written as a compact record list.
 #include "ctx.cuh"
 
 namespace cb {
-
-template <int NW>
-__device__ __forceinline__ void load_read_c(const u64* __restrict__ reads, u32 idx, u64 (&r)[NW]) {
-  const uint4* row = reinterpret_cast<const uint4*>(reads + (size_t)idx * NW);
-#pragma unroll
-  for (int i = 0; i < NW / 2; i++) {
-    uint4 v = __ldg(row + i);
-    r[2 * i] = (u64)v.x | ((u64)v.y << 32);
-    r[2 * i + 1] = (u64)v.z | ((u64)v.w << 32);
-  }
-}
 
 struct StringParams {
   const u64* edges;    // slot array; list lid owns [adj_off[lid], adj_off[lid+1]); ~0 = empty slot
@@ -640,7 +632,7 @@ template <int NW>
 __device__ __forceinline__ u32 list_owner_s(const u64* __restrict__ node_seq, u32 lid, int L, int K, int pbit,
                                             u32 wmask) {
   u64 r[NW];
-  load_read_c<NW>(node_seq, lid >> 1, r);
+  load_read_row<NW>(node_seq, lid >> 1, r);
   u64 km = extract_kmer<NW>(r, (lid & 1u) ? 0 : L - K, K);
   u64 rk = revcomp_kmer(km, K);
   u64 canon = km < rk ? km : rk;
