@@ -244,7 +244,7 @@ def bench_reference(args):
 # --------------------------------------------------------------------------------------------
 KERNELS = ["parse_lines", "dedupe_runs", "keygen", "join_verify", "cut", "tr",
            "rs_scatter:dedupe", "rs_upsweep:dedupe", "rs_scatter:tuples", "rs_upsweep:tuples",
-           "rs_scatter:edges", "rs_upsweep:edges", "rs_scatter:export", "rs_upsweep:export", "group_walk", "side_insert", "consistency", "tr_final"]
+           "group_walk", "side_insert", "consistency", "tr_final"]
 
 
 def bench_ours(args):

@@ -144,6 +144,16 @@ struct cb_ctx {
   size_t n_edges_c = 0;             // records of 01-overlap.chl2
 };
 
+// kernels are templated on the words per packed read (NW = 2, 4, 6, 8 <=> reads of up to 64 .. 256 bases)
+#define CB_DISPATCH_NW(nw, CALL)                                             \
+  switch (nw) {                                                              \
+    case 2: { constexpr int NW_ = 2; CALL; } break;                          \
+    case 4: { constexpr int NW_ = 4; CALL; } break;                          \
+    case 6: { constexpr int NW_ = 6; CALL; } break;                          \
+    case 8: { constexpr int NW_ = 8; CALL; } break;                          \
+    default: throw Error(CB_E_UNSUPPORTED, "read length above 256 bases");   \
+  }
+
 namespace cb {
 
 void timer_start(cb_ctx* c, const char* name);

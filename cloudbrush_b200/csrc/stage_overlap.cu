@@ -607,15 +607,6 @@ static int bits_for(u64 nvalues) {  // bits needed to store values 0 .. nvalues-
   return b;
 }
 
-#define CB_DISPATCH_NW(nw, CALL)                                             \
-  switch (nw) {                                                              \
-    case 2: { constexpr int NW_ = 2; CALL; } break;                          \
-    case 4: { constexpr int NW_ = 4; CALL; } break;                          \
-    case 6: { constexpr int NW_ = 6; CALL; } break;                          \
-    case 8: { constexpr int NW_ = 8; CALL; } break;                          \
-    default: throw Error(CB_E_UNSUPPORTED, "read length above 256 bases");   \
-  }
-
 static u32 read_u32(cb_ctx* c, const u32* p) {
   u32 v = 0;
   CB_CUDA(cudaMemcpyAsync(&v, p, 4, cudaMemcpyDeviceToHost, c->stream));

@@ -482,15 +482,6 @@ __global__ void __launch_bounds__(256) dd_scatter_kernel(const u32* __restrict__
   cov[line] = recs[2 * i + 1];
 }
 
-#define CB_DISPATCH_NW(nw, CALL)                                             \
-  switch (nw) {                                                              \
-    case 2: { constexpr int NW_ = 2; CALL; } break;                          \
-    case 4: { constexpr int NW_ = 4; CALL; } break;                          \
-    case 6: { constexpr int NW_ = 6; CALL; } break;                          \
-    case 8: { constexpr int NW_ = 8; CALL; } break;                          \
-    default: throw Error(CB_E_UNSUPPORTED, "read length above 256 bases");   \
-  }
-
 void stage_parse_and_pack(cb_ctx* c) {
   cudaStream_t s = c->stream;
   const size_t n = c->text_n;

@@ -647,15 +647,6 @@ __global__ void __launch_bounds__(256) key_owner_s_kernel(const u64* __restrict_
   if (i < n) dest[i] = list_owner_s<NW>(node_seq, lay.list(keys[i]), L, K, pbit, wmask);
 }
 
-#define CB_DISPATCH_NW(nw, CALL)                                             \
-  switch (nw) {                                                              \
-    case 2: { constexpr int NW_ = 2; CALL; } break;                          \
-    case 4: { constexpr int NW_ = 4; CALL; } break;                          \
-    case 6: { constexpr int NW_ = 6; CALL; } break;                          \
-    case 8: { constexpr int NW_ = 8; CALL; } break;                          \
-    default: throw Error(CB_E_UNSUPPORTED, "read length above 256 bases");   \
-  }
-
 static StringParams make_params(cb_ctx* c, const u64* keys) {
   StringParams P;
   P.edges = keys;
