@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcloudbrush_gpu.so")
+LIB_PATH = os.environ.get("CB_LIB") or os.path.join(_HERE, "libcloudbrush_gpu.so")  # CB_LIB: an instrumented build
 
 CB_ABI_VERSION = 1
 CB_OK = 0

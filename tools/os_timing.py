@@ -1,4 +1,9 @@
-"""Experiment: per-phase clock64 breakdown of the onesweep kernel (needs the -DCB_OS_TIMING build)."""
+"""Experiment: per-phase clock64 breakdown of the onesweep kernel.
+
+    make -C cloudbrush_b200/csrc timing
+    CB_LIB=cloudbrush_b200/libcloudbrush_gpu_timing.so python tools/os_timing.py
+
+Results of round 1: profiles/r01_onesweep_phases.md."""
 import ctypes as C, sys, os
 sys.path.insert(0, ".")
 import numpy as np, torch
