@@ -186,6 +186,14 @@ class BrushGpu:
     def write_nodes(self, checkpoint, out_dir):
         self._check(self._L.cb_write_nodes(self._h, checkpoint, str(out_dir).encode()))
 
+    def debug_sort(self, keys, vals=None, begin_bit=0, end_bit=64):
+        """Test hook: the library's stable LSD radix sort on key bits [begin_bit, end_bit), in place on numpy
+        arrays (keys uint64, vals uint32 or None)."""
+        assert keys.dtype == np.uint64 and keys.flags.c_contiguous
+        assert vals is None or (vals.dtype == np.uint32 and vals.flags.c_contiguous and len(vals) == len(keys))
+        self._check(self._L.cb_debug_sort(self._h, keys.ctypes.data, vals.ctypes.data if vals is not None else None,
+                                          len(keys), begin_bit, end_bit))
+
     def time_ms(self, what):
         v = C.c_double()
         self._check(self._L.cb_get_time_ms(self._h, what.encode(), C.byref(v)))

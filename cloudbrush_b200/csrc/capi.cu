@@ -261,6 +261,7 @@ int cb_load_sfa_device(cb_ctx* c, const void* dev_buf, size_t n) {
   c->text_n = n;
   if (n) CB_CUDA(cudaMemcpyAsync(c->text.p, dev_buf, n, cudaMemcpyDeviceToDevice, c->stream));
   CB_CUDA(cudaMemsetAsync(c->text.p + n, 0, 32, c->stream));
+  CB_CUDA(cudaStreamSynchronize(c->stream));  // the caller's buffer is only borrowed for the call
   c->text_ptr = c->text.p;
   reset_after_load(c);
   CB_API_END(c)
@@ -269,6 +270,9 @@ int cb_load_sfa_device(cb_ctx* c, const void* dev_buf, size_t n) {
 int cb_borrow_sfa_device(cb_ctx* c, const void* dev_buf, size_t n) {
   CB_API_BEGIN(c)
   if (!dev_buf && n) throw Error(CB_E_INVALID, "null buffer");
+  // the parser reads the text in aligned 16-byte vectors (stage_preprocess.cu: thread_term_mask, parse_lines)
+  if (((uintptr_t)dev_buf & 15) != 0)
+    throw Error(CB_E_INVALID, "cb_borrow_sfa_device: the buffer must be 16-byte aligned (use cb_load_sfa_device to copy)");
   c->text.release();
   c->text_ptr = (const char*)dev_buf;
   c->text_n = n;
@@ -526,6 +530,30 @@ int cb_get_time_ms(cb_ctx* c, const char* what, double* ms) {
   float f = 0;
   CB_CUDA(cudaEventElapsedTime(&f, it->second.a, it->second.b));
   *ms = f;
+  CB_API_END(c)
+}
+
+int cb_debug_sort(cb_ctx* c, uint64_t* keys, uint32_t* vals, size_t n, int begin_bit, int end_bit) {
+  CB_API_BEGIN(c)
+  if (!keys && n) throw Error(CB_E_INVALID, "null keys");
+  if (begin_bit < 0 || end_bit > 64 || end_bit < begin_bit) throw Error(CB_E_INVALID, "bad bit range");
+  cudaStream_t s = c->stream;
+  const size_t n1 = n ? n : 1;
+  DevBuf<u64> ka, kb;
+  DevBuf<u32> va, vb;
+  ka.alloc(n1, s);
+  kb.alloc(n1, s);
+  if (vals) { va.alloc(n1, s); vb.alloc(n1, s); }
+  if (n) {
+    CB_CUDA(cudaMemcpyAsync(ka.p, keys, n * 8, cudaMemcpyHostToDevice, s));
+    if (vals) CB_CUDA(cudaMemcpyAsync(va.p, vals, n * 4, cudaMemcpyHostToDevice, s));
+  }
+  const int w = radix_sort(ka.p, kb.p, vals ? va.p : nullptr, vals ? vb.p : nullptr, n, begin_bit, end_bit, s, c->lc, "debug");
+  if (n) {
+    CB_CUDA(cudaMemcpyAsync(keys, w ? kb.p : ka.p, n * 8, cudaMemcpyDeviceToHost, s));
+    if (vals) CB_CUDA(cudaMemcpyAsync(vals, w ? vb.p : va.p, n * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CB_CUDA(cudaStreamSynchronize(s));
   CB_API_END(c)
 }
 

@@ -156,16 +156,34 @@ struct cb_ctx {
 
 namespace cb {
 
+inline bool distributed(const cb_ctx* c) { return c->cfg.world > 1; }
 void timer_start(cb_ctx* c, const char* name);
 void timer_stop(cb_ctx* c, const char* name);
 void download_counters(cb_ctx* c);
 
 // dist.cu -- routing helpers of the multi-GPU path
-inline bool distributed(const cb_ctx* c) { return c->cfg.world > 1; }
 int nccl_unique_id(void* id128, std::string& err);
 void nccl_init(cb_ctx* c, const void* id128);
 void nccl_shutdown(cb_ctx* c);
 void ex_allreduce(cb_ctx* c, u64* vals, int n, int op);
+// Rank-local failures ahead of a collective: every rank calls this at the same point with its own
+// code (0 = fine); if any rank failed, EVERY rank throws (a rank that returned early would leave
+// its peers blocked inside the next NCCL call).  On a single GPU it simply throws.
+void sync_error(cb_ctx* c, int local_code, const std::string& msg);
+// runs f(); a cb::Error it throws is turned into a collective failure (sync_error)
+template <class F>
+inline void guarded(cb_ctx* c, F&& f) {
+  int code = 0;
+  std::string msg;
+  try {
+    f();
+  } catch (const Error& e) {
+    code = e.code;
+    msg = e.what();
+    if (!distributed(c)) throw;
+  }
+  sync_error(c, code, msg);
+}
 // in-place max over the ranks of a DEVICE byte array
 void ex_allreduce_max_u8(cb_ctx* c, uint8_t* dev, size_t n);
 void ex_counts(cb_ctx* c, const u64* send, u64* recv, int n_per_rank);

@@ -136,6 +136,17 @@ void ex_allreduce(cb_ctx* c, u64* vals, int n, int op) {
   if (rc) ex_fail("allreduce_u64", rc);
 }
 
+void sync_error(cb_ctx* c, int local_code, const std::string& msg) {
+  if (!distributed(c)) {
+    if (local_code) throw Error(local_code, msg);
+    return;
+  }
+  u64 v = local_code ? 1 : 0;
+  ex_allreduce(c, &v, 1, 1);
+  if (local_code) throw Error(local_code, msg);
+  if (v) throw Error(CB_E_CAPACITY, "another rank of the sharded run failed (its cb_last_error has the reason)");
+}
+
 void ex_allreduce_max_u8(cb_ctx* c, uint8_t* dev, size_t n) {
   if (!distributed(c)) return;
   need_ex(c);
@@ -273,7 +284,8 @@ void route_records(cb_ctx* c, const void* recs, size_t elem_bytes, const u32* de
   if (elem_bytes % 4) throw Error(CB_E_INVALID, "route_records: record size must be a multiple of 4");
   std::vector<u64> cnt(world + 1, 0), send_bytes(world), recv_bytes(world);
   DevBuf<char> send;
-  if (n) {
+  guarded(c, [&] {  // every rank reaches the exchange below, whatever happens locally
+    if (!n) { send.alloc(elem_bytes, s); return; }
     DevBuf<u64> ka, kb;
     DevBuf<u32> va, vb;
     DevBuf<u64> dcnt;
@@ -296,9 +308,7 @@ void route_records(cb_ctx* c, const void* recs, size_t elem_bytes, const u32* de
                                                                        n_send, (u32*)send.p);
     c->lc.n += 3;
     CB_CUDA(cudaGetLastError());
-  } else {
-    send.alloc(elem_bytes, s);
-  }
+  });
   std::vector<u64> rcnt(world);
   ex_counts(c, cnt.data(), rcnt.data(), 1);
   n_out = 0;

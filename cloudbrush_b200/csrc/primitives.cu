@@ -595,12 +595,10 @@ static void launch_onesweep(u32 tiles, cudaStream_t s, const u64* kin, u64* kout
                             u32* ctl, const u32* gbase, u32 n, int bit, u32 mask, const u32* ent_in, u32* ent_out,
                             int next_shift, u32 next_mask, int force_rank) {
   constexpr size_t dyn = os_smem_bytes<HAS_VALS, S, RB>();
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    CB_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<HAS_VALS, S, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)dyn));
-    configured = true;
-  }
+  // the attribute is per device and contexts may live on several devices and threads: set it on every
+  // launch (a driver-side table write, no synchronisation)
+  CB_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<HAS_VALS, S, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)dyn));
   rs_onesweep_kernel<HAS_VALS, S, RB><<<tiles, RS_THREADS, dyn, s>>>(kin, kout, vin, vout, status, ctl, gbase, ctl + 1, n,
                                                                     bit, mask, ent_in, ent_out, next_shift, next_mask,
                                                                     force_rank);

@@ -241,9 +241,11 @@ __global__ void __launch_bounds__(GW_THREADS) group_walk_kernel(JoinParams P) {
         }
         if ((long long)sum > P.up_kmer) atomicAdd(&P.dcount[DC_HKMER], 1ull);
       }
-      if (live && (long long)g > P.up_kmer) atomicAdd(&P.dcount[DC_UPKMER_LISTS], 1ull);
     }
     if (cand && live) {
+      // MatchPrefix.java:366-368: the elist of a k-mer that has a node entry is cut to its first UP_KMER
+      // entries by overlap; which entries survive depends on Hadoop's value order (refused by the host)
+      if ((long long)g > P.up_kmer) atomicAdd(&P.dcount[DC_UPKMER_LISTS], 1ull);
       const u32 lid = 2 * (u32)(m >> (P.pb + 1)) + (pos == 0 ? 1u : 0u);  // list (b, flip y)
       const u32 v = lid | ((u32)(m & 1) << 31);
       if (inside) {  // position = number of NODEMSG tuples of the group before this one: no atomics
@@ -627,7 +629,7 @@ void stage_build_overlap(cb_ctx* c) {
   const int world = c->cfg.world;
   const u32 wmask = (u32)world - 1;
   size_t Tmax = (size_t)n_own * W;  // tuple slots generated here
-  if (Tmax >= (1ull << 32)) throw Error(CB_E_CAPACITY, "more than 2^32 k-mer tuples per context");
+  sync_error(c, Tmax >= (1ull << 32) ? CB_E_CAPACITY : 0, "more than 2^32 k-mer tuples per context");
   c->lay.nb = nbits;
   c->lay.ob = bits_for((u64)(L - K + 1));
   c->lay.L = L;
@@ -659,8 +661,11 @@ void stage_build_overlap(cb_ctx* c) {
     // all-to-all that replaces the MapReduce shuffle.  Received order is (source rank, node,
     // window), i.e. ascending (node, window): the join relies on it.
     timer_start(c, "exchange_tuples");
-    int w0 = radix_sort(keys[0].p, keys[1].p, vals[0].p, vals[1].p, Tmax, c->pbit, c->pbit + c->lg_world, s, c->lc,
-                        "partition");
+    int w0 = 0;
+    guarded(c, [&] {
+      w0 = radix_sort(keys[0].p, keys[1].p, vals[0].p, vals[1].p, Tmax, c->pbit, c->pbit + c->lg_world, s, c->lc,
+                      "partition");
+    });
     DevBuf<u64> dcnt;
     dcnt.alloc(world, s);
     CB_CUDA(cudaMemsetAsync(dcnt.p, 0, world * sizeof(u64), s));
@@ -676,7 +681,7 @@ void stage_build_overlap(cb_ctx* c) {
     ex_counts(c, cnt.data(), rcnt.data(), 1);
     size_t Trecv = 0;
     for (int r = 0; r < world; r++) Trecv += (size_t)rcnt[r];
-    if (Trecv >= (1ull << 32)) throw Error(CB_E_CAPACITY, "more than 2^32 k-mer tuples per context");
+    sync_error(c, Trecv >= (1ull << 32) ? CB_E_CAPACITY : 0, "more than 2^32 k-mer tuples per context");
     DevBuf<u64> rkeys;
     DevBuf<u32> rvals;
     rkeys.alloc(Trecv ? Trecv : 1, s);
@@ -702,7 +707,8 @@ void stage_build_overlap(cb_ctx* c) {
     timer_stop(c, "exchange_tuples");
   }
   timer_start(c, "sort_tuples");
-  int where = radix_sort(keys[0].p, keys[1].p, vals[0].p, vals[1].p, Tmax, 0, 2 * K, s, c->lc, "tuples");
+  int where = 0;
+  guarded(c, [&] { where = radix_sort(keys[0].p, keys[1].p, vals[0].p, vals[1].p, Tmax, 0, 2 * K, s, c->lc, "tuples"); });
   timer_stop(c, "sort_tuples");
   download_counters(c);
   const u32 T = (u32)(Tmax - c->hcount[DC_TUPLES_INVALID]);
@@ -842,6 +848,10 @@ void stage_build_overlap(cb_ctx* c) {
   c->counters["side_buffer_edges"] = (int64_t)c->gcount[DC_EDGES_RAW];
   c->counters["upkmer_truncated_lists"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
   c->counters["order_dependent"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
+  if (c->gcount[DC_UPKMER_LISTS] > 0)
+    throw Error(CB_E_UNSUPPORTED,
+                "a k-mer group with a node entry holds more than -kmerup tuples: the reference truncates its "
+                "candidate list in Hadoop's value order (MatchPrefix.java:366-368), parity undefined");
   if (hkmer > 0)
     throw Error(CB_E_UNSUPPORTED,
                 "non-empty high-frequency k-mer list: the reference's stopword loader (MatchPrefix.java:81) is "

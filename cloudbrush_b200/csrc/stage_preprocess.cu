@@ -487,7 +487,6 @@ void stage_parse_and_pack(cb_ctx* c) {
   const size_t n = c->text_n;
   const int world = c->cfg.world;
   if (n == 0 && !distributed(c)) throw Error(CB_E_NOREADS, "No good reads");
-  if (n >= (1ull << 32)) throw Error(CB_E_CAPACITY, "SFA input of 4 GiB or more per context");
   c->K = c->cfg.k;
   c->L = c->cfg.readlen;
   if (c->K < 1 || c->K > 31 || (c->K % 2) == 0)
@@ -497,6 +496,7 @@ void stage_parse_and_pack(cb_ctx* c) {
   if (world < 1 || (world & (world - 1)) || world > 256) throw Error(CB_E_UNSUPPORTED, "world must be a power of two <= 256");
   if (distributed(c) && !c->has_ex && !c->nccl_comm)
     throw Error(CB_E_INVALID, "cfg.world > 1 needs cb_init_nccl or cb_set_exchange before cb_preprocess");
+  sync_error(c, n >= (1ull << 32) ? CB_E_CAPACITY : 0, "SFA input of 4 GiB or more per context");
   c->lg_world = 0;
   while ((1 << c->lg_world) < world) c->lg_world++;
   c->pbit = c->K;  // owner of a k-mer group: bits [K, K + lg_world) of the canonical key (its middle bases)
@@ -538,7 +538,7 @@ void stage_parse_and_pack(cb_ctx* c) {
     std::vector<u64> snd(world, (u64)c->n_lines), rcv(world, 0);
     ex_counts(c, snd.data(), rcv.data(), 1);
     for (int r = 0; r < world; r++) c->line_bases[r + 1] = c->line_bases[r] + rcv[r];
-    if (c->line_bases[world] >= (1ull << 32)) throw Error(CB_E_CAPACITY, "more than 2^32 SFA lines");
+    if (c->line_bases[world] >= (1ull << 32)) throw Error(CB_E_CAPACITY, "more than 2^32 SFA lines");  // same on every rank
     c->line_base = (u32)c->line_bases[c->cfg.rank];
   } else {
     c->line_bases[1] = c->n_lines;
@@ -624,10 +624,14 @@ void stage_parse_and_pack(cb_ctx* c) {
     rline.alloc(g1, s); rsurv.alloc(g1, s); rcov.alloc(g1, s); rid.alloc(g1, s); rreads.alloc(g1 * NW, s);
     CB_CUDA(cudaMemsetAsync(rsurv.p, 0, g1 * 4, s));
     CB_CUDA(cudaMemsetAsync(rcov.p, 0, g1 * 4, s));
-    if (n_got) {
+    int where = 0;
+    guarded(c, [&] {  // a rank-local sort failure must not leave the peers blocked in the next exchange
+      if (!n_got) return;
       CB_DISPATCH_NW(NW, (dd_unpack_kernel<NW_><<<div_up(n_got, 256), 256, 0, s>>>((const u64*)got.p, n_got, rk[0].p,
                                                                                   rv[0].p, rline.p, rid.p, rreads.p)));
-      int where = radix_sort(rk[0].p, rk[1].p, rv[0].p, rv[1].p, n_got, 0, hb, s, c->lc, "dedupe");
+      where = radix_sort(rk[0].p, rk[1].p, rv[0].p, rv[1].p, n_got, 0, hb, s, c->lc, "dedupe");
+    });
+    if (n_got) {
       c->lc.begin("dedupe_runs");
       CB_DISPATCH_NW(NW, (dedupe_runs_kernel<NW_><<<min(div_up(n_got, 128), kNumSMs * 16), 128, 0, s>>>(
                              rk[where].p, rv[where].p, (u32)n_got, keymask, rreads.p, rid.p, c->L, rsurv.p, rcov.p,

@@ -826,7 +826,8 @@ void stage_string_graph(cb_ctx* c) {
       size_t n_req_applied = 0;
       if (dist) {  // removal requests for mirrors -> owner rank of the mirror's list
         u32 nr = read_u32s(c, nwork.p + 4);
-        if (nr > P.req_cap) throw Error(CB_E_CAPACITY, "removal request buffer overflow");
+        sync_error(c, nr > P.req_cap ? CB_E_CAPACITY : 0, "removal request buffer overflow");
+        if (nr > P.req_cap) nr = P.req_cap;
         DevBuf<char> got;
         size_t n_got = route_keys(c, req.p, nr, got);
         n_req_applied = n_got;
@@ -866,7 +867,7 @@ void stage_string_graph(cb_ctx* c) {
       download_counters(c);
       cur_n -= (size_t)c->hcount[DC_EDGES_C];
       c->n_cut_log = read_u32s(c, nwork.p + 7);
-      if (c->n_cut_log > log_cap) throw Error(CB_E_CAPACITY, "cut log overflow");
+      sync_error(c, c->n_cut_log > log_cap ? CB_E_CAPACITY : 0, "cut log overflow");
       // round 2 only has to look at the lists that changed: an unchanged list cuts nothing again
       work = dirty;
       n_work = nd;
@@ -923,7 +924,7 @@ void stage_string_graph(cb_ctx* c) {
         c->lc.n++;
       }
       u32 nv = read_u32s(c, nwork.p + 5);
-      if (nv > P.req_cap) throw Error(CB_E_CAPACITY, "vote buffer overflow");
+      sync_error(c, nv > P.req_cap ? CB_E_CAPACITY : 0, "vote buffer overflow");
       u64 any_votes = nv;
       ex_allreduce(c, &any_votes, 1, 0);
       if (any_votes) {

@@ -107,7 +107,10 @@ int cb_load_sfa(cb_ctx* ctx, const char* path_or_dir);
 int cb_load_sfa_buffer(cb_ctx* ctx, const char* buf, size_t n);
 int cb_load_sfa_device(cb_ctx* ctx, const void* dev_buf, size_t n);
 /* Zero-copy variant: the context reads the caller's DEVICE buffer in place; it must stay valid
- * and unchanged until the next cb_load_* / cb_borrow_* / cb_destroy. */
+ * and unchanged until the next cb_load_* / cb_borrow_* / cb_destroy.  The buffer must be 16-byte
+ * aligned (CB_E_INVALID otherwise: the parser reads aligned 16-byte vectors).  For both *_device
+ * calls the work that PRODUCES the buffer must be complete (synchronise the producing stream)
+ * before the call; cb_load_sfa_device has finished its copy when it returns. */
 int cb_borrow_sfa_device(cb_ctx* ctx, const void* dev_buf, size_t n);
 
 /* The three stage groups, run to completion on the calling thread (see top of file). */
@@ -145,6 +148,11 @@ int cb_get_launch_count(cb_ctx* ctx, int64_t* n);
  * "dedupe_runs", "keygen", "join_verify", "cut", "tr"). */
 int cb_set_profile(cb_ctx* ctx, int on);
 int cb_get_kernel_stat(cb_ctx* ctx, const char* name, double* total_ms, int64_t* launches);
+
+/* Test hook (kernel-level parity of the shuffle replacement, tests/test_gpu_sort.py): sorts the
+ * caller's HOST arrays in place on the device with the library's LSD radix sort -- stable, on key
+ * bits [begin_bit, end_bit) -- and copies them back.  vals may be NULL (keys only).  n < 2^32. */
+int cb_debug_sort(cb_ctx* ctx, uint64_t* keys, uint32_t* vals, size_t n, int begin_bit, int end_bit);
 
 /* ---- multi-GPU: one process (and one context) per GPU -------------------------------------
  * The MapReduce shuffle of the reference (HashPartitioner on the Text key inside every

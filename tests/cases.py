@@ -93,3 +93,15 @@ def all_cases():
     reads += [(f"b{n}", rep2 + rand_dna(15, 8000 + n)) for n in range(40)]
     cases["many_branches"] = (sfa(reads), 21, 36)
     return cases
+
+
+def upkmer_case():
+    """A k-mer group that has node entries and MORE tuples than a (small) -kmerup, while BuildHighKmerList's
+    weighted count over windows [0, L-K) stays below it (the last-window tuples are not counted there,
+    BuildHighKmerList.java:59-60): the reference truncates the candidate list in Hadoop's value order
+    (MatchPrefix.java:366-368).  Returns (sfa, k, readlen, up_kmer)."""
+    rep = rand_dna(21, 43)
+    reads = [(f"s{n}", rand_dna(15, 9000 + n) + rep) for n in range(30)]        # last window: not counted
+    reads += [(f"p{n}", rep + rand_dna(15, 9100 + n)) for n in range(3)]        # window 0
+    reads += [(f"i{n}", rand_dna(7, 9200 + n) + rep + rand_dna(8, 9300 + n)) for n in range(10)]
+    return sfa(reads), 21, 36, 20
