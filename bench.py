@@ -244,7 +244,8 @@ def bench_reference(args):
 # --------------------------------------------------------------------------------------------
 KERNELS = ["parse_lines", "dedupe_runs", "keygen", "join_verify", "cut", "tr",
            "rs_scatter:dedupe", "rs_upsweep:dedupe", "rs_scatter:tuples", "rs_upsweep:tuples",
-           "group_walk", "side_insert", "consistency", "tr_final"]
+           "group_walk", "side_insert", "consistency", "tr_final",
+           "ph_scatter1", "ph_hist2", "ph_scatter2", "bucket_join"]
 
 
 def bench_ours(args):

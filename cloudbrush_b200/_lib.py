@@ -14,12 +14,14 @@ CB_OK = 0
 ERRORS = {-1: "CB_E_INVALID", -2: "CB_E_NODEVICE", -3: "CB_E_CUDA", -4: "CB_E_NOMEM", -5: "CB_E_IO",
           -6: "CB_E_NOREADS", -7: "CB_E_UNSUPPORTED", -8: "CB_E_CAPACITY"}
 CK_PREPROCESS, CK_OVERLAP, CK_CHL2, CK_RE = 0, 1, 2, 3
+FLAG_FLAT_PIPELINE = 1
 
 
 class cb_config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("k", C.c_int32), ("readlen", C.c_int32),
                 ("up_kmer", C.c_int64), ("low_kmer", C.c_int64), ("majority", C.c_float), ("pwm_n", C.c_float),
-                ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("flags", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class cb_edge(C.Structure):

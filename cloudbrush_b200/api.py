@@ -32,6 +32,7 @@ class BrushConfig:
     device: int = 0
     rank: int = 0
     world: int = 1
+    flat_pipeline: bool = False  # CB_FLAG_FLAT_PIPELINE: LSD sort + flat join instead of the hash-bucket path
 
 
 class BrushGpu:
@@ -43,6 +44,7 @@ class BrushGpu:
         c.up_kmer, c.low_kmer = cfg.up_kmer, cfg.low_kmer
         c.majority, c.pwm_n = cfg.majority, cfg.pwm_n
         c.device, c.rank, c.world = cfg.device, cfg.rank, cfg.world
+        c.flags = L.FLAG_FLAT_PIPELINE if cfg.flat_pipeline else 0
         self.cfg = cfg
         self._h = C.c_void_p()
         rc = self._L.cb_create(C.byref(c), C.byref(self._h))

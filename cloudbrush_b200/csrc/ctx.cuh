@@ -37,6 +37,7 @@ enum DevCounter {
   DC_EDGES_C,          // edges after CutChimericLinks + EdgeRemoval
   DC_EDGES_B,          // edges of checkpoint B
   DC_MAX_LIST,         // longest adjacency list
+  DC_BUCKET_OVER,      // hash buckets larger than the bucket kernel holds (flat pipeline takes over)
   DC_COUNT
 };
 
@@ -70,9 +71,9 @@ struct Timer {
 };
 
 // One checkpoint of the graph: adjacency list `lid` = node*2 + x owns the slot range
-// keys[adj_off[lid] .. adj_off[lid+1]); a slot holds a record or ~0 (empty), in no particular
-// order.  All checkpoints share cb_ctx::adj_off and the slot positions, so removing an edge is
-// writing ~0 into its slot.
+// keys[adj[lid].x .. adj[lid].x + adj[lid].y); a slot holds a record or ~0 (empty), in no
+// particular order (the ranges are handed out per k-mer bucket, not in list order).  All
+// checkpoints share cb_ctx::adj and the slot positions, so removing an edge is writing ~0 into its slot.
 struct EdgeSet {
   DevBuf<u64> keys;  // [slots], ~0 = empty slot; or, if compact, the n records back to back in no order
   size_t n = 0;      // records
@@ -130,8 +131,10 @@ struct cb_ctx {
 
   // graph
   cb::EdgeLayout lay;
-  cb::DevBuf<u32> adj_off;          // [2*n_nodes + 1] slot offset of list node*2 + x
+  cb::DevBuf<uint2> adj;            // [2*n_nodes] (first slot, slots) of list node*2 + x
   size_t slots = 0;
+  cb::DevBuf<uint4> list_order;     // bucket path: (list, first slot, slots) of the lists that own slots, in slot order
+  size_t n_list_order = 0;
   cb::DevBuf<uint8_t> list_flag;    // [2*n_nodes] 1: all overhangs nest (consistent), 0: not, 2: unknown
   cb::DevBuf<u32> ovh;              // [slots][NWo] overhang nbr^y[ov:] of the record in the slot (any checkpoint),
   int NWo = 0;                      //   2-bit packed, left aligned, 16 bases per word; NWo = ceil((L-K)/16)

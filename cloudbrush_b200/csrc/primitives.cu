@@ -723,4 +723,251 @@ int radix_sort(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int
   return where;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// hash partition (see primitives.cuh): level-1 / level-2 digit histograms, the segment and tile
+// tables, and the atomic-reserve scatter
+// ------------------------------------------------------------------------------------------
+constexpr int PS_THREADS = 512;
+constexpr int PS_ITEMS = 8;
+constexpr int PS_TILE = PS_THREADS * PS_ITEMS;  // 4096 tuples per tile
+
+BucketPlan make_bucket_plan(size_t n_tuples) {
+  // digit widths the scatter kernel is instantiated for; two passes, the smallest total that reaches the
+  // wanted number of buckets (more buckets than wanted only makes them smaller)
+  static const int widths[4] = {3, 6, 8, 9};
+  BucketPlan pl;
+  int nbits = 2;
+  while (nbits < 18 && ((size_t)576 << nbits) < n_tuples) nbits++;
+  pl.fits = ((size_t)1400 << nbits) >= n_tuples;  // beyond 2^18 buckets of <= 1400: a third pass would be needed
+  int best = 99;
+  for (int a : widths)
+    for (int b : widths)
+      if (a >= b && a + b >= nbits && a + b < best) { best = a + b; pl.b1 = a; pl.b2 = b; }
+  pl.NB = 1u << (pl.b1 + pl.b2);
+  pl.shift1 = 64 - pl.b1;
+  pl.shift2 = 64 - pl.b1 - pl.b2;
+  pl.lshift = 64 - pl.b1 - pl.b2 - kLocalBits;
+  return pl;
+}
+
+// where the tiles of a pass come from: a flat array of n slots (tile_seg == nullptr), or the tiles
+// of the level-1 segments (a tile never straddles two segments)
+struct TileSrc {
+  const u32* tile_seg;   // segment of tile t, ~0 beyond the last tile
+  const u32* tile_off;   // index of tile t within its segment
+  const u32* seg_start;  // [S + 1]
+  u32 n;
+};
+__device__ __forceinline__ bool tile_range(const TileSrc& ts, u32 tile, u32& seg, u32& base, u32& count) {
+  if (!ts.tile_seg) {
+    seg = 0;
+    if ((size_t)tile * PS_TILE >= (size_t)ts.n) return false;
+    base = tile * (u32)PS_TILE;
+    count = min((u32)PS_TILE, ts.n - base);
+    return true;
+  }
+  seg = ts.tile_seg[tile];
+  if (seg == 0xffffffffu) return false;
+  const u32 s0 = ts.seg_start[seg], s1 = ts.seg_start[seg + 1];
+  base = s0 + ts.tile_off[tile] * (u32)PS_TILE;
+  count = min((u32)PS_TILE, s1 - base);
+  return true;
+}
+
+// digit counts of one pass: per tile in shared memory, then one global add per non-empty bin
+__global__ void __launch_bounds__(256) ph_hist_kernel(const u64* __restrict__ kin, TileSrc ts, u64 kmask, int shift,
+                                                      int bits, u32* __restrict__ ghist) {
+  extern __shared__ u32 ph_h[];
+  const u32 bins = 1u << bits, mask = bins - 1;
+  u32 seg, base, count;
+  if (!tile_range(ts, blockIdx.x, seg, base, count)) return;  // uniform
+  for (u32 t = threadIdx.x; t < bins; t += blockDim.x) ph_h[t] = 0;
+  __syncthreads();
+  for (u32 e = threadIdx.x; e < count; e += blockDim.x) {
+    const u64 k = kin[base + e];
+    if (k != ~0ull) atomicAdd(&ph_h[(u32)(kmer_hash(k & kmask) >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  for (u32 t = threadIdx.x; t < bins; t += blockDim.x) {
+    const u32 v = ph_h[t];
+    if (v) atomicAdd(&ghist[((size_t)seg << bits) + t], v);
+  }
+}
+
+// one block: level-1 digit counts -> segment offsets, the scatter cursors of pass 1, and the tile table
+// of the passes that read the segments (S <= 2048 segments, two per thread)
+__global__ void __launch_bounds__(1024) ph_segments_kernel(const u32* __restrict__ cnt, int S, u32* __restrict__ seg_start,
+                                                           u32* __restrict__ cursor, u32* __restrict__ tile_seg,
+                                                           u32* __restrict__ tile_off, u32 max_tiles,
+                                                           u32* __restrict__ total_out) {
+  __shared__ u32 tmp[1024 / 32 + 1];
+  const int s0 = 2 * (int)threadIdx.x, s1 = s0 + 1;
+  const u32 c0 = s0 < S ? cnt[s0] : 0u, c1 = s1 < S ? cnt[s1] : 0u;
+  const u32 t0 = (c0 + PS_TILE - 1) / PS_TILE, t1 = (c1 + PS_TILE - 1) / PS_TILE;
+  u32 total, ttotal;
+  const u32 ex = block_excl_scan(c0 + c1, tmp, total);
+  const u32 et = block_excl_scan(t0 + t1, tmp, ttotal);
+  if (s0 < S) { seg_start[s0] = ex; cursor[s0] = ex; }
+  if (s1 < S) { seg_start[s1] = ex + c0; cursor[s1] = ex + c0; }
+  if (threadIdx.x == 0) { seg_start[S] = total; *total_out = total; }
+  for (u32 i = 0; i < t0; i++)
+    if (et + i < max_tiles) { tile_seg[et + i] = (u32)s0; tile_off[et + i] = i; }
+  for (u32 i = 0; i < t1; i++)
+    if (et + t0 + i < max_tiles) { tile_seg[et + t0 + i] = (u32)s1; tile_off[et + t0 + i] = i; }
+}
+
+// One tile: rank the tuples by digit inside every warp (ballots over the digit bits, a warp-private
+// histogram -- a shared-memory atomic per tuple costs 64 LSU cycles per warp instruction on this part and
+// made the pass 70 % slower than the LSD pass it replaces), scan the warp histograms per digit, reserve the
+// tile's range of every bin with ONE global atomic per bin, stage the tuples by bin in shared memory and
+// write every bin's run as one contiguous piece.  Hashed digits are uniformly random, so the ballots win
+// over MATCH.ANY (see digit_peers).  Slots whose key is ~0 (windows that emit nothing) are dropped.
+template <int RB>
+__global__ void __launch_bounds__(PS_THREADS, 2) ph_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin,
+                                                                   u64* __restrict__ kout, u32* __restrict__ vout,
+                                                                   TileSrc ts, u64 kmask, int shift,
+                                                                   u32* __restrict__ cursor) {
+  constexpr int RADIX = 1 << RB;
+  constexpr int WARPS = PS_THREADS / 32;
+  static_assert(RADIX <= PS_THREADS, "one thread per digit bin");
+  extern __shared__ __align__(16) unsigned char ps_smem[];
+  u64* stage = reinterpret_cast<u64*>(ps_smem);                 // [PS_TILE]
+  u32* vstage = reinterpret_cast<u32*>(ps_smem + PS_TILE * 8);  // [PS_TILE]
+  unsigned short(*warp_hist)[RADIX] = reinterpret_cast<unsigned short(*)[RADIX]>(vstage + PS_TILE);  // [WARPS][RADIX]
+  u32* excl = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(warp_hist) + WARPS * RADIX * 2);  // [RADIX]
+  u32* gbase = excl + RADIX;                                                                            // [RADIX]
+  __shared__ u32 scan_tmp[WARPS + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt_mask = (1u << lane) - 1;
+  u32 seg, base, count;
+  if (!tile_range(ts, blockIdx.x, seg, base, count)) return;  // uniform
+  for (int t = tid; t < WARPS * RADIX / 2; t += PS_THREADS) reinterpret_cast<u32*>(&warp_hist[0][0])[t] = 0;
+  u64 key[PS_ITEMS];
+  u32 pos[PS_ITEMS];
+  const u32 e0 = (u32)warp * (PS_ITEMS * 32) + lane;  // warp-striped
+#pragma unroll
+  for (int i = 0; i < PS_ITEMS; i++) {
+    const u32 e = e0 + i * 32;
+    key[i] = e < count ? kin[base + e] : ~0ull;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < PS_ITEMS; i++) {
+    const bool valid = key[i] != ~0ull;
+    const u32 d = (u32)(kmer_hash(key[i] & kmask) >> shift) & (RADIX - 1);
+    u32 peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < RB; b++) {
+      const bool bit = (d >> b) & 1u;
+      const u32 bal = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? bal : ~bal;
+    }
+    const u32 prev = warp_hist[warp][d];
+    __syncwarp();
+    if (valid && lane == __ffs(peers) - 1) warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
+    __syncwarp();
+    pos[i] = valid ? prev + __popc(peers & lt_mask) : 0xffffffffu;
+  }
+  __syncthreads();
+  u32 run = 0;
+  if (tid < RADIX) {
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) {
+      const u32 c = warp_hist[w][tid];
+      warp_hist[w][tid] = (unsigned short)run;
+      run += c;
+    }
+  }
+  u32 total;
+  const u32 ex = block_excl_scan(run, scan_tmp, total);  // threads >= RADIX contribute 0
+  if (tid < RADIX) {
+    excl[tid] = ex;
+    if (run) gbase[tid] = atomicAdd(&cursor[((size_t)seg << RB) + tid], run) - ex;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < PS_ITEMS; i++) {
+    if (pos[i] != 0xffffffffu) {
+      const u32 d = (u32)(kmer_hash(key[i] & kmask) >> shift) & (RADIX - 1);
+      pos[i] += excl[d] + warp_hist[warp][d];
+      stage[pos[i]] = key[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PS_ITEMS; i++)  // the key registers are dead now
+    if (pos[i] != 0xffffffffu) vstage[pos[i]] = vin[base + e0 + i * 32];
+  __syncthreads();
+  for (u32 p = tid; p < total; p += PS_THREADS) {
+    const u64 k = stage[p];
+    const u32 g = gbase[(u32)(kmer_hash(k & kmask) >> shift) & (RADIX - 1)] + p;
+    kout[g] = k;
+    vout[g] = vstage[p];
+  }
+}
+
+template <int RB>
+static void launch_scatter_rb(u32 tiles, cudaStream_t s, const u64* kin, const u32* vin, u64* kout, u32* vout,
+                              const TileSrc& ts, u64 kmask, int shift, u32* cursor) {
+  constexpr size_t dyn = (size_t)PS_TILE * 12 + (PS_THREADS / 32) * ((size_t)2 << RB) + 2 * ((size_t)4 << RB);
+  CB_CUDA(cudaFuncSetAttribute(ph_scatter_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  ph_scatter_kernel<RB><<<tiles, PS_THREADS, dyn, s>>>(kin, vin, kout, vout, ts, kmask, shift, cursor);
+}
+static void launch_scatter(u32 tiles, cudaStream_t s, const u64* kin, const u32* vin, u64* kout, u32* vout, const TileSrc& ts,
+                           u64 kmask, int shift, int bits, u32* cursor) {
+  switch (bits) {
+    case 3: launch_scatter_rb<3>(tiles, s, kin, vin, kout, vout, ts, kmask, shift, cursor); break;
+    case 6: launch_scatter_rb<6>(tiles, s, kin, vin, kout, vout, ts, kmask, shift, cursor); break;
+    case 8: launch_scatter_rb<8>(tiles, s, kin, vin, kout, vout, ts, kmask, shift, cursor); break;
+    case 9: launch_scatter_rb<9>(tiles, s, kin, vin, kout, vout, ts, kmask, shift, cursor); break;
+    default: throw Error(CB_E_INVALID, "bucket_partition: unsupported digit width");
+  }
+  CB_CUDA(cudaGetLastError());
+}
+
+void bucket_partition(u64* ka, u32* va, u64* kb, u32* vb, size_t n_slots, u64 kmask, const BucketPlan& pl,
+                      const u32* d_cnt1, u32* bstart, u32* d_total, cudaStream_t s, LaunchCounter& lc) {
+  if (n_slots >= (1ull << 32)) throw Error(CB_E_CAPACITY, "bucket_partition: more than 2^32-1 tuple slots");
+  const int S = 1 << pl.b1;
+  const u32 tiles1 = (u32)((n_slots + PS_TILE - 1) / PS_TILE);
+  const u32 max_tiles2 = tiles1 + (u32)S + 1;
+  DevBuf<u32> cnt1, seg_start, cursor1, tile_seg, tile_off, hist2, cursor2;
+  seg_start.alloc((size_t)S + 1, s);
+  cursor1.alloc(S, s);
+  tile_seg.alloc(max_tiles2, s);
+  tile_off.alloc(max_tiles2, s);
+  hist2.alloc((size_t)pl.NB + 1, s);
+  cursor2.alloc(pl.NB, s);
+  TileSrc flat{nullptr, nullptr, nullptr, (u32)n_slots};
+  TileSrc segs{tile_seg.p, tile_off.p, seg_start.p, 0u};
+  if (!d_cnt1) {
+    cnt1.alloc(S, s);
+    CB_CUDA(cudaMemsetAsync(cnt1.p, 0, (size_t)S * 4, s));
+    lc.begin("ph_hist1");
+    if (tiles1) ph_hist_kernel<<<tiles1, 256, (size_t)4 << pl.b1, s>>>(ka, flat, kmask, pl.shift1, pl.b1, cnt1.p);
+    lc.end("ph_hist1");
+    lc.n++;
+    d_cnt1 = cnt1.p;
+  }
+  CB_CUDA(cudaMemsetAsync(tile_seg.p, 0xff, (size_t)max_tiles2 * 4, s));
+  CB_CUDA(cudaMemsetAsync(hist2.p, 0, ((size_t)pl.NB + 1) * 4, s));
+  ph_segments_kernel<<<1, 1024, 0, s>>>(d_cnt1, S, seg_start.p, cursor1.p, tile_seg.p, tile_off.p, max_tiles2, d_total);
+  lc.n++;
+  CB_CUDA(cudaGetLastError());
+  lc.begin("ph_scatter1");
+  if (tiles1) launch_scatter(tiles1, s, ka, va, kb, vb, flat, kmask, pl.shift1, pl.b1, cursor1.p);
+  lc.end("ph_scatter1");
+  lc.begin("ph_hist2");
+  ph_hist_kernel<<<max_tiles2, 256, (size_t)4 << pl.b2, s>>>(kb, segs, kmask, pl.shift2, pl.b2, hist2.p);
+  lc.end("ph_hist2");
+  lc.n += 2;
+  CB_CUDA(cudaGetLastError());
+  exclusive_scan_u32(hist2.p, bstart, (size_t)pl.NB + 1, s, lc);
+  CB_CUDA(cudaMemcpyAsync(cursor2.p, bstart, (size_t)pl.NB * 4, cudaMemcpyDeviceToDevice, s));
+  lc.begin("ph_scatter2");
+  launch_scatter(max_tiles2, s, kb, vb, ka, va, segs, kmask, pl.shift2, pl.b2, cursor2.p);
+  lc.end("ph_scatter2");
+  lc.n++;
+}
+
 }  // namespace cb

@@ -75,6 +75,38 @@ void exclusive_scan_u32(const u32* in, u32* out, size_t n, cudaStream_t s, Launc
 int radix_sort(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, size_t n, int begin_bit, int end_bit,
                cudaStream_t s, LaunchCounter& lc, const char* tag = "misc");
 
+// ---------------------------------------------------------------------------------------------
+// Hash partition of k-mer tuples into buckets (the shuffle replacement of the overlap path).
+// Grouping tuples by k-mer needs no total order: two scatter passes on the top bits of a hash of
+// the canonical k-mer leave buckets of a few hundred tuples, which one CTA groups in shared
+// memory (stage_overlap.cu: bucket_join_kernel).  The scatter is NOT stable: every tile reserves
+// its output ranges with one atomic add per bin on the bin's global cursor, so tiles never wait
+// for one another (the LSD passes above spend a third of their time in the decoupled look-back).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u64 kmer_hash(u64 x) {
+  x *= 0x9E3779B97F4A7C15ull;
+  x ^= x >> 32;
+  x *= 0xD6E8FEB86659FD93ull;
+  return x;  // the TOP bits are the well mixed ones
+}
+
+struct BucketPlan {
+  int b1 = 1, b2 = 1;   // digit bits of the two scatter passes
+  int shift1 = 0, shift2 = 0, lshift = 0;  // digit = (hash >> shift) & mask; lshift: the 10-bit local digit
+  u32 NB = 4;           // buckets = 2^(b1 + b2)
+  bool fits = true;     // false: more tuples than two passes can cut into buckets the bucket kernel holds
+};
+constexpr int kLocalBits = 10;
+// buckets of 288..576 tuples on average (the bucket kernel holds up to 2048)
+BucketPlan make_bucket_plan(size_t n_tuples);
+
+// Tuples (ka, va)[n_slots] -- slots whose key is ~0 are skipped -- end up bucketed in (ka, va) again
+// ((kb, vb) is the intermediate buffer); bstart[NB + 1] receives the bucket offsets and *d_total the
+// number of tuples kept.  d_cnt1 (2^b1 level-1 digit counts) may come from the producer of the tuples
+// (keygen counts while it writes); nullptr = counted here with one more read of the keys.
+void bucket_partition(u64* ka, u32* va, u64* kb, u32* vb, size_t n_slots, u64 kmask, const BucketPlan& pl,
+                      const u32* d_cnt1, u32* bstart, u32* d_total, cudaStream_t s, LaunchCounter& lc);
+
 // bytes moved per element by one pass of radix_sort (read for histogram + read + write)
 inline size_t radix_pass_bytes(bool has_vals) { return 8 + (has_vals ? 24 : 16); }
 

@@ -14,6 +14,7 @@
 // inside the group and candidates never have to be materialised: the join emits verified edges
 // and their GenReverseEdge mirrors directly (SURVEY.md 8a').
 #include <cstdlib>
+#include <cstring>
 
 #include "ctx.cuh"
 
@@ -35,7 +36,14 @@ template <int NW>
 __global__ void __launch_bounds__(256) keygen_kernel(const u64* __restrict__ node_seq,
                                                      const u32* __restrict__ node_cov, u32 node_lo, u32 n_nodes,
                                                      int L, int K, int W, int pb, u64* __restrict__ keys,
-                                                     u32* __restrict__ vals, ull* __restrict__ dcount) {
+                                                     u32* __restrict__ vals, ull* __restrict__ dcount,
+                                                     u32* __restrict__ cnt1, int shift1, int bits1) {
+  // cnt1 != nullptr: the level-1 digit counts of the hash partition (primitives.cuh) are taken while the
+  // tuples are written, so the first scatter pass needs no counting read of its own
+  extern __shared__ u32 kg_hist[];
+  const u32 bins1 = cnt1 ? (1u << bits1) : 0u;
+  for (u32 t = threadIdx.x; t < bins1; t += blockDim.x) kg_hist[t] = 0;
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const u32 total = n_nodes * (u32)W;  // < 2^32 (checked by the host)
   const u32 stride = gridDim.x * blockDim.x;
@@ -64,11 +72,17 @@ __global__ void __launch_bounds__(256) keygen_kernel(const u64* __restrict__ nod
       keys[slot] = emit ? (canon | ((meta >> 32) << (2 * K))) : ~0ull;
       vals[slot] = emit ? (u32)meta : ~0u;
       if (!emit) invalid++;
+      else if (cnt1) atomicAdd(&kg_hist[(u32)(kmer_hash(canon) >> shift1) & (bins1 - 1)], 1u);
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) invalid += __shfl_xor_sync(0xffffffffu, invalid, o);
   if (lane == 0 && invalid) atomicAdd(&dcount[DC_TUPLES_INVALID], (ull)invalid);
+  __syncthreads();
+  for (u32 t = threadIdx.x; t < bins1; t += blockDim.x) {
+    const u32 v = kg_hist[t];
+    if (v) atomicAdd(&cnt1[t], v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -100,6 +114,14 @@ struct JoinParams {
   u32* seg_head;       // [T] first tuple of the tuple's group
   u32* ne_list;        // [T+1] positions s.. of a group: (list id | entry's dir bit << 31) of its node entries, ~0 ends
   const u32* off1;     // slot offsets of the lists
+  // bucket path (bucket_join_kernel): tuples bucketed by k-mer hash, lists sized and placed per bucket
+  const u32* bstart;   // [NB + 1] bucket offsets into keys / vals
+  int lshift;          // local digit of a tuple = (kmer_hash >> lshift) & 1023
+  uint2* adj;          // [n_lists] (first slot, slots) of every list that has a node entry
+  const u32* extra;    // [n_lists] additional slots per list (retry after a slot overflow), or nullptr
+  ull* slot_cursor;    // [0] slots handed out so far, [1] lists published so far
+  ull slot_cap;        // slots allocated
+  uint4* list_order;   // [n_lists] (list, first slot, slots) of the lists that own slots, in slot order
   u64* slots;          // list storage
   u32* ovh;            // [slots][nwo] overhang of the record in the slot
   int nwo;
@@ -259,7 +281,36 @@ __global__ void __launch_bounds__(GW_THREADS) group_walk_kernel(JoinParams P) {
   }
 }
 
-constexpr int JN_XW = 64;  // side-buffer records staged per warp (flushed once 32 are waiting)
+constexpr int JN_XW = 64;
+
+// exclusive scan of one value per thread across a block; tmp holds blockDim.x / 32 + 1 values
+__device__ __forceinline__ u32 block_excl_scan_bj(u32 v, u32* tmp, u32& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  u32 inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) tmp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const u32 w = lane < nw ? tmp[lane] : 0;
+    u32 wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < nw) tmp[lane] = wi - w;
+    if (lane == nw - 1) tmp[nw] = wi;
+  }
+  __syncthreads();
+  const u32 r = tmp[warp] + inc - v;
+  total = tmp[nw];
+  __syncthreads();
+  return r;
+}  // side-buffer records staged per warp (flushed once 32 are waiting)
 
 template <int NW>
 __device__ __forceinline__ void unpack_row(const uint4 (&q)[NW / 2], u64 (&r)[NW]) {
@@ -491,6 +542,322 @@ __global__ void __launch_bounds__(256, MINB) join_verify_kernel(JoinParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bucket path: grouping + join + verify + mirror in ONE kernel, one CTA per hash bucket.
+//
+// bucket_partition (primitives.cu) leaves the tuples of every k-mer in one bucket of a few hundred
+// tuples, in no particular order.  The CTA loads its bucket once, groups it by k-mer in shared memory
+// (counting sort on 10 more hash bits; two k-mers that share those bits are separated afterwards, by
+// one thread per such bin), finds the node entries of every group, reserves the slot ranges of the
+// lists they produce (one global atomic per CTA) and runs the join on the groups where they lie.
+// Against the flat pipeline (LSD sort + group_walk_kernel + join_verify_kernel, kept below as the path
+// for buckets that do not fit) the sorted tuple array, seg_head, ne_list, the list-size scan and the
+// pre-clearing of the slot array never touch HBM: every slot of a list is written exactly once, with
+// its record or with ~0.
+//
+// Nothing here depends on the order of the tuples inside a group: "another tuple of the same read in
+// this group" (maximal-overlap filter, `certain`) is found by scanning the group in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int BJ_THREADS = 256;
+constexpr int BJ_CAP = 2048;                   // tuples per bucket the kernel holds
+constexpr int BJ_LBINS = 1 << kLocalBits;      // 1024 local bins
+// per position: key 8, payload 4, group 4, slot offset 4, node-entry list 2 bytes
+constexpr size_t BJ_SMEM = (size_t)BJ_CAP * (8 + 4 + 4 + 4 + 2) + (BJ_LBINS + 1) * 4 + BJ_LBINS * 4 + (BJ_LBINS / 32) * 4 + 64;
+static_assert(BJ_CAP / 2 <= BJ_LBINS, "node-entry counters are packed two per word of scnt");
+static_assert(BJ_CAP <= (1 << 11), "list index of a node entry is packed into 11 bits");
+
+// M32: node | window | dir of every tuple fit the 32-bit payload (no payload bits above the k-mer in
+// the key), which is the case up to 2^26 nodes at W <= 32 and 2^24 nodes at W <= 128
+template <int NW, int MINB, bool M32>
+__global__ void __launch_bounds__(BJ_THREADS, MINB) bucket_join_kernel(JoinParams P) {
+  extern __shared__ __align__(16) unsigned char bj_smem[];
+  u64* skey = reinterpret_cast<u64*>(bj_smem);          // [CAP] tuples grouped by k-mer
+  u32* sval = reinterpret_cast<u32*>(skey + BJ_CAP);     // [CAP]
+  u32* sgrp = sval + BJ_CAP;                             // [CAP] head | end << 16 of the group of position p
+  u32* soff = sgrp + BJ_CAP;                             // [CAP] node entry i: slot offset in the CTA's range | list index << 21
+  u32* sstart = soff + BJ_CAP;                           // [LBINS + 1] bin counts, then bin offsets
+  u32* scnt = sstart + BJ_LBINS + 1;                     // [LBINS] node entries per group head, two 16-bit counters per word
+  u32* smixed = scnt + BJ_LBINS;                         // [LBINS / 32] bins that hold more than one k-mer
+  unsigned short* sne = reinterpret_cast<unsigned short*>(smixed + BJ_LBINS / 32);  // [CAP] positions head.. : node entries of the group
+  __shared__ u32 scan_tmp[BJ_THREADS / 32 + 1];
+  __shared__ u32 s_any_mixed, s_slots, s_lists;
+  __shared__ ull s_base, s_lbase;
+
+  const int L = P.L, K = P.K;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const u32 lt_mask = (1u << lane) - 1;
+  const u32 posmask = (1u << P.pb) - 1;
+  const int nsh = P.pb + 1;  // node = meta >> nsh
+  const u32 lo = P.bstart[blockIdx.x];
+  const u32 n = P.bstart[blockIdx.x + 1] - lo;
+  if (n == 0) return;
+  if (n > (u32)BJ_CAP) {  // the host falls back to the flat pipeline
+    if (tid == 0) atomicAdd(&P.dcount[DC_BUCKET_OVER], 1ull);
+    return;
+  }
+  auto ldigit = [&](u64 k) { return (u32)(kmer_hash(k & P.kmask) >> P.lshift) & (BJ_LBINS - 1); };
+  auto meta_at = [&](u32 p) -> u64 { return M32 ? (u64)sval[p] : (((skey[p] >> (2 * K)) << 32) | (u64)sval[p]); };
+  auto node_at = [&](u32 p) -> u32 { return M32 ? (sval[p] >> nsh) : (u32)(meta_at(p) >> nsh); };
+  auto necnt = [&](u32 head) { return (scnt[head >> 1] >> ((head & 1u) * 16)) & 0xffffu; };
+
+  // ---- group the bucket by k-mer ----
+  for (int t = tid; t < BJ_LBINS; t += BJ_THREADS) { sstart[t] = 0; scnt[t] = 0; }
+  if (tid < BJ_LBINS / 32) smixed[tid] = 0;
+  if (tid == 0) { s_any_mixed = 0; s_slots = 0; s_lists = 0; }
+  __syncthreads();
+  // one shared-memory atomic per tuple: its return value is the tuple's rank inside its bin
+  u32 dr[BJ_CAP / BJ_THREADS];
+#pragma unroll
+  for (int i = 0; i < BJ_CAP / BJ_THREADS; i++) {
+    const u32 e = (u32)i * BJ_THREADS + tid;
+    dr[i] = 0;
+    if (e < n) {
+      const u32 d = ldigit(P.keys[lo + e]);
+      dr[i] = (d << 16) | atomicAdd(&sstart[d], 1u);
+    }
+  }
+  __syncthreads();
+  {
+    u32 c[BJ_LBINS / BJ_THREADS], run = 0;
+#pragma unroll
+    for (int q = 0; q < BJ_LBINS / BJ_THREADS; q++) { c[q] = sstart[tid * (BJ_LBINS / BJ_THREADS) + q]; run += c[q]; }
+    u32 total;
+    u32 ex = block_excl_scan_bj(run, scan_tmp, total);
+#pragma unroll
+    for (int q = 0; q < BJ_LBINS / BJ_THREADS; q++) { sstart[tid * (BJ_LBINS / BJ_THREADS) + q] = ex; ex += c[q]; }
+    if (tid == 0) sstart[BJ_LBINS] = n;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < BJ_CAP / BJ_THREADS; i++) {  // the bucket is in L1 now
+    const u32 e = (u32)i * BJ_THREADS + tid;
+    if (e < n) {
+      const u32 pos = sstart[dr[i] >> 16] + (dr[i] & 0xffffu);
+      skey[pos] = P.keys[lo + e];
+      sval[pos] = P.vals[lo + e];
+    }
+  }
+  __syncthreads();
+  // bins that hold more than one k-mer (two of the ~35 k-mers of a bucket share the 10 bits): rare enough
+  // that one thread per such bin gathers equal k-mers together
+  for (u32 p = tid; p < n; p += BJ_THREADS) {
+    const u32 d = ldigit(skey[p]);
+    if ((skey[p] ^ skey[sstart[d]]) & P.kmask) {
+      atomicOr(&smixed[d >> 5], 1u << (d & 31));
+      s_any_mixed = 1;
+    }
+  }
+  __syncthreads();
+  if (s_any_mixed) {  // block-uniform
+    for (u32 d = tid; d < (u32)BJ_LBINS; d += BJ_THREADS) {
+      if (!((smixed[d >> 5] >> (d & 31)) & 1u)) continue;
+      u32 i = sstart[d];
+      const u32 e = sstart[d + 1];
+      while (i < e) {
+        const u64 pivot = skey[i] & P.kmask;
+        u32 j = i + 1;
+        for (u32 t = i + 1; t < e; t++) {
+          if ((skey[t] & P.kmask) == pivot) {
+            if (t != j) {
+              const u64 tk = skey[t]; skey[t] = skey[j]; skey[j] = tk;
+              const u32 tv = sval[t]; sval[t] = sval[j]; sval[j] = tv;
+            }
+            j++;
+          }
+        }
+        i = j;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- [head, end) of every position's group; node entries (MatchPrefix.java:366: groups above LOW_KMER) ----
+  for (u32 p = tid; p < n; p += BJ_THREADS) {
+    const u64 kp = skey[p];
+    const u32 d = ldigit(kp);
+    u32 head = sstart[d], end = sstart[d + 1];
+    if ((smixed[d >> 5] >> (d & 31)) & 1u) {
+      const u64 ck = kp & P.kmask;
+      u32 h = p, e = p + 1;
+      while (h > head && (skey[h - 1] & P.kmask) == ck) h--;
+      while (e < end && (skey[e] & P.kmask) == ck) e++;
+      head = h;
+      end = e;
+    }
+    sgrp[p] = head | (end << 16);
+    const u64 m = meta_at(p);
+    const int pos = (int)((m >> 1) & posmask);
+    const u32 g = end - head;
+    if (p == head) {
+      // BuildHighKmerList.java:96-117: weighted count over windows [0, L-K) above UP_KMER
+      if ((kp & P.kmask) != 0 && (long long)g * (long long)P.max_cov > P.up_kmer) {
+        ull sum = 0;
+        for (u32 t = head; t < end; t++) {
+          const u64 m2 = meta_at(t);
+          if ((int)((m2 >> 1) & posmask) < L - K) sum += P.node_cov[(u32)(m2 >> nsh)];
+        }
+        if ((long long)sum > P.up_kmer) atomicAdd(&P.dcount[DC_HKMER], 1ull);
+      }
+    }
+    if ((pos == 0 || pos == L - K) && (long long)g > P.low_kmer) {  // a live NODEMSG tuple
+      if ((long long)g > P.up_kmer) atomicAdd(&P.dcount[DC_UPKMER_LISTS], 1ull);  // MatchPrefix.java:366-368 (refused by the host)
+      const u32 lid = 2 * (u32)(m >> nsh) + (pos == 0 ? 1u : 0u);  // list (b, flip y)
+      const u32 len = g + (P.extra ? P.extra[lid] : 0u);
+      const u32 old = atomicAdd(&scnt[head >> 1], (head & 1u) ? 0x10000u : 1u);
+      const u32 kk = (old >> ((head & 1u) * 16)) & 0xffffu;
+      sne[head + kk] = (unsigned short)p;
+      soff[head + kk] = atomicAdd(&s_slots, len) | (atomicAdd(&s_lists, 1u) << 21);
+    }
+  }
+  __syncthreads();
+  const u32 n_slots = s_slots, n_lists = s_lists;
+  if (n_lists == 0) return;       // no node entry in this bucket: nothing to join
+  if (n_slots >= (1u << 21)) {    // packed offsets overflowed (thousands of node entries in one group): flat pipeline
+    if (tid == 0) atomicAdd(&P.dcount[DC_BUCKET_OVER], 1ull);
+    return;
+  }
+  if (tid == 0) {
+    s_base = atomicAdd(&P.slot_cursor[0], (ull)n_slots);
+    s_lbase = atomicAdd(&P.slot_cursor[1], (ull)n_lists);
+  }
+  __syncthreads();
+  const ull base = s_base;
+  if (base + n_slots > P.slot_cap) return;  // the host sees slot_cursor > slot_cap and retries with the exact size
+  for (u32 i = tid; i < n; i += BJ_THREADS) {  // publish the lists; the tail beyond the group's own slots is empty
+    const u32 head = sgrp[i] & 0xffffu, end = sgrp[i] >> 16;
+    if (i - head < necnt(head)) {
+      const u64 m = meta_at(sne[i]);
+      const u32 lid = 2 * (u32)(m >> nsh) + ((int)((m >> 1) & posmask) == 0 ? 1u : 0u);
+      const u32 g = end - head, len = g + (P.extra ? P.extra[lid] : 0u);
+      const u32 off = (u32)(base + (soff[i] & 0x1fffffu));
+      P.adj[lid] = make_uint2(off, len);
+      P.list_order[s_lbase + (soff[i] >> 21)] = make_uint4(lid, off, len, 0u);
+      for (u32 t = g; t < len; t++) P.slots[(size_t)off + t] = ~0ull;
+    }
+  }
+
+  // ---- join + verify + mirror: every (node entry, tuple) pair of a group, one thread per tuple ----
+  const int sh_node = P.lay.nb + P.lay.ob + 2, sh_x = P.lay.nb + P.lay.ob + 1, sh_ov = P.lay.nb + 1, sh_y = P.lay.nb;
+  u32 n_verified = 0;
+  for (u32 p = tid; p < n; p += BJ_THREADS) {
+    const u32 head = sgrp[p] & 0xffffu, end = sgrp[p] >> 16;
+    const u32 nne = necnt(head);
+    if (nne == 0) continue;
+    const u64 m = meta_at(p);
+    const u32 a = (u32)(m >> nsh);
+    uint4 qa[NW / 2];
+    load_row<NW>(P.node_seq, a, qa);
+    // the first two node entries of the group (most groups have at most two) are requested up front
+    const u64 me0 = meta_at(sne[head]), me1 = nne > 1 ? meta_at(sne[head + 1]) : 0ull;
+    uint4 qb0[NW / 2], qb1[NW / 2];
+    load_row<NW>(P.node_seq, (u32)(me0 >> nsh), qb0);
+    if (nne > 1) load_row<NW>(P.node_seq, (u32)(me1 >> nsh), qb1);
+    // another tuple of the same read in this group?
+    bool multi = false;
+    for (u32 t = head; t < end; t++) multi = multi || (node_at(t) == a && t != p);
+    const int pos = (int)((m >> 1) & posmask);
+    const int d = (int)(m & 1);
+    u64 R[NW], Rc[NW];
+    unpack_row<NW>(qa, R);
+    revcomp_read<NW>(R, Rc, L);
+    // sel 0: candidate in the list of the canonical k-mer c, sel 1: of rc(c) (entry_of); the oriented read
+    // shifted so that its last ov bases lead
+    int x0, ov0, x1, ov1;
+    entry_of(L, K, pos, d, 0, x0, ov0);
+    entry_of(L, K, pos, d, 1, x1, ov1);
+    u64 A0[NW], A1[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) { A0[w] = d ? Rc[w] : R[w]; A1[w] = d ? R[w] : Rc[w]; }  // x0 = d, x1 = d ^ 1
+    shl_bases<NW>(A0, L - ov0);
+    shl_bases<NW>(A1, L - ov1);
+    // is the mirror candidate proposed in the group of X' = a^(flip x)[0:K]?  (SURVEY.md 8a': ov > K and X' not
+    // poly-A/T, or ov == K and X' > rc(X')).  X' of x = f is rc(last k-mer of a), of x = r the first k-mer of a.
+    const u64 kfirst = R[0] >> (64 - 2 * K), klast = extract_kmer<NW>(R, L - K, K);
+    const u64 rc_first = revcomp_kmer(kfirst, K), rc_last = revcomp_kmer(klast, K);
+    const bool pf_gt = (rc_last < klast ? rc_last : klast) != 0, pf_eq = rc_last > klast;
+    const bool pr_gt = (kfirst < rc_first ? kfirst : rc_first) != 0, pr_eq = kfirst > rc_first;
+    const bool prop0 = d ? (ov0 > K ? pr_gt : pr_eq) : (ov0 > K ? pf_gt : pf_eq);
+    const bool prop1 = d ? (ov1 > K ? pf_gt : pf_eq) : (ov1 > K ? pr_gt : pr_eq);
+    const bool lone = !multi && (skey[p] & P.kmask) != 0 && P.low_kmer == 1;
+    // the tuple's half of the mirror record (b, flip y, ov, flip x, a) for both lists
+    const u64 apart0 = ((u64)(u32)(L - ov0) << sh_ov) | ((u64)(u32)(x0 ^ 1) << sh_y) | (u64)a;
+    const u64 apart1 = ((u64)(u32)(L - ov1) << sh_ov) | ((u64)(u32)(x1 ^ 1) << sh_y) | (u64)a;
+    // one node entry (its tuple's payload me, first slot off_l of its list) against this tuple
+    auto process = [&](const u64 me, const u32 off_l, u64 (&B)[NW]) {
+      const u32 b = (u32)(me >> nsh);
+      const int y = ((int)((me >> 1) & posmask) == 0) ? 0 : 1;  // window-0 entry: y = f
+      const int sel = y ^ (int)(me & 1);                          // MatchPrefix.java:275-296
+      const int x = sel ? x1 : x0, ov = sel ? ov1 : ov0;
+      if (y) {
+        u64 r[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) r[w] = B[w];
+        revcomp_read<NW>(r, B, L);
+      }
+      u64 A[NW];
+#pragma unroll
+      for (int w = 0; w < NW; w++) A[w] = sel ? A1[w] : A0[w];
+      // VerifyOverlap.java:295-309; self candidates skipped at MatchPrefix.java:405-407
+      bool ok = a != b && prefix_equal<NW>(A, B, ov);
+      if (ok && multi) {
+        // maximal-overlap filter (VerifyOverlap.java:275-283) against the other tuples of read a in the
+        // group; an identical entry (MatchPrefix.java:409 hasEdge) is emitted by the first of them only
+        for (u32 t = head; t < end && ok; t++) {
+          if (t == p || node_at(t) != a) continue;
+          const u64 m2 = meta_at(t);
+          int x2, ov2;
+          entry_of(L, K, (int)((m2 >> 1) & posmask), (int)(m2 & 1), sel, x2, ov2);
+          if (x2 == x && ov2 == ov && t < p) ok = false;
+          else if (x2 == x && ov2 > ov) {
+            u64 A2[NW];
+#pragma unroll
+            for (int w = 0; w < NW; w++) A2[w] = x ? Rc[w] : R[w];
+            shl_bases<NW>(A2, L - ov2);
+            if (prefix_equal<NW>(A2, B, ov2)) ok = false;
+          }
+        }
+      }
+      const size_t slot = (size_t)off_l + (p - head);
+      if (ok) {
+        P.slots[slot] = ((u64)b << sh_node) | ((u64)(u32)(y ^ 1) << sh_x) | (sel ? apart1 : apart0);  // GenReverseEdge
+        u64 H[NW];  // the record's overhang as seen from b: a^(flip x)[ov:]
+#pragma unroll
+        for (int w = 0; w < NW; w++) H[w] = x ? R[w] : Rc[w];
+        shl_bases<NW>(H, ov);
+        store_overhang<NW>(P.ovh + slot * (size_t)P.nwo, H, P.nwo);
+        n_verified++;
+        // Is the mirror candidate certain to be proposed and kept at a's own node entry?  Then that entry
+        // writes this edge into list (a, x) itself (see join_verify_kernel); the others (~3 %) go through
+        // the side buffer
+        if (!(lone && (sel ? prop1 : prop0))) {
+          const ull gp = atomicAdd(&P.dcount[DC_EDGES_RAW], 1ull);
+          if (gp < P.xcap) P.xbuf[gp] = P.lay.encode(a, (u32)x, (u32)ov, (u32)y, b);
+        }
+      } else {
+        P.slots[slot] = ~0ull;  // every slot is written exactly once: the slot array is never pre-cleared
+      }
+    };
+    u64 B[NW];
+    unpack_row<NW>(qb0, B);
+    process(me0, (u32)(base + (soff[head] & 0x1fffffu)), B);
+    if (nne > 1) {
+      unpack_row<NW>(qb1, B);
+      process(me1, (u32)(base + (soff[head + 1] & 0x1fffffu)), B);
+      for (u32 q = 2; q < nne; q++) {
+        const u64 me = meta_at(sne[head + q]);
+        load_read_row<NW>(P.node_seq, (u32)(me >> nsh), B);
+        process(me, (u32)(base + (soff[head + q] & 0x1fffffu)), B);
+      }
+    }
+  }
+  (void)lt_mask;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_verified += __shfl_xor_sync(0xffffffffu, n_verified, o);
+  if (lane == 0 && n_verified) {
+    atomicAdd(&P.dcount[DC_CAND_VERIFIED], (ull)n_verified);
+    atomicAdd(&P.dcount[DC_EDGES_M], (ull)n_verified);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Side-buffer records: edge (a,x,ov,y,b) goes into a free slot of list (a,x) unless a's own node
 // entry already wrote it.  One thread per record.  A record that finds no free slot (only
 // possible around poly-A/T k-mers, whose interior windows have no tuple and therefore no slot)
@@ -498,7 +865,7 @@ __global__ void __launch_bounds__(256, MINB) join_verify_kernel(JoinParams P) {
 // ---------------------------------------------------------------------------------------------
 template <int NW>
 __global__ void __launch_bounds__(256) side_insert_kernel(const u64* __restrict__ xs, size_t n, EdgeLayout lay,
-                                                          const u32* __restrict__ off, u64* __restrict__ slots,
+                                                          const uint2* __restrict__ adj, u64* __restrict__ slots,
                                                           u32* __restrict__ extra, ull* __restrict__ dcount,
                                                           const u64* __restrict__ node_seq, u32* __restrict__ ovh,
                                                           int nwo, int L) {
@@ -506,7 +873,8 @@ __global__ void __launch_bounds__(256) side_insert_kernel(const u64* __restrict_
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const u64 key = xs[i];
     const u32 lid = lay.list(key);
-    const u32 lo = off[lid], hi = off[lid + 1];
+    const uint2 lr = adj[lid];
+    const u32 lo = lr.x, hi = lr.x + lr.y;
     // the record's overhang b^y[ov:] (requested before the list is scanned)
     u64 H[NW];
     load_read_row<NW>(node_seq, lay.nbr(key), H);
@@ -616,6 +984,81 @@ static u32 read_u32(cb_ctx* c, const u32* p) {
   return v;
 }
 
+// lists that receive side-buffer edges but have no node entry of their own (the entry's k-mer group is
+// below LOW_KMER, or its k-mer emits no tuple): their slots are the extra ones alone
+__global__ void __launch_bounds__(256) orphan_lists_kernel(const u32* __restrict__ extra, u32 n_lists, uint2* __restrict__ adj,
+                                                           u64* __restrict__ slots, ull* __restrict__ cursor, ull slot_cap,
+                                                           uint4* __restrict__ list_order) {
+  const u32 lid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lid >= n_lists) return;
+  const u32 x = extra[lid];
+  if (x == 0 || adj[lid].y != 0) return;
+  const ull off = atomicAdd(&cursor[0], (ull)x);
+  const ull li = atomicAdd(&cursor[1], 1ull);
+  if (off + x > slot_cap) return;  // retried by the host with the exact size
+  adj[lid] = make_uint2((u32)off, x);
+  list_order[li] = make_uint4(lid, (u32)off, x, 0u);
+  for (u32 t = 0; t < x; t++) slots[off + t] = ~0ull;
+}
+
+template <int NW, int MINB>
+static void launch_bucket_join(const JoinParams& P, u32 n_buckets, bool m32, cudaStream_t s) {
+  if (m32) {
+    CB_CUDA(cudaFuncSetAttribute(bucket_join_kernel<NW, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_SMEM));
+    bucket_join_kernel<NW, MINB, true><<<n_buckets, BJ_THREADS, BJ_SMEM, s>>>(P);
+  } else {
+    CB_CUDA(cudaFuncSetAttribute(bucket_join_kernel<NW, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_SMEM));
+    bucket_join_kernel<NW, MINB, false><<<n_buckets, BJ_THREADS, BJ_SMEM, s>>>(P);
+  }
+}
+
+__global__ void __launch_bounds__(256) make_adj_kernel(const u32* __restrict__ off, const u32* __restrict__ cnt, u32 n,
+                                                       uint2* __restrict__ adj) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) adj[i] = make_uint2(off[i], cnt[i]);
+}
+
+// CB_SORT=classic: the flat pipeline (LSD sort + group_walk + join_verify) for every input
+static bool use_bucket_path() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CB_SORT");
+    v = (e && std::string(e) == "classic") ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// node_seq is gathered by every tuple of the join (16..64-byte rows at random): while the join runs it
+// is pinned in the L2 (persisting access window on the context's stream) so that the gathers do not go
+// to HBM in 64-byte granules (ncu r01: 7.9 GB read for 2.2 GB of rows).
+static void set_l2_window(cb_ctx* c, const void* p, size_t bytes) {
+  int dev = c->cfg.device, max_win = 0, max_persist = 0;
+  cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+  if (max_win <= 0 || max_persist <= 0) return;
+  static const bool off = getenv("CB_NO_L2_WINDOW") != nullptr;
+  if (off) return;
+  const size_t carve = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaStreamAttrValue a;
+  memset(&a, 0, sizeof(a));
+  a.accessPolicyWindow.base_ptr = const_cast<void*>(p);
+  a.accessPolicyWindow.num_bytes = bytes < (size_t)max_win ? bytes : (size_t)max_win;
+  a.accessPolicyWindow.hitRatio = bytes <= carve ? 1.0f : (float)((double)carve / (double)bytes);
+  a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) cudaGetLastError();
+}
+static void clear_l2_window(cb_ctx* c) {
+  cudaStreamAttrValue a;
+  memset(&a, 0, sizeof(a));
+  a.accessPolicyWindow.num_bytes = 0;
+  a.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+  a.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+  if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) cudaGetLastError();
+  cudaCtxResetPersistingL2Cache();
+}
+
 void stage_build_overlap(cb_ctx* c) {
   cudaStream_t s = c->stream;
   const u32 nn = c->n_nodes;
@@ -634,6 +1077,18 @@ void stage_build_overlap(cb_ctx* c) {
   c->lay.ob = bits_for((u64)(L - K + 1));
   c->lay.L = L;
   const u32 n_lists = 2 * nn;
+  const u64 kmask = (2 * K == 64) ? ~0ull : ((1ull << (2 * K)) - 1);
+  bool bucket = use_bucket_path() && !(c->cfg.flags & CB_FLAG_FLAT_PIPELINE);
+  // single GPU: the tuples go straight from keygen into the hash partition, whose level-1 digit counts
+  // keygen takes while it writes
+  BucketPlan plan = make_bucket_plan(Tmax);
+  if (!distributed(c) && !plan.fits) bucket = false;  // more tuples than two scatter passes cut small enough
+  DevBuf<u32> cnt1;
+  const bool fused_count = bucket && !distributed(c);
+  if (fused_count) {
+    cnt1.alloc((size_t)1 << plan.b1, s);
+    CB_CUDA(cudaMemsetAsync(cnt1.p, 0, ((size_t)1 << plan.b1) * 4, s));
+  }
 
   // ---- keygen ----
   timer_start(c, "keygen");
@@ -646,9 +1101,9 @@ void stage_build_overlap(cb_ctx* c) {
     int cap = kNumSMs * 8 * 4;
     if (blocks > cap) blocks = cap;
     c->lc.begin("keygen");
-    CB_DISPATCH_NW(c->NW, (keygen_kernel<NW_><<<blocks, 256, 0, s>>>(c->node_seq.p, c->node_cov.p, c->node_lo, n_own, L,
-                                                                    K, W, pb, keys[0].p, vals[0].p,
-                                                                    (ull*)c->dcount.p)));
+    CB_DISPATCH_NW(c->NW, (keygen_kernel<NW_><<<blocks, 256, fused_count ? ((size_t)4 << plan.b1) : 0, s>>>(
+                              c->node_seq.p, c->node_cov.p, c->node_lo, n_own, L, K, W, pb, keys[0].p, vals[0].p,
+                              (ull*)c->dcount.p, fused_count ? cnt1.p : nullptr, plan.shift1, plan.b1)));
     c->lc.end("keygen");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
@@ -658,8 +1113,7 @@ void stage_build_overlap(cb_ctx* c) {
   // ---- shuffle replacement ----
   if (distributed(c)) {
     // partition by owner rank (one stable radix pass over the owner bits of the key), then the
-    // all-to-all that replaces the MapReduce shuffle.  Received order is (source rank, node,
-    // window), i.e. ascending (node, window): the join relies on it.
+    // all-to-all that replaces the MapReduce shuffle
     timer_start(c, "exchange_tuples");
     int w0 = 0;
     guarded(c, [&] {
@@ -697,37 +1151,17 @@ void stage_build_overlap(cb_ctx* c) {
     vals[0] = std::move(rvals);
     keys[1].alloc(Tmax ? Tmax : 1, s);
     vals[1].alloc(Tmax ? Tmax : 1, s);
-    CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_TUPLES_INVALID, 0, sizeof(u64), s));
-    if (Tmax) {
-      int blocks = div_up(Tmax, 256 * 16);
-      if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-      count_invalid_kernel<<<blocks, 256, 0, s>>>(keys[0].p, Tmax, (ull*)c->dcount.p + DC_TUPLES_INVALID);
-      c->lc.n++;
-    }
+    plan = make_bucket_plan(Tmax);
+    u64 nofit = plan.fits ? 0 : 1;
+    ex_allreduce(c, &nofit, 1, 1);  // the same pipeline on every rank
+    if (nofit) bucket = false;
     timer_stop(c, "exchange_tuples");
   }
-  timer_start(c, "sort_tuples");
-  int where = 0;
-  guarded(c, [&] { where = radix_sort(keys[0].p, keys[1].p, vals[0].p, vals[1].p, Tmax, 0, 2 * K, s, c->lc, "tuples"); });
-  timer_stop(c, "sort_tuples");
-  download_counters(c);
-  const u32 T = (u32)(Tmax - c->hcount[DC_TUPLES_INVALID]);
-  {
-    u64 tg = T;
-    ex_allreduce(c, &tg, 1, 0);
-    c->counters["tuples"] = (int64_t)tg;
-  }
-  keys[where ^ 1].release();
-  vals[where ^ 1].release();
 
-  // ---- join + verify + mirror ----
-  timer_start(c, "join_verify");
   JoinParams P;
-  P.keys = keys[where].p;
-  P.vals = vals[where].p;
-  P.T = T;
+  memset(&P, 0, sizeof(P));
   P.L = L; P.K = K; P.pb = pb;
-  P.kmask = (2 * K == 64) ? ~0ull : ((1ull << (2 * K)) - 1);
+  P.kmask = kmask;
   P.node_seq = c->node_seq.p;
   P.node_cov = c->node_cov.p;
   P.max_cov = (u32)c->gcount[DC_MAX_COV];
@@ -735,64 +1169,184 @@ void stage_build_overlap(cb_ctx* c) {
   P.up_kmer = c->cfg.up_kmer;
   P.lay = c->lay;
   P.dcount = (ull*)c->dcount.p;
-  int wblocks = div_up((size_t)T, GW_THREADS);
-  if (wblocks > kNumSMs * 8) wblocks = kNumSMs * 8;
-  if (wblocks < 1) wblocks = 1;
-  DevBuf<u32> slotcnt, off1, seg_head, ne_list, extra;
-  slotcnt.alloc((size_t)n_lists + 1, s);
-  off1.alloc((size_t)n_lists + 1, s);
-  seg_head.alloc(T ? T : 1, s);
-  ne_list.alloc((size_t)T + 1, s);
-  extra.alloc(n_lists ? n_lists : 1, s);
-  CB_CUDA(cudaMemsetAsync(slotcnt.p, 0, ((size_t)n_lists + 1) * 4, s));
-  CB_CUDA(cudaMemsetAsync(ne_list.p, 0xff, ((size_t)T + 1) * 4, s));  // terminators; node entries claim from the left
-  P.slotcnt = slotcnt.p;
-  P.seg_head = seg_head.p;
-  P.ne_list = ne_list.p;
-  c->lc.begin("group_walk");
-  group_walk_kernel<<<wblocks, GW_THREADS, 0, s>>>(P);
-  c->lc.end("group_walk");
-  c->lc.n++;
-  exclusive_scan_u32(slotcnt.p, off1.p, (size_t)n_lists + 1, s, c->lc);
-  size_t slots1 = read_u32(c, off1.p + n_lists);
-  int jgrid = div_up((size_t)T, 256);
-  if (jgrid > kNumSMs * 8) jgrid = kNumSMs * 8;
-  if (jgrid < 1) jgrid = 1;
+  c->NWo = (L - K + 15) / 16;
+  P.nwo = c->NWo;
+
+  DevBuf<u32> bstart, d_total, extra;
+  DevBuf<ull> slot_cursor;
+  DevBuf<uint2> adj;
+  DevBuf<uint4> list_order;
+  size_t n_list_order = 0;
   DevBuf<u64> slots, xbuf;
   DevBuf<u32> ovh;
-  c->NWo = (L - K + 15) / 16;
-  u64 xcap = (u64)T / 4 + 4096;
+  adj.alloc(n_lists ? n_lists : 1, s);
+  extra.alloc(n_lists ? n_lists : 1, s);
+  u32 T = 0;
+  size_t slots1 = 0;
   u64 n_x = 0;
+  int where = 0;        // which of keys[]/vals[] holds the tuples the join reads
+  bool sorted = false;  // flat path: the tuples are sorted by k-mer
+
+  timer_start(c, "sort_tuples");
+  if (bucket) {
+    bstart.alloc((size_t)plan.NB + 1, s);
+    d_total.alloc(1, s);
+    guarded(c, [&] {
+      bucket_partition(keys[0].p, vals[0].p, keys[1].p, vals[1].p, Tmax, kmask, plan, fused_count ? cnt1.p : nullptr,
+                       bstart.p, d_total.p, s, c->lc);
+    });
+    T = read_u32(c, d_total.p);
+    where = 0;
+  }
+  // the LSD sort of the flat pipeline over the first n_sort tuple slots (all-ones keys of windows that emit
+  // nothing go last and are dropped)
+  auto flat_sort = [&](size_t n_sort) {
+    guarded(c, [&] { where = radix_sort(keys[0].p, keys[1].p, vals[0].p, vals[1].p, n_sort, 0, 2 * K, s, c->lc, "tuples"); });
+    DevBuf<ull> inval;
+    inval.alloc(1, s);
+    CB_CUDA(cudaMemsetAsync(inval.p, 0, sizeof(ull), s));
+    if (n_sort) {
+      int blocks = div_up(n_sort, 256 * 16);
+      if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+      count_invalid_kernel<<<blocks, 256, 0, s>>>(keys[where].p, n_sort, inval.p);
+      c->lc.n++;
+    }
+    ull h_inval = 0;
+    CB_CUDA(cudaMemcpyAsync(&h_inval, inval.p, sizeof(ull), cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    T = (u32)(n_sort - h_inval);
+    sorted = true;
+  };
+  if (!bucket) flat_sort(Tmax);
+  timer_stop(c, "sort_tuples");
+
+  // ---- join + verify + mirror ----
+  timer_start(c, "join_verify");
+  struct L2Window {  // cleared on every way out of this function
+    cb_ctx* c;
+    ~L2Window() { clear_l2_window(c); }
+  } l2_window{c};
+  set_l2_window(c, c->node_seq.p, c->node_seq.bytes());
+  DevBuf<u32> slotcnt, off1, seg_head, ne_list;  // flat path only
+  DevBuf<u32> extra_total;                       // bucket path: slots added to the lists over the attempts
+  u64 xcap = (u64)T / 4 + 4096;
+  bool have_extra = false;
+  auto flat_prepare = [&] {  // group walk: seg_head, ne_list, list sizes
+    slotcnt.alloc((size_t)n_lists + 1, s);
+    off1.alloc((size_t)n_lists + 1, s);
+    seg_head.alloc(T ? T : 1, s);
+    ne_list.alloc((size_t)T + 1, s);
+    CB_CUDA(cudaMemsetAsync(slotcnt.p, 0, ((size_t)n_lists + 1) * 4, s));
+    CB_CUDA(cudaMemsetAsync(ne_list.p, 0xff, ((size_t)T + 1) * 4, s));  // terminators; node entries claim from the left
+    CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_HKMER, 0, sizeof(u64), s));
+    CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_UPKMER_LISTS, 0, sizeof(u64), s));
+    P.keys = keys[where].p;
+    P.vals = vals[where].p;
+    P.T = T;
+    P.slotcnt = slotcnt.p;
+    P.seg_head = seg_head.p;
+    P.ne_list = ne_list.p;
+    int wblocks = div_up((size_t)T, GW_THREADS);
+    if (wblocks > kNumSMs * 8) wblocks = kNumSMs * 8;
+    if (wblocks < 1) wblocks = 1;
+    c->lc.begin("group_walk");
+    group_walk_kernel<<<wblocks, GW_THREADS, 0, s>>>(P);
+    c->lc.end("group_walk");
+    c->lc.n++;
+    exclusive_scan_u32(slotcnt.p, off1.p, (size_t)n_lists + 1, s, c->lc);
+    slots1 = read_u32(c, off1.p + n_lists);
+  };
+  if (bucket) slots1 = (size_t)T * 2 + (size_t)T / 8 + 65536;  // two node entries per group is the rule; retried if short
+  else flat_prepare();
   for (int attempt = 0;; attempt++) {
+    if (slots1 >= (1ull << 32)) throw Error(CB_E_CAPACITY, "more than 2^32 adjacency slots per context");
     slots.alloc(slots1 ? slots1 : 1, s);
-    CB_CUDA(cudaMemsetAsync(slots.p, 0xff, (slots1 ? slots1 : 1) * sizeof(u64), s));  // empty slots read as ~0
     xbuf.alloc(xcap, s);
     ovh.alloc((slots1 ? slots1 : 1) * (size_t)c->NWo, s);
-    P.off1 = off1.p;
     P.slots = slots.p;
     P.ovh = ovh.p;
-    P.nwo = c->NWo;
     P.xbuf = xbuf.p;
     P.xcap = xcap;
-    // (DC_HKMER and DC_UPKMER_LISTS were counted by group_walk_kernel and stay)
+    // (DC_HKMER and DC_UPKMER_LISTS of the flat path were counted by group_walk_kernel and stay)
     CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGES_RAW, 0, (DC_UPKMER_LISTS - DC_EDGES_RAW) * sizeof(u64), s));
     CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_MAX_LIST, 0, sizeof(u64), s));
-    c->lc.begin("join_verify");
-    {
-      static const int minb = getenv("CB_JOIN_MINB") ? atoi(getenv("CB_JOIN_MINB")) : 4;
-      if (c->NW == 2 && minb == 4) join_verify_kernel<2, 4><<<jgrid, 256, 0, s>>>(P);
-      else if (c->NW == 2 && minb == 3) join_verify_kernel<2, 3><<<jgrid, 256, 0, s>>>(P);
-      else CB_DISPATCH_NW(c->NW, (join_verify_kernel<NW_, 2><<<jgrid, 256, 0, s>>>(P)));
+    if (bucket) {
+      slot_cursor.alloc(2, s);
+      list_order.alloc(n_lists ? n_lists : 1, s);
+      CB_CUDA(cudaMemsetAsync(slot_cursor.p, 0, 2 * sizeof(ull), s));
+      CB_CUDA(cudaMemsetAsync(adj.p, 0, (size_t)(n_lists ? n_lists : 1) * sizeof(uint2), s));
+      CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_HKMER, 0, sizeof(u64), s));
+      CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_UPKMER_LISTS, 0, sizeof(u64), s));
+      CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_BUCKET_OVER, 0, sizeof(u64), s));
+      P.keys = keys[where].p;
+      P.vals = vals[where].p;
+      P.T = T;
+      P.bstart = bstart.p;
+      P.lshift = plan.lshift;
+      P.adj = adj.p;
+      P.extra = have_extra ? extra_total.p : nullptr;
+      P.slot_cursor = slot_cursor.p;
+      P.slot_cap = slots1;
+      P.list_order = list_order.p;
+      c->lc.begin("bucket_join");
+      const bool m32 = nbits + pb + 1 <= 32;  // node | window | dir fit the 32-bit payload
+      if (c->NW == 2) launch_bucket_join<2, 4>(P, plan.NB, m32, s);
+      else CB_DISPATCH_NW(c->NW, (launch_bucket_join<NW_, 2>(P, plan.NB, m32, s)));
+      c->lc.end("bucket_join");
+      c->lc.n++;
+      if (have_extra && n_lists) {
+        orphan_lists_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(extra_total.p, n_lists, adj.p, slots.p, slot_cursor.p,
+                                                                        (ull)slots1, list_order.p);
+        c->lc.n++;
+      }
+      CB_CUDA(cudaGetLastError());
+      download_counters(c);
+      ull cur[2] = {0, 0};
+      CB_CUDA(cudaMemcpyAsync(cur, slot_cursor.p, 2 * sizeof(ull), cudaMemcpyDeviceToHost, s));
+      CB_CUDA(cudaStreamSynchronize(s));
+      const ull used = cur[0];
+      n_list_order = (size_t)cur[1];
+      u64 flags[2] = {c->hcount[DC_BUCKET_OVER] ? 1ull : 0ull, used > slots1 ? 1ull : 0ull};
+      ex_allreduce(c, flags, 2, 1);  // every rank takes the same branch: collectives follow
+      if (flags[0]) {
+        // a bucket does not fit the kernel (one k-mer with thousands of tuples, or a degenerate hash
+        // distribution): the flat pipeline takes over for this input
+        bucket = false;
+        flat_sort(T);  // the partition has compacted the T valid tuples to the front of keys[0] / vals[0]
+        flat_prepare();
+        attempt = -1;
+        continue;
+      }
+      if (flags[1]) {  // more node entries per group than expected: the exact need is known now
+        if (attempt >= 4) throw Error(CB_E_CAPACITY, "adjacency slot capacity");
+        if (used > slots1) slots1 = (size_t)used + 1024;
+        continue;
+      }
+      slots1 = (size_t)used;
+    } else {
+      CB_CUDA(cudaMemsetAsync(slots.p, 0xff, (slots1 ? slots1 : 1) * sizeof(u64), s));  // empty slots read as ~0
+      P.off1 = off1.p;
+      make_adj_kernel<<<div_up((size_t)(n_lists ? n_lists : 1), 256), 256, 0, s>>>(off1.p, slotcnt.p, n_lists, adj.p);
+      int jgrid = div_up((size_t)T, 256);
+      if (jgrid > kNumSMs * 8) jgrid = kNumSMs * 8;
+      if (jgrid < 1) jgrid = 1;
+      c->lc.begin("join_verify");
+      {
+        static const int minb = getenv("CB_JOIN_MINB") ? atoi(getenv("CB_JOIN_MINB")) : 4;
+        if (c->NW == 2 && minb == 4) join_verify_kernel<2, 4><<<jgrid, 256, 0, s>>>(P);
+        else if (c->NW == 2 && minb == 3) join_verify_kernel<2, 3><<<jgrid, 256, 0, s>>>(P);
+        else CB_DISPATCH_NW(c->NW, (join_verify_kernel<NW_, 2><<<jgrid, 256, 0, s>>>(P)));
+      }
+      c->lc.end("join_verify");
+      c->lc.n += 2;
+      CB_CUDA(cudaGetLastError());
+      download_counters(c);
     }
-    c->lc.end("join_verify");
-    c->lc.n++;
-    CB_CUDA(cudaGetLastError());
-    download_counters(c);
     n_x = c->hcount[DC_EDGES_RAW];
     u64 x_over = n_x > xcap ? 1 : 0;
     ex_allreduce(c, &x_over, 1, 1);  // every rank must take the same branch: collectives follow
     if (x_over) {  // side buffer too small: its exact size is known now
-      if (attempt >= 3) throw Error(CB_E_CAPACITY, "side buffer overflow");
+      if (attempt >= 4) throw Error(CB_E_CAPACITY, "side buffer overflow");
       if (n_x > xcap) xcap = n_x;
       continue;
     }
@@ -818,7 +1372,7 @@ void stage_build_overlap(cb_ctx* c) {
       int blocks = div_up(n_xin, 256);
       if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
       c->lc.begin("side_insert");
-      CB_DISPATCH_NW(c->NW, (side_insert_kernel<NW_><<<blocks, 256, 0, s>>>(xin, n_xin, c->lay, off1.p, slots.p, extra.p,
+      CB_DISPATCH_NW(c->NW, (side_insert_kernel<NW_><<<blocks, 256, 0, s>>>(xin, n_xin, c->lay, adj.p, slots.p, extra.p,
                                                                            (ull*)c->dcount.p, c->node_seq.p, ovh.p,
                                                                            c->NWo, L)));
       c->lc.end("side_insert");
@@ -829,16 +1383,33 @@ void stage_build_overlap(cb_ctx* c) {
     u64 slot_over = c->hcount[DC_MAX_LIST];
     ex_allreduce(c, &slot_over, 1, 0);
     if (slot_over == 0) break;
-    if (attempt >= 3) throw Error(CB_E_CAPACITY, "adjacency slot overflow");
+    if (attempt >= 4) throw Error(CB_E_CAPACITY, "adjacency slot overflow");
     // enlarge the slot ranges of the lists that overflowed and run the join again
-    add_u32_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(slotcnt.p, extra.p, n_lists);
-    c->lc.n++;
-    exclusive_scan_u32(slotcnt.p, off1.p, (size_t)n_lists + 1, s, c->lc);
-    slots1 = read_u32(c, off1.p + n_lists);
+    if (bucket) {
+      if (!have_extra) {
+        extra_total.alloc(n_lists ? n_lists : 1, s);
+        CB_CUDA(cudaMemsetAsync(extra_total.p, 0, (size_t)(n_lists ? n_lists : 1) * 4, s));
+        have_extra = true;
+      }
+      add_u32_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(extra_total.p, extra.p, n_lists);
+      c->lc.n++;
+      slots1 += (size_t)c->hcount[DC_MAX_LIST] + 1024;
+    } else {
+      add_u32_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(slotcnt.p, extra.p, n_lists);
+      c->lc.n++;
+      exclusive_scan_u32(slotcnt.p, off1.p, (size_t)n_lists + 1, s, c->lc);
+      slots1 = read_u32(c, off1.p + n_lists);
+    }
   }
   timer_stop(c, "join_verify");
-  keys[where].release();
-  vals[where].release();
+  {
+    u64 tg = T;
+    ex_allreduce(c, &tg, 1, 0);
+    c->counters["tuples"] = (int64_t)tg;
+  }
+  keys[0].release(); keys[1].release();
+  vals[0].release(); vals[1].release();
+  (void)sorted;
 
   // BuildHighKmerList's counter (poly-A/T k-mer handled through its global weight)
   reduce_counters(c);
@@ -848,6 +1419,7 @@ void stage_build_overlap(cb_ctx* c) {
   c->counters["side_buffer_edges"] = (int64_t)c->gcount[DC_EDGES_RAW];
   c->counters["upkmer_truncated_lists"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
   c->counters["order_dependent"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
+  c->counters["bucket_path"] = bucket ? 1 : 0;
   if (c->gcount[DC_UPKMER_LISTS] > 0)
     throw Error(CB_E_UNSUPPORTED,
                 "a k-mer group with a node entry holds more than -kmerup tuples: the reference truncates its "
@@ -858,7 +1430,9 @@ void stage_build_overlap(cb_ctx* c) {
                 "ill-defined for it, parity undefined");
 
   // checkpoint A: the slot array is the adjacency structure
-  c->adj_off = std::move(off1);
+  c->adj = std::move(adj);
+  if (bucket) { c->list_order = std::move(list_order); c->n_list_order = n_list_order; }
+  else { c->list_order.release(); c->n_list_order = 0; }
   c->slots = slots1;
   c->ckA.keys = std::move(slots);
   c->ovh = std::move(ovh);

@@ -10,7 +10,7 @@
 //
 // The graph of checkpoint A is symmetric (S u mirror(S)), so the neighbour messages each
 // reducer rebuilds its lists from (DARKMSG / OVALMSG, sent by the mirror edge) are exactly the
-// node's own adjacency list: the records in keys[adj_off[lid] .. adj_off[lid+1]), lid = 2a + x, in
+// node's own adjacency list: the records in keys[adj[lid].x .. adj[lid].x + adj[lid].y), lid = 2a + x, in
 // no particular order, empty slots ~0.  The overhang of an entry is b^y[ov:], the bases of the
 // neighbour that extend past the node; the join stored it next to the record (ovh[slot]).
 //
@@ -28,8 +28,8 @@
 namespace cb {
 
 struct StringParams {
-  const u64* edges;    // slot array; list lid owns [adj_off[lid], adj_off[lid+1]); ~0 = empty slot
-  const u32* adj_off;  // [n_lists + 1]
+  const u64* edges;    // slot array; list lid owns [adj[lid].x, adj[lid].x + adj[lid].y); ~0 = empty slot
+  const uint2* adj;    // [n_lists] (first slot, slots) of list lid
   u32 n_lists;         // 2 * n_nodes
   size_t slots;
   EdgeLayout lay;
@@ -43,10 +43,10 @@ struct StringParams {
   uint8_t* removed;    // cut output, per slot
   uint8_t* kept;       // tr output, per slot
   uint8_t* list_flag;  // per list: 1 consistent, 0 not, dirty bits 2 / 4 (lost an entry in cut round 1 / 2)
-  uint8_t* ovmax;      // per list, from consistency_kernel: the maximal overlap of the list (0: empty list)
-  u32* lmax;           // per list: [2*lid], [2*lid+1] = (nbr | y << 31) of the first two records of maximal
-                       // overlap (~0: none); lnmax[lid] = how many there are (saturating at 255)
-  uint8_t* lnmax;
+  uint4* lsumm;        // per list, from consistency_kernel, ONE 16-byte record (lists lie in bucket order in HBM, so
+                       // per-list results are scattered writes: one store instead of three): .x, .y = (nbr | y << 31) of
+                       // the first two records of maximal overlap (~0: none), .z = maximal overlap | count of such
+                       // records (saturating at 255) << 8
   const uint8_t* lsum; // per list, all ranks: ovmax if the list is consistent and untouched by the cut rounds
                        // (TransitiveReduction keeps exactly its records of that overlap), else 0
   const u32* work;     // work list of list ids (literal kernels)
@@ -84,7 +84,7 @@ __device__ __forceinline__ int base_at(const u64 (&h)[NW], int j) {
 // tr_final_kernel: 2.71 vs 1.87 ms -- the early exit matters more than the loads in flight)
 __device__ __forceinline__ long long find_edge(const StringParams& P, u64 key) {
   const u32 list = P.lay.list(key);
-  const u32 lo = P.adj_off[list], hi = P.adj_off[list + 1];
+  const uint2 lr_ = P.adj[list]; const u32 lo = lr_.x, hi = lr_.x + lr_.y;
   for (u32 t = lo; t < hi; t++)
     if (P.edges[t] == key) return (long long)t;
   return -1;
@@ -103,10 +103,19 @@ constexpr int ST_WARPS = 8;
 template <int NW>
 __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* __restrict__ work_out,
                                                           u32* __restrict__ n_work_out, int force_slow,
-                                                          const u32* __restrict__ lists, u32 n_iter) {
+                                                          const u32* __restrict__ lists,
+                                                          const uint4* __restrict__ lists4, u32 n_iter) {
   for (u32 it = blockIdx.x * blockDim.x + threadIdx.x; it < n_iter; it += gridDim.x * blockDim.x) {
-    const u32 lid = lists ? lists[it] : it;
-    const u32 lo = P.adj_off[lid], hi = P.adj_off[lid + 1];
+    // lists4 (bucket path): (list, first slot, slots) in slot order -- no gather of adj[]
+    u32 lid, lo, hi;
+    if (lists4) {
+      const uint4 q = lists4[it];
+      lid = q.x; lo = q.y; hi = q.y + q.z;
+    } else {
+      lid = lists ? lists[it] : it;
+      const uint2 lr_ = P.adj[lid];
+      lo = lr_.x; hi = lr_.x + lr_.y;
+    }
     // ONE pass over the list: the overhangs nest iff every record nests with the longest overhang
     // seen so far (if the new one is longer it must extend that one, and then everything before it
     // is a prefix of the new one as well)
@@ -141,11 +150,8 @@ __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* _
         }
       }
     }
-    if (n == 0) continue;
-    P.ovmax[lid] = (uint8_t)ovmax;
-    P.lmax[2 * (size_t)lid] = m0;
-    P.lmax[2 * (size_t)lid + 1] = m1;
-    P.lnmax[lid] = (uint8_t)(nmax > 255 ? 255 : nmax);
+    if (n == 0) { P.lsumm[lid] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u); continue; }
+    P.lsumm[lid] = make_uint4(m0, m1, ovmax | ((nmax > 255 ? 255u : nmax) << 8), 0u);
     if (n > 1 && (bad || force_slow)) {  // only this thread writes the list's flag here
       P.list_flag[lid] = 0;
       work_out[atomicAdd(n_work_out, 1u)] = lid;
@@ -154,11 +160,11 @@ __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* _
 }
 
 // non-empty lists in ascending order of their id within a warp (warp-aggregated append)
-__global__ void __launch_bounds__(256) own_lists_kernel(const u32* __restrict__ adj_off, u32 n_lists,
+__global__ void __launch_bounds__(256) own_lists_kernel(const uint2* __restrict__ adj, u32 n_lists,
                                                         u32* __restrict__ out, u32* __restrict__ n_out) {
   const u32 lid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const bool have = lid < n_lists && adj_off[lid + 1] > adj_off[lid];
+  const bool have = lid < n_lists && adj[lid].y > 0;
   const u32 bal = __ballot_sync(0xffffffffu, have);
   if (bal == 0) return;
   u32 base = 0;
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
   const int L = P.L;
   for (u32 wi = warp_global; wi < P.n_work; wi += nwarps) {
     const u32 list = P.work[wi];
-    const u32 lo = P.adj_off[list], hi = P.adj_off[list + 1];
+    const uint2 lr_ = P.adj[list]; const u32 lo = lr_.x, hi = lr_.x + lr_.y;
     u32 n = 0;
     if (P.check_consistency) {
       const bool cons = list_consistent_warp<NW>(P, lo, hi, lane, n);
@@ -360,7 +366,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) cut_kernel(StringParams P) {
 // that lost a record in this round are visited (one warp per list); the record and its slot are
 // logged so that 01-overlap can be restored for an export.  Clears the flags it consumes.
 __global__ void __launch_bounds__(256) remove_flagged_kernel(u64* __restrict__ keys, uint8_t* __restrict__ drop,
-                                                             const u32* __restrict__ adj_off,
+                                                             const uint2* __restrict__ adj,
                                                              const u32* __restrict__ lists, u32 n_lists_dirty,
                                                              u64* __restrict__ log, u32* __restrict__ n_log, u32 log_cap,
                                                              ull* __restrict__ dcount) {
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(256) remove_flagged_kernel(u64* __restrict__ k
   u32 removed = 0;
   for (u32 wi = warp_global; wi < n_lists_dirty; wi += nwarps) {
     const u32 lid = lists[wi];
-    const u32 lo = adj_off[lid], hi = adj_off[lid + 1];
+    const uint2 lr_ = adj[lid]; const u32 lo = lr_.x, hi = lr_.x + lr_.y;
     for (u32 t = lo + lane; t < hi; t += 32)
       if (drop[t]) {
         const u32 at = atomicAdd(n_log, 1u);
@@ -397,15 +403,15 @@ __global__ void __launch_bounds__(256) restore_log_kernel(u64* __restrict__ keys
 // lists whose flag is not "consistent" -> work list for the literal kernel; every list's summary
 // byte for the final pass (lsum)
 __global__ void __launch_bounds__(256) tr_worklist_kernel(const uint8_t* __restrict__ list_flag,
-                                                          const u32* __restrict__ adj_off,
-                                                          const uint8_t* __restrict__ ovmax, u32 n_lists,
+                                                          const uint2* __restrict__ adj,
+                                                          const uint4* __restrict__ lsumm, u32 n_lists,
                                                           u32* __restrict__ work, u32* __restrict__ n_work,
                                                           uint8_t* __restrict__ lsum) {
   u32 lid = blockIdx.x * blockDim.x + threadIdx.x;
   if (lid >= n_lists) return;
-  const bool nonempty = adj_off[lid + 1] > adj_off[lid];
+  const bool nonempty = adj[lid].y > 0;
   const bool fast = list_flag[lid] == 1;
-  lsum[lid] = (nonempty && fast) ? ovmax[lid] : (uint8_t)0;
+  lsum[lid] = (nonempty && fast) ? (uint8_t)(lsumm[lid].z & 0xffu) : (uint8_t)0;
   if (nonempty && !fast) work[atomicAdd(n_work, 1u)] = lid;
 }
 
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) tr_kernel(StringParams P) {
   u32 trans = 0, contained = 0;
   for (u32 wi = warp_global; wi < P.n_work; wi += nwarps) {
     const u32 list = P.work[wi];
-    const u32 lo = P.adj_off[list], hi = P.adj_off[list + 1];
+    const uint2 lr_ = P.adj[list]; const u32 lo = lr_.x, hi = lr_.x + lr_.y;
     if (lane == 0) atomicAdd(&P.dcount[DC_SLOW_LISTS], 1ull);
     u32 nk = 0;
     int level = L + 1;  // overlap levels strictly below `level` are still to do
@@ -535,10 +541,10 @@ __global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __re
         contained += (int)ov == P.L;  // TransitiveReduction.java:319-323 (equal-length reads)
         if (!kept_here) {
           const u32 nby = P.lay.nbr(k) | (P.lay.y(k) << 31);
-          const uint2 mm = *reinterpret_cast<const uint2*>(P.lmax + 2 * (size_t)lid);
+          const uint4 mm = P.lsumm[lid];
           bool step2 = mm.x == nby || mm.y == nby;
-          if (!step2 && P.lnmax[lid] > 2) {
-            const u32 lo = P.adj_off[lid], hi = P.adj_off[lid + 1];
+          if (!step2 && ((mm.z >> 8) & 0xffu) > 2) {
+            const uint2 lr_ = P.adj[lid]; const u32 lo = lr_.x, hi = lr_.x + lr_.y;
             for (u32 q = lo; q < hi && !step2; q++) {
               const u64 kq = P.edges[q];
               if (kq != ~0ull && P.lay.ov(kq) == om && (P.lay.nbr(kq) | (P.lay.y(kq) << 31)) == nby) step2 = true;
@@ -612,7 +618,7 @@ __global__ void __launch_bounds__(256) tr_votes_kernel(StringParams P) {
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
   for (u32 wi = warp_global; wi < P.n_work; wi += nwarps) {
     const u32 list = P.work[wi];
-    const u32 lo = P.adj_off[list], hi = P.adj_off[list + 1];
+    const uint2 lr_ = P.adj[list]; const u32 lo = lr_.x, hi = lr_.x + lr_.y;
     for (u32 t = lo + lane; t < hi; t += 32)
       if (P.kept[t] & 1) {
         u32 ri = atomicAdd(P.n_req, 1u);
@@ -650,7 +656,7 @@ __global__ void __launch_bounds__(256) key_owner_s_kernel(const u64* __restrict_
 static StringParams make_params(cb_ctx* c, const u64* keys) {
   StringParams P;
   P.edges = keys;
-  P.adj_off = c->adj_off.p;
+  P.adj = c->adj.p;
   P.n_lists = 2 * c->n_nodes;
   P.slots = c->slots;
   P.lay = c->lay;
@@ -666,9 +672,7 @@ static StringParams make_params(cb_ctx* c, const u64* keys) {
   P.removed = nullptr;
   P.kept = nullptr;
   P.list_flag = c->list_flag.p;
-  P.ovmax = nullptr;
-  P.lmax = nullptr;
-  P.lnmax = nullptr;
+  P.lsumm = nullptr;
   P.lsum = nullptr;
   P.work = nullptr;
   P.n_work = 0;
@@ -748,13 +752,10 @@ void stage_string_graph(cb_ctx* c) {
   DevBuf<uint8_t> flags;  // per slot: "removed" during the cut rounds, then "kept" for TR
   flags.alloc(slots, s);
   CB_CUDA(cudaMemsetAsync(flags.p, 0, slots, s));
-  DevBuf<uint8_t> ovmax, lsum, lnmax;  // per list: maximal overlap / summary byte of the final pass / #maximal records
-  DevBuf<u32> lmax;                    // per list: the first two records of maximal overlap
-  ovmax.alloc(nl, s);
+  DevBuf<uint8_t> lsum;   // per list: summary byte of the final pass
+  DevBuf<uint4> lsumm;    // per list: maximal overlap, its first two records and their number
   lsum.alloc(nl, s);
-  lnmax.alloc(nl, s);
-  lmax.alloc(2 * nl, s);
-  CB_CUDA(cudaMemsetAsync(ovmax.p, 0, nl, s));
+  lsumm.alloc(nl, s);
   DevBuf<u64> req;  // multi-GPU: mirror keys to act on at their owner
   if (dist) req.alloc(slots, s);
 
@@ -772,14 +773,16 @@ void stage_string_graph(cb_ctx* c) {
   int64_t e1 = 0, e2 = 0;
   {
     StringParams P = make_params(c, cur_keys);
-    P.ovmax = ovmax.p;
-    P.lmax = lmax.p;
-    P.lnmax = lnmax.p;
+    P.lsumm = lsumm.p;
     if (c->ckA.n) {
       const u32* lists = nullptr;
+      const uint4* lists4 = nullptr;
       u32 n_iter = n_lists;
-      if (dist) {  // workB is free until the first cut round writes its dirty list
-        own_lists_kernel<<<div_up((size_t)nl, 256), 256, 0, s>>>(c->adj_off.p, n_lists, workB.p, nwork.p + 6);
+      if (c->n_list_order) {  // bucket path: the lists that own slots, in slot order (coalesced list reads)
+        lists4 = c->list_order.p;
+        n_iter = (u32)c->n_list_order;
+      } else if (dist) {  // workB is free until the first cut round writes its dirty list
+        own_lists_kernel<<<div_up((size_t)nl, 256), 256, 0, s>>>(c->adj.p, n_lists, workB.p, nwork.p + 6);
         c->lc.n++;
         n_iter = read_u32s(c, nwork.p + 6);
         lists = workB.p;
@@ -787,7 +790,7 @@ void stage_string_graph(cb_ctx* c) {
       c->lc.begin("consistency");
       if (n_iter)
         CB_DISPATCH_NW(c->NW, (consistency_kernel<NW_><<<min(div_up((size_t)n_iter, 256), kNumSMs * 16), 256, 0, s>>>(
-                                  P, workA.p, nwork.p + 0, c->cfg.majority < 1.0f ? 0 : 1, lists, n_iter)));
+                                  P, workA.p, nwork.p + 0, c->cfg.majority < 1.0f ? 0 : 1, lists, lists4, n_iter)));
       c->lc.end("consistency");
       c->lc.n++;
       CB_CUDA(cudaGetLastError());
@@ -858,7 +861,7 @@ void stage_string_graph(cb_ctx* c) {
       }
       CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGES_C, 0, sizeof(u64), s));
       if (nd) {
-        remove_flagged_kernel<<<warp_grid(nd), ST_WARPS * 32, 0, s>>>(cur_keys, flags.p, c->adj_off.p, dirty, nd,
+        remove_flagged_kernel<<<warp_grid(nd), ST_WARPS * 32, 0, s>>>(cur_keys, flags.p, c->adj.p, dirty, nd,
                                                                      c->cut_log.p, nwork.p + 7, log_cap,
                                                                      (ull*)c->dcount.p);
         c->lc.n++;
@@ -891,13 +894,11 @@ void stage_string_graph(cb_ctx* c) {
     // `flags` is all zero again here (remove_flagged_kernel clears what it consumed)
     StringParams P = make_params(c, cur_keys);
     P.kept = flags.p;
-    P.ovmax = ovmax.p;
-    P.lmax = lmax.p;
-    P.lnmax = lnmax.p;
+    P.lsumm = lsumm.p;
     P.lsum = lsum.p;
     // literal path first: lists that are inconsistent or lost an entry in a cut round
     CB_CUDA(cudaMemsetAsync(nwork.p + 3, 0, 4, s));
-    tr_worklist_kernel<<<div_up((size_t)nl, 256), 256, 0, s>>>(c->list_flag.p, c->adj_off.p, ovmax.p, n_lists,
+    tr_worklist_kernel<<<div_up((size_t)nl, 256), 256, 0, s>>>(c->list_flag.p, c->adj.p, lsumm.p, n_lists,
                                                               workA.p, nwork.p + 3, lsum.p);
     c->lc.n++;
     u32 n_slow = read_u32s(c, nwork.p + 3);

@@ -72,8 +72,14 @@ typedef struct cb_config {
   int32_t device;      /* CUDA device ordinal                                          */
   int32_t rank;        /* this process' shard index   (0 for a single GPU)             */
   int32_t world;       /* number of shards / GPUs     (1 for a single GPU)             */
-  int32_t reserved[5];
+  int32_t flags;       /* CB_FLAG_* (0 = defaults)                                     */
+  int32_t reserved[4];
 } cb_config;
+
+/* cb_config.flags.  CB_FLAG_FLAT_PIPELINE: use the flat shuffle replacement (LSD radix sort of the
+ * k-mer tuples + flat join) for every input instead of the hash-bucket path; the library falls back
+ * to it on its own when a hash bucket does not fit the bucket kernel.  Results are identical. */
+#define CB_FLAG_FLAT_PIPELINE 1
 
 /* One directed adjacency entry: the last `ov` bases of read `node` in orientation x equal the
  * first `ov` bases of read `nbr` in orientation y; type = 0 ff, 1 fr, 2 rf, 3 rr (Node.java:78).

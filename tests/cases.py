@@ -95,6 +95,17 @@ def all_cases():
     return cases
 
 
+def huge_group_case():
+    """One k-mer in the interior of 2500 reads (a group larger than a hash bucket of the bucket kernel holds:
+    the library must fall back to the flat pipeline on its own) plus node entries of that group.  -kmerup is
+    raised so that the input stays inside the contract.  Returns (sfa, k, readlen, up_kmer)."""
+    rep = rand_dna(21, 44)
+    reads = [(f"i{n}", rand_dna(7, 11000 + n) + rep + rand_dna(8, 14000 + n)) for n in range(2500)]
+    reads += [(f"p{n}", rep + rand_dna(15, 17000 + n)) for n in range(3)]
+    reads += [(f"s{n}", rand_dna(15, 18000 + n) + rep) for n in range(3)]
+    return sfa(reads), 21, 36, 100000
+
+
 def upkmer_case():
     """A k-mer group that has node entries and MORE tuples than a (small) -kmerup, while BuildHighKmerList's
     weighted count over windows [0, L-K) stays below it (the last-window tuples are not counted there,

@@ -97,6 +97,29 @@ def test_error_codes_for_bad_input():
     g2.close()
 
 
+def test_bucket_overflow_falls_back_to_flat_pipeline():
+    """A k-mer group larger than a hash bucket of the bucket kernel: the flat pipeline takes over, same result."""
+    from cases import huge_group_case
+    buf, k, L, up = huge_group_case()
+    r = run_oracle(buf, k, L, up_kmer=up)
+    g = run_gpu(buf, k, L, up_kmer=up)
+    assert g.counter("bucket_path") == 0
+    assert compare(g, r, "huge_group") == []
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["tiling_both_strands", "branch", "many_branches", "long_group", "periodic", "prefix_rc_suffix"])
+def test_flat_pipeline_flag_gives_the_same_graph(name):
+    """CB_FLAG_FLAT_PIPELINE (LSD sort + flat join) and the default hash-bucket path agree with the oracle."""
+    buf, k, L = CASES[name]
+    r = run_oracle(buf, k, L)
+    for flat in (True, False):
+        g = run_gpu(buf, k, L, flat_pipeline=flat)
+        assert g.counter("bucket_path") == (0 if flat else 1)
+        assert compare(g, r, f"{name} flat={flat}") == []
+        g.close()
+
+
 def test_upkmer_truncation_is_refused_not_approximated():
     """MatchPrefix.java:366-368 keeps the first -kmerup entries of a candidate list in Hadoop's (unspecified)
     value order.  The oracle reports the list as truncated / order dependent; the CUDA path must refuse the

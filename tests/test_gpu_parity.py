@@ -29,9 +29,11 @@ def test_ec10k_config1_parity_and_golden(ec10k_sfa, ec10k_golden):
 
 @pytest.mark.parametrize("name,genome", [("cfg2_50k", 20_000), ("cfg3_50k", 20_000), ("cfg5_50k", 20_000)])
 def test_synthetic_configs_parity(name, genome):
-    """Reduced-genome versions of BASELINE configs 2, 3 and 5 (same read length, coverage, k)."""
+    """Reduced-genome versions of BASELINE configs 2, 3 and 5 (same read length, coverage, k); the default
+    hash-bucket path and the flat pipeline (CB_FLAG_FLAT_PIPELINE)."""
     sfa, meta = _synth(name, genome)
     r = run_oracle(sfa, meta["k"], meta["readlen"])
-    g = run_gpu(sfa, meta["k"], meta["readlen"])
-    assert compare(g, r, name) == []
-    g.close()
+    for flat in (False, True):
+        g = run_gpu(sfa, meta["k"], meta["readlen"], flat_pipeline=flat)
+        assert compare(g, r, f"{name} flat={flat}") == []
+        g.close()
