@@ -193,7 +193,11 @@ def bench_reference(args):
     meta = dict(genome=args.genome or G, readlen=L, coverage=cov, both_strands=both, k=k)
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, args.ref_threads or cores, 32))
-    sample_g = cpu_sample_genome(meta, target_reads=args.ref_sample_reads)
+    # every step is a bounded sample sized so that the whole (warm-up + steps) run ends within a few minutes:
+    # the port does about 14 k reads/s per thread on this shape
+    per_step_s = 170.0 / max(1, args.steps + args.warmup)
+    sample_reads = args.ref_sample_reads or int(min(250_000, max(20_000, per_step_s * 14_000)))
+    sample_g = cpu_sample_genome(meta, target_reads=sample_reads)
     samples = []
     for t in range(threads):  # one independent sample (own genome seed) per host thread
         sfa, m = make_workload(name, genome=sample_g, seed_shift=1000 + t)
@@ -214,7 +218,7 @@ def bench_reference(args):
             th.join()
         return time.perf_counter() - t0, sum(r[1] for r in res)
 
-    for _ in range(args.warmup if args.warmup < 1 else 1):
+    for _ in range(args.warmup):
         step()
     times, edges = [], 0
     for _ in range(args.steps):
@@ -242,10 +246,146 @@ def bench_reference(args):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+
+PARITY_COUNTERS = ["reads_good", "nodes", "contained", "tuples", "edges_overlap", "edges_chl2", "edges_re", "trans_edge",
+                   "edge_removal_1", "edge_removal_2"]
+
+
+def checkpoint_digest(g):
+    """(rows of the three checkpoints, node table, counters) of a finished context"""
+    return dict(a=g.edge_rows(1), c=g.edge_rows(2), b=g.edge_rows(3), nodes=g.nodes(),
+                counters=[g.counter(x) for x in PARITY_COUNTERS])
+
+
+def sharded_parity(name, world, rank, local_rank, transport, genome):
+    """N > 1, before the timed loop: a reduced genome of the same shape runs sharded over the SAME transport the
+    timed run uses (native NCCL by default) and, on rank 0, on one context; the union of the shards' checkpoints,
+    the node table and the counters must be identical.  Returns the "parity" object of the JSON line (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    from cloudbrush_b200 import BrushConfig, BrushGpu, synth
+    from cloudbrush_b200.dist import TorchExchange, shard_lines
+    buf, m = synth.make_config(name, scale_genome=genome)
+    sfa = bytes(buf)
+    g = BrushGpu(BrushConfig(k=m["k"], readlen=m["readlen"], device=local_rank, rank=rank, world=world))
+    if transport == "nccl":
+        g.init_nccl()
+    else:
+        g.set_exchange(TorchExchange(device=torch.device("cuda", local_rank)))
+    g.load_sfa_buffer(shard_lines(sfa, rank, world))
+    g.run()
+    mine = checkpoint_digest(g)
+    g.close()
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    res = None
+    if rank == 0:
+        s1 = BrushGpu(BrushConfig(k=m["k"], readlen=m["readlen"], device=local_rank))
+        s1.load_sfa_buffer(sfa)
+        s1.run()
+        one = checkpoint_digest(s1)
+        s1.close()
+        bad = []
+        for key in ("a", "c", "b"):
+            got = np.concatenate([q[key] for q in parts])
+            got = got[np.lexsort((got[:, 3], got[:, 2], got[:, 1], got[:, 0]))]
+            if not np.array_equal(got, one[key]):
+                bad.append(f"checkpoint {key}: {len(got)} vs {len(one[key])} edges")
+        if not np.array_equal(np.concatenate([q["nodes"] for q in parts]), one["nodes"]):
+            bad.append("node table")
+        for r_, q in enumerate(parts):
+            if q["counters"] != one["counters"]:
+                bad.append(f"counters of rank {r_}")
+        res = {"world": world, "ok": not bad, "transport": transport, "against": "one context on rank 0",
+               "input": f"{name} shape, {genome} bp genome, {m['n_reads_total']} reads",
+               "edges_overlap": int(len(one["a"])), "edges_re": int(len(one["b"])), "nodes": int(len(one["nodes"])),
+               "differences": bad}
+    flag = [res["ok"] if rank == 0 else None]
+    dist.broadcast_object_list(flag, src=0)
+    if not flag[0]:
+        if rank == 0:
+            log("PARITY FAILURE (sharded run differs from one context): " + "; ".join(res["differences"]))
+        raise SystemExit(3)
+    return res
+
+
+def oracle_parity(sfa_bytes_, k, L, device):
+    """N = 1: the sample the cpu_baseline leg times on the oracle also runs through the C ABI on the GPU, and the
+    node set, the three checkpoints and the driver-visible counters are compared."""
+    from cloudbrush_b200 import BrushConfig, BrushGpu
+    from oracle import oracle as O
+    t = time.perf_counter()
+    r = O.OracleRun(sfa_bytes_, k, L)
+    dt = time.perf_counter() - t
+    if r.error:
+        raise RuntimeError(r.error)
+    g = BrushGpu(BrushConfig(k=k, readlen=L, device=device))
+    g.load_sfa_buffer(sfa_bytes_)
+    g.run()
+    bad = []
+    line, cov, _ = r.nodes(O.CK_PREPROCESS)
+    gn = g.nodes()
+    if len(gn) != len(line) or not np.array_equal(gn["line"].astype(np.int64), line) or \
+            not np.array_equal(gn["cov"].astype(np.int64), cov.astype(np.int64)):
+        bad.append("node table")
+    n_edges = {}
+    for nm, ock, gck in (("A", O.CK_A, 1), ("chl2", O.CK_CHL2, 2), ("B", O.CK_B, 3)):
+        oe, ge = r.edges(ock), g.edge_rows(gck)
+        n_edges[nm] = int(len(oe))
+        if oe.shape != ge.shape or not np.array_equal(oe, ge):
+            bad.append(f"checkpoint {nm}: oracle {len(oe)} gpu {len(ge)}")
+    for c_ in ("reads_good", "nodes", "contained", "edge_removal_1", "edge_removal_2", "trans_edge"):
+        if max(r.counter(c_), 0) != g.counter(c_):
+            bad.append(f"counter {c_}")
+    g.close()
+    r.close()
+    return dt, n_edges["A"], {"world": 1, "ok": not bad, "against": "CPU oracle (oracle/brush_oracle.cpp)",
+                              "edges_overlap": n_edges["A"], "edges_re": n_edges["B"], "differences": bad}
+
 KERNELS = ["parse_lines", "dedupe_runs", "keygen", "join_verify", "cut", "tr",
            "rs_scatter:dedupe", "rs_upsweep:dedupe", "rs_scatter:tuples", "rs_upsweep:tuples",
            "group_walk", "side_insert", "consistency", "tr_final",
-           "ph_scatter1", "ph_hist2", "ph_scatter2", "bucket_join"]
+           "ph_hist1", "ph_scatter1", "ph_hist2", "ph_scatter2", "bucket_join"]
+
+
+def kernel_rooflines(stats, steps, ms, counters, L, k, world, peak, peak_src):
+    """Achieved algorithmic GB/s of the main kernels (DESIGN.md section 5 gives the bytes per unit), sorted by
+    their share of the step.  The first entry is the dominant kernel (largest ms per step)."""
+    T = counters["tuples"] / world
+    N = counters["nodes"] / world
+    C = counters["candidates_verified"] / world
+    R = 4 * ((2 * L + 31) // 32)          # packed read, SURVEY.md 8(d)
+    nwo = (L - k + 15) // 16              # 32-bit words of a stored overhang
+    slots = counters.get("slots", 0) / world or 2.0 * T
+    T_slots = N * (L - k + 1)             # tuple slots keygen writes (windows that emit nothing included)
+    alg = {
+        "bucket_join": ("group + join + verify + mirror of one hash bucket per CTA", T * (12 + R) + slots * 8 + C * 4 * nwo),
+        "ph_scatter1": ("hash partition pass 1 (atomic-reserve scatter)", 24.0 * T),
+        "ph_scatter2": ("hash partition pass 2 (atomic-reserve scatter)", 24.0 * T),
+        "rs_scatter:tuples": ("one 8/9-bit LSD pass of the flat tuple sort", 24.0 * T_slots),
+        "join_verify": ("flat join + verify + mirror", T * (12 + R + 8) + C * (8 + 4 * nwo)),
+        "parse_lines": ("SFA line parser / 2-bit packer", counters["reads_good"] / world * (L + 10 + R + 16 + 12 + 1)),
+        "consistency": ("per-list overhang nesting test", C * (8 + 4 * nwo)),
+        "tr_final": ("TransitiveReduction + EdgeRemoval over the slots", slots * 10),
+    }
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    out = []
+    for name, (what, b) in alg.items():
+        st = stats.get(name)
+        if not st or st[1] <= 0:
+            continue
+        per_launch_ms = st[0] / st[1]
+        ach = b / (per_launch_ms * 1e-3) / 1e9
+        out.append({"bound": "hbm", "kernel": f"{name} ({what})", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": traffic.get(name, {}).get("dram_bytes_per_launch"),
+                    "peak_source": peak_src, "alg_bytes_per_launch": b, "ms_per_launch": per_launch_ms,
+                    "launches_per_step": st[1] / steps, "ms_per_step": st[0] / steps, "share_of_step": st[0] / steps / ms})
+    out.sort(key=lambda r: -r["ms_per_step"])
+    return out
 
 
 def bench_ours(args):
@@ -284,6 +424,10 @@ def bench_ours(args):
             exch = TorchExchange(device=torch.device("cuda", local_rank))
             g.set_exchange(exch)
 
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = sharded_parity(name, world, rank, local_rank, args.transport, args.parity_genome)
+
     def step_resident():
         g.borrow_sfa_device(dev.data_ptr(), dev.numel())
         g.run()
@@ -314,7 +458,8 @@ def bench_ours(args):
     g.set_profile(False)
     ms = float(np.mean(dev_ms))
     counters = {c: g.counter(c) for c in ["reads_good", "nodes", "tuples", "candidates_verified", "edges_overlap",
-                                          "edges_chl2", "edges_re", "trans_edge", "edge_removal_1", "slow_lists"]}
+                                          "edges_chl2", "edges_re", "trans_edge", "edge_removal_1", "slow_lists",
+                                          "bucket_path", "slots"]}
     stage_ms = {t: g.time_ms(t) for t in ["parse", "dedupe", "keygen", "sort_tuples", "join_verify",
                                           "cut", "tr"] + (["exchange_tuples", "dd_route", "dd_return", "node_gather",
                                                            "side_route", "tr_votes", "a2a_tuples"] if world > 1 else [])}
@@ -363,27 +508,9 @@ def bench_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        # dominant kernel
-        W = L - k + 1
-        T_slots = counters["nodes"] * W / world  # tuple slots sorted per GPU (even shards)
-        st = stats.get("rs_scatter:tuples")
-        roof = None
-        if st and st[1] > 0:
-            per_launch_ms = st[0] / st[1]
-            alg_bytes = 24.0 * T_slots
-            achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-            traffic = None
-            try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-                traffic = tj.get("rs_scatter:tuples", {}).get("dram_bytes_per_launch")
-            except Exception:
-                pass
-            roof = {"bound": "hbm", "kernel": "rs_onesweep<pairs> (k-mer tuple sort, one 8/9-bit LSD pass)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
-                    "ms_per_launch": per_launch_ms, "launches_per_step": st[1] / args.steps,
-                    "share_of_step": st[0] / args.steps / ms,
-                    "share_of_step_all_sorts": (st[0] + (stats.get("rs_scatter:dedupe") or (0, 0))[0]) / args.steps / ms}
+        # the dominant kernel (largest ms per step) first, the other main kernels after it
+        roofs = kernel_rooflines(stats, args.steps, ms, counters, L, k, world, peak, peak_src)
+        roof = roofs[0] if roofs else None
         kern = {kn: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                 for kn, v in stats.items() if v}
         # ---- whole-path figure of BASELINE.md / SURVEY.md 8(d): B_alg from the run's measured counts ----
@@ -405,7 +532,14 @@ def bench_ours(args):
         if not args.no_cpu_baseline:
             sg = cpu_sample_genome(meta, target_reads=args.cpu_sample_reads)
             ssfa, sm = make_workload(name, genome=sg, seed_shift=1000)
-            dt, _ = run_oracle_once(bytes(ssfa), k, L)
+            if world == 1 and not args.no_parity:
+                dt, _, parity = oracle_parity(bytes(ssfa), k, L, local_rank)
+                if not parity["ok"]:
+                    log("PARITY FAILURE (CUDA path differs from the oracle): " + "; ".join(parity["differences"]))
+                    raise SystemExit(3)
+                parity["input"] = f"{sm['n_reads']} reads, {sg} bp genome (the cpu_baseline sample)"
+            else:
+                dt, _ = run_oracle_once(bytes(ssfa), k, L)
             cpu = {"value": sm["n_reads"] / dt, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"{sm['n_reads']} reads: {sg} bp random genome, {L} bp reads at {meta['coverage']}x, "
                              f"k={k} (oracle/brush_oracle.cpp, single thread, {dt:.1f}s)"}
@@ -428,8 +562,10 @@ def bench_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
+            "roofline_kernels": roofs[1:],
             "roofline_path": path,
             "cpu_baseline": cpu,
+            "parity": parity,
             "counters": counters,
             "stage_ms": stage_ms,
             "kernels": kern,
@@ -467,9 +603,11 @@ def main():
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--genome", type=int, default=None, help="override the genome length (reduced runs)")
     ap.add_argument("--cpu-sample-reads", type=int, default=250_000)
-    ap.add_argument("--ref-sample-reads", type=int, default=120_000)
+    ap.add_argument("--ref-sample-reads", type=int, default=0, help="reads per host thread and step (0: sized to the run)")
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity check that precedes the timing")
+    ap.add_argument("--parity-genome", type=int, default=200_000, help="genome length of the N>1 parity input")
     ap.add_argument("--transport", default="nccl", choices=["nccl", "torch"],
                     help="N>1: native NCCL inside the library (default) or the torch.distributed callbacks")
     args = ap.parse_args()

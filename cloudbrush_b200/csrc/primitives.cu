@@ -738,8 +738,9 @@ BucketPlan make_bucket_plan(size_t n_tuples) {
   static const int widths[4] = {3, 6, 8, 9};
   BucketPlan pl;
   int nbits = 2;
-  while (nbits < 18 && ((size_t)576 << nbits) < n_tuples) nbits++;
-  pl.fits = ((size_t)1400 << nbits) >= n_tuples;  // beyond 2^18 buckets of <= 1400: a third pass would be needed
+  static const size_t avg = getenv("CB_BUCKET_AVG") ? (size_t)atoi(getenv("CB_BUCKET_AVG")) : 640;  // experiment knob
+  while (nbits < 18 && (avg << nbits) < n_tuples) nbits++;
+  pl.fits = ((size_t)640 << nbits) >= n_tuples;  // beyond 2^18 buckets of <= 640: a third pass would be needed
   int best = 99;
   for (int a : widths)
     for (int b : widths)
@@ -837,6 +838,7 @@ __global__ void __launch_bounds__(PS_THREADS, 2) ph_scatter_kernel(const u64* __
   unsigned short(*warp_hist)[RADIX] = reinterpret_cast<unsigned short(*)[RADIX]>(vstage + PS_TILE);  // [WARPS][RADIX]
   u32* excl = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(warp_hist) + WARPS * RADIX * 2);  // [RADIX]
   u32* gbase = excl + RADIX;                                                                            // [RADIX]
+  unsigned short* sdig = reinterpret_cast<unsigned short*>(gbase + RADIX);                              // [PS_TILE] digit of the staged tuple
   __shared__ u32 scan_tmp[WARPS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt_mask = (1u << lane) - 1;
@@ -867,7 +869,7 @@ __global__ void __launch_bounds__(PS_THREADS, 2) ph_scatter_kernel(const u64* __
     __syncwarp();
     if (valid && lane == __ffs(peers) - 1) warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
     __syncwarp();
-    pos[i] = valid ? prev + __popc(peers & lt_mask) : 0xffffffffu;
+    pos[i] = valid ? ((prev + __popc(peers & lt_mask)) | (d << 12)) : 0xffffffffu;  // the hash is taken once per tuple
   }
   __syncthreads();
   u32 run = 0;
@@ -889,9 +891,10 @@ __global__ void __launch_bounds__(PS_THREADS, 2) ph_scatter_kernel(const u64* __
 #pragma unroll
   for (int i = 0; i < PS_ITEMS; i++) {
     if (pos[i] != 0xffffffffu) {
-      const u32 d = (u32)(kmer_hash(key[i] & kmask) >> shift) & (RADIX - 1);
-      pos[i] += excl[d] + warp_hist[warp][d];
+      const u32 d = pos[i] >> 12;
+      pos[i] = (pos[i] & 4095u) + excl[d] + warp_hist[warp][d];
       stage[pos[i]] = key[i];
+      sdig[pos[i]] = (unsigned short)d;
     }
   }
 #pragma unroll
@@ -899,9 +902,8 @@ __global__ void __launch_bounds__(PS_THREADS, 2) ph_scatter_kernel(const u64* __
     if (pos[i] != 0xffffffffu) vstage[pos[i]] = vin[base + e0 + i * 32];
   __syncthreads();
   for (u32 p = tid; p < total; p += PS_THREADS) {
-    const u64 k = stage[p];
-    const u32 g = gbase[(u32)(kmer_hash(k & kmask) >> shift) & (RADIX - 1)] + p;
-    kout[g] = k;
+    const u32 g = gbase[sdig[p]] + p;
+    kout[g] = stage[p];
     vout[g] = vstage[p];
   }
 }
@@ -909,7 +911,7 @@ __global__ void __launch_bounds__(PS_THREADS, 2) ph_scatter_kernel(const u64* __
 template <int RB>
 static void launch_scatter_rb(u32 tiles, cudaStream_t s, const u64* kin, const u32* vin, u64* kout, u32* vout,
                               const TileSrc& ts, u64 kmask, int shift, u32* cursor) {
-  constexpr size_t dyn = (size_t)PS_TILE * 12 + (PS_THREADS / 32) * ((size_t)2 << RB) + 2 * ((size_t)4 << RB);
+  constexpr size_t dyn = (size_t)PS_TILE * 14 + (PS_THREADS / 32) * ((size_t)2 << RB) + 2 * ((size_t)4 << RB);
   CB_CUDA(cudaFuncSetAttribute(ph_scatter_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   ph_scatter_kernel<RB><<<tiles, PS_THREADS, dyn, s>>>(kin, vin, kout, vout, ts, kmask, shift, cursor);
 }

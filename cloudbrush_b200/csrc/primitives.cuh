@@ -97,7 +97,7 @@ struct BucketPlan {
   bool fits = true;     // false: more tuples than two passes can cut into buckets the bucket kernel holds
 };
 constexpr int kLocalBits = 10;
-// buckets of 288..576 tuples on average (the bucket kernel holds up to 2048)
+// buckets of 320..640 tuples on average (the bucket kernel holds 1024)
 BucketPlan make_bucket_plan(size_t n_tuples);
 
 // Tuples (ka, va)[n_slots] -- slots whose key is ~0 are skipped -- end up bucketed in (ka, va) again

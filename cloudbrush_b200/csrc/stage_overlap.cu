@@ -557,8 +557,7 @@ __global__ void __launch_bounds__(256, MINB) join_verify_kernel(JoinParams P) {
 // Nothing here depends on the order of the tuples inside a group: "another tuple of the same read in
 // this group" (maximal-overlap filter, `certain`) is found by scanning the group in shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int BJ_THREADS = 256;
-constexpr int BJ_CAP = 2048;                   // tuples per bucket the kernel holds
+constexpr int BJ_CAP = 1024;                   // tuples per bucket the kernel holds (the plan aims at <= 320 on average)
 constexpr int BJ_LBINS = 1 << kLocalBits;      // 1024 local bins
 // per position: key 8, payload 4, group 4, slot offset 4, node-entry list 2 bytes
 constexpr size_t BJ_SMEM = (size_t)BJ_CAP * (8 + 4 + 4 + 4 + 2) + (BJ_LBINS + 1) * 4 + BJ_LBINS * 4 + (BJ_LBINS / 32) * 4 + 64;
@@ -566,11 +565,18 @@ static_assert(BJ_CAP / 2 <= BJ_LBINS, "node-entry counters are packed two per wo
 static_assert(BJ_CAP <= (1 << 11), "list index of a node entry is packed into 11 bits");
 
 // M32: node | window | dir of every tuple fit the 32-bit payload (no payload bits above the k-mer in
-// the key), which is the case up to 2^26 nodes at W <= 32 and 2^24 nodes at W <= 128
-template <int NW, int MINB, bool M32>
-__global__ void __launch_bounds__(BJ_THREADS, MINB) bucket_join_kernel(JoinParams P) {
+// the key), which is the case up to 2^26 nodes at W <= 32 and 2^24 nodes at W <= 128.
+//
+// All per-position loops are warp-granular (warp w takes the 32-position chunks w, w + 8, ...), so a
+// bucket of n tuples costs ceil(n / 32) warp iterations whatever n is.  (Measured dead end: fetching the
+// packed reads of the bucket's tuples into shared memory with cp.async while the grouping runs -- the join
+// then reads nothing from global memory -- was 5 % slower: the gathers hit the L2, which holds node_seq
+// in its persisting window, and the 16 KB of rows cost occupancy.)
+template <int NW, int TPB, int MINB, bool M32>
+__global__ void __launch_bounds__(TPB, MINB) bucket_join_kernel(JoinParams P) {
+  constexpr int BJ_THREADS = TPB, BJ_WARPS = TPB / 32, BJ_CHUNKS = BJ_CAP / 32 / BJ_WARPS;
   extern __shared__ __align__(16) unsigned char bj_smem[];
-  u64* skey = reinterpret_cast<u64*>(bj_smem);          // [CAP] tuples grouped by k-mer
+  u64* skey = reinterpret_cast<u64*>(bj_smem);           // [CAP] tuples grouped by k-mer
   u32* sval = reinterpret_cast<u32*>(skey + BJ_CAP);     // [CAP]
   u32* sgrp = sval + BJ_CAP;                             // [CAP] head | end << 16 of the group of position p
   u32* soff = sgrp + BJ_CAP;                             // [CAP] node entry i: slot offset in the CTA's range | list index << 21
@@ -583,7 +589,7 @@ __global__ void __launch_bounds__(BJ_THREADS, MINB) bucket_join_kernel(JoinParam
   __shared__ ull s_base, s_lbase;
 
   const int L = P.L, K = P.K;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt_mask = (1u << lane) - 1;
   const u32 posmask = (1u << P.pb) - 1;
   const int nsh = P.pb + 1;  // node = meta >> nsh
@@ -594,6 +600,7 @@ __global__ void __launch_bounds__(BJ_THREADS, MINB) bucket_join_kernel(JoinParam
     if (tid == 0) atomicAdd(&P.dcount[DC_BUCKET_OVER], 1ull);
     return;
   }
+  const u32 n_chunks = (n + 31) >> 5;
   auto ldigit = [&](u64 k) { return (u32)(kmer_hash(k & P.kmask) >> P.lshift) & (BJ_LBINS - 1); };
   auto meta_at = [&](u32 p) -> u64 { return M32 ? (u64)sval[p] : (((skey[p] >> (2 * K)) << 32) | (u64)sval[p]); };
   auto node_at = [&](u32 p) -> u32 { return M32 ? (sval[p] >> nsh) : (u32)(meta_at(p) >> nsh); };
@@ -605,13 +612,16 @@ __global__ void __launch_bounds__(BJ_THREADS, MINB) bucket_join_kernel(JoinParam
   if (tid == 0) { s_any_mixed = 0; s_slots = 0; s_lists = 0; }
   __syncthreads();
   // one shared-memory atomic per tuple: its return value is the tuple's rank inside its bin
-  u32 dr[BJ_CAP / BJ_THREADS];
+  u64 kreg[BJ_CHUNKS];
+  u32 vreg[BJ_CHUNKS], dr[BJ_CHUNKS];
 #pragma unroll
-  for (int i = 0; i < BJ_CAP / BJ_THREADS; i++) {
-    const u32 e = (u32)i * BJ_THREADS + tid;
-    dr[i] = 0;
+  for (int i = 0; i < BJ_CHUNKS; i++) {
+    const u32 e = ((u32)(warp + i * BJ_WARPS) << 5) + lane;
+    dr[i] = 0xffffffffu;
     if (e < n) {
-      const u32 d = ldigit(P.keys[lo + e]);
+      kreg[i] = P.keys[lo + e];
+      vreg[i] = P.vals[lo + e];  // requested together with the key: one DRAM round trip per CTA, not two
+      const u32 d = ldigit(kreg[i]);
       dr[i] = (d << 16) | atomicAdd(&sstart[d], 1u);
     }
   }
@@ -628,16 +638,15 @@ __global__ void __launch_bounds__(BJ_THREADS, MINB) bucket_join_kernel(JoinParam
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < BJ_CAP / BJ_THREADS; i++) {  // the bucket is in L1 now
-    const u32 e = (u32)i * BJ_THREADS + tid;
-    if (e < n) {
+  for (int i = 0; i < BJ_CHUNKS; i++) {
+    if (dr[i] != 0xffffffffu) {
       const u32 pos = sstart[dr[i] >> 16] + (dr[i] & 0xffffu);
-      skey[pos] = P.keys[lo + e];
-      sval[pos] = P.vals[lo + e];
+      skey[pos] = kreg[i];
+      sval[pos] = vreg[i];
     }
   }
   __syncthreads();
-  // bins that hold more than one k-mer (two of the ~35 k-mers of a bucket share the 10 bits): rare enough
+  // bins that hold more than one k-mer (two of the k-mers of a bucket share the 10 bits): rare enough
   // that one thread per such bin gathers equal k-mers together
   for (u32 p = tid; p < n; p += BJ_THREADS) {
     const u32 d = ldigit(skey[p]);
@@ -670,41 +679,67 @@ __global__ void __launch_bounds__(BJ_THREADS, MINB) bucket_join_kernel(JoinParam
     __syncthreads();
   }
   // ---- [head, end) of every position's group; node entries (MatchPrefix.java:366: groups above LOW_KMER) ----
-  for (u32 p = tid; p < n; p += BJ_THREADS) {
-    const u64 kp = skey[p];
-    const u32 d = ldigit(kp);
-    u32 head = sstart[d], end = sstart[d + 1];
-    if ((smixed[d >> 5] >> (d & 31)) & 1u) {
-      const u64 ck = kp & P.kmask;
-      u32 h = p, e = p + 1;
-      while (h > head && (skey[h - 1] & P.kmask) == ck) h--;
-      while (e < end && (skey[e] & P.kmask) == ck) e++;
-      head = h;
-      end = e;
-    }
-    sgrp[p] = head | (end << 16);
-    const u64 m = meta_at(p);
-    const int pos = (int)((m >> 1) & posmask);
-    const u32 g = end - head;
-    if (p == head) {
-      // BuildHighKmerList.java:96-117: weighted count over windows [0, L-K) above UP_KMER
-      if ((kp & P.kmask) != 0 && (long long)g * (long long)P.max_cov > P.up_kmer) {
-        ull sum = 0;
-        for (u32 t = head; t < end; t++) {
-          const u64 m2 = meta_at(t);
-          if ((int)((m2 >> 1) & posmask) < L - K) sum += P.node_cov[(u32)(m2 >> nsh)];
+  for (u32 ch = warp; ch < n_chunks; ch += BJ_WARPS) {  // warp-uniform trip count: the reservation below is warp-collective
+    const u32 p = (ch << 5) + lane;
+    const bool valid = p < n;
+    bool entry = false;
+    u32 lid = 0, len = 0, head = 0;
+    if (valid) {
+      const u64 kp = skey[p];
+      const u32 d = ldigit(kp);
+      u32 end = sstart[d + 1];
+      head = sstart[d];
+      if ((smixed[d >> 5] >> (d & 31)) & 1u) {
+        const u64 ck = kp & P.kmask;
+        u32 h = p, e = p + 1;
+        while (h > head && (skey[h - 1] & P.kmask) == ck) h--;
+        while (e < end && (skey[e] & P.kmask) == ck) e++;
+        head = h;
+        end = e;
+      }
+      sgrp[p] = head | (end << 16);
+      const u64 m = meta_at(p);
+      const int pos = (int)((m >> 1) & posmask);
+      const u32 g = end - head;
+      if (p == head) {
+        // BuildHighKmerList.java:96-117: weighted count over windows [0, L-K) above UP_KMER
+        if ((kp & P.kmask) != 0 && (long long)g * (long long)P.max_cov > P.up_kmer) {
+          ull sum = 0;
+          for (u32 t = head; t < end; t++) {
+            const u64 m2 = meta_at(t);
+            if ((int)((m2 >> 1) & posmask) < L - K) sum += P.node_cov[(u32)(m2 >> nsh)];
+          }
+          if ((long long)sum > P.up_kmer) atomicAdd(&P.dcount[DC_HKMER], 1ull);
         }
-        if ((long long)sum > P.up_kmer) atomicAdd(&P.dcount[DC_HKMER], 1ull);
+      }
+      entry = (pos == 0 || pos == L - K) && (long long)g > P.low_kmer;  // a live NODEMSG tuple
+      if (entry) {
+        if ((long long)g > P.up_kmer) atomicAdd(&P.dcount[DC_UPKMER_LISTS], 1ull);  // MatchPrefix.java:366-368 (refused by the host)
+        lid = 2 * (u32)(m >> nsh) + (pos == 0 ? 1u : 0u);  // list (b, flip y)
+        len = g + (P.extra ? P.extra[lid] : 0u);
       }
     }
-    if ((pos == 0 || pos == L - K) && (long long)g > P.low_kmer) {  // a live NODEMSG tuple
-      if ((long long)g > P.up_kmer) atomicAdd(&P.dcount[DC_UPKMER_LISTS], 1ull);  // MatchPrefix.java:366-368 (refused by the host)
-      const u32 lid = 2 * (u32)(m >> nsh) + (pos == 0 ? 1u : 0u);  // list (b, flip y)
-      const u32 len = g + (P.extra ? P.extra[lid] : 0u);
-      const u32 old = atomicAdd(&scnt[head >> 1], (head & 1u) ? 0x10000u : 1u);
-      const u32 kk = (old >> ((head & 1u) * 16)) & 0xffffu;
-      sne[head + kk] = (unsigned short)p;
-      soff[head + kk] = atomicAdd(&s_slots, len) | (atomicAdd(&s_lists, 1u) << 21);
+    // slots and list indices of the CTA's ranges: one shared atomic pair per warp (a same-address atomic per
+    // node entry was 23 % of the kernel's stall samples), lanes take consecutive pieces
+    const u32 ebal = __ballot_sync(0xffffffffu, entry);
+    if (ebal) {
+      u32 incl = len;  // inclusive prefix sum of len over the lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const u32 wtotal = __shfl_sync(0xffffffffu, incl, 31);
+      u32 wbase = 0, lbase = 0;
+      if (lane == 31) { wbase = atomicAdd(&s_slots, wtotal); lbase = atomicAdd(&s_lists, (u32)__popc(ebal)); }
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      lbase = __shfl_sync(0xffffffffu, lbase, 31);
+      if (entry) {
+        const u32 old = atomicAdd(&scnt[head >> 1], (head & 1u) ? 0x10000u : 1u);
+        const u32 kk = (old >> ((head & 1u) * 16)) & 0xffffu;
+        sne[head + kk] = (unsigned short)p;
+        soff[head + kk] = (wbase + incl - len) | ((lbase + (u32)__popc(ebal & lt_mask)) << 21);
+      }
     }
   }
   __syncthreads();
@@ -737,22 +772,25 @@ __global__ void __launch_bounds__(BJ_THREADS, MINB) bucket_join_kernel(JoinParam
   // ---- join + verify + mirror: every (node entry, tuple) pair of a group, one thread per tuple ----
   const int sh_node = P.lay.nb + P.lay.ob + 2, sh_x = P.lay.nb + P.lay.ob + 1, sh_ov = P.lay.nb + 1, sh_y = P.lay.nb;
   u32 n_verified = 0;
-  for (u32 p = tid; p < n; p += BJ_THREADS) {
-    const u32 head = sgrp[p] & 0xffffu, end = sgrp[p] >> 16;
-    const u32 nne = necnt(head);
-    if (nne == 0) continue;
-    const u64 m = meta_at(p);
+  for (u32 ch = warp; ch < n_chunks; ch += BJ_WARPS) {  // warp-uniform trip count: the MATCH.ANY below is warp-collective
+    const u32 p = (ch << 5) + lane;
+    const bool valid = p < n;
+    const u32 head = valid ? (sgrp[p] & 0xffffu) : 0u, end = valid ? (sgrp[p] >> 16) : 0u;
+    const u64 m = valid ? meta_at(p) : 0ull;
     const u32 a = (u32)(m >> nsh);
+    // Another tuple of the same read in this group?  The lanes of a warp hold consecutive positions, so the
+    // part of the group inside the warp's window is one MATCH.ANY; only the part outside is scanned.
+    const u32 peers = __match_any_sync(0xffffffffu, valid ? (((u64)head << 32) | (u64)a) : (0xffffffff00000000ull | (u64)lane));
+    const u32 nne = valid ? necnt(head) : 0u;
+    if (nne == 0) continue;
     uint4 qa[NW / 2];
     load_row<NW>(P.node_seq, a, qa);
-    // the first two node entries of the group (most groups have at most two) are requested up front
-    const u64 me0 = meta_at(sne[head]), me1 = nne > 1 ? meta_at(sne[head + 1]) : 0ull;
-    uint4 qb0[NW / 2], qb1[NW / 2];
-    load_row<NW>(P.node_seq, (u32)(me0 >> nsh), qb0);
-    if (nne > 1) load_row<NW>(P.node_seq, (u32)(me1 >> nsh), qb1);
-    // another tuple of the same read in this group?
-    bool multi = false;
-    for (u32 t = head; t < end; t++) multi = multi || (node_at(t) == a && t != p);
+    bool multi = (peers & (peers - 1)) != 0;
+    {
+      const u32 w0 = ch << 5, w1 = w0 + 32;
+      for (u32 t = head; t < end && t < w0; t++) multi = multi || node_at(t) == a;
+      for (u32 t = w1 > head ? w1 : head; t < end; t++) multi = multi || node_at(t) == a;
+    }
     const int pos = (int)((m >> 1) & posmask);
     const int d = (int)(m & 1);
     u64 R[NW], Rc[NW];
@@ -780,12 +818,16 @@ __global__ void __launch_bounds__(BJ_THREADS, MINB) bucket_join_kernel(JoinParam
     // the tuple's half of the mirror record (b, flip y, ov, flip x, a) for both lists
     const u64 apart0 = ((u64)(u32)(L - ov0) << sh_ov) | ((u64)(u32)(x0 ^ 1) << sh_y) | (u64)a;
     const u64 apart1 = ((u64)(u32)(L - ov1) << sh_ov) | ((u64)(u32)(x1 ^ 1) << sh_y) | (u64)a;
-    // one node entry (its tuple's payload me, first slot off_l of its list) against this tuple
-    auto process = [&](const u64 me, const u32 off_l, u64 (&B)[NW]) {
+    for (u32 q = 0; q < nne; q++) {  // one node entry (b, y) against this tuple
+      const u32 pe = sne[head + q];
+      const u64 me = meta_at(pe);
+      const u32 off_l = (u32)(base + (soff[head + q] & 0x1fffffu));
       const u32 b = (u32)(me >> nsh);
       const int y = ((int)((me >> 1) & posmask) == 0) ? 0 : 1;  // window-0 entry: y = f
       const int sel = y ^ (int)(me & 1);                          // MatchPrefix.java:275-296
       const int x = sel ? x1 : x0, ov = sel ? ov1 : ov0;
+      u64 B[NW];
+      load_read_row<NW>(P.node_seq, b, B);  // L1: every tuple of the group reads the same row
       if (y) {
         u64 r[NW];
 #pragma unroll
@@ -834,21 +876,8 @@ __global__ void __launch_bounds__(BJ_THREADS, MINB) bucket_join_kernel(JoinParam
       } else {
         P.slots[slot] = ~0ull;  // every slot is written exactly once: the slot array is never pre-cleared
       }
-    };
-    u64 B[NW];
-    unpack_row<NW>(qb0, B);
-    process(me0, (u32)(base + (soff[head] & 0x1fffffu)), B);
-    if (nne > 1) {
-      unpack_row<NW>(qb1, B);
-      process(me1, (u32)(base + (soff[head + 1] & 0x1fffffu)), B);
-      for (u32 q = 2; q < nne; q++) {
-        const u64 me = meta_at(sne[head + q]);
-        load_read_row<NW>(P.node_seq, (u32)(me >> nsh), B);
-        process(me, (u32)(base + (soff[head + q] & 0x1fffffu)), B);
-      }
     }
   }
-  (void)lt_mask;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_verified += __shfl_xor_sync(0xffffffffu, n_verified, o);
   if (lane == 0 && n_verified) {
@@ -1001,14 +1030,17 @@ __global__ void __launch_bounds__(256) orphan_lists_kernel(const u32* __restrict
   for (u32 t = 0; t < x; t++) slots[off + t] = ~0ull;
 }
 
+// 128 threads per CTA: the kernel is bound by the latency chain of a CTA's phases (loads -> grouping ->
+// slot reservation -> join), so what counts is the number of CTAs in flight: 7 x 128 threads per SM ran
+// the join in 4.6 ms where 4 x 256 threads took 6.1 ms (config 2)
 template <int NW, int MINB>
 static void launch_bucket_join(const JoinParams& P, u32 n_buckets, bool m32, cudaStream_t s) {
   if (m32) {
-    CB_CUDA(cudaFuncSetAttribute(bucket_join_kernel<NW, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_SMEM));
-    bucket_join_kernel<NW, MINB, true><<<n_buckets, BJ_THREADS, BJ_SMEM, s>>>(P);
+    CB_CUDA(cudaFuncSetAttribute(bucket_join_kernel<NW, 128, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_SMEM));
+    bucket_join_kernel<NW, 128, MINB, true><<<n_buckets, 128, BJ_SMEM, s>>>(P);
   } else {
-    CB_CUDA(cudaFuncSetAttribute(bucket_join_kernel<NW, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_SMEM));
-    bucket_join_kernel<NW, MINB, false><<<n_buckets, BJ_THREADS, BJ_SMEM, s>>>(P);
+    CB_CUDA(cudaFuncSetAttribute(bucket_join_kernel<NW, 128, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_SMEM));
+    bucket_join_kernel<NW, 128, MINB, false><<<n_buckets, 128, BJ_SMEM, s>>>(P);
   }
 }
 
@@ -1290,8 +1322,8 @@ void stage_build_overlap(cb_ctx* c) {
       P.list_order = list_order.p;
       c->lc.begin("bucket_join");
       const bool m32 = nbits + pb + 1 <= 32;  // node | window | dir fit the 32-bit payload
-      if (c->NW == 2) launch_bucket_join<2, 4>(P, plan.NB, m32, s);
-      else CB_DISPATCH_NW(c->NW, (launch_bucket_join<NW_, 2>(P, plan.NB, m32, s)));
+      if (c->NW == 2) launch_bucket_join<2, 7>(P, plan.NB, m32, s);
+      else CB_DISPATCH_NW(c->NW, (launch_bucket_join<NW_, 4>(P, plan.NB, m32, s)));
       c->lc.end("bucket_join");
       c->lc.n++;
       if (have_extra && n_lists) {
@@ -1420,6 +1452,11 @@ void stage_build_overlap(cb_ctx* c) {
   c->counters["upkmer_truncated_lists"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
   c->counters["order_dependent"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
   c->counters["bucket_path"] = bucket ? 1 : 0;
+  {
+    u64 sg = slots1;
+    ex_allreduce(c, &sg, 1, 0);
+    c->counters["slots"] = (int64_t)sg;
+  }
   if (c->gcount[DC_UPKMER_LISTS] > 0)
     throw Error(CB_E_UNSUPPORTED,
                 "a k-mer group with a node entry holds more than -kmerup tuples: the reference truncates its "
