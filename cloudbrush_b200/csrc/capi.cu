@@ -413,6 +413,7 @@ int cb_export_edges(cb_ctx* c, int checkpoint, cb_edge* out, size_t cap, size_t*
   if (!n) throw Error(CB_E_INVALID, "null size pointer");
   const long long cnt = edge_count(c, checkpoint);
   if (cnt < 0) throw Error(CB_E_INVALID, "checkpoint not available");
+  wait_node_table(c, true);  // node -> SFA line of every rank's nodes (sharded contexts gather it in the background)
   *n = (size_t)cnt;
   if (out && cap >= (size_t)cnt && cnt) export_edges_to(c, checkpoint, out);
   CB_API_END(c)
@@ -422,6 +423,7 @@ int cb_export_nodes(cb_ctx* c, cb_node* out, size_t cap, size_t* n) {
   CB_API_BEGIN(c)
   if (!n) throw Error(CB_E_INVALID, "null size pointer");
   if (!c->preprocessed) throw Error(CB_E_INVALID, "nodes not available");
+  wait_node_table(c, true);
   // a sharded context exports the nodes built from ITS shard of the SFA lines (the union over the
   // ranks, in rank order, is the node table sorted by line)
   const u32 lo = distributed(c) ? c->node_lo : 0, hi = distributed(c) ? c->node_hi : c->n_nodes;

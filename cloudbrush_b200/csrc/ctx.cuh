@@ -96,6 +96,14 @@ struct cb_ctx {
   cb_exchange ex = {};
   bool has_ex = false;
   void* nccl_comm = nullptr;      // native transport (cb_init_nccl); takes precedence over the callbacks
+  cudaStream_t side_stream = nullptr;  // the node-table all-gather runs here, behind keygen + tuple exchange + partition
+  cudaStream_t ex_stream = nullptr;    // stream the transport calls are enqueued on (nullptr: the context's stream)
+  cudaEvent_t ev_fork = nullptr, ev_seq = nullptr, ev_rest = nullptr;
+  bool gather_pending_seq = false, gather_pending_rest = false;
+  cb::DevBuf<u64> own_seq;        // packed reads / coverage of the nodes built from this shard (keygen reads these
+  cb::DevBuf<u32> own_cov;        //   while the replicated table is still being gathered)
+  cb::DevBuf<u32> own_line_tmp;   // send buffers of the pending gather
+  cb::DevBuf<cb::IdKey> own_id_tmp;
   u64* ex_scratch = nullptr;      // small device scratch of the native transport
   size_t ex_scratch_words = 0;
   int lg_world = 0;               // log2(world)
@@ -191,6 +199,11 @@ inline void guarded(cb_ctx* c, F&& f) {
 void ex_allreduce_max_u8(cb_ctx* c, uint8_t* dev, size_t n);
 void ex_counts(cb_ctx* c, const u64* send, u64* recv, int n_per_rank);
 void ex_alltoallv(cb_ctx* c, const void* send, const u64* send_bytes, void* recv, const u64* recv_bytes);
+// two all-to-alls with the same element counts (keys and payloads of the k-mer tuples) as ONE transfer group
+void ex_alltoallv2(cb_ctx* c, const void* send_a, void* recv_a, size_t elem_a, const void* send_b, void* recv_b,
+                   size_t elem_b, const u64* send_cnt, const u64* recv_cnt);
+// the main stream waits for the replicated node table (rest: id keys and SFA lines too)
+void wait_node_table(cb_ctx* c, bool rest);
 void ex_allgatherv(cb_ctx* c, const void* send, u64 send_bytes, void* recv, const u64* recv_bytes);
 // routes n records of elem_bytes (multiple of 4) to rank dest[i] (dest[i] == world: dropped);
 // out receives the records addressed to this rank, grouped by source rank

@@ -99,6 +99,12 @@ void nccl_init(cb_ctx* c, const void* id128) {
   ncclComm_t comm = nullptr;
   CB_NCCL(A->CommInitRank(&comm, c->cfg.world, id, c->cfg.rank));
   c->nccl_comm = comm;
+  if (!c->side_stream) {
+    CB_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    CB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CB_CUDA(cudaEventCreateWithFlags(&c->ev_seq, cudaEventDisableTiming));
+    CB_CUDA(cudaEventCreateWithFlags(&c->ev_rest, cudaEventDisableTiming));
+  }
   const size_t W = (size_t)c->cfg.world;
   const size_t words = W * W * 4 + 4 * W + (size_t)DC_COUNT + 64;
   CB_CUDA(cudaMalloc(&c->ex_scratch, words * sizeof(u64)));
@@ -108,11 +114,20 @@ void nccl_init(cb_ctx* c, const void* id128) {
 void nccl_shutdown(cb_ctx* c) {
   if (c->nccl_comm && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)c->nccl_comm);
   c->nccl_comm = nullptr;
+  if (c->side_stream) {
+    cudaStreamSynchronize(c->side_stream);
+    cudaStreamDestroy(c->side_stream);
+    cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_seq);
+    cudaEventDestroy(c->ev_rest);
+    c->side_stream = nullptr;
+  }
   if (c->ex_scratch) cudaFree(c->ex_scratch);
   c->ex_scratch = nullptr;
 }
 
 static inline ncclComm_t comm_of(cb_ctx* c) { return (ncclComm_t)c->nccl_comm; }
+static inline cudaStream_t xs(cb_ctx* c) { return c->ex_stream ? c->ex_stream : c->stream; }
 
 static void need_ex(cb_ctx* c) {
   if (!c->has_ex && !c->nccl_comm)
@@ -193,10 +208,10 @@ void ex_alltoallv(cb_ctx* c, const void* send, const u64* send_bytes, void* recv
       const char* sp = (const char*)send + so;
       char* rp = (char*)recv + ro;
       if (r == me) {
-        if (send_bytes[r]) CB_CUDA(cudaMemcpyAsync(rp, sp, send_bytes[r], cudaMemcpyDeviceToDevice, c->stream));
+        if (send_bytes[r]) CB_CUDA(cudaMemcpyAsync(rp, sp, send_bytes[r], cudaMemcpyDeviceToDevice, xs(c)));
       } else {
-        if (send_bytes[r]) CB_NCCL(A->Send(sp, send_bytes[r], ncclUint8, r, comm_of(c), c->stream));
-        if (recv_bytes[r]) CB_NCCL(A->Recv(rp, recv_bytes[r], ncclUint8, r, comm_of(c), c->stream));
+        if (send_bytes[r]) CB_NCCL(A->Send(sp, send_bytes[r], ncclUint8, r, comm_of(c), xs(c)));
+        if (recv_bytes[r]) CB_NCCL(A->Recv(rp, recv_bytes[r], ncclUint8, r, comm_of(c), xs(c)));
       }
       so += send_bytes[r];
       ro += recv_bytes[r];
@@ -204,7 +219,7 @@ void ex_alltoallv(cb_ctx* c, const void* send, const u64* send_bytes, void* recv
     CB_NCCL(A->GroupEnd());
     return;
   }
-  CB_CUDA(cudaStreamSynchronize(c->stream));
+  CB_CUDA(cudaStreamSynchronize(xs(c)));
   int rc = c->ex.alltoallv(c->ex.user, send, (const uint64_t*)send_bytes, recv, (const uint64_t*)recv_bytes);
   if (rc) ex_fail("alltoallv", rc);
 }
@@ -219,19 +234,63 @@ void ex_allgatherv(cb_ctx* c, const void* send, u64 send_bytes, void* recv, cons
     for (int r = 0; r < W; r++) {
       char* rp = (char*)recv + ro;
       if (r == me) {
-        if (send_bytes) CB_CUDA(cudaMemcpyAsync(rp, send, send_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        if (send_bytes) CB_CUDA(cudaMemcpyAsync(rp, send, send_bytes, cudaMemcpyDeviceToDevice, xs(c)));
       } else {
-        if (send_bytes) CB_NCCL(A->Send(send, send_bytes, ncclUint8, r, comm_of(c), c->stream));
-        if (recv_bytes[r]) CB_NCCL(A->Recv(rp, recv_bytes[r], ncclUint8, r, comm_of(c), c->stream));
+        if (send_bytes) CB_NCCL(A->Send(send, send_bytes, ncclUint8, r, comm_of(c), xs(c)));
+        if (recv_bytes[r]) CB_NCCL(A->Recv(rp, recv_bytes[r], ncclUint8, r, comm_of(c), xs(c)));
       }
       ro += recv_bytes[r];
     }
     CB_NCCL(A->GroupEnd());
     return;
   }
-  CB_CUDA(cudaStreamSynchronize(c->stream));
+  CB_CUDA(cudaStreamSynchronize(xs(c)));
   int rc = c->ex.allgatherv(c->ex.user, send, send_bytes, recv, (const uint64_t*)recv_bytes);
   if (rc) ex_fail("allgatherv", rc);
+}
+
+void ex_alltoallv2(cb_ctx* c, const void* send_a, void* recv_a, size_t elem_a, const void* send_b, void* recv_b,
+                   size_t elem_b, const u64* send_cnt, const u64* recv_cnt) {
+  need_ex(c);
+  const int W = c->cfg.world, me = c->cfg.rank;
+  if (c->nccl_comm) {
+    NcclApi* A = nccl_api();
+    size_t so = 0, ro = 0;
+    CB_NCCL(A->GroupStart());
+    for (int r = 0; r < W; r++) {
+      const void* sp[2] = {(const char*)send_a + so * elem_a, (const char*)send_b + so * elem_b};
+      void* rp[2] = {(char*)recv_a + ro * elem_a, (char*)recv_b + ro * elem_b};
+      const size_t el[2] = {elem_a, elem_b};
+      for (int q = 0; q < 2; q++) {
+        if (r == me) {
+          if (send_cnt[r]) CB_CUDA(cudaMemcpyAsync(rp[q], sp[q], send_cnt[r] * el[q], cudaMemcpyDeviceToDevice, xs(c)));
+        } else {
+          if (send_cnt[r]) CB_NCCL(A->Send(sp[q], send_cnt[r] * el[q], ncclUint8, r, comm_of(c), xs(c)));
+          if (recv_cnt[r]) CB_NCCL(A->Recv(rp[q], recv_cnt[r] * el[q], ncclUint8, r, comm_of(c), xs(c)));
+        }
+      }
+      so += send_cnt[r];
+      ro += recv_cnt[r];
+    }
+    CB_NCCL(A->GroupEnd());
+    return;
+  }
+  std::vector<u64> sb(W), rb(W);
+  for (int r = 0; r < W; r++) { sb[r] = send_cnt[r] * elem_a; rb[r] = recv_cnt[r] * elem_a; }
+  ex_alltoallv(c, send_a, sb.data(), recv_a, rb.data());
+  for (int r = 0; r < W; r++) { sb[r] = send_cnt[r] * elem_b; rb[r] = recv_cnt[r] * elem_b; }
+  ex_alltoallv(c, send_b, sb.data(), recv_b, rb.data());
+}
+
+void wait_node_table(cb_ctx* c, bool rest) {
+  if (c->gather_pending_seq) {
+    CB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_seq, 0));
+    c->gather_pending_seq = false;
+  }
+  if (rest && c->gather_pending_rest) {
+    CB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_rest, 0));
+    c->gather_pending_rest = false;
+  }
 }
 
 void reduce_counters(cb_ctx* c) {

@@ -486,6 +486,7 @@ void stage_parse_and_pack(cb_ctx* c) {
   cudaStream_t s = c->stream;
   const size_t n = c->text_n;
   const int world = c->cfg.world;
+  wait_node_table(c, true);  // a gather of the previous run still in flight: its buffers are reused below
   if (n == 0 && !distributed(c)) throw Error(CB_E_NOREADS, "No good reads");
   c->K = c->cfg.k;
   c->L = c->cfg.readlen;
@@ -705,10 +706,30 @@ void stage_parse_and_pack(cb_ctx* c) {
     const size_t t1 = total ? total : 1;
     timer_start(c, "node_gather");
     c->node_line.alloc(t1, s); c->node_cov.alloc(t1, s); c->node_seq.alloc(t1 * c->NW, s); c->node_idkey.alloc(t1, s);
-    gather_all(c, l_line.p, 4, n_local_nodes, counts, c->node_line.p);
-    gather_all(c, l_cov.p, 4, n_local_nodes, counts, c->node_cov.p);
+    // Native transport: the replicated table is gathered on a side stream while the main stream goes on with
+    // keygen (which reads this shard's own nodes from own_seq / own_cov), the tuple exchange and the hash
+    // partition; the join waits for the packed reads and coverage, the string stage for id keys and lines.
+    const bool overlap = c->nccl_comm && c->side_stream;
+    if (overlap) {
+      CB_CUDA(cudaEventRecord(c->ev_fork, s));
+      CB_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+      c->ex_stream = c->side_stream;
+    }
     gather_all(c, l_seq.p, (size_t)c->NW * 8, n_local_nodes, counts, c->node_seq.p);
+    gather_all(c, l_cov.p, 4, n_local_nodes, counts, c->node_cov.p);
+    if (overlap) CB_CUDA(cudaEventRecord(c->ev_seq, c->side_stream));
+    gather_all(c, l_line.p, 4, n_local_nodes, counts, c->node_line.p);
     gather_all(c, l_id.p, sizeof(IdKey), n_local_nodes, counts, c->node_idkey.p);
+    if (overlap) {
+      CB_CUDA(cudaEventRecord(c->ev_rest, c->side_stream));
+      c->ex_stream = nullptr;
+      c->gather_pending_seq = c->gather_pending_rest = true;
+      // the send buffers must outlive the transfers: they stay with the context (keygen reads them too)
+      c->own_seq = std::move(l_seq);
+      c->own_cov = std::move(l_cov);
+      c->own_line_tmp = std::move(l_line);
+      c->own_id_tmp = std::move(l_id);
+    }
     timer_stop(c, "node_gather");
   }
   timer_stop(c, "dedupe");

@@ -741,6 +741,7 @@ void stage_string_graph(cb_ctx* c) {
   const size_t nl = n_lists ? n_lists : 1;
   const size_t slots = c->slots ? c->slots : 1;
   const bool dist = distributed(c);
+  wait_node_table(c, true);  // id keys (CutChimericLinks tie-breaks) and SFA lines of every rank's nodes
   CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGE_REMOVAL, 0, (DC_COUNT - DC_EDGE_REMOVAL) * sizeof(u64), s));
   c->list_flag.alloc((nl + 3) & ~(size_t)3, s);
   CB_CUDA(cudaMemsetAsync(c->list_flag.p, 1, (nl + 3) & ~(size_t)3, s));
