@@ -732,15 +732,11 @@ constexpr int PS_THREADS = 512;
 constexpr int PS_ITEMS = 8;
 constexpr int PS_TILE = PS_THREADS * PS_ITEMS;  // 4096 tuples per tile
 
-BucketPlan make_bucket_plan(size_t n_tuples) {
+BucketPlan make_bucket_plan_bits(int nbits) {
   // digit widths the scatter kernel is instantiated for; two passes, the smallest total that reaches the
   // wanted number of buckets (more buckets than wanted only makes them smaller)
-  static const int widths[4] = {3, 6, 8, 9};
+  static const int widths[5] = {3, 6, 8, 9, 10};
   BucketPlan pl;
-  int nbits = 2;
-  static const size_t avg = getenv("CB_BUCKET_AVG") ? (size_t)atoi(getenv("CB_BUCKET_AVG")) : 640;  // experiment knob
-  while (nbits < 18 && (avg << nbits) < n_tuples) nbits++;
-  pl.fits = ((size_t)640 << nbits) >= n_tuples;  // beyond 2^18 buckets of <= 640: a third pass would be needed
   int best = 99;
   for (int a : widths)
     for (int b : widths)
@@ -749,6 +745,15 @@ BucketPlan make_bucket_plan(size_t n_tuples) {
   pl.shift1 = 64 - pl.b1;
   pl.shift2 = 64 - pl.b1 - pl.b2;
   pl.lshift = 64 - pl.b1 - pl.b2 - kLocalBits;
+  return pl;
+}
+
+BucketPlan make_bucket_plan(size_t n_tuples) {
+  static const size_t avg = getenv("CB_BUCKET_AVG") ? (size_t)atoi(getenv("CB_BUCKET_AVG")) : 640;  // experiment knob
+  int nbits = 2;
+  while (nbits < 20 && (avg << nbits) < n_tuples) nbits++;
+  BucketPlan pl = make_bucket_plan_bits(nbits);
+  pl.fits = nbits < 20 || ((size_t)640 << nbits) >= n_tuples;  // beyond 2^20 buckets of <= 640: a third pass would be needed
   return pl;
 }
 
@@ -831,7 +836,8 @@ __global__ void __launch_bounds__(PS_THREADS, 2) ph_scatter_kernel(const u64* __
                                                                    u32* __restrict__ cursor) {
   constexpr int RADIX = 1 << RB;
   constexpr int WARPS = PS_THREADS / 32;
-  static_assert(RADIX <= PS_THREADS, "one thread per digit bin");
+  constexpr int BPT = RADIX > PS_THREADS ? RADIX / PS_THREADS : 1;  // adjacent digit bins per thread (RB = 10: two)
+  static_assert(RADIX <= 2 * PS_THREADS, "at most two digit bins per thread");
   extern __shared__ __align__(16) unsigned char ps_smem[];
   u64* stage = reinterpret_cast<u64*>(ps_smem);                 // [PS_TILE]
   u32* vstage = reinterpret_cast<u32*>(ps_smem + PS_TILE * 8);  // [PS_TILE]
@@ -877,20 +883,33 @@ __global__ void __launch_bounds__(PS_THREADS, 2) ph_scatter_kernel(const u64* __
     pos[i] = valid ? ((prev + __popc(peers & lt_mask)) | (d << 12)) : 0xffffffffu;  // the hash is taken once per tuple
   }
   __syncthreads();
-  u32 run = 0;
-  if (tid < RADIX) {
+  u32 run = 0, cnt_b[BPT];
 #pragma unroll
-    for (int w = 0; w < WARPS; w++) {
-      const u32 c = warp_hist[w][tid];
-      warp_hist[w][tid] = (unsigned short)run;
-      run += c;
+  for (int q = 0; q < BPT; q++) {
+    const int b = tid * BPT + q;
+    cnt_b[q] = 0;
+    if (b < RADIX) {
+      u32 r = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; w++) {
+        const u32 c = warp_hist[w][b];
+        warp_hist[w][b] = (unsigned short)r;
+        r += c;
+      }
+      cnt_b[q] = r;
+      run += r;
     }
   }
   u32 total;
-  const u32 ex = block_excl_scan(run, scan_tmp, total);  // threads >= RADIX contribute 0
-  if (tid < RADIX) {
-    excl[tid] = ex;
-    if (run) gbase[tid] = atomicAdd(&cursor[((size_t)seg << RB) + tid], run) - ex;
+  u32 ex = block_excl_scan(run, scan_tmp, total);  // threads beyond the bins contribute 0
+#pragma unroll
+  for (int q = 0; q < BPT; q++) {
+    const int b = tid * BPT + q;
+    if (b < RADIX) {
+      excl[b] = ex;
+      if (cnt_b[q]) gbase[b] = atomicAdd(&cursor[((size_t)seg << RB) + b], cnt_b[q]) - ex;
+      ex += cnt_b[q];
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -927,6 +946,7 @@ static void launch_scatter(u32 tiles, cudaStream_t s, const u64* kin, const u32*
     case 6: launch_scatter_rb<6>(tiles, s, kin, vin, kout, vout, ts, kmask, shift, cursor); break;
     case 8: launch_scatter_rb<8>(tiles, s, kin, vin, kout, vout, ts, kmask, shift, cursor); break;
     case 9: launch_scatter_rb<9>(tiles, s, kin, vin, kout, vout, ts, kmask, shift, cursor); break;
+    case 10: launch_scatter_rb<10>(tiles, s, kin, vin, kout, vout, ts, kmask, shift, cursor); break;
     default: throw Error(CB_E_INVALID, "bucket_partition: unsupported digit width");
   }
   CB_CUDA(cudaGetLastError());

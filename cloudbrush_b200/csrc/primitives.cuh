@@ -99,6 +99,7 @@ struct BucketPlan {
 constexpr int kLocalBits = 10;
 // buckets of 320..640 tuples on average (the bucket kernel holds 1024)
 BucketPlan make_bucket_plan(size_t n_tuples);
+BucketPlan make_bucket_plan_bits(int nbits);  // at least 2^nbits buckets (nbits <= 20)
 
 // Tuples (ka, va)[n_slots] -- slots whose key is ~0 are skipped -- end up bucketed in (ka, va) again
 // ((kb, vb) is the intermediate buffer); bstart[NB + 1] receives the bucket offsets and *d_total the

@@ -557,12 +557,11 @@ __global__ void __launch_bounds__(256, MINB) join_verify_kernel(JoinParams P) {
 // Nothing here depends on the order of the tuples inside a group: "another tuple of the same read in
 // this group" (maximal-overlap filter, `certain`) is found by scanning the group in shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int BJ_CAP = 1024;                   // tuples per bucket the kernel holds (the plan aims at <= 320 on average)
 constexpr int BJ_LBINS = 1 << kLocalBits;      // 1024 local bins
 // per position: key 8, payload 4, group 4, slot offset 4, node-entry list 2 bytes
-constexpr size_t BJ_SMEM = (size_t)BJ_CAP * (8 + 4 + 4 + 4 + 2) + (BJ_LBINS + 1) * 4 + BJ_LBINS * 4 + (BJ_LBINS / 32) * 4 + 64;
-static_assert(BJ_CAP / 2 <= BJ_LBINS, "node-entry counters are packed two per word of scnt");
-static_assert(BJ_CAP <= (1 << 11), "list index of a node entry is packed into 11 bits");
+constexpr size_t bj_smem_bytes(int cap) {
+  return (size_t)cap * (8 + 4 + 4 + 4 + 2) + (BJ_LBINS + 1) * 4 + BJ_LBINS * 4 + (BJ_LBINS / 32) * 4 + 64;
+}
 
 // M32: node | window | dir of every tuple fit the 32-bit payload (no payload bits above the k-mer in
 // the key), which is the case up to 2^26 nodes at W <= 32 and 2^24 nodes at W <= 128.
@@ -572,8 +571,13 @@ static_assert(BJ_CAP <= (1 << 11), "list index of a node entry is packed into 11
 // packed reads of the bucket's tuples into shared memory with cp.async while the grouping runs -- the join
 // then reads nothing from global memory -- was 5 % slower: the gathers hit the L2, which holds node_seq
 // in its persisting window, and the 16 KB of rows cost occupancy.)
-template <int NW, int TPB, int MINB, bool M32>
+// CAP: tuples per bucket the kernel holds.  1024 for reads of up to 64 bases (22.5 KB + 8 KB of shared memory:
+// seven CTAs per SM), 2048 for longer reads, whose kernel is limited to four CTAs per SM by its registers.
+template <int NW, int TPB, int MINB, bool M32, int CAP>
 __global__ void __launch_bounds__(TPB, MINB) bucket_join_kernel(JoinParams P) {
+  constexpr int BJ_CAP = CAP;
+  static_assert(BJ_CAP / 2 <= BJ_LBINS, "node-entry counters are packed two per word of scnt");
+  static_assert(BJ_CAP <= (1 << 11), "list index of a node entry is packed into 11 bits");
   constexpr int BJ_THREADS = TPB, BJ_WARPS = TPB / 32, BJ_CHUNKS = BJ_CAP / 32 / BJ_WARPS;
   extern __shared__ __align__(16) unsigned char bj_smem[];
   u64* skey = reinterpret_cast<u64*>(bj_smem);           // [CAP] tuples grouped by k-mer
@@ -612,16 +616,22 @@ __global__ void __launch_bounds__(TPB, MINB) bucket_join_kernel(JoinParams P) {
   if (tid == 0) { s_any_mixed = 0; s_slots = 0; s_lists = 0; }
   __syncthreads();
   // one shared-memory atomic per tuple: its return value is the tuple's rank inside its bin
-  u64 kreg[BJ_CHUNKS];
-  u32 vreg[BJ_CHUNKS], dr[BJ_CHUNKS];
+  // up to 8 chunks per warp the tuples stay in registers between the two passes; beyond that they are read
+  // again (from L1 / L2) when they are placed
+  constexpr bool KEEP = BJ_CHUNKS <= 8;
+  u64 kreg[KEEP ? BJ_CHUNKS : 1];
+  u32 vreg[KEEP ? BJ_CHUNKS : 1], dr[BJ_CHUNKS];
 #pragma unroll
   for (int i = 0; i < BJ_CHUNKS; i++) {
     const u32 e = ((u32)(warp + i * BJ_WARPS) << 5) + lane;
     dr[i] = 0xffffffffu;
     if (e < n) {
-      kreg[i] = P.keys[lo + e];
-      vreg[i] = P.vals[lo + e];  // requested together with the key: one DRAM round trip per CTA, not two
-      const u32 d = ldigit(kreg[i]);
+      const u64 k = P.keys[lo + e];
+      if (KEEP) {
+        kreg[i] = k;
+        vreg[i] = P.vals[lo + e];  // requested together with the key: one DRAM round trip per CTA, not two
+      }
+      const u32 d = ldigit(k);
       dr[i] = (d << 16) | atomicAdd(&sstart[d], 1u);
     }
   }
@@ -641,8 +651,14 @@ __global__ void __launch_bounds__(TPB, MINB) bucket_join_kernel(JoinParams P) {
   for (int i = 0; i < BJ_CHUNKS; i++) {
     if (dr[i] != 0xffffffffu) {
       const u32 pos = sstart[dr[i] >> 16] + (dr[i] & 0xffffu);
-      skey[pos] = kreg[i];
-      sval[pos] = vreg[i];
+      if (KEEP) {
+        skey[pos] = kreg[i];
+        sval[pos] = vreg[i];
+      } else {
+        const u32 e = ((u32)(warp + i * BJ_WARPS) << 5) + lane;
+        skey[pos] = P.keys[lo + e];
+        sval[pos] = P.vals[lo + e];
+      }
     }
   }
   __syncthreads();
@@ -1038,14 +1054,15 @@ __global__ void __launch_bounds__(256) orphan_lists_kernel(const u32* __restrict
 // 128 threads per CTA: the kernel is bound by the latency chain of a CTA's phases (loads -> grouping ->
 // slot reservation -> join), so what counts is the number of CTAs in flight: 7 x 128 threads per SM ran
 // the join in 4.6 ms where 4 x 256 threads took 6.1 ms (config 2)
-template <int NW, int MINB>
+template <int NW, int MINB, int CAP>
 static void launch_bucket_join(const JoinParams& P, u32 n_buckets, bool m32, cudaStream_t s) {
+  constexpr size_t smem = bj_smem_bytes(CAP);
   if (m32) {
-    CB_CUDA(cudaFuncSetAttribute(bucket_join_kernel<NW, 128, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_SMEM));
-    bucket_join_kernel<NW, 128, MINB, true><<<n_buckets, 128, BJ_SMEM, s>>>(P);
+    CB_CUDA(cudaFuncSetAttribute(bucket_join_kernel<NW, 128, MINB, true, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bucket_join_kernel<NW, 128, MINB, true, CAP><<<n_buckets, 128, smem, s>>>(P);
   } else {
-    CB_CUDA(cudaFuncSetAttribute(bucket_join_kernel<NW, 128, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_SMEM));
-    bucket_join_kernel<NW, 128, MINB, false><<<n_buckets, 128, BJ_SMEM, s>>>(P);
+    CB_CUDA(cudaFuncSetAttribute(bucket_join_kernel<NW, 128, MINB, false, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bucket_join_kernel<NW, 128, MINB, false, CAP><<<n_buckets, 128, smem, s>>>(P);
   }
 }
 
@@ -1275,6 +1292,7 @@ void stage_build_overlap(cb_ctx* c) {
   DevBuf<u32> extra_total;                       // bucket path: slots added to the lists over the attempts
   u64 xcap = (u64)T / 4 + 4096;
   bool have_extra = false;
+  int refine = 0;  // bucket path: times the partition was refined after a bucket overflow
   auto flat_prepare = [&] {  // group walk: seg_head, ne_list, list sizes
     slotcnt.alloc((size_t)n_lists + 1, s);
     off1.alloc((size_t)n_lists + 1, s);
@@ -1334,8 +1352,13 @@ void stage_build_overlap(cb_ctx* c) {
       P.list_order = list_order.p;
       c->lc.begin("bucket_join");
       const bool m32 = nbits + pb + 1 <= 32;  // node | window | dir fit the 32-bit payload
-      if (c->NW == 2) launch_bucket_join<2, 7>(P, plan.NB, m32, s);
-      else CB_DISPATCH_NW(c->NW, (launch_bucket_join<NW_, 4>(P, plan.NB, m32, s)));
+      switch (c->NW) {
+        case 2: launch_bucket_join<2, 7, 1024>(P, plan.NB, m32, s); break;
+        case 4: launch_bucket_join<4, 4, 2048>(P, plan.NB, m32, s); break;
+        case 6: launch_bucket_join<6, 4, 2048>(P, plan.NB, m32, s); break;
+        case 8: launch_bucket_join<8, 4, 2048>(P, plan.NB, m32, s); break;
+        default: throw Error(CB_E_UNSUPPORTED, "read length above 256 bases");
+      }
       c->lc.end("bucket_join");
       c->lc.n++;
       if (have_extra && n_lists) {
@@ -1352,9 +1375,21 @@ void stage_build_overlap(cb_ctx* c) {
       n_list_order = (size_t)cur[1];
       u64 flags[2] = {c->hcount[DC_BUCKET_OVER] ? 1ull : 0ull, used > slots1 ? 1ull : 0ull};
       ex_allreduce(c, flags, 2, 1);  // every rank takes the same branch: collectives follow
+      if (flags[0] && plan.b1 + plan.b2 < 20 && refine < 2) {
+        // a bucket does not fit the kernel: cut the tuples (already compacted to the front of keys[0]) into
+        // four times as many buckets first
+        refine++;
+        plan = make_bucket_plan_bits(plan.b1 + plan.b2 + 2 > 20 ? 20 : plan.b1 + plan.b2 + 2);
+        bstart.alloc((size_t)plan.NB + 1, s);
+        guarded(c, [&] {
+          bucket_partition(keys[0].p, vals[0].p, keys[1].p, vals[1].p, T, kmask, plan, nullptr, bstart.p, d_total.p, s, c->lc);
+        });
+        attempt = -1;
+        continue;
+      }
       if (flags[0]) {
-        // a bucket does not fit the kernel (one k-mer with thousands of tuples, or a degenerate hash
-        // distribution): the flat pipeline takes over for this input
+        // still does not fit (one k-mer with thousands of tuples, or thousands of node entries in one group):
+        // the flat pipeline takes over for this input
         bucket = false;
         flat_sort(T);  // the partition has compacted the T valid tuples to the front of keys[0] / vals[0]
         flat_prepare();
@@ -1464,6 +1499,8 @@ void stage_build_overlap(cb_ctx* c) {
   c->counters["upkmer_truncated_lists"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
   c->counters["order_dependent"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
   c->counters["bucket_path"] = bucket ? 1 : 0;
+  c->counters["bucket_refine"] = refine;
+  c->counters["bucket_bits"] = plan.b1 + plan.b2;
   {
     u64 sg = slots1;
     ex_allreduce(c, &sg, 1, 0);

@@ -204,3 +204,27 @@ def test_full_size_properties():
     assert g.counter("edges_overlap") == len(sets[0]) and g.counter("edges_re") == len(sets[2])
     assert g.counter("trans_edge") + g.counter("edges_re") >= g.counter("edges_chl2") - g.counter("edges_re")
     g.close()
+
+
+def test_bucket_overflow_refines_the_partition_first(tmp_path):
+    """Buckets that do not fit the bucket kernel are cut four times finer (twice at most) before the flat
+    pipeline takes over: forced here with a coarse plan (CB_BUCKET_AVG, read once per process -> subprocess)."""
+    import subprocess
+    import sys
+    script = tmp_path / "run.py"
+    script.write_text(
+        "import sys\n"
+        f"sys.path.insert(0, {str(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))!r})\n"
+        f"sys.path.insert(0, {str(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "from cloudbrush_b200 import synth\n"
+        "from parity_util import compare, run_gpu, run_oracle\n"
+        "buf, m = synth.make_config('cfg2_50k', scale_genome=40_000)\n"
+        "g = run_gpu(bytes(buf), m['k'], m['readlen'])\n"
+        "r = run_oracle(bytes(buf), m['k'], m['readlen'])\n"
+        "d = compare(g, r, 'refine')\n"
+        "assert d == [], d\n"
+        "print('bucket_path', g.counter('bucket_path'), 'refine', g.counter('bucket_refine'), 'bits', g.counter('bucket_bits'), 'tuples', g.counter('tuples'))\n")
+    env = dict(os.environ, CB_BUCKET_AVG="4000")
+    p = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "bucket_path 1 refine" in p.stdout and "refine 0" not in p.stdout, p.stdout
