@@ -257,6 +257,89 @@ def checkpoint_digest(g):
                 counters=[g.counter(x) for x in PARITY_COUNTERS])
 
 
+
+def path_alg_bytes(counters, L, k, world):
+    """SURVEY.md 8(d) B_alg per GPU from the run's measured counts."""
+    N_in, N, T = counters["reads_good"] / world, counters["nodes"] / world, counters["tuples"] / world
+    C, E_A = counters["candidates_verified"] / world, counters["edges_overlap"] / world
+    E_c, E_B = counters["edges_chl2"] / world, counters["edges_re"] / world
+    A_, R_, P_, Pn_ = L + 10, 4 * ((2 * L + 31) // 32), (2 * k + 7) // 8, 4
+    return (N_in * (A_ + R_) + N_in * (2 * R_ + 24 + 24 * P_) + N * R_ + 12 * T + T * (8 + 24 * P_) + 12 * T + 12 * C
+            + C * (12 + 2 * R_) + 12 * E_A + 24 * E_A + E_A * (8 + 24 * Pn_) + E_A * (12 + R_) + E_c * (12 + R_)
+            + 12 * E_B)
+
+
+def time_other_config(name, steps, warmup, rank, world, local_rank, transport, peak):
+    """One more BASELINE config next to the headline: device-resident step time, e2e with host
+    buffers, reads/s, edges/s and the whole-path roofline fraction.  Same rules as the main measurement."""
+    import torch
+    import torch.distributed as dist
+    from cloudbrush_b200 import BrushConfig, BrushGpu
+    from cloudbrush_b200 import _lib as L_
+    sfa_np, meta = make_workload(name, rank=rank, world=world)
+    k, L = meta["k"], meta["readlen"]
+    host = torch.from_numpy(sfa_np).pin_memory()
+    dev = host.cuda()
+    g = BrushGpu(BrushConfig(k=k, readlen=L, device=local_rank, rank=rank, world=world))
+    if world > 1:
+        if transport == "nccl":
+            g.init_nccl()
+        else:
+            from cloudbrush_b200.dist import TorchExchange
+            g.set_exchange(TorchExchange(device=torch.device("cuda", local_rank)))
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        g.borrow_sfa_device(dev.data_ptr(), dev.numel())
+        g.run()
+        return g.time_ms("preprocess") + g.time_ms("overlap") + g.time_ms("string")
+
+    for _ in range(warmup):
+        step()
+    sync()
+    ms = float(np.mean([step() for _ in range(steps)]))
+    sync()
+    counters = {c: g.counter(c) for c in ["reads_good", "nodes", "tuples", "candidates_verified", "edges_overlap",
+                                          "edges_chl2", "edges_re", "bucket_path"]}
+    stage_ms = {t: g.time_ms(t) for t in ["parse", "dedupe", "keygen", "sort_tuples", "join_verify", "cut", "tr"]}
+    e2e = []
+    for i in range(3):
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        g.load_sfa_buffer(host)
+        g.run()
+        g.edges(L_.CK_RE)
+        g.nodes()
+        if i:
+            e2e.append(time.perf_counter() - t1)
+    e2e_ms = float(np.mean(e2e)) * 1e3
+    n_reads = float(meta["n_reads"])
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        tot = torch.tensor([n_reads], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        n_reads = float(tot[0])
+    g.close()
+    del dev, host
+    torch.cuda.empty_cache()
+    b_alg = path_alg_bytes(counters, L, k, world)
+    return {"workload": f"{name}: {meta['genome']} bp random genome, {L} bp reads at {meta['coverage']}x"
+                        f"{' both strands' if meta['both_strands'] else ''}, k={k}, {meta['n_reads']} reads per GPU",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "reads_per_sec": n_reads / (ms * 1e-3),
+            "edges_per_sec": counters["edges_overlap"] / (ms * 1e-3), "e2e_ms_per_step": e2e_ms,
+            "e2e_reads_per_sec": n_reads / (e2e_ms * 1e-3),
+            "roofline_path": {"alg_bytes_per_gpu": b_alg, "achieved": b_alg / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                              "frac_of_measured_peak": b_alg / (ms * 1e-3) / 1e9 / peak},
+            "counters": counters, "stage_ms": stage_ms}
+
+
 def sharded_parity(name, world, rank, local_rank, transport, genome):
     """N > 1, before the timed loop: a reduced genome of the same shape runs sharded over the SAME transport the
     timed run uses (native NCCL by default) and, on rank 0, on one context; the union of the shards' checkpoints,
@@ -473,6 +556,7 @@ def bench_ours(args):
     out_n = pin_n.numpy().view(NODE_DTYPE)
     e2e_t, e2e_parts = [], []
     d2h = 0
+    # (1) single shot: load (H2D) -> three stage groups -> export (D2H), nothing overlapped
     for i in range(max(1, min(args.steps, 3)) + 1):
         torch.cuda.synchronize()
         t1 = time.perf_counter()
@@ -485,10 +569,25 @@ def bench_ours(args):
         t4 = time.perf_counter()
         d2h = eb.nbytes + nd.nbytes
         if i > 0:  # first one warms the export path
+            e2e_parts.append((t2 - t1, t3 - t2, t4 - t3, t4 - t1))
+    # (2) steady state of a caller that processes batch after batch (cb_prefetch_sfa_buffer): the H2D copy of the
+    # NEXT batch runs on the context's copy stream behind the overlap / string-graph stage groups and the export
+    # of the current one.  Every timed iteration still contains one full H2D and one D2H.
+    g.prefetch_sfa_buffer(host)
+    for i in range(max(2, min(args.steps, 5)) + 1):
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        g.preprocess()
+        g.prefetch_sfa_buffer(host)
+        g.build_overlap()
+        g.string_graph()
+        eb = g.edges(L_.CK_RE, out=out_e)
+        nd = g.nodes(out=out_n)
+        t4 = time.perf_counter()
+        if i > 0:
             e2e_t.append(t4 - t1)
-            e2e_parts.append((t2 - t1, t3 - t2, t4 - t3))
     e2e_s = float(np.mean(e2e_t))
-    e2e_split = [float(np.mean([p[k] for p in e2e_parts])) * 1e3 for k in range(3)]
+    e2e_split = [float(np.mean([p[k] for p in e2e_parts])) * 1e3 for k in range(4)]
 
     if world > 1:
         t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
@@ -500,13 +599,26 @@ def bench_ours(args):
     else:
         total_reads, total_edges = float(n_reads), float(counters["edges_overlap"])
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    # the other BASELINE configs this GPU count is quoted on: config 3 on one GPU, config 4 on eight
+    other = {}
+    if not args.no_other_configs and name == "cfg2" and not args.genome:
+        for oname in ({1: ["cfg3"], 8: ["cfg4"]}.get(world, [])):
+            if g is not None:  # free the headline workload's device memory first
+                g.close()
+                g = None
+                dev = None
+                torch.cuda.empty_cache()
+            try:
+                other[oname] = time_other_config(oname, 3, 2, rank, world, local_rank, args.transport, peak)
+            except Exception as e:  # the headline line must not be lost to a side measurement
+                other[oname] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         # the dominant kernel (largest ms per step) first, the other main kernels after it
         roofs = kernel_rooflines(stats, args.steps, ms, counters, L, k, world, peak, peak_src)
@@ -516,13 +628,7 @@ def bench_ours(args):
         # ---- whole-path figure of BASELINE.md / SURVEY.md 8(d): B_alg from the run's measured counts ----
         # (the byte budget of a sort-based pipeline; this build replaces its edge sort by slot writes and
         # still reports against it.  C = verified candidates only: rejected ones are never materialised.)
-        N_in, N, T = counters["reads_good"] / world, counters["nodes"] / world, counters["tuples"] / world
-        C, E_A = counters["candidates_verified"] / world, counters["edges_overlap"] / world
-        E_c, E_B = counters["edges_chl2"] / world, counters["edges_re"] / world
-        A_, R_, P_, Pn_ = L + 10, 4 * ((2 * L + 31) // 32), (2 * k + 7) // 8, 4
-        b_alg = (N_in * (A_ + R_) + N_in * (2 * R_ + 24 + 24 * P_) + N * R_ + 12 * T + T * (8 + 24 * P_) + 12 * T + 12 * C
-                 + C * (12 + 2 * R_) + 12 * E_A + 24 * E_A + E_A * (8 + 24 * Pn_) + E_A * (12 + R_) + E_c * (12 + R_)
-                 + 12 * E_B)
+        b_alg = path_alg_bytes(counters, L, k, world)
         path = {"alg_bytes_per_gpu": b_alg, "achieved": b_alg / (ms * 1e-3) / 1e9, "unit": "GB/s",
                 "frac_of_measured_peak": b_alg / (ms * 1e-3) / 1e9 / peak,
                 "frac_of_nominal_8TBs": b_alg / (ms * 1e-3) / 1e9 / 8000.0,
@@ -558,7 +664,11 @@ def bench_ours(args):
             "wall_ms_per_step": wall * 1e3,
             "e2e": {"value": total_reads / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(len(sfa_np)),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
-                    "ms_h2d_load": e2e_split[0], "ms_stages": e2e_split[1], "ms_export_d2h": e2e_split[2]},
+                    "how": "steady state through the C ABI with host buffers: cb_preprocess, cb_prefetch_sfa_buffer "
+                           "(H2D of the next batch behind the other two stage groups), cb_build_overlap, cb_string_graph, "
+                           "cb_export_edges(B) + cb_export_nodes into pinned host memory; one H2D + one D2H per step",
+                    "single_shot": {"ms_per_step": e2e_split[3], "ms_h2d_load": e2e_split[0], "ms_stages": e2e_split[1],
+                                    "ms_export_d2h": e2e_split[2], "reads_per_sec": n_reads / (e2e_split[3] * 1e-3)}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
@@ -566,12 +676,14 @@ def bench_ours(args):
             "roofline_path": path,
             "cpu_baseline": cpu,
             "parity": parity,
+            "other_configs": other,
             "counters": counters,
             "stage_ms": stage_ms,
             "kernels": kern,
         }
         emit(line)
-    g.close()
+    if g is not None:
+        g.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -606,6 +718,7 @@ def main():
     ap.add_argument("--ref-sample-reads", type=int, default=0, help="reads per host thread and step (0: sized to the run)")
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip config 3 (N=1) / config 4 (N=8)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity check that precedes the timing")
     ap.add_argument("--parity-genome", type=int, default=200_000, help="genome length of the N>1 parity input")
     ap.add_argument("--transport", default="nccl", choices=["nccl", "torch"],

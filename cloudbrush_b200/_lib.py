@@ -38,7 +38,7 @@ SYMBOLS = ["cb_default_config", "cb_create", "cb_destroy", "cb_last_error", "cb_
            "cb_load_sfa_buffer", "cb_load_sfa_device", "cb_preprocess", "cb_build_overlap", "cb_string_graph",
            "cb_get_counter", "cb_export_edges", "cb_export_nodes", "cb_write_nodes", "cb_get_time_ms",
            "cb_get_launch_count", "cb_borrow_sfa_device", "cb_set_profile", "cb_get_kernel_stat", "cb_set_exchange",
-           "cb_nccl_get_unique_id", "cb_init_nccl", "cb_debug_sort"]
+           "cb_nccl_get_unique_id", "cb_init_nccl", "cb_debug_sort", "cb_prefetch_sfa_buffer"]
 
 _lib = None
 
@@ -65,6 +65,7 @@ def load():
     L.cb_load_sfa.argtypes = [P, C.c_char_p]
     L.cb_load_sfa_buffer.argtypes = [P, C.c_void_p, C.c_size_t]
     L.cb_load_sfa_device.argtypes = [P, C.c_void_p, C.c_size_t]
+    L.cb_prefetch_sfa_buffer.argtypes = [P, C.c_void_p, C.c_size_t]
     for f in (L.cb_preprocess, L.cb_build_overlap, L.cb_string_graph):
         f.argtypes = [P]
     L.cb_get_counter.argtypes = [P, C.c_char_p, C.POINTER(C.c_int64)]

@@ -90,6 +90,16 @@ class BrushGpu:
             ptr, n = C.cast(C.c_char_p(b), C.c_void_p).value, len(b)
         self._check(self._L.cb_load_sfa_buffer(self._h, ptr, n))
 
+    def prefetch_sfa_buffer(self, buf):
+        """Starts the host-to-device copy of the NEXT input (pinned torch uint8 CPU tensor or numpy array over
+        page-locked memory) and returns at once; it becomes the current input at the next preprocess()."""
+        if hasattr(buf, "data_ptr"):
+            ptr, n = buf.data_ptr(), buf.numel()
+        else:
+            ptr, n = buf.ctypes.data, buf.nbytes
+        self._prefetched = buf  # keep the host buffer alive until it is consumed
+        self._check(self._L.cb_prefetch_sfa_buffer(self._h, ptr, n))
+
     def load_sfa_device(self, dev_ptr, n):
         self._check(self._L.cb_load_sfa_device(self._h, dev_ptr, n))
 

@@ -247,6 +247,12 @@ void cb_destroy(cb_ctx* c) {
     if (kv.second.b) cudaEventDestroy(kv.second.b);
   }
   cb::nccl_shutdown(c);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->ev_copy);
+    cudaEventDestroy(c->ev_main);
+  }
   cudaStream_t s = c->stream;
   delete c;  // DevBufs return to the arena, the arena returns everything to the driver
   cudaStreamDestroy(s);
@@ -333,6 +339,27 @@ int cb_load_sfa_buffer(cb_ctx* c, const char* buf, size_t n) {
   CB_API_END(c)
 }
 
+int cb_prefetch_sfa_buffer(cb_ctx* c, const char* buf, size_t n) {
+  CB_API_BEGIN(c)
+  if (!buf && n) throw Error(CB_E_INVALID, "null buffer");
+  if (!c->copy_stream) {
+    CB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CB_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    CB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+  }
+  if (c->next_pending) CB_CUDA(cudaStreamSynchronize(c->copy_stream));  // a prefetch that was never consumed
+  c->text_next.alloc(n + 32, c->stream);
+  c->text_next_n = n;
+  // the block may have been used by work still queued on the context's stream: the copy starts after it
+  CB_CUDA(cudaEventRecord(c->ev_main, c->stream));
+  CB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+  if (n) CB_CUDA(cudaMemcpyAsync(c->text_next.p, buf, n, cudaMemcpyHostToDevice, c->copy_stream));
+  CB_CUDA(cudaMemsetAsync(c->text_next.p + n, 0, 32, c->copy_stream));
+  CB_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
+  c->next_pending = true;
+  CB_API_END(c)
+}
+
 int cb_load_sfa(cb_ctx* c, const char* path) {
   CB_API_BEGIN(c)
   if (!path) throw Error(CB_E_INVALID, "null path");
@@ -364,6 +391,17 @@ int cb_load_sfa(cb_ctx* c, const char* path) {
 
 int cb_preprocess(cb_ctx* c) {
   CB_API_BEGIN(c)
+  if (c->next_pending) {  // cb_prefetch_sfa_buffer: the prefetched input becomes the current one
+    c->next_pending = false;
+    std::swap(c->text.p, c->text_next.p);
+    std::swap(c->text.n, c->text_next.n);
+    std::swap(c->text.a, c->text_next.a);
+    c->text_next.release();
+    c->text_n = c->text_next_n;
+    c->text_ptr = c->text.p;
+    reset_after_load(c);
+    CB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+  }
   if (!c->loaded) throw Error(CB_E_INVALID, "cb_preprocess: no input loaded");
   c->preprocessed = c->overlapped = c->reduced = false;
   timer_start(c, "preprocess");

@@ -114,6 +114,11 @@ struct cb_ctx {
   uint64_t gcount[cb::DC_COUNT] = {0};  // counters reduced over the ranks
 
   // input text
+  cb::DevBuf<char> text_next;     // cb_prefetch_sfa_buffer: the NEXT input, copied on copy_stream while this one is processed
+  size_t text_next_n = 0;
+  bool next_pending = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr, ev_main = nullptr;
   cb::DevBuf<char> text;          // owned copy (cb_load_sfa / cb_load_sfa_buffer / cb_load_sfa_device)
   const char* text_ptr = nullptr; // what the kernels read: text.p or a borrowed device buffer
   size_t text_n = 0;

@@ -1082,16 +1082,19 @@ static bool use_bucket_path() {
   return v == 1;
 }
 
-// node_seq is gathered by every tuple of the join (16..64-byte rows at random): while the join runs it
-// is pinned in the L2 (persisting access window on the context's stream) so that the gathers do not go
-// to HBM in 64-byte granules (ncu r01: 7.9 GB read for 2.2 GB of rows).
+// node_seq is gathered by every tuple of the join (16..64-byte rows at random).  Experiment (CB_L2_WINDOW=1):
+// pin it in the L2 with a persisting access window while the join runs.  It cuts the kernel's DRAM reads
+// (ncu: 7.9 -> 1.5 GB on config 2) but not its time (4.57 ms either way: the kernel is bound by instruction
+// issue and latency chains, not by bandwidth), the set-aside must be given back afterwards (left in place it
+// starved the scatter passes: 0.62 -> 0.85 ms) and cudaDeviceSetLimit synchronises the whole device, which
+// serialises the join behind the copy stream's prefetch of the next input (e2e 24.0 vs 15.9 ms).  Off by default.
 static void set_l2_window(cb_ctx* c, const void* p, size_t bytes) {
   int dev = c->cfg.device, max_win = 0, max_persist = 0;
   cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
   cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
   if (max_win <= 0 || max_persist <= 0) return;
-  static const bool off = getenv("CB_NO_L2_WINDOW") != nullptr;
-  if (off) return;
+  static const bool on = getenv("CB_L2_WINDOW") != nullptr;
+  if (!on) return;
   // only when the whole table fits the set-aside part: a partial window (hitRatio < 1, the rest streaming)
   // made the gathers of a 138 MB table slower than plain LRU (2 GPUs)
   if (bytes > (size_t)max_persist || bytes > (size_t)max_win) return;
@@ -1107,6 +1110,8 @@ static void set_l2_window(cb_ctx* c, const void* p, size_t bytes) {
   if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) cudaGetLastError();
 }
 static void clear_l2_window(cb_ctx* c) {
+  static const bool on = getenv("CB_L2_WINDOW") != nullptr;
+  if (!on) return;
   cudaStreamAttrValue a;
   memset(&a, 0, sizeof(a));
   a.accessPolicyWindow.num_bytes = 0;

@@ -119,6 +119,14 @@ int cb_load_sfa_device(cb_ctx* ctx, const void* dev_buf, size_t n);
  * before the call; cb_load_sfa_device has finished its copy when it returns. */
 int cb_borrow_sfa_device(cb_ctx* ctx, const void* dev_buf, size_t n);
 
+/* Pipelined input for callers that process one batch after another: starts the host-to-device copy of
+ * the NEXT input on a copy stream of the context's own and returns at once; the copy runs while the stage
+ * groups of the current input execute.  The prefetched input becomes the current one at the next
+ * cb_preprocess (which waits for the copy).  `buf` must be page-locked host memory and must stay valid
+ * and unchanged until that cb_preprocess has returned.  Results of the current input stay available
+ * until then. */
+int cb_prefetch_sfa_buffer(cb_ctx* ctx, const char* buf, size_t n);
+
 /* The three stage groups, run to completion on the calling thread (see top of file). */
 int cb_preprocess(cb_ctx* ctx);
 int cb_build_overlap(cb_ctx* ctx);

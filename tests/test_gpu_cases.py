@@ -228,3 +228,29 @@ def test_bucket_overflow_refines_the_partition_first(tmp_path):
     p = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "bucket_path 1 refine" in p.stdout and "refine 0" not in p.stdout, p.stdout
+
+
+def test_prefetch_next_input_while_the_current_one_is_processed():
+    """cb_prefetch_sfa_buffer: the copy of the next input runs behind the stage groups of the current one; the
+    current input's results stay valid until the next cb_preprocess, which adopts the prefetched input."""
+    import torch
+    a, k, L = CASES["tiling_both_strands"]
+    b, _, _ = CASES["branch"]
+    ref_a, ref_b = run_gpu(a, k, L), run_gpu(b, k, L)
+    want_a, want_b = ref_a.edge_rows(1), ref_b.edge_rows(3)
+    from cloudbrush_b200 import BrushConfig, BrushGpu
+    g = BrushGpu(BrushConfig(k=k, readlen=L))
+    pin_a = torch.frombuffer(bytearray(a), dtype=torch.uint8).pin_memory()
+    pin_b = torch.frombuffer(bytearray(b), dtype=torch.uint8).pin_memory()
+    g.prefetch_sfa_buffer(pin_a)
+    g.preprocess()
+    g.prefetch_sfa_buffer(pin_b)        # in flight while A is processed
+    g.build_overlap()
+    g.string_graph()
+    assert np.array_equal(g.edge_rows(1), want_a)
+    g.preprocess()                      # B becomes the current input
+    g.build_overlap()
+    g.string_graph()
+    assert np.array_equal(g.edge_rows(3), want_b)
+    for x in (g, ref_a, ref_b):
+        x.close()
