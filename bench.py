@@ -144,13 +144,15 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # workload
 # --------------------------------------------------------------------------------------------
-def make_workload(name, genome=None, seed_shift=0, rank=0, world=1):
-    """SFA shard of `rank` (weak scaling: the genome grows with the GPU count, reads per GPU stay fixed)."""
+def make_workload(name, genome=None, seed_shift=0, rank=0, world=1, weak=True):
+    """SFA shard of `rank`.  weak: the genome grows with the GPU count, reads per GPU stay fixed (the headline
+    config); not weak: the named genome is split over the ranks (config 4 is DEFINED on eight GPUs)."""
     from cloudbrush_b200 import synth
     G, L, cov, both, k, seed = synth.CONFIGS[name]
     if genome:
         G = genome
-    G *= world
+    if weak:
+        G *= world
     n_total = int(round(G * cov / L))
     per = synth.N_PARTS // world
     codes = synth.synth_reads(G, L, cov, both, seed + seed_shift, parts=list(range(rank * per, (rank + 1) * per)))
@@ -276,7 +278,7 @@ def time_other_config(name, steps, warmup, rank, world, local_rank, transport, p
     import torch.distributed as dist
     from cloudbrush_b200 import BrushConfig, BrushGpu
     from cloudbrush_b200 import _lib as L_
-    sfa_np, meta = make_workload(name, rank=rank, world=world)
+    sfa_np, meta = make_workload(name, rank=rank, world=world, weak=False)  # the config's own genome, split over the ranks
     k, L = meta["k"], meta["readlen"]
     host = torch.from_numpy(sfa_np).pin_memory()
     dev = host.cuda()

@@ -98,13 +98,13 @@ __global__ void __launch_bounds__(256) export_recode_kernel(const u64* __restric
 // device-to-host copy run at PCIe speed).  01-overlap.re is a compact record list; 01-overlap and
 // 01-overlap.chl2 share the slot array (ctx.cuh): once CutChimericLinks has removed records in
 // place, 01-overlap is exported from a restored private copy.
-static void export_edges_to(cb_ctx* c, int ck, cb_edge* out) {
+// the records of a checkpoint this context holds, re-encoded as (node | type | nbr | ov - K) so that an
+// ascending sort gives the canonical export order; unsorted, on the device
+static void export_encoded(cb_ctx* c, int ck, DevBuf<u64>& a) {
   cudaStream_t s = c->stream;
   const size_t n = (size_t)edge_count(c, ck);
+  a.alloc(n ? n : 1, s);
   if (n == 0) return;
-  DevBuf<u64> a, b;
-  a.alloc(n, s);
-  b.alloc(n, s);
   if (ck == CB_CK_RE) {
     export_recode_kernel<<<div_up(n, 256), 256, 0, s>>>(c->ckB.keys.p, n, c->lay, c->K, a.p);
     c->lc.n++;
@@ -124,6 +124,15 @@ static void export_edges_to(cb_ctx* c, int ck, cb_edge* out) {
     export_gather_kernel<<<div_up(slots, 256), 256, 0, s>>>(keys, flag.p, idx.p, slots, c->lay, c->K, a.p);
     c->lc.n += 2;
   }
+}
+
+static void export_edges_to(cb_ctx* c, int ck, cb_edge* out) {
+  cudaStream_t s = c->stream;
+  const size_t n = (size_t)edge_count(c, ck);
+  if (n == 0) return;
+  DevBuf<u64> a, b;
+  export_encoded(c, ck, a);
+  b.alloc(n, s);
   int w = radix_sort(a.p, b.p, nullptr, nullptr, n, 0, c->lay.total_bits(), s, c->lc, "export");
   DevBuf<cb_edge> d;
   d.alloc(n, s);
@@ -131,6 +140,18 @@ static void export_edges_to(cb_ctx* c, int ck, cb_edge* out) {
   c->lc.n++;
   CB_CUDA(cudaMemcpyAsync(out, d.p, n * sizeof(cb_edge), cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
+}
+
+// owner rank of the node of an export-encoded record: the rank whose SFA shard the node was built from
+__global__ void __launch_bounds__(256) node_owner_kernel(const u64* __restrict__ recs, size_t n, int shift,
+                                                         const u64* __restrict__ node_bases, int world,
+                                                         u32* __restrict__ dest) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 node = recs[i] >> shift;
+  int d = 0;
+  while (d + 1 < world && node >= node_bases[d + 1]) d++;
+  dest[i] = (u32)d;
 }
 
 static void export_edges_host(cb_ctx* c, int ck, std::vector<cb_edge>& out) {
@@ -482,39 +503,72 @@ int cb_write_nodes(cb_ctx* c, int checkpoint, const char* out_dir) {
   CB_API_BEGIN(c)
   if (!out_dir) throw Error(CB_E_INVALID, "null path");
   if (!c->preprocessed) throw Error(CB_E_INVALID, "nodes not available");
-  if (distributed(c))
-    throw Error(CB_E_UNSUPPORTED,
-                "cb_write_nodes on a sharded context: the two adjacency lists of a node may be owned by different "
-                "ranks and the ids live in the line's shard; export edges/nodes per rank and merge by node");
   const bool with_edges = checkpoint != CB_CK_PREPROCESS;
   if (with_edges && edge_count(c, checkpoint) < 0) throw Error(CB_E_INVALID, "checkpoint not available");
   cudaStream_t s = c->stream;
-  if (c->host_text.empty() && c->text_n) {
-    c->host_text.resize(c->text_n);
-    CB_CUDA(cudaMemcpyAsync(c->host_text.data(), c->text_ptr, c->text_n, cudaMemcpyDeviceToHost, s));
+  wait_node_table(c, true);
+  const bool dist = distributed(c);
+  const int world = c->cfg.world, rank = c->cfg.rank;
+  // A sharded context writes the nodes built from ITS shard of the SFA lines as part-000<rank> (a Hadoop
+  // output directory is multi-part anyway, BrushAssembler.java:75-89): the adjacency records of a node's two
+  // lists may be owned by other ranks, so every rank routes the records it holds to the rank of the record's
+  // node.  Read ids come from the replicated 16-byte id keys (ids longer than that are refused at preprocess).
+  const u32 lo = dist ? c->node_lo : 0, hi = dist ? c->node_hi : c->n_nodes;
+  const u32 nn = hi - lo;
+  std::vector<u64> recs;  // export-encoded records of the nodes [lo, hi), sorted
+  if (with_edges) {
+    DevBuf<u64> a, b;
+    export_encoded(c, checkpoint, a);
+    size_t n = (size_t)edge_count(c, checkpoint);
+    const u64* src = a.p;
+    DevBuf<char> got;
+    if (dist) {
+      DevBuf<u64> bases;
+      DevBuf<u32> dest;
+      bases.alloc(world + 1, s);
+      dest.alloc(n ? n : 1, s);
+      CB_CUDA(cudaMemcpyAsync(bases.p, c->node_bases.data(), (world + 1) * sizeof(u64), cudaMemcpyHostToDevice, s));
+      if (n) {
+        node_owner_kernel<<<div_up(n, 256), 256, 0, s>>>(a.p, n, c->lay.nb + c->lay.ob + 2, bases.p, world, dest.p);
+        c->lc.n++;
+      }
+      size_t n_got = 0;
+      route_records(c, a.p, 8, dest.p, n, got, n_got);
+      n = n_got;
+      src = (const u64*)got.p;
+    }
+    if (n) {
+      DevBuf<u64> ka;
+      ka.alloc(n, s);
+      b.alloc(n, s);
+      CB_CUDA(cudaMemcpyAsync(ka.p, src, n * 8, cudaMemcpyDeviceToDevice, s));
+      int w = radix_sort(ka.p, b.p, nullptr, nullptr, n, 0, c->lay.total_bits(), s, c->lc, "export");
+      recs.resize(n);
+      CB_CUDA(cudaMemcpyAsync(recs.data(), w ? b.p : ka.p, n * 8, cudaMemcpyDeviceToHost, s));
+    }
   }
-  const u32 nn = c->n_nodes;
-  std::vector<u32> line_start((size_t)c->n_lines + 1), node_line(nn), node_cov(nn);
-  std::vector<u64> seq((size_t)nn * c->NW);
-  CB_CUDA(cudaMemcpyAsync(line_start.data(), c->line_start.p, line_start.size() * 4, cudaMemcpyDeviceToHost, s));
-  CB_CUDA(cudaMemcpyAsync(node_line.data(), c->node_line.p, (size_t)nn * 4, cudaMemcpyDeviceToHost, s));
-  CB_CUDA(cudaMemcpyAsync(node_cov.data(), c->node_cov.p, (size_t)nn * 4, cudaMemcpyDeviceToHost, s));
-  CB_CUDA(cudaMemcpyAsync(seq.data(), c->node_seq.p, seq.size() * 8, cudaMemcpyDeviceToHost, s));
+  std::vector<u32> node_cov(nn ? nn : 1);
+  std::vector<u64> seq((size_t)(nn ? nn : 1) * c->NW);
+  std::vector<IdKey> idkeys(c->n_nodes ? c->n_nodes : 1);
+  if (nn) {
+    CB_CUDA(cudaMemcpyAsync(node_cov.data(), c->node_cov.p + lo, (size_t)nn * 4, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaMemcpyAsync(seq.data(), c->node_seq.p + (size_t)lo * c->NW, (size_t)nn * c->NW * 8, cudaMemcpyDeviceToHost, s));
+  }
+  if (c->n_nodes)
+    CB_CUDA(cudaMemcpyAsync(idkeys.data(), c->node_idkey.p, (size_t)c->n_nodes * sizeof(IdKey), cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
-  std::vector<cb_edge> edges;
-  if (with_edges) export_edges_host(c, checkpoint, edges);
-  auto id_of = [&](u32 line) {
-    const char* p = c->host_text.data() + line_start[line];
-    const char* e = c->host_text.data() + line_start[line + 1];
-    const char* q = p;
-    while (q < e && *q != '\t') q++;
-    return std::string(p, q - p);
+  auto id_of = [&](u32 node) {
+    char buf[16];
+    const IdKey& k = idkeys[node];
+    for (int i = 0; i < 8; i++) { buf[i] = (char)(k.hi >> (56 - 8 * i)); buf[8 + i] = (char)(k.lo >> (56 - 8 * i)); }
+    size_t len = 0;
+    while (len < 16 && buf[len]) len++;
+    return std::string(buf, len);
   };
-  // FileSystem.delete(outputPath, true) then one part file (e.g. VerifyOverlap.java:379)
+  // FileSystem.delete(outputPath, true), then the part files (e.g. VerifyOverlap.java:379); rank 0 clears the
+  // directory, the others wait for it
   std::string dir(out_dir);
-  {
-    std::string part = dir + "/part-00000";
-    unlink(part.c_str());
+  if (rank == 0) {
     DIR* d = opendir(dir.c_str());
     if (d) {
       while (dirent* de = readdir(d)) {
@@ -526,38 +580,52 @@ int cb_write_nodes(cb_ctx* c, int checkpoint, const char* out_dir) {
     }
     mkdir(dir.c_str(), 0777);
   }
-  std::ofstream f(dir + "/part-00000", std::ios::binary);
-  if (!f) throw Error(CB_E_IO, "cannot write " + dir + "/part-00000");
-  static const char* TY[4] = {"ff", "fr", "rf", "rr"};
-  size_t ei = 0;
-  std::string rec;
-  for (u32 i = 0; i < nn; i++) {
-    u32 line = node_line[i];
-    rec.clear();
-    rec += id_of(line);
-    rec += "\tN\t*s\t";
-    rec += encode_dna(seq.data() + (size_t)i * c->NW, c->L);
-    rec += "\t*v\t";
-    rec += std::to_string(node_cov[i]);
-    rec += ".00";  // DecimalFormat("0.00") of an integral coverage (Node.java:1761,1775)
-    int cur_type = -1;
-    while (ei < edges.size() && edges[ei].node == line) {
-      if ((int)edges[ei].type != cur_type) {
-        cur_type = edges[ei].type;
-        rec += "\t*";
-        rec += TY[cur_type];
-      }
-      rec += "\t";
-      rec += id_of(edges[ei].nbr);
-      rec += "!";
-      rec += std::to_string(edges[ei].ov);
-      ei++;
-    }
-    rec += "\n";
-    f.write(rec.data(), (std::streamsize)rec.size());
+  if (dist) {
+    u64 token = 1;
+    ex_allreduce(c, &token, 1, 0);  // barrier: the directory is clean
   }
-  f.close();
-  if (!f) throw Error(CB_E_IO, "write failed in " + dir);
+  char part[32];
+  snprintf(part, sizeof(part), "/part-%05d", rank);
+  int io_err = 0;
+  {
+    std::ofstream f(dir + part, std::ios::binary);
+    if (!f) io_err = 1;
+    static const char* TY[4] = {"ff", "fr", "rf", "rr"};
+    const int nb = c->lay.nb, ob = c->lay.ob;
+    const u64 nmask = (1ull << nb) - 1, omask = (1ull << ob) - 1;
+    size_t ei = 0;
+    std::string rec;
+    for (u32 i = 0; i < nn && !io_err; i++) {
+      const u32 node = lo + i;
+      rec.clear();
+      rec += id_of(node);
+      rec += "\tN\t*s\t";
+      rec += encode_dna(seq.data() + (size_t)i * c->NW, c->L);
+      rec += "\t*v\t";
+      rec += std::to_string(node_cov[i]);
+      rec += ".00";  // DecimalFormat("0.00") of an integral coverage (Node.java:1761,1775)
+      int cur_type = -1;
+      while (ei < recs.size() && (u32)(recs[ei] >> (nb + ob + 2)) == node) {
+        const u64 k = recs[ei];
+        const int type = (int)((k >> (nb + ob)) & 3);
+        if (type != cur_type) {
+          cur_type = type;
+          rec += "\t*";
+          rec += TY[cur_type];
+        }
+        rec += "\t";
+        rec += id_of((u32)((k >> ob) & nmask));
+        rec += "!";
+        rec += std::to_string((u32)(k & omask) + (u32)c->K);
+        ei++;
+      }
+      rec += "\n";
+      f.write(rec.data(), (std::streamsize)rec.size());
+    }
+    f.close();
+    if (!f) io_err = 1;
+  }
+  sync_error(c, io_err ? CB_E_IO : 0, "cannot write " + dir + part);
   CB_API_END(c)
 }
 

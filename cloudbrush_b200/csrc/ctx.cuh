@@ -111,6 +111,7 @@ struct cb_ctx {
   u32 line_base = 0;              // global index of this shard's first SFA line
   std::vector<u64> line_bases;    // [world + 1]
   u32 node_lo = 0, node_hi = 0;   // nodes built from this shard (global node indices)
+  std::vector<u64> node_bases;    // [world + 1] first node of every rank's shard
   uint64_t gcount[cb::DC_COUNT] = {0};  // counters reduced over the ranks
 
   // input text

@@ -1356,7 +1356,8 @@ void stage_build_overlap(cb_ctx* c) {
       P.slot_cap = slots1;
       P.list_order = list_order.p;
       c->lc.begin("bucket_join");
-      const bool m32 = nbits + pb + 1 <= 32;  // node | window | dir fit the 32-bit payload
+      static const bool force_m64 = getenv("CB_FORCE_M64") != nullptr;  // test hook: the wide-payload variant on small inputs
+      const bool m32 = nbits + pb + 1 <= 32 && !force_m64;  // node | window | dir fit the 32-bit payload
       switch (c->NW) {
         case 2: launch_bucket_join<2, 7, 1024>(P, plan.NB, m32, s); break;
         case 4: launch_bucket_join<4, 4, 2048>(P, plan.NB, m32, s); break;

@@ -685,6 +685,8 @@ void stage_parse_and_pack(cb_ctx* c) {
     c->n_nodes = n_local_nodes;
     c->node_lo = 0;
     c->node_hi = n_local_nodes;
+    c->node_bases.assign(2, 0);
+    c->node_bases[1] = n_local_nodes;
     c->node_line = std::move(l_line);
     c->node_cov = std::move(l_cov);
     c->node_seq = std::move(l_seq);
@@ -695,9 +697,11 @@ void stage_parse_and_pack(cb_ctx* c) {
     std::vector<u64> snd(world, (u64)n_local_nodes), counts(world, 0);
     ex_counts(c, snd.data(), counts.data(), 1);
     u64 total = 0, lo = 0;
+    c->node_bases.assign(world + 1, 0);
     for (int r = 0; r < world; r++) {
       if (r == c->cfg.rank) lo = total;
       total += counts[r];
+      c->node_bases[r + 1] = total;
     }
     if (total >= (1ull << 27)) throw Error(CB_E_CAPACITY, "more than 2^27 nodes");
     c->n_nodes = (u32)total;

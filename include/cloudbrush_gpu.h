@@ -144,8 +144,12 @@ int cb_get_counter(cb_ctx* ctx, const char* name, int64_t* value);
 int cb_export_edges(cb_ctx* ctx, int checkpoint, cb_edge* out, size_t cap, size_t* n);
 int cb_export_nodes(cb_ctx* ctx, cb_node* out, size_t cap, size_t* n);
 
-/* Writes <out_dir>/part-00000 in Node.toNodeMsg format (out_dir is deleted first, like
- * FileSystem.delete(outputPath, true) in every stage's run()). */
+/* Writes <out_dir>/part-000<rank> in Node.toNodeMsg format (out_dir is emptied first, like
+ * FileSystem.delete(outputPath, true) in every stage's run()): part-00000 on a single GPU.  On a sharded
+ * context the call is COLLECTIVE (every rank calls it for the same checkpoint and directory, which all
+ * ranks must be able to reach): each rank writes the nodes built from its shard of the SFA lines, with ALL
+ * their edges (records held by other ranks are routed to it), so the directory is a multi-part Hadoop
+ * output that the unchanged compressChains reads (BrushAssembler.java:75-89, :381). */
 int cb_write_nodes(cb_ctx* ctx, int checkpoint, const char* out_dir);
 
 /* Device time (ms, CUDA events) of the last run of a stage group: "preprocess", "overlap",

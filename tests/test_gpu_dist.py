@@ -26,6 +26,8 @@ def _sharded_worker(rank, world, sfa_path, k, L, outdir):
     g.run()
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), a=g.edge_rows(1), c=g.edge_rows(2), b=g.edge_rows(3),
              nodes=g.nodes(), counters=np.array([g.counter(x) for x in COUNTERS]))
+    for ck in (0, 1, 2, 3):  # collective: every rank writes part-000<rank> of the checkpoint's directory
+        g.write_nodes(ck, os.path.join(outdir, f"text{ck}"))
     g.close()
 
 
@@ -50,6 +52,15 @@ def _check(sfa, k, L, tmp_path, world=2):
     assert np.array_equal(np.concatenate([q["nodes"] for q in parts]), g.nodes())
     for q in parts:  # the counters are global
         assert q["counters"].tolist() == [g.counter(x) for x in COUNTERS]
+    # node text of a sharded run: one part file per rank; their union is the single-context directory
+    from test_gpu_cases import _canon_text
+    for ck in (0, 1, 2, 3):
+        d1 = tmp_path / f"single{ck}"
+        g.write_nodes(ck, d1)
+        names = sorted(os.listdir(tmp_path / f"text{ck}"))
+        assert names == [f"part-{r:05d}" for r in range(world)]
+        sharded = "".join(open(tmp_path / f"text{ck}" / nm).read() for nm in names)
+        assert _canon_text(sharded) == _canon_text(open(d1 / "part-00000").read()), f"node text of checkpoint {ck}"
     g.close()
 
 
