@@ -62,48 +62,74 @@ __device__ __forceinline__ u32 thread_term_mask(const char* __restrict__ text, s
   return m;
 }
 
+// Both line-terminator kernels handle PT_SUB consecutive 4 KB sub-blocks per CTA with all their 16-byte loads
+// issued before the first is consumed (one 16-byte load per thread left the kernels at 1.8 TB/s: too few
+// bytes in flight); the per-sub-block counts and offsets keep their layout.
+constexpr int PT_SUB = 4;
+
 __global__ void __launch_bounds__(PT_THREADS) count_terms_kernel(const char* __restrict__ text, size_t n,
-                                                                 u32* __restrict__ block_counts) {
-  __shared__ u32 tmp[PT_THREADS / 32 + 1];
-  size_t base = (size_t)blockIdx.x * PT_BLOCK + (size_t)threadIdx.x * PT_BYTES;
-  u32 cnt = base < n ? __popc(thread_term_mask(text, base, n)) : 0;
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  u32 v = cnt;
+                                                                 u32* __restrict__ block_counts, u32 n_sub) {
+  __shared__ u32 tmp[PT_SUB][PT_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 cnt[PT_SUB];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) tmp[warp] = v;
+  for (int q = 0; q < PT_SUB; q++) {
+    const size_t base = ((size_t)blockIdx.x * PT_SUB + q) * PT_BLOCK + (size_t)threadIdx.x * PT_BYTES;
+    cnt[q] = base < n ? __popc(thread_term_mask(text, base, n)) : 0;
+  }
+#pragma unroll
+  for (int q = 0; q < PT_SUB; q++) {
+    u32 v = cnt[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) tmp[q][warp] = v;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < PT_SUB) {
+    const u32 sub = blockIdx.x * PT_SUB + threadIdx.x;
     u32 total = 0;
-    for (int w = 0; w < PT_THREADS / 32; w++) total += tmp[w];
-    block_counts[blockIdx.x] = total;
+    for (int w = 0; w < PT_THREADS / 32; w++) total += tmp[threadIdx.x][w];
+    if (sub < n_sub) block_counts[sub] = total;
   }
 }
 
 __global__ void __launch_bounds__(PT_THREADS) fill_line_starts_kernel(const char* __restrict__ text, size_t n,
                                                                       const u32* __restrict__ block_offs,
-                                                                      u32* __restrict__ line_start) {
-  __shared__ u32 tmp[PT_THREADS / 32 + 1];
-  size_t base = (size_t)blockIdx.x * PT_BLOCK + (size_t)threadIdx.x * PT_BYTES;
-  u32 m = base < n ? thread_term_mask(text, base, n) : 0;
-  u32 cnt = __popc(m);
-  // block exclusive scan of cnt
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  u32 inc = cnt;
+                                                                      u32* __restrict__ line_start, u32 n_sub) {
+  __shared__ u32 tmp[PT_SUB][PT_THREADS / 32 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 m[PT_SUB], inc[PT_SUB];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    u32 t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
+  for (int q = 0; q < PT_SUB; q++) {
+    const size_t base = ((size_t)blockIdx.x * PT_SUB + q) * PT_BLOCK + (size_t)threadIdx.x * PT_BYTES;
+    m[q] = base < n ? thread_term_mask(text, base, n) : 0;
   }
-  if (lane == 31) tmp[warp] = inc;
+#pragma unroll
+  for (int q = 0; q < PT_SUB; q++) {  // inclusive scan of the counts inside the warp
+    u32 v = __popc(m[q]);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    inc[q] = v;
+    if (lane == 31) tmp[q][warp] = v;
+  }
   __syncthreads();
-  u32 woff = 0;
-  for (int w = 0; w < warp; w++) woff += tmp[w];
-  u32 rank = block_offs[blockIdx.x] + woff + inc - cnt;
-  while (m) {
-    int j = __ffs(m) - 1;
-    m &= m - 1;
-    line_start[++rank] = (u32)(base + j + 1);  // line (rank) starts after terminator #(rank-1)
+#pragma unroll
+  for (int q = 0; q < PT_SUB; q++) {
+    const u32 sub = blockIdx.x * PT_SUB + q;
+    if (sub >= n_sub) break;
+    const size_t base = (size_t)sub * PT_BLOCK + (size_t)threadIdx.x * PT_BYTES;
+    u32 woff = 0;
+    for (int w = 0; w < warp; w++) woff += tmp[q][w];
+    u32 rank = block_offs[sub] + woff + inc[q] - __popc(m[q]);
+    u32 mm = m[q];
+    while (mm) {
+      const int j = __ffs(mm) - 1;
+      mm &= mm - 1;
+      line_start[++rank] = (u32)(base + j + 1);  // line (rank) starts after terminator #(rank-1)
+    }
   }
 }
 
@@ -513,7 +539,7 @@ void stage_parse_and_pack(cb_ctx* c) {
   if (n) {
     bcnt.alloc(nb, s);
     boff.alloc(nb, s);
-    count_terms_kernel<<<nb, PT_THREADS, 0, s>>>(c->text_ptr, n, bcnt.p);
+    count_terms_kernel<<<(nb + PT_SUB - 1) / PT_SUB, PT_THREADS, 0, s>>>(c->text_ptr, n, bcnt.p, nb);
     c->lc.n++;
     exclusive_scan_u32(bcnt.p, boff.p, nb, s, c->lc);
     u32 last_cnt = 0, last_off = 0;
@@ -528,7 +554,7 @@ void stage_parse_and_pack(cb_ctx* c) {
   }
   c->line_start.alloc((size_t)c->n_lines + 1, s);
   set_u32_kernel<<<1, 1, 0, s>>>(c->line_start.p, 0u);
-  if (n) fill_line_starts_kernel<<<nb, PT_THREADS, 0, s>>>(c->text_ptr, n, boff.p, c->line_start.p);
+  if (n) fill_line_starts_kernel<<<(nb + PT_SUB - 1) / PT_SUB, PT_THREADS, 0, s>>>(c->text_ptr, n, boff.p, c->line_start.p, nb);
   set_u32_kernel<<<1, 1, 0, s>>>(c->line_start.p + c->n_lines, (u32)n);
   c->lc.n += 3;
 
