@@ -38,7 +38,7 @@ SYMBOLS = ["cb_default_config", "cb_create", "cb_destroy", "cb_last_error", "cb_
            "cb_load_sfa_buffer", "cb_load_sfa_device", "cb_preprocess", "cb_build_overlap", "cb_string_graph",
            "cb_get_counter", "cb_export_edges", "cb_export_nodes", "cb_write_nodes", "cb_get_time_ms",
            "cb_get_launch_count", "cb_borrow_sfa_device", "cb_set_profile", "cb_get_kernel_stat", "cb_set_exchange",
-           "cb_nccl_get_unique_id", "cb_init_nccl", "cb_debug_sort", "cb_prefetch_sfa_buffer"]
+           "cb_nccl_get_unique_id", "cb_init_nccl", "cb_debug_sort", "cb_prefetch_sfa_buffer", "cb_nccl_last_error"]
 
 _lib = None
 
@@ -79,6 +79,7 @@ def load():
     L.cb_set_profile.argtypes = [P, C.c_int]
     L.cb_nccl_get_unique_id.argtypes = [C.c_void_p]
     L.cb_init_nccl.argtypes = [P, C.c_void_p]
+    L.cb_nccl_last_error.restype = C.c_char_p
     L.cb_debug_sort.argtypes = [P, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
     L.cb_get_kernel_stat.argtypes = [P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = L

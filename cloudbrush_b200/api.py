@@ -123,7 +123,7 @@ class BrushGpu:
         if dist.get_rank(group) == 0:
             rc = self._L.cb_nccl_get_unique_id(buf)
             if rc != 0:
-                raise BrushGpuError(rc, "cb_nccl_get_unique_id failed (libnccl.so.2 not loadable?)")
+                raise BrushGpuError(rc, "cb_nccl_get_unique_id failed: " + self._L.cb_nccl_last_error().decode(errors="replace"))
         t = torch.tensor(list(buf), dtype=torch.uint8)
         if dist.get_backend(group) == "nccl":
             t = t.cuda(self.cfg.device)

@@ -315,11 +315,18 @@ int cb_set_exchange(cb_ctx* c, const cb_exchange* ex) {
   return CB_OK;
 }
 
+static std::string& nccl_error_string() {
+  static thread_local std::string e;
+  return e;
+}
+
 int cb_nccl_get_unique_id(void* id128) {
   if (!id128) return CB_E_INVALID;
-  std::string err;
-  return cb::nccl_unique_id(id128, err);
+  nccl_error_string().clear();
+  return cb::nccl_unique_id(id128, nccl_error_string());
 }
+
+const char* cb_nccl_last_error(void) { return nccl_error_string().c_str(); }
 
 int cb_init_nccl(cb_ctx* c, const void* id128) {
   CB_API_BEGIN(c)

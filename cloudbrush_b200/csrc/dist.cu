@@ -37,6 +37,8 @@ struct NcclApi {
   std::string why;
 };
 
+static std::string g_nccl_why;  // the loader's words when libnccl could not be used
+
 static NcclApi* nccl_api() {
   static NcclApi api;
   static bool tried = false;
@@ -49,10 +51,10 @@ static NcclApi* nccl_api() {
     if (api.lib) break;
     api.why = dlerror();
   }
-  if (!api.lib) return nullptr;
+  if (!api.lib) { g_nccl_why = api.why; return nullptr; }
 #define CB_NCCL_SYM(field, name)                                          \
   api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name)); \
-  if (!api.field) { api.why = std::string("missing symbol ") + name; api.lib = nullptr; return nullptr; }
+  if (!api.field) { api.why = std::string("missing symbol ") + name; g_nccl_why = api.why; api.lib = nullptr; return nullptr; }
   CB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
   CB_NCCL_SYM(CommInitRank, "ncclCommInitRank")
   CB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
@@ -67,6 +69,7 @@ static NcclApi* nccl_api() {
   return &api;
 }
 
+static std::string nccl_load_error();
 #define CB_NCCL(expr)                                                                                  \
   do {                                                                                                 \
     ncclResult_t r_ = (expr);                                                                          \
@@ -74,9 +77,14 @@ static NcclApi* nccl_api() {
       throw Error(CB_E_CUDA, std::string(#expr) + ": " + nccl_api()->GetErrorString(r_));             \
   } while (0)
 
+static std::string nccl_load_error() { return g_nccl_why.empty() ? std::string("libnccl.so.2 could not be loaded") : g_nccl_why; }
+
 int nccl_unique_id(void* id128, std::string& err) {
   NcclApi* A = nccl_api();
-  if (!A) { err = "NCCL is not available: " + (nccl_api() ? std::string() : std::string("dlopen failed")); return CB_E_UNSUPPORTED; }
+  if (!A) {  // the loader's own words (dlopen / dlsym), so that a missing library can be diagnosed
+    err = "NCCL is not available: " + nccl_load_error();
+    return CB_E_UNSUPPORTED;
+  }
   ncclUniqueId id;
   ncclResult_t r = A->GetUniqueId(&id);
   if (r != ncclSuccess) { err = A->GetErrorString(r); return CB_E_CUDA; }

@@ -215,6 +215,7 @@ int cb_set_exchange(cb_ctx* ctx, const cb_exchange* ex);
  * environment variable CB_NCCL_LIB overrides the name); CB_E_UNSUPPORTED if it cannot be loaded. */
 #define CB_NCCL_ID_BYTES 128
 int cb_nccl_get_unique_id(void* id128);
+const char* cb_nccl_last_error(void); /* why the last cb_nccl_get_unique_id of this thread failed (library-owned) */
 int cb_init_nccl(cb_ctx* ctx, const void* id128);
 
 #ifdef __cplusplus

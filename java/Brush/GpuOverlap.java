@@ -27,7 +27,7 @@ public class GpuOverlap implements AutoCloseable {
 
     // ---- native side: java/jni/cloudbrush_jni.c, one call per C-ABI entry point ----
     private static native long nCreate(int k, int readlen, long upKmer, long lowKmer, float majority, float pwmN,
-                                       int device);
+                                       int device, int rank, int world);
     private static native void nDestroy(long ctx);
     private static native String nLastError(long ctx);
     private static native int nLoadSfa(long ctx, String pathOrDir);
@@ -39,12 +39,30 @@ public class GpuOverlap implements AutoCloseable {
     private static native double nTimeMs(long ctx, String what);
     private static native byte[] nNcclUniqueId();                      // multi-GPU launchers: rank 0
     private static native int nInitNccl(long ctx, byte[] id128);      // every rank, before preprocess
+    private static native String nNcclLastError();                    // why nNcclUniqueId returned null
 
     public GpuOverlap() throws IOException {
+        this(0, 0, 1);
+    }
+
+    /** One JVM per GPU: shard `rank` of `world` on CUDA device `device` (the launcher then hands rank 0's
+     *  ncclUniqueId() to every rank and each calls initNccl before preprocess; cb_write_nodes is collective
+     *  and leaves one part-000<rank> per rank in every output directory). */
+    public GpuOverlap(int device, int rank, int world) throws IOException {
         // the options the path reads, straight from BrushConfig (BrushConfig.java:55-84)
         ctx = nCreate((int) BrushConfig.K, (int) BrushConfig.READLEN, BrushConfig.UP_KMER, BrushConfig.LOW_KMER,
-                      BrushConfig.MAJORITY, BrushConfig.PWM_N, 0);
+                      BrushConfig.MAJORITY, BrushConfig.PWM_N, device, rank, world);
         if (ctx == 0) throw new IOException("cb_create failed: no CUDA device (there is no CPU fallback)");
+    }
+
+    public static byte[] ncclUniqueId() throws IOException {
+        byte[] id = nNcclUniqueId();
+        if (id == null) throw new IOException("NCCL is not available: " + nNcclLastError());
+        return id;
+    }
+
+    public void initNccl(byte[] id128) throws IOException {
+        check(nInitNccl(ctx, id128));
     }
 
     private void check(int rc) throws IOException {

@@ -11,12 +11,14 @@
 #define CTX(h) ((cb_ctx*)(intptr_t)(h))
 
 JNIEXPORT jlong JNICALL Java_Brush_GpuOverlap_nCreate(JNIEnv* env, jclass cls, jint k, jint readlen, jlong up,
-                                                      jlong low, jfloat maj, jfloat pwmn, jint device) {
+                                                      jlong low, jfloat maj, jfloat pwmn, jint device, jint rank,
+                                                      jint world) {
   cb_config cfg;
   cb_ctx* ctx = NULL;
   cb_default_config(&cfg);
   cfg.k = k; cfg.readlen = readlen; cfg.up_kmer = up; cfg.low_kmer = low;
   cfg.majority = maj; cfg.pwm_n = pwmn; cfg.device = device;
+  cfg.rank = rank; cfg.world = world;  /* one JVM per GPU: shard `rank` of `world` (0 / 1 on a single GPU) */
   return cb_create(&cfg, &ctx) == CB_OK ? (jlong)(intptr_t)ctx : 0;
 }
 
@@ -64,10 +66,14 @@ JNIEXPORT jdouble JNICALL Java_Brush_GpuOverlap_nTimeMs(JNIEnv* env, jclass cls,
  * 128 bytes over its own channel, every rank initialises the library's native transport */
 JNIEXPORT jbyteArray JNICALL Java_Brush_GpuOverlap_nNcclUniqueId(JNIEnv* env, jclass cls) {
   jbyte id[CB_NCCL_ID_BYTES];
-  if (cb_nccl_get_unique_id(id) != CB_OK) return NULL;
+  if (cb_nccl_get_unique_id(id) != CB_OK) return NULL; /* the reason: cb_nccl_last_error() */
   jbyteArray out = (*env)->NewByteArray(env, CB_NCCL_ID_BYTES);
   (*env)->SetByteArrayRegion(env, out, 0, CB_NCCL_ID_BYTES, id);
   return out;
+}
+
+JNIEXPORT jstring JNICALL Java_Brush_GpuOverlap_nNcclLastError(JNIEnv* env, jclass cls) {
+  return (*env)->NewStringUTF(env, cb_nccl_last_error());
 }
 
 JNIEXPORT jint JNICALL Java_Brush_GpuOverlap_nInitNccl(JNIEnv* env, jclass cls, jlong h, jbyteArray id) {
