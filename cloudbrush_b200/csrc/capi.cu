@@ -4,6 +4,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <fstream>
 
@@ -140,6 +141,114 @@ static void export_edges_to(cb_ctx* c, int ck, cb_edge* out) {
   c->lc.n++;
   CB_CUDA(cudaMemcpyAsync(out, d.p, n * sizeof(cb_edge), cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Node text on the device (Node.toNodeMsg, Node.java:1757-1982): the host formatter
+// spent 9 s on the 1.4 GB of 01-overlap at config 2 (tools/dropin_e2e.py).  One thread per node: the
+// record's length, an exclusive scan, then the bytes:
+//   id \t N \t *s \t <pair-coded dna> \t *v \t <cov>.00 [\t *ff \t id!ov ...] [*fr] [*rf] [*rr] \n
+// Records arrive sorted by (node, type, nbr, ov) in the export encoding.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 idkey_len(const IdKey& k) {
+  if (k.lo) return 16u - (u32)(__ffsll((long long)k.lo) - 1) / 8u;
+  if (k.hi) return 8u - (u32)(__ffsll((long long)k.hi) - 1) / 8u;
+  return 0u;
+}
+__device__ __forceinline__ u32 dec_digits(u32 v) {
+  u32 d = 1;
+  while (v >= 10u) { v /= 10u; d++; }
+  return d;
+}
+__device__ __forceinline__ char* put_id(char* p, const IdKey& k) {
+  const u32 n = idkey_len(k);
+  for (u32 i = 0; i < n; i++) *p++ = (char)((i < 8 ? k.hi >> (56 - 8 * i) : k.lo >> (56 - 8 * (i - 8))) & 0xff);
+  return p;
+}
+__device__ __forceinline__ char* put_dec(char* p, u32 v) {
+  const u32 d = dec_digits(v);
+  for (u32 i = d; i-- > 0;) { p[i] = (char)('0' + v % 10u); v /= 10u; }
+  return p + d;
+}
+
+// first record of node lo + i in the sorted records (lower bound); first[nn] = n
+__global__ void __launch_bounds__(256) text_first_kernel(const u64* __restrict__ recs, size_t n, int shift, u32 lo, u32 nn,
+                                                         u32* __restrict__ first) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nn) return;
+  const u64 want = (u64)lo + i;
+  size_t a = 0, b = n;
+  while (a < b) {
+    const size_t m = a + ((b - a) >> 1);
+    if ((recs[m] >> shift) < want) a = m + 1;
+    else b = m;
+  }
+  first[i] = (u32)a;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) text_nodes_kernel(const u64* __restrict__ recs, const u32* __restrict__ first,
+                                                         u32 lo, u32 nn, EdgeLayout lay, int K, int L, int NW,
+                                                         const u64* __restrict__ node_seq, const u32* __restrict__ node_cov,
+                                                         const IdKey* __restrict__ idkey, u32* __restrict__ len,
+                                                         const u32* __restrict__ off, char* __restrict__ out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  const u32 node = lo + i;
+  const int nb = lay.nb, ob = lay.ob;
+  const u64 nmask = (1ull << nb) - 1, omask = (1ull << ob) - 1;
+  const u32 e0 = first[i], e1 = first[i + 1];
+  if (!WRITE) {
+    u32 n = idkey_len(idkey[node]) + 6u + (u32)(L + 1) / 2u + 4u + dec_digits(node_cov[node]) + 3u + 1u;
+    int cur = -1;
+    for (u32 e = e0; e < e1; e++) {
+      const u64 k = recs[e];
+      const int type = (int)((k >> (nb + ob)) & 3);
+      if (type != cur) { cur = type; n += 4u; }
+      n += 1u + idkey_len(idkey[(u32)((k >> ob) & nmask)]) + 1u + dec_digits((u32)(k & omask) + (u32)K);
+    }
+    len[i] = n;
+    return;
+  }
+  char* p = out + off[i];
+  p = put_id(p, idkey[node]);
+  *p++ = '\t'; *p++ = 'N'; *p++ = '\t'; *p++ = '*'; *p++ = 's'; *p++ = '\t';
+  const u64* row = node_seq + (size_t)node * NW;
+  for (int b = 0; b < L; b += 2) {  // Node.str2dna (Node.java:186-211): two bases per letter, a lone last base alone
+    const int c0 = (int)((row[b >> 5] >> (62 - 2 * (b & 31))) & 3);
+    if (b + 1 < L) {
+      const int c1 = (int)((row[(b + 1) >> 5] >> (62 - 2 * ((b + 1) & 31))) & 3);
+      *p++ = (char)('A' + 5 * c0 + 1 + c1);
+    } else {
+      *p++ = (char)('A' + 5 * c0);
+    }
+  }
+  *p++ = '\t'; *p++ = '*'; *p++ = 'v'; *p++ = '\t';
+  p = put_dec(p, node_cov[node]);
+  *p++ = '.'; *p++ = '0'; *p++ = '0';  // DecimalFormat("0.00") of an integral coverage (Node.java:1761,1775)
+  int cur = -1;
+  for (u32 e = e0; e < e1; e++) {
+    const u64 k = recs[e];
+    const int type = (int)((k >> (nb + ob)) & 3);
+    if (type != cur) {
+      cur = type;
+      *p++ = '\t'; *p++ = '*'; *p++ = (type & 2) ? 'r' : 'f'; *p++ = (type & 1) ? 'r' : 'f';
+    }
+    *p++ = '\t';
+    p = put_id(p, idkey[(u32)((k >> ob) & nmask)]);
+    *p++ = '!';
+    p = put_dec(p, (u32)(k & omask) + (u32)K);
+  }
+  *p++ = '\n';
+}
+
+__global__ void __launch_bounds__(256) sum_u32_kernel(const u32* __restrict__ v, u32 n, ull* __restrict__ out) {
+  ull acc = 0;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
 // owner rank of the node of an export-encoded record: the rank whose SFA shard the node was built from
@@ -522,13 +631,15 @@ int cb_write_nodes(cb_ctx* c, int checkpoint, const char* out_dir) {
   // node.  Read ids come from the replicated 16-byte id keys (ids longer than that are refused at preprocess).
   const u32 lo = dist ? c->node_lo : 0, hi = dist ? c->node_hi : c->n_nodes;
   const u32 nn = hi - lo;
-  std::vector<u64> recs;  // export-encoded records of the nodes [lo, hi), sorted
+  // export-encoded records of the nodes [lo, hi), sorted, on the device
+  DevBuf<u64> enc, ka, kb;
+  DevBuf<char> got;
+  const u64* d_recs = nullptr;
+  size_t n_recs = 0;
   if (with_edges) {
-    DevBuf<u64> a, b;
-    export_encoded(c, checkpoint, a);
+    export_encoded(c, checkpoint, enc);
     size_t n = (size_t)edge_count(c, checkpoint);
-    const u64* src = a.p;
-    DevBuf<char> got;
+    const u64* src = enc.p;
     if (dist) {
       DevBuf<u64> bases;
       DevBuf<u32> dest;
@@ -536,42 +647,62 @@ int cb_write_nodes(cb_ctx* c, int checkpoint, const char* out_dir) {
       dest.alloc(n ? n : 1, s);
       CB_CUDA(cudaMemcpyAsync(bases.p, c->node_bases.data(), (world + 1) * sizeof(u64), cudaMemcpyHostToDevice, s));
       if (n) {
-        node_owner_kernel<<<div_up(n, 256), 256, 0, s>>>(a.p, n, c->lay.nb + c->lay.ob + 2, bases.p, world, dest.p);
+        node_owner_kernel<<<div_up(n, 256), 256, 0, s>>>(enc.p, n, c->lay.nb + c->lay.ob + 2, bases.p, world, dest.p);
         c->lc.n++;
       }
       size_t n_got = 0;
-      route_records(c, a.p, 8, dest.p, n, got, n_got);
+      route_records(c, enc.p, 8, dest.p, n, got, n_got);
       n = n_got;
       src = (const u64*)got.p;
     }
     if (n) {
-      DevBuf<u64> ka;
       ka.alloc(n, s);
-      b.alloc(n, s);
+      kb.alloc(n, s);
       CB_CUDA(cudaMemcpyAsync(ka.p, src, n * 8, cudaMemcpyDeviceToDevice, s));
-      int w = radix_sort(ka.p, b.p, nullptr, nullptr, n, 0, c->lay.total_bits(), s, c->lc, "export");
-      recs.resize(n);
-      CB_CUDA(cudaMemcpyAsync(recs.data(), w ? b.p : ka.p, n * 8, cudaMemcpyDeviceToHost, s));
+      const int w = radix_sort(ka.p, kb.p, nullptr, nullptr, n, 0, c->lay.total_bits(), s, c->lc, "export");
+      d_recs = w ? kb.p : ka.p;
     }
+    n_recs = n;
   }
-  std::vector<u32> node_cov(nn ? nn : 1);
-  std::vector<u64> seq((size_t)(nn ? nn : 1) * c->NW);
-  std::vector<IdKey> idkeys(c->n_nodes ? c->n_nodes : 1);
-  if (nn) {
-    CB_CUDA(cudaMemcpyAsync(node_cov.data(), c->node_cov.p + lo, (size_t)nn * 4, cudaMemcpyDeviceToHost, s));
-    CB_CUDA(cudaMemcpyAsync(seq.data(), c->node_seq.p + (size_t)lo * c->NW, (size_t)nn * c->NW * 8, cudaMemcpyDeviceToHost, s));
+  // the text of this rank's part, formatted on the device
+  std::vector<char> text;
+  {
+    DevBuf<u32> first, len, off;
+    DevBuf<ull> sum64;
+    first.alloc((size_t)nn + 2, s);
+    len.alloc((size_t)nn + 1, s);
+    off.alloc((size_t)nn + 1, s);
+    sum64.alloc(1, s);
+    text_first_kernel<<<div_up((size_t)nn + 1, 256), 256, 0, s>>>(d_recs, n_recs, c->lay.nb + c->lay.ob + 2, lo, nn, first.p);
+    CB_CUDA(cudaMemsetAsync(len.p + nn, 0, 4, s));
+    CB_CUDA(cudaMemsetAsync(sum64.p, 0, sizeof(ull), s));
+    if (nn) {
+      text_nodes_kernel<false><<<div_up((size_t)nn, 256), 256, 0, s>>>(d_recs, first.p, lo, nn, c->lay, c->K, c->L, c->NW,
+                                                                      c->node_seq.p, c->node_cov.p, c->node_idkey.p, len.p,
+                                                                      nullptr, nullptr);
+      int sb = div_up((size_t)nn, 256 * 8);
+      if (sb > kNumSMs * 8) sb = kNumSMs * 8;
+      sum_u32_kernel<<<sb, 256, 0, s>>>(len.p, nn, sum64.p);
+    }
+    exclusive_scan_u32(len.p, off.p, (size_t)nn + 1, s, c->lc);
+    ull total64 = 0;
+    CB_CUDA(cudaMemcpyAsync(&total64, sum64.p, sizeof(ull), cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    // the offsets are 32-bit: a part of 4 GiB or more is refused (shard the run over more ranks)
+    sync_error(c, total64 >= (1ull << 32) ? CB_E_CAPACITY : 0, "node text of one part is 4 GiB or more");
+    const size_t total = (size_t)total64;
+    DevBuf<char> dtext;
+    dtext.alloc(total ? total : 1, s);
+    if (nn)
+      text_nodes_kernel<true><<<div_up((size_t)nn, 256), 256, 0, s>>>(d_recs, first.p, lo, nn, c->lay, c->K, c->L, c->NW,
+                                                                     c->node_seq.p, c->node_cov.p, c->node_idkey.p, nullptr,
+                                                                     off.p, dtext.p);
+    c->lc.n += 4;
+    CB_CUDA(cudaGetLastError());
+    text.resize(total);
+    if (total) CB_CUDA(cudaMemcpyAsync(text.data(), dtext.p, total, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
   }
-  if (c->n_nodes)
-    CB_CUDA(cudaMemcpyAsync(idkeys.data(), c->node_idkey.p, (size_t)c->n_nodes * sizeof(IdKey), cudaMemcpyDeviceToHost, s));
-  CB_CUDA(cudaStreamSynchronize(s));
-  auto id_of = [&](u32 node) {
-    char buf[16];
-    const IdKey& k = idkeys[node];
-    for (int i = 0; i < 8; i++) { buf[i] = (char)(k.hi >> (56 - 8 * i)); buf[8 + i] = (char)(k.lo >> (56 - 8 * i)); }
-    size_t len = 0;
-    while (len < 16 && buf[len]) len++;
-    return std::string(buf, len);
-  };
   // FileSystem.delete(outputPath, true), then the part files (e.g. VerifyOverlap.java:379); rank 0 clears the
   // directory, the others wait for it
   std::string dir(out_dir);
@@ -595,42 +726,12 @@ int cb_write_nodes(cb_ctx* c, int checkpoint, const char* out_dir) {
   snprintf(part, sizeof(part), "/part-%05d", rank);
   int io_err = 0;
   {
-    std::ofstream f(dir + part, std::ios::binary);
+    FILE* f = fopen((dir + part).c_str(), "wb");
     if (!f) io_err = 1;
-    static const char* TY[4] = {"ff", "fr", "rf", "rr"};
-    const int nb = c->lay.nb, ob = c->lay.ob;
-    const u64 nmask = (1ull << nb) - 1, omask = (1ull << ob) - 1;
-    size_t ei = 0;
-    std::string rec;
-    for (u32 i = 0; i < nn && !io_err; i++) {
-      const u32 node = lo + i;
-      rec.clear();
-      rec += id_of(node);
-      rec += "\tN\t*s\t";
-      rec += encode_dna(seq.data() + (size_t)i * c->NW, c->L);
-      rec += "\t*v\t";
-      rec += std::to_string(node_cov[i]);
-      rec += ".00";  // DecimalFormat("0.00") of an integral coverage (Node.java:1761,1775)
-      int cur_type = -1;
-      while (ei < recs.size() && (u32)(recs[ei] >> (nb + ob + 2)) == node) {
-        const u64 k = recs[ei];
-        const int type = (int)((k >> (nb + ob)) & 3);
-        if (type != cur_type) {
-          cur_type = type;
-          rec += "\t*";
-          rec += TY[cur_type];
-        }
-        rec += "\t";
-        rec += id_of((u32)((k >> ob) & nmask));
-        rec += "!";
-        rec += std::to_string((u32)(k & omask) + (u32)c->K);
-        ei++;
-      }
-      rec += "\n";
-      f.write(rec.data(), (std::streamsize)rec.size());
+    else {
+      if (!text.empty() && fwrite(text.data(), 1, text.size(), f) != text.size()) io_err = 1;
+      if (fclose(f) != 0) io_err = 1;
     }
-    f.close();
-    if (!f) io_err = 1;
   }
   sync_error(c, io_err ? CB_E_IO : 0, "cannot write " + dir + part);
   CB_API_END(c)

@@ -602,9 +602,10 @@ void stage_parse_and_pack(cb_ctx* c) {
   timer_start(c, "dedupe");
   int bits = 0;
   while ((1ull << bits) < c->gcount[DC_READS_GOOD]) bits++;
-  // hash bits that are sorted on: enough that equal masked hashes of different reads stay rare
-  // (~2^(bits-11) pairs, each costing one extra compare), a whole number of 9-bit digit passes
-  int hb = ((bits + 10 + 8) / 9) * 9;
+  // hash bits that are sorted on: enough that equal masked hashes of different reads stay rare (about
+  // 2^(bits-3) of the reads meet one, each costing one extra 64-bit compare in dedupe_runs), a whole number
+  // of 9-bit digit passes -- three for the 12.8 M reads of config 2 (four measured 0.15 ms slower)
+  int hb = ((bits + 3 + 8) / 9) * 9;
   if (hb > 64) hb = 64;
   const u64 keymask = hb == 64 ? ~0ull : ((1ull << hb) - 1);
   DevBuf<u32> surv_flag, surv_idx, cov;

@@ -47,6 +47,9 @@ struct StringParams {
                        // per-list results are scattered writes: one store instead of three): .x, .y = (nbr | y << 31) of
                        // the first two records of maximal overlap (~0: none), .z = maximal overlap | count of such
                        // records (saturating at 255) << 8
+  uint4* lseq;         // bucket path, per list_order entry (sequential writes): .x, .y = slots of the first two records of
+                       // maximal overlap, .z = maximal overlap | count of such records (sat. 255) << 8 | contained
+                       // records (ov == L, sat. 65535) << 16, .w = records TransitiveReduction counts as transitive
   const uint8_t* lsum; // per list, all ranks: ovmax if the list is consistent and untouched by the cut rounds
                        // (TransitiveReduction keeps exactly its records of that overlap), else 0
   const u32* work;     // work list of list ids (literal kernels)
@@ -121,6 +124,7 @@ __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* _
     // is a prefix of the new one as well)
     u32 ovmax = 0, n = 0, nmax = 0;
     u32 m0 = 0xffffffffu, m1 = 0xffffffffu;  // (nbr | y << 31) of the first two records of maximal overlap
+    u32 s0 = 0xffffffffu, s1 = 0xffffffffu;  // ... and their slots
     u64 H[NW];
     int lenH = -1;
     bool bad = false;
@@ -130,8 +134,8 @@ __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* _
       n++;
       const u32 o = P.lay.ov(k);
       const u32 nby = P.lay.nbr(k) | (P.lay.y(k) << 31);
-      if (o > ovmax) { ovmax = o; nmax = 1; m0 = nby; m1 = 0xffffffffu; }
-      else if (o == ovmax) { if (nmax == 1) m1 = nby; nmax++; }
+      if (o > ovmax) { ovmax = o; nmax = 1; m0 = nby; m1 = 0xffffffffu; s0 = t; s1 = 0xffffffffu; }
+      else if (o == ovmax) { if (nmax == 1) { m1 = nby; s1 = t; } nmax++; }
       if (!force_slow) {
         u64 h[NW];
         int len;
@@ -150,8 +154,33 @@ __global__ void __launch_bounds__(256) consistency_kernel(StringParams P, u32* _
         }
       }
     }
-    if (n == 0) { P.lsumm[lid] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u); continue; }
-    P.lsumm[lid] = make_uint4(m0, m1, ovmax | ((nmax > 255 ? 255u : nmax) << 8), 0u);
+    if (lists4) {
+      // bucket path: the summary goes to the list's place in slot order (sequential), and what
+      // TransitiveReduction will count on this list if it stays consistent is taken now, while the list is in
+      // L1: records below the maximal overlap are transitive unless a kept record has their type and
+      // neighbour (TransitiveReduction.java:325-334), records with ov == L are "contained" (:319-323)
+      u32 trans = 0, contained = 0;
+      for (u32 t = lo; t < hi && n > nmax; t++) {
+        const u64 k = P.edges[t];
+        if (k == ~0ull) continue;
+        const u32 o = P.lay.ov(k);
+        if (o == ovmax) continue;
+        const u32 nby = P.lay.nbr(k) | (P.lay.y(k) << 31);
+        bool step2 = nby == m0 || nby == m1;
+        for (u32 q = lo; nmax > 2 && !step2 && q < hi; q++) {
+          const u64 kq = P.edges[q];
+          step2 = kq != ~0ull && P.lay.ov(kq) == ovmax && (P.lay.nbr(kq) | (P.lay.y(kq) << 31)) == nby;
+        }
+        trans += !step2;
+      }
+      if ((int)ovmax == P.L) contained = nmax;  // only the maximal overlap can be L
+      P.lseq[it] = make_uint4(s0, s1, (n ? ovmax : 0u) | ((nmax > 255 ? 255u : nmax) << 8) |
+                                          ((contained > 65535u ? 65535u : contained) << 16), trans);
+      if (n == 0) continue;
+    } else {
+      if (n == 0) { P.lsumm[lid] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u); continue; }
+      P.lsumm[lid] = make_uint4(m0, m1, ovmax | ((nmax > 255 ? 255u : nmax) << 8), 0u);
+    }
     if (n > 1 && (bad || force_slow)) {  // only this thread writes the list's flag here
       P.list_flag[lid] = 0;
       work_out[atomicAdd(n_work_out, 1u)] = lid;
@@ -415,6 +444,21 @@ __global__ void __launch_bounds__(256) tr_worklist_kernel(const uint8_t* __restr
   if (nonempty && !fast) work[atomicAdd(n_work, 1u)] = lid;
 }
 
+// bucket path: the same over the lists that own slots (list_order); every other list keeps lsum = 0 (memset)
+__global__ void __launch_bounds__(256) tr_worklist_seq_kernel(const uint8_t* __restrict__ list_flag,
+                                                              const uint4* __restrict__ list_order,
+                                                              const uint4* __restrict__ lseq, u32 n_order,
+                                                              u32* __restrict__ work, u32* __restrict__ n_work,
+                                                              uint8_t* __restrict__ lsum) {
+  const u32 it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= n_order) return;
+  const u32 lid = list_order[it].x;
+  const u32 om = lseq[it].z & 0xffu;  // 0: no record in the list
+  const bool fast = list_flag[lid] == 1;
+  if (om && fast) lsum[lid] = (uint8_t)om;
+  if (om && !fast) work[atomicAdd(n_work, 1u)] = lid;
+}
+
 constexpr int TR_KC = 64;  // kept entries per list in the literal scan
 
 // literal greedy scan (TransitiveReduction.java:300-409), one warp per queued list.  Entries are
@@ -601,6 +645,94 @@ __global__ void __launch_bounds__(256) tr_final_kernel(StringParams P, u64* __re
   }
 }
 
+// Bucket path: TransitiveReduction + EdgeRemoval per LIST instead of per slot.  A consistent list keeps exactly its
+// records of maximal overlap, whose slots consistency_kernel left in lseq, so the 146 M slots of config 2 are
+// not streamed again: one thread per list (8.6 M), in slot order, looks at its one or two kept records and at
+// the summary byte of their mirrors' lists.  What the list counts as transitive / contained was taken by
+// consistency_kernel.  Lists that took the literal path are scanned for their kept flags.
+template <bool VOTED>
+__global__ void __launch_bounds__(256) tr_final_lists_kernel(StringParams P, const uint4* __restrict__ list_order,
+                                                             u32 n_order, u64* __restrict__ out) {
+  u32 trans = 0, contained = 0;
+  const int lane = threadIdx.x & 31;
+  const u32 lt_mask = (1u << lane) - 1;
+  auto mirror_kept = [&](u64 k, size_t slot) {
+    const u64 mk = P.lay.mirror(k);
+    const uint8_t ms = P.lsum[P.lay.list(mk)];
+    if (ms) return P.lay.ov(k) == (u32)ms;
+    if (VOTED) return (P.kept[slot] & 2) != 0;
+    const long long mi = find_edge(P, mk);
+    return mi < 0 ? true : (P.kept[mi] != 0);  // no mirror: nobody can ask for the removal
+  };
+  auto append = [&](bool have, u64 k) {  // warp-aggregated append of the survivors
+    const u32 bal = __ballot_sync(0xffffffffu, have);
+    if (bal == 0) return;
+    ull base = 0;
+    if (lane == 0) base = atomicAdd(&P.dcount[DC_EDGES_B], (ull)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (have) out[base + __popc(bal & lt_mask)] = k;
+  };
+  // block-uniform trip count: the appends are warp-collective
+  for (u32 it0 = blockIdx.x * blockDim.x; it0 < n_order; it0 += gridDim.x * blockDim.x) {
+    const u32 it = it0 + threadIdx.x;
+    u64 k0 = ~0ull, k1 = ~0ull;
+    bool keep0 = false, keep1 = false;
+    bool scan = false;  // the list is walked slot by slot (more than two maximal records, or the literal path)
+    uint4 q = make_uint4(0, 0, 0, 0), sq = make_uint4(0, 0, 0, 0);
+    u32 om = 0;
+    if (it < n_order) {
+      q = list_order[it];
+      sq = P.lseq[it];
+      om = P.lsum[q.x];
+      if (om) {
+        trans += sq.w;
+        contained += sq.z >> 16;
+        const u32 nmax = (sq.z >> 8) & 0xffu;
+        if (nmax <= 2) {
+          k0 = P.edges[sq.x];
+          keep0 = mirror_kept(k0, sq.x);
+          if (nmax == 2) {
+            k1 = P.edges[sq.y];
+            keep1 = mirror_kept(k1, sq.y);
+          }
+        } else {
+          scan = true;
+        }
+      } else if (sq.z & 0xffu) {
+        scan = true;  // records, but not on the fast path: literal kernel
+      }
+    }
+    append(keep0, k0);
+    append(keep1, k1);
+    // rare: lists walked slot by slot; the warp stays together for the collective appends
+    u32 t = q.y;
+    const u32 hi = q.y + q.z;
+    while (__any_sync(0xffffffffu, scan)) {
+      bool have = false;
+      u64 k = ~0ull;
+      while (scan && !have) {
+        if (t >= hi) { scan = false; break; }
+        k = P.edges[t];
+        if (k != ~0ull) {
+          const bool kept_here = om ? P.lay.ov(k) == om : (P.kept[t] & 1) != 0;
+          have = kept_here && mirror_kept(k, t);
+        }
+        t++;
+      }
+      append(have, k);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    trans += __shfl_xor_sync(0xffffffffu, trans, o);
+    contained += __shfl_xor_sync(0xffffffffu, contained, o);
+  }
+  if (lane == 0) {
+    if (trans) atomicAdd(&P.dcount[DC_TRANS_EDGE], (ull)trans);
+    if (contained) atomicAdd(&P.dcount[DC_CONTAINED_EDGE], (ull)contained);
+  }
+}
+
 // ---- multi-GPU helpers: act on routed mirror keys at the rank that owns their list ----
 __global__ void __launch_bounds__(256) apply_removal_requests_kernel(StringParams P, const u64* __restrict__ keys,
                                                                      size_t n) {
@@ -673,6 +805,7 @@ static StringParams make_params(cb_ctx* c, const u64* keys) {
   P.kept = nullptr;
   P.list_flag = c->list_flag.p;
   P.lsumm = nullptr;
+  P.lseq = nullptr;
   P.lsum = nullptr;
   P.work = nullptr;
   P.n_work = 0;
@@ -756,7 +889,10 @@ void stage_string_graph(cb_ctx* c) {
   DevBuf<uint8_t> lsum;   // per list: summary byte of the final pass
   DevBuf<uint4> lsumm;    // per list: maximal overlap, its first two records and their number
   lsum.alloc(nl, s);
-  lsumm.alloc(nl, s);
+  const bool by_list = c->n_list_order > 0;  // bucket path: per-list summaries in slot order, TR per list
+  DevBuf<uint4> lseq;
+  if (by_list) lseq.alloc(c->n_list_order, s);
+  else lsumm.alloc(nl, s);
   DevBuf<u64> req;  // multi-GPU: mirror keys to act on at their owner
   if (dist) req.alloc(slots, s);
 
@@ -775,6 +911,7 @@ void stage_string_graph(cb_ctx* c) {
   {
     StringParams P = make_params(c, cur_keys);
     P.lsumm = lsumm.p;
+    P.lseq = lseq.p;
     if (c->ckA.n) {
       const u32* lists = nullptr;
       const uint4* lists4 = nullptr;
@@ -896,11 +1033,18 @@ void stage_string_graph(cb_ctx* c) {
     StringParams P = make_params(c, cur_keys);
     P.kept = flags.p;
     P.lsumm = lsumm.p;
+    P.lseq = lseq.p;
     P.lsum = lsum.p;
     // literal path first: lists that are inconsistent or lost an entry in a cut round
     CB_CUDA(cudaMemsetAsync(nwork.p + 3, 0, 4, s));
-    tr_worklist_kernel<<<div_up((size_t)nl, 256), 256, 0, s>>>(c->list_flag.p, c->adj.p, lsumm.p, n_lists,
-                                                              workA.p, nwork.p + 3, lsum.p);
+    if (by_list) {
+      CB_CUDA(cudaMemsetAsync(lsum.p, 0, nl, s));
+      tr_worklist_seq_kernel<<<div_up(c->n_list_order, 256), 256, 0, s>>>(c->list_flag.p, c->list_order.p, lseq.p,
+                                                                         (u32)c->n_list_order, workA.p, nwork.p + 3, lsum.p);
+    } else {
+      tr_worklist_kernel<<<div_up((size_t)nl, 256), 256, 0, s>>>(c->list_flag.p, c->adj.p, lsumm.p, n_lists,
+                                                                workA.p, nwork.p + 3, lsum.p);
+    }
     c->lc.n++;
     u32 n_slow = read_u32s(c, nwork.p + 3);
     if (n_slow) {
@@ -941,7 +1085,11 @@ void stage_string_graph(cb_ctx* c) {
     }
     if (cur_n) {
       c->lc.begin("tr_final");
-      if (dist) tr_final_kernel<true><<<slot_grid(slots), 256, 0, s>>>(P, c->ckB.keys.p);
+      if (by_list) {
+        const int grid = slot_grid(c->n_list_order);
+        if (dist) tr_final_lists_kernel<true><<<grid, 256, 0, s>>>(P, c->list_order.p, (u32)c->n_list_order, c->ckB.keys.p);
+        else tr_final_lists_kernel<false><<<grid, 256, 0, s>>>(P, c->list_order.p, (u32)c->n_list_order, c->ckB.keys.p);
+      } else if (dist) tr_final_kernel<true><<<slot_grid(slots), 256, 0, s>>>(P, c->ckB.keys.p);
       else tr_final_kernel<false><<<slot_grid(slots), 256, 0, s>>>(P, c->ckB.keys.p);
       c->lc.end("tr_final");
       c->lc.n++;
