@@ -331,9 +331,15 @@ __global__ void __launch_bounds__(128) dedupe_runs_kernel(const u64* __restrict_
                                                           u32* __restrict__ surv_flag, u32* __restrict__ cov,
                                                           ull* __restrict__ dcount) {
   u32 ns = 0, mx = 0;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_good; i += gridDim.x * blockDim.x) {
-    const u64 ki = keys[i], km = ki & keymask;
-    const u32 li = vals[i];
+  const int lane = threadIdx.x & 31;
+  // block-uniform trip count: the neighbours' rows and id keys come over warp shuffles (every entry gathers
+  // ITS OWN row and id key once; the entries next to it in the sorted order are the lanes next to it, so the
+  // four neighbours need no gathers of their own: 250 -> ~100 bytes of DRAM traffic per read)
+  for (u32 i0 = blockIdx.x * blockDim.x; i0 < n_good; i0 += gridDim.x * blockDim.x) {
+    const u32 i = i0 + threadIdx.x;
+    const bool valid = i < n_good;
+    const u64 ki = valid ? keys[i] : 0ull, km = ki & keymask;
+    const u32 li = valid ? vals[i] : 0u;
     // offsets -2, -1, +1, +2 (index 0..3)
     u64 kn[4];
     u32 ln[4];
@@ -341,34 +347,51 @@ __global__ void __launch_bounds__(128) dedupe_runs_kernel(const u64* __restrict_
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const long long j = (long long)i + (q < 2 ? q - 2 : q - 1);
-      const bool in = j >= 0 && j < (long long)n_good;
+      const bool in = valid && j >= 0 && j < (long long)n_good;
       kn[q] = in ? keys[j] : ~ki;
       ln[q] = in ? vals[j] : 0u;
     }
     // an entry takes part iff the masked hashes agree all the way from i to it
-    const bool run_l1 = (kn[1] & keymask) == km, run_l2 = run_l1 && (kn[0] & keymask) == km;
-    const bool run_r1 = (kn[2] & keymask) == km, run_r2 = run_r1 && (kn[3] & keymask) == km;
+    const bool run_l1 = valid && (kn[1] & keymask) == km, run_l2 = run_l1 && (kn[0] & keymask) == km;
+    const bool run_r1 = valid && (kn[2] & keymask) == km, run_r2 = run_r1 && (kn[3] & keymask) == km;
     hit[0] = run_l2 && kn[0] == ki;
     hit[1] = run_l1 && kn[1] == ki;
     hit[2] = run_r1 && kn[2] == ki;
     hit[3] = run_r2 && kn[3] == ki;
     uint4 qi[NW / 2], qn[4][NW / 2];
     IdKey idn[4];
-    {
+    IdKey mine;
+    mine.hi = mine.lo = 0;
+#pragma unroll
+    for (int w = 0; w < NW / 2; w++) qi[w] = make_uint4(0, 0, 0, 0);
+    if (valid) {
       const uint4* row = reinterpret_cast<const uint4*>(reads + (size_t)li * NW);
 #pragma unroll
       for (int w = 0; w < NW / 2; w++) qi[w] = __ldg(row + w);
+      mine = idkey[li];
     }
-    const IdKey mine = idkey[li];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      if (hit[q]) {
+      const int src = lane + (q < 2 ? q - 2 : q - 1);
+      const bool in_warp = src >= 0 && src < 32;
+      const int from = in_warp ? src : lane;
+#pragma unroll
+      for (int w = 0; w < NW / 2; w++) {
+        qn[q][w].x = __shfl_sync(0xffffffffu, qi[w].x, from);
+        qn[q][w].y = __shfl_sync(0xffffffffu, qi[w].y, from);
+        qn[q][w].z = __shfl_sync(0xffffffffu, qi[w].z, from);
+        qn[q][w].w = __shfl_sync(0xffffffffu, qi[w].w, from);
+      }
+      idn[q].hi = __shfl_sync(0xffffffffu, mine.hi, from);
+      idn[q].lo = __shfl_sync(0xffffffffu, mine.lo, from);
+      if (hit[q] && !in_warp) {  // the neighbour sits in another warp: gather it
         const uint4* row = reinterpret_cast<const uint4*>(reads + (size_t)ln[q] * NW);
 #pragma unroll
         for (int w = 0; w < NW / 2; w++) qn[q][w] = __ldg(row + w);
         idn[q] = idkey[ln[q]];
       }
     }
+    if (!valid) continue;
     u64 ci[NW], cj[NW];
     bool self, self2;
     canon_of<NW>(qi, L, ci, self);
