@@ -206,6 +206,22 @@ class BrushGpu:
         self._check(self._L.cb_debug_sort(self._h, keys.ctypes.data, vals.ctypes.data if vals is not None else None,
                                           len(keys), begin_bit, end_bit))
 
+    def debug_partition(self, keys, vals, kmer_bits):
+        """Test hook: the hash partition of the default path on numpy arrays (keys uint64, vals uint32), in place.
+        Returns (keys[:kept], vals[:kept], bstart) with bstart[b] .. bstart[b+1] the tuples of bucket b."""
+        assert keys.dtype == np.uint64 and vals.dtype == np.uint32 and len(keys) == len(vals)
+        nb, kept = C.c_uint32(), C.c_size_t()
+        self._check(self._L.cb_debug_partition(self._h, keys.ctypes.data, vals.ctypes.data, len(keys), kmer_bits, None, 0,
+                                               C.byref(nb), C.byref(kept)))
+        bstart = np.zeros(nb.value + 1, np.uint32)
+        self._check(self._L.cb_debug_partition(self._h, keys.ctypes.data, vals.ctypes.data, len(keys), kmer_bits,
+                                               bstart.ctypes.data, len(bstart), C.byref(nb), C.byref(kept)))
+        return keys[:kept.value], vals[:kept.value], bstart
+
+    def write_fasta(self, out_dir):
+        """The nodes in Graph2Fasta's format (Graph2Fasta.java:49-75), one part file per rank."""
+        self._check(self._L.cb_write_fasta(self._h, str(out_dir).encode()))
+
     def time_ms(self, what):
         v = C.c_double()
         self._check(self._L.cb_get_time_ms(self._h, what.encode(), C.byref(v)))

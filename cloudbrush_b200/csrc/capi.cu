@@ -280,23 +280,9 @@ static void read_file(const std::string& path, std::vector<char>& out) {
   if (!out.empty() && out.back() != '\n' && out.back() != '\r') out.push_back('\n');  // files are split separately
 }
 
-// Node.str2dna (Node.java:186-211) over a 2-bit packed row
-static std::string encode_dna(const u64* row, int L) {
-  auto code = [&](int i) { return (int)((row[i >> 5] >> (62 - 2 * (i & 31))) & 3); };
-  std::string o;
-  int i = 0;
-  while (i < L) {
-    int r = L - i;
-    if (r >= 2) { o.push_back((char)('A' + 5 * code(i) + 1 + code(i + 1))); i += 2; }
-    else { o.push_back((char)('A' + 5 * code(i))); i += 1; }
-  }
-  return o;
-}
-
 static void reset_after_load(cb_ctx* c) {
   c->loaded = true;
   c->preprocessed = c->overlapped = c->reduced = false;
-  c->host_text.clear();
   c->counters.clear();
   c->ckA = EdgeSet();
   c->ckB = EdgeSet();
@@ -522,7 +508,6 @@ int cb_load_sfa(cb_ctx* c, const char* path) {
   }
   int rc = cb_load_sfa_buffer(c, all.data(), all.size());
   if (rc != CB_OK) return rc;
-  c->host_text.swap(all);
   CB_API_END(c)
 }
 
@@ -737,6 +722,77 @@ int cb_write_nodes(cb_ctx* c, int checkpoint, const char* out_dir) {
   CB_API_END(c)
 }
 
+int cb_write_fasta(cb_ctx* c, const char* out_dir) {
+  CB_API_BEGIN(c)
+  if (!out_dir) throw Error(CB_E_INVALID, "null path");
+  if (!c->preprocessed) throw Error(CB_E_INVALID, "nodes not available");
+  cudaStream_t s = c->stream;
+  wait_node_table(c, true);
+  const bool dist = distributed(c);
+  const u32 lo = dist ? c->node_lo : 0, hi = dist ? c->node_hi : c->n_nodes;
+  const u32 nn = hi - lo;
+  std::vector<u32> cov(nn ? nn : 1);
+  std::vector<u64> seq((size_t)(nn ? nn : 1) * c->NW);
+  std::vector<IdKey> ids(nn ? nn : 1);
+  if (nn) {
+    CB_CUDA(cudaMemcpyAsync(cov.data(), c->node_cov.p + lo, (size_t)nn * 4, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaMemcpyAsync(seq.data(), c->node_seq.p + (size_t)lo * c->NW, (size_t)nn * c->NW * 8, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaMemcpyAsync(ids.data(), c->node_idkey.p + lo, (size_t)nn * sizeof(IdKey), cudaMemcpyDeviceToHost, s));
+  }
+  CB_CUDA(cudaStreamSynchronize(s));
+  std::string dir(out_dir);
+  if (c->cfg.rank == 0) {
+    DIR* d = opendir(dir.c_str());
+    if (d) {
+      while (dirent* de = readdir(d)) {
+        std::string nm = de->d_name;
+        if (nm == "." || nm == "..") continue;
+        unlink((dir + "/" + nm).c_str());
+      }
+      closedir(d);
+    }
+    mkdir(dir.c_str(), 0777);
+  }
+  if (dist) {
+    u64 token = 1;
+    ex_allreduce(c, &token, 1, 0);  // barrier: the directory is clean
+  }
+  char part[32];
+  snprintf(part, sizeof(part), "/part-%05d", c->cfg.rank);
+  int io_err = 0;
+  FILE* f = fopen((dir + part).c_str(), "wb");
+  if (!f) io_err = 1;
+  std::string rec;
+  const int L = c->L;
+  for (u32 i = 0; i < nn && !io_err; i++) {
+    // Graph2Fasta.java:49-75: ">id \t len=<L> \t cov=<Float.toString(cov)>", then the sequence in lines of 60
+    rec.assign(">");
+    char buf[16];
+    const IdKey& k = ids[i];
+    for (int b = 0; b < 8; b++) { buf[b] = (char)(k.hi >> (56 - 8 * b)); buf[8 + b] = (char)(k.lo >> (56 - 8 * b)); }
+    size_t len = 0;
+    while (len < 16 && buf[len]) len++;
+    rec.append(buf, len);
+    rec += "\tlen=" + std::to_string(L) + "\tcov=";
+    if (cov[i] < 10000000u) rec += std::to_string(cov[i]) + ".0";  // Float.toString of an integral value below 1e7
+    else {
+      char e[32];
+      snprintf(e, sizeof(e), "%.7gE7", (double)cov[i] / 1e7);  // (never reached by real inputs)
+      rec += e;
+    }
+    rec += "\n";
+    const u64* row = seq.data() + (size_t)i * c->NW;
+    for (int b = 0; b < L; b++) {
+      rec.push_back("ACGT"[(row[b >> 5] >> (62 - 2 * (b & 31))) & 3]);
+      if ((b + 1) % 60 == 0 || b + 1 == L) rec.push_back('\n');
+    }
+    if (fwrite(rec.data(), 1, rec.size(), f) != rec.size()) io_err = 1;
+  }
+  if (f && fclose(f) != 0) io_err = 1;
+  sync_error(c, io_err ? CB_E_IO : 0, "cannot write " + dir + part);
+  CB_API_END(c)
+}
+
 int cb_get_time_ms(cb_ctx* c, const char* what, double* ms) {
   CB_API_BEGIN(c)
   if (!what || !ms) throw Error(CB_E_INVALID, "null argument");
@@ -770,6 +826,51 @@ int cb_debug_sort(cb_ctx* c, uint64_t* keys, uint32_t* vals, size_t n, int begin
     if (vals) CB_CUDA(cudaMemcpyAsync(vals, w ? vb.p : va.p, n * 4, cudaMemcpyDeviceToHost, s));
   }
   CB_CUDA(cudaStreamSynchronize(s));
+  CB_API_END(c)
+}
+
+int cb_debug_bucket_plan(size_t n_tuples, int32_t* b1, int32_t* b2, uint32_t* n_buckets, int32_t* fits) {
+  if (!b1 || !b2 || !n_buckets || !fits) return CB_E_INVALID;
+  const cb::BucketPlan pl = cb::make_bucket_plan(n_tuples);
+  *b1 = pl.b1;
+  *b2 = pl.b2;
+  *n_buckets = pl.NB;
+  *fits = pl.fits ? 1 : 0;
+  return CB_OK;
+}
+
+int cb_debug_partition(cb_ctx* c, uint64_t* keys, uint32_t* vals, size_t n, int kmer_bits, uint32_t* bstart, size_t bstart_cap,
+                       uint32_t* n_buckets, size_t* n_kept) {
+  CB_API_BEGIN(c)
+  if ((!keys || !vals) && n) throw Error(CB_E_INVALID, "null arrays");
+  if (!n_buckets || !n_kept) throw Error(CB_E_INVALID, "null output");
+  if (kmer_bits < 2 || kmer_bits > 64) throw Error(CB_E_INVALID, "bad k-mer width");
+  cudaStream_t s = c->stream;
+  const BucketPlan pl = make_bucket_plan(n);
+  *n_buckets = pl.NB;
+  if (!bstart || bstart_cap < (size_t)pl.NB + 1) { *n_kept = 0; return CB_OK; }  // size query
+  const size_t n1 = n ? n : 1;
+  DevBuf<u64> ka, kb;
+  DevBuf<u32> va, vb, bs, tot;
+  ka.alloc(n1, s); kb.alloc(n1, s); va.alloc(n1, s); vb.alloc(n1, s);
+  bs.alloc((size_t)pl.NB + 1, s);
+  tot.alloc(1, s);
+  if (n) {
+    CB_CUDA(cudaMemcpyAsync(ka.p, keys, n * 8, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(va.p, vals, n * 4, cudaMemcpyHostToDevice, s));
+  }
+  const u64 kmask = kmer_bits == 64 ? ~0ull : ((1ull << kmer_bits) - 1);
+  bucket_partition(ka.p, va.p, kb.p, vb.p, n, kmask, pl, nullptr, bs.p, tot.p, s, c->lc);
+  u32 kept = 0;
+  CB_CUDA(cudaMemcpyAsync(&kept, tot.p, 4, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaMemcpyAsync(bstart, bs.p, ((size_t)pl.NB + 1) * 4, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  if (kept) {
+    CB_CUDA(cudaMemcpyAsync(keys, ka.p, (size_t)kept * 8, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaMemcpyAsync(vals, va.p, (size_t)kept * 4, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+  }
+  *n_kept = kept;
   CB_API_END(c)
 }
 

@@ -123,7 +123,6 @@ struct cb_ctx {
   cb::DevBuf<char> text;          // owned copy (cb_load_sfa / cb_load_sfa_buffer / cb_load_sfa_device)
   const char* text_ptr = nullptr; // what the kernels read: text.p or a borrowed device buffer
   size_t text_n = 0;
-  std::vector<char> host_text;  // filled lazily (ids are only needed when node text is written)
   bool loaded = false, preprocessed = false, overlapped = false, reduced = false;
 
   // parse

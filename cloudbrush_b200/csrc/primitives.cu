@@ -749,7 +749,7 @@ BucketPlan make_bucket_plan_bits(int nbits) {
 }
 
 BucketPlan make_bucket_plan(size_t n_tuples) {
-  static const size_t avg = getenv("CB_BUCKET_AVG") ? (size_t)atoi(getenv("CB_BUCKET_AVG")) : 640;  // experiment knob
+  static const size_t avg = (getenv("CB_BUCKET_AVG") && atoi(getenv("CB_BUCKET_AVG")) > 0) ? (size_t)atoi(getenv("CB_BUCKET_AVG")) : 640;  // experiment knob
   int nbits = 2;
   while (nbits < 20 && (avg << nbits) < n_tuples) nbits++;
   BucketPlan pl = make_bucket_plan_bits(nbits);

@@ -152,6 +152,10 @@ int cb_export_nodes(cb_ctx* ctx, cb_node* out, size_t cap, size_t* n);
  * output that the unchanged compressChains reads (BrushAssembler.java:75-89, :381). */
 int cb_write_nodes(cb_ctx* ctx, int checkpoint, const char* out_dir);
 
+/* The nodes as FASTA, the format of Graph2Fasta.java:49-75 (">id\tlen=<L>\tcov=<cov>.0", sequence in lines
+ * of 60): <out_dir>/part-000<rank>, emptied first; collective on a sharded context like cb_write_nodes. */
+int cb_write_fasta(cb_ctx* ctx, const char* out_dir);
+
 /* Device time (ms, CUDA events) of the last run of a stage group: "preprocess", "overlap",
  * "string", or one of the per-kernel-group names listed in DESIGN.md ("sort_tuples", ...). */
 int cb_get_time_ms(cb_ctx* ctx, const char* what, double* ms);
@@ -171,6 +175,16 @@ int cb_get_kernel_stat(cb_ctx* ctx, const char* name, double* total_ms, int64_t*
  * caller's HOST arrays in place on the device with the library's LSD radix sort -- stable, on key
  * bits [begin_bit, end_bit) -- and copies them back.  vals may be NULL (keys only).  n < 2^32. */
 int cb_debug_sort(cb_ctx* ctx, uint64_t* keys, uint32_t* vals, size_t n, int begin_bit, int end_bit);
+
+/* Test hooks of the hash partition that replaces the shuffle on the default path (tests/test_gpu_sort.py,
+ * tests/test_capi_host.py).  cb_debug_bucket_plan: the two digit widths, the bucket count and whether two
+ * passes suffice for n_tuples (host only, no device needed).  cb_debug_partition: partitions the caller's HOST
+ * tuples (key = k-mer in the low kmer_bits bits, all-ones keys are dropped) in place on the device:
+ * keys/vals come back bucketed (n_kept of them), bstart[n_buckets + 1] holds the bucket offsets; with
+ * bstart == NULL or too small only *n_buckets is set. */
+int cb_debug_bucket_plan(size_t n_tuples, int32_t* b1, int32_t* b2, uint32_t* n_buckets, int32_t* fits);
+int cb_debug_partition(cb_ctx* ctx, uint64_t* keys, uint32_t* vals, size_t n, int kmer_bits, uint32_t* bstart,
+                       size_t bstart_cap, uint32_t* n_buckets, size_t* n_kept);
 
 /* ---- multi-GPU: one process (and one context) per GPU -------------------------------------
  * The MapReduce shuffle of the reference (HashPartitioner on the Text key inside every

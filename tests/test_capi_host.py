@@ -93,3 +93,20 @@ def test_synthetic_generator_is_deterministic_and_well_formed():
     # forward-only config: every read is a substring of one genome
     c, mc = synth.make_config("cfg2_50k", scale_genome=3000)
     assert mc["both_strands"] is False
+
+
+def test_bucket_plan_sizes_buckets_for_the_bucket_kernel():
+    """make_bucket_plan (host logic, no device): digit widths from {3, 6, 8, 9, 10}, enough buckets that the
+    average stays at or below 640 tuples, two passes refused beyond 2^20 buckets of 640."""
+    from cloudbrush_b200 import _lib
+    lib = _lib.load()
+    b1, b2, nb, fits = C.c_int32(), C.c_int32(), C.c_uint32(), C.c_int32()
+    for n in (0, 1, 1000, 264_112, 69_014_800, 126_674_380, 344_000_000, 671_088_640, 671_088_641, 2_754_195_570):
+        assert lib.cb_debug_bucket_plan(n, C.byref(b1), C.byref(b2), C.byref(nb), C.byref(fits)) == 0
+        assert b1.value in (3, 6, 8, 9, 10) and b2.value in (3, 6, 8, 9, 10) and b1.value >= b2.value
+        assert nb.value == 1 << (b1.value + b2.value)
+        if fits.value:
+            assert n <= 640 * nb.value
+        assert bool(fits.value) == (n <= 640 << 20)
+    assert lib.cb_debug_bucket_plan(69_014_800, C.byref(b1), C.byref(b2), C.byref(nb), C.byref(fits)) == 0
+    assert (b1.value, b2.value) == (9, 8)   # config 2: 131 072 buckets of 526 tuples

@@ -83,3 +83,24 @@ def test_load_paths_agree(tmp_path, ec10k_sfa):
         g.borrow_sfa_device(dev.data_ptr() + 17, 100)
     assert e.value.code == -1
     g.close()
+
+
+def test_fasta_of_the_nodes(tmp_path):
+    """cb_write_fasta: Graph2Fasta.java:49-75 on the node set (id, len, cov, sequence in lines of 60)."""
+    from cases import all_cases
+    buf, k, L = all_cases()["rc_duplicates"]   # ids 9 / 10 / 7 / 8: "10" survives its class with cov 3
+    from parity_util import run_gpu
+    g = run_gpu(buf, k, L)
+    g.write_fasta(tmp_path / "fa")
+    txt = open(tmp_path / "fa" / "part-00000").read().split("\n")
+    reads = dict(l.split("\t") for l in buf.decode().strip().split("\n"))
+    assert txt[0] == ">10\tlen=40\tcov=3.0" and txt[1] == reads["10"]
+    assert txt[2] == ">7\tlen=40\tcov=1.0" and txt[3] == reads["7"] and txt[4] == ""
+    g.close()
+    buf, meta = __import__("cloudbrush_b200").synth.make_config("cfg3_50k", scale_genome=3000)
+    g = run_gpu(bytes(buf), meta["k"], meta["readlen"])
+    g.write_fasta(tmp_path / "fb")
+    lines = open(tmp_path / "fb" / "part-00000").read().split("\n")
+    assert lines[0].startswith(">") and len(lines[1]) == 60 and len(lines[2]) == 40   # 100 bp in lines of 60
+    assert sum(l.startswith(">") for l in lines) == g.counter("nodes")
+    g.close()

@@ -52,3 +52,41 @@ def test_sort_full_tuple_count():
     assert np.array_equal(keys[v], k)                 # a permutation that carries its payload
     same = k[1:] == k[:-1]
     assert np.all(v[1:][same] > v[:-1][same])         # stable
+
+
+def _kmer_hash(x):
+    x = (x * np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    x ^= x >> np.uint64(32)
+    return (x * np.uint64(0xD6E8FEB86659FD93)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+@pytest.mark.parametrize("n,kind", [(0, "random"), (1, "random"), (4097, "random"), (300_000, "random"),
+                                    (300_000, "few_kmers"), (300_000, "invalid_tail"), (5_000_000, "random")])
+def test_hash_partition_buckets(n, kind):
+    """The shuffle replacement of the default path (primitives.cu: bucket_partition): the tuples come back as a
+    permutation of the valid input (all-ones keys dropped), every bucket holds exactly the tuples whose k-mer hash
+    has the bucket's top bits, and payload bits above the k-mer in the key do not influence the bucket."""
+    rng = np.random.default_rng(n + len(kind))
+    kbits = 42
+    kmer = rng.integers(0, 1 << kbits, size=n, dtype=np.uint64)
+    if kind == "few_kmers":
+        kmer = rng.integers(0, 50, size=n, dtype=np.uint64) * np.uint64(0x9E3779B1)
+    high = rng.integers(0, 1 << 20, size=n, dtype=np.uint64) << np.uint64(kbits)  # payload bits above the k-mer
+    keys = kmer | high
+    if kind == "invalid_tail":
+        keys[rng.random(n) < 0.2] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    vals = np.arange(n, dtype=np.uint32)
+    g = _ctx()
+    with np.errstate(over="ignore"):
+        k, v, bstart = g.debug_partition(keys.copy(), vals.copy(), kbits)
+        g.close()
+        valid = keys != np.uint64(0xFFFFFFFFFFFFFFFF)
+        assert len(k) == int(valid.sum()) == int(bstart[-1]) and bstart[0] == 0
+        assert np.all(np.diff(bstart.astype(np.int64)) >= 0)
+        assert np.array_equal(np.sort(v), vals[valid])          # a permutation of the valid tuples ...
+        assert np.array_equal(keys[v], k)                       # ... that carries its key
+        nb = len(bstart) - 1
+        bits = nb.bit_length() - 1
+        want = (_kmer_hash(k & np.uint64((1 << kbits) - 1)) >> np.uint64(64 - bits)).astype(np.int64)
+        got = np.searchsorted(bstart.astype(np.int64), np.arange(len(k)), side="right") - 1
+        assert np.array_equal(got, want)
