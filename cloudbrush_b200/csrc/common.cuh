@@ -119,6 +119,12 @@ struct DevBuf {
     n = count;
     if (count) p = (T*)a->alloc(count * sizeof(T));
   }
+  void borrow(T* ptr, size_t count) {  // a view of memory owned elsewhere (a == nullptr: never freed here)
+    release();
+    p = ptr;
+    n = count;
+    a = nullptr;
+  }
   void release() {
     if (p && a) a->free(p);
     p = nullptr;

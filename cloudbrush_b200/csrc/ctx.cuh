@@ -106,6 +106,16 @@ struct cb_ctx {
   cb::DevBuf<cb::IdKey> own_id_tmp;
   u64* ex_scratch = nullptr;      // small device scratch of the native transport
   size_t ex_scratch_words = 0;
+  u64* ex_host = nullptr;         // its pinned host mirror (same size)
+  // One-sided exchange (native transport, every rank on one NVLink domain): each rank owns a mailbox that
+  // every other rank maps over CUDA IPC; the big exchanges of the path are stores into the peers' mailboxes.
+  bool p2p_tried = false, p2p_on = false;
+  char* p2p_box = nullptr;        // this rank's mailbox (cudaMalloc; valid until the next big exchange)
+  size_t p2p_cap = 0;
+  std::vector<char*> p2p_peer;    // [world] every rank's mailbox as mapped here (own entry: p2p_box)
+  int64_t n_host_coll = 0;        // host-synchronous collectives since cb_preprocess began (counter "host_collectives")
+  int carried_code = 0;           // first rank-local failure since the last checked gather (defer_error)
+  std::string carried_msg;
   int lg_world = 0;               // log2(world)
   int pbit = 0;                   // k-mer groups are owned by rank (key >> pbit) & (world - 1)
   u32 line_base = 0;              // global index of this shard's first SFA line
@@ -200,25 +210,60 @@ inline void guarded(cb_ctx* c, F&& f) {
   }
   sync_error(c, code, msg);
 }
+// The cheaper form of the same rule: the failure is remembered and travels as one extra word with the NEXT
+// checked gather (ex_gather_checked / reduce_counters / route_records), where every rank throws.  Until then
+// the failing rank goes on to that gather and must skip the device work that depended on what failed
+// (failed_locally).  On a single GPU the failure is thrown where it happens.
+void defer_error(cb_ctx* c, int code, const std::string& msg);
+inline bool failed_locally(const cb_ctx* c) { return c->carried_code != 0; }
+template <class F>
+inline void guarded_defer(cb_ctx* c, F&& f) {
+  try {
+    f();
+  } catch (const Error& e) {
+    if (!distributed(c)) throw;
+    defer_error(c, e.code, e.what());
+  }
+}
+// n values of every rank on every rank, through ONE host-synchronous collective
+struct Gathered {
+  int world = 1, n = 0;
+  std::vector<u64> v;  // [world][n]
+  u64 at(int r, int j) const { return v[(size_t)r * n + j]; }
+  u64 sum(int j) const { u64 t = 0; for (int r = 0; r < world; r++) t += at(r, j); return t; }
+  u64 max(int j) const { u64 t = 0; for (int r = 0; r < world; r++) t = at(r, j) > t ? at(r, j) : t; return t; }
+};
+// gathers mine[0..n) and, with them, every rank's deferred failure: if any rank carries one, every rank throws here
+Gathered ex_gather_checked(cb_ctx* c, const u64* mine, int n);
 // in-place max over the ranks of a DEVICE byte array
 void ex_allreduce_max_u8(cb_ctx* c, uint8_t* dev, size_t n);
-void ex_counts(cb_ctx* c, const u64* send, u64* recv, int n_per_rank);
 void ex_alltoallv(cb_ctx* c, const void* send, const u64* send_bytes, void* recv, const u64* recv_bytes);
 // two all-to-alls with the same element counts (keys and payloads of the k-mer tuples) as ONE transfer group
 void ex_alltoallv2(cb_ctx* c, const void* send_a, void* recv_a, size_t elem_a, const void* send_b, void* recv_b,
                    size_t elem_b, const u64* send_cnt, const u64* recv_cnt);
+// The big exchanges (k-mer tuples, duplicate-detection records) as ONE kernel of stores into the peers' mailboxes
+// over NVLink, when the one-sided path is available: M is the gathered count matrix (M.at(src, dst) elements),
+// send[q] holds array q grouped by destination rank.  On success recv[q] points INTO THIS RANK'S MAILBOX (valid
+// until the next big exchange) and the stream has passed a barrier after which every peer's stores have landed.
+// Returns false when the path is not available (callback transport, ranks on different hosts, no peer access):
+// the caller then uses ex_alltoallv.  Collective: every rank takes the same branch.
+bool p2p_exchange(cb_ctx* c, const Gathered& M, int narr, const void* const* send, const size_t* elem, void** recv);
+void p2p_release(cb_ctx* c);
 // the main stream waits for the replicated node table (rest: id keys and SFA lines too)
 void wait_node_table(cb_ctx* c, bool rest);
 void ex_allgatherv(cb_ctx* c, const void* send, u64 send_bytes, void* recv, const u64* recv_bytes);
 // routes n records of elem_bytes (multiple of 4) to rank dest[i] (dest[i] == world: dropped);
 // out receives the records addressed to this rank, grouped by source rank
+// (a checked gather: deferred failures surface here; piggy[0..n_piggy) are summed over the ranks on the way)
+// big: one of the big exchanges -- `out` may then be a view of this rank's mailbox (see p2p_exchange)
 void route_records(cb_ctx* c, const void* recs, size_t elem_bytes, const u32* dest, size_t n, DevBuf<char>& out,
-                   size_t& n_out);
+                   size_t& n_out, u64* piggy = nullptr, int n_piggy = 0, bool big = false);
 // all-gathers a per-rank array of `count` elements into `out` (rank order); counts[r] of every rank
 void gather_all(cb_ctx* c, const void* local, size_t elem_bytes, size_t count, const std::vector<u64>& counts,
                 void* out);
-// global counters (sum over ranks; max for the two maxima); identity on a single GPU
-void reduce_counters(cb_ctx* c);
+// global counters (sum over ranks; max for the two maxima); identity on a single GPU.  One checked gather, which
+// also carries the caller's n_extra values: they come back per rank in columns DC_COUNT + j of the result.
+Gathered reduce_counters(cb_ctx* c, const u64* extra = nullptr, int n_extra = 0);
 
 // stage_preprocess.cu
 void stage_parse_and_pack(cb_ctx* c);

@@ -4,8 +4,10 @@
 // This replaces Hadoop's HashPartitioner + shuffle (every JobClient.runJob of the path, e.g.
 // MatchPrefix.java:468) with: partition on the device -> exchange byte counts -> one all-to-all.
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -114,8 +116,9 @@ void nccl_init(cb_ctx* c, const void* id128) {
     CB_CUDA(cudaEventCreateWithFlags(&c->ev_rest, cudaEventDisableTiming));
   }
   const size_t W = (size_t)c->cfg.world;
-  const size_t words = W * W * 4 + 4 * W + (size_t)DC_COUNT + 64;
+  const size_t words = (W + 1) * (4 * W + (size_t)DC_COUNT + 64);  // a gather of that many values per rank fits
   CB_CUDA(cudaMalloc(&c->ex_scratch, words * sizeof(u64)));
+  CB_CUDA(cudaMallocHost(&c->ex_host, words * sizeof(u64)));
   c->ex_scratch_words = words;
 }
 
@@ -130,8 +133,11 @@ void nccl_shutdown(cb_ctx* c) {
     cudaEventDestroy(c->ev_rest);
     c->side_stream = nullptr;
   }
+  p2p_release(c);
   if (c->ex_scratch) cudaFree(c->ex_scratch);
   c->ex_scratch = nullptr;
+  if (c->ex_host) cudaFreeHost(c->ex_host);
+  c->ex_host = nullptr;
 }
 
 static inline ncclComm_t comm_of(cb_ctx* c) { return (ncclComm_t)c->nccl_comm; }
@@ -145,6 +151,7 @@ static void need_ex(cb_ctx* c) {
 void ex_allreduce(cb_ctx* c, u64* vals, int n, int op) {
   if (!distributed(c)) return;
   need_ex(c);
+  c->n_host_coll++;
   if (c->nccl_comm) {
     if ((size_t)n > c->ex_scratch_words) throw Error(CB_E_INVALID, "ex_allreduce: too many values");
     NcclApi* A = nccl_api();
@@ -170,6 +177,59 @@ void sync_error(cb_ctx* c, int local_code, const std::string& msg) {
   if (v) throw Error(CB_E_CAPACITY, "another rank of the sharded run failed (its cb_last_error has the reason)");
 }
 
+void defer_error(cb_ctx* c, int code, const std::string& msg) {
+  if (!code) return;
+  if (!distributed(c)) throw Error(code, msg);
+  if (!c->carried_code) { c->carried_code = code; c->carried_msg = msg; }
+}
+
+Gathered ex_gather_checked(cb_ctx* c, const u64* mine, int n) {
+  Gathered G;
+  G.world = c->cfg.world;
+  G.n = n;
+  if (!distributed(c)) {
+    G.v.assign(mine, mine + n);
+    return G;
+  }
+  const int code = c->carried_code;
+  const std::string msg = c->carried_msg;
+  c->carried_code = 0;
+  c->carried_msg.clear();
+  need_ex(c);
+  c->n_host_coll++;
+  const size_t W = (size_t)G.world, m = (size_t)n + 1;  // the last word is the failure flag
+  std::vector<u64> all(W * m);
+  if (c->nccl_comm) {
+    if (m + W * m > c->ex_scratch_words) throw Error(CB_E_INVALID, "ex_gather_checked: too many values");
+    u64* h = c->ex_host;
+    for (int j = 0; j < n; j++) h[j] = mine[j];
+    h[n] = code ? 1 : 0;
+    CB_CUDA(cudaMemcpyAsync(c->ex_scratch, h, m * 8, cudaMemcpyHostToDevice, c->stream));
+    CB_NCCL(nccl_api()->AllGather(c->ex_scratch, c->ex_scratch + m, m, ncclUint64, comm_of(c), c->stream));
+    CB_CUDA(cudaMemcpyAsync(h + m, c->ex_scratch + m, W * m * 8, cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(all.data(), h + m, W * m * 8);
+  } else {
+    // the callbacks have an all-to-all of counts: the same m values go to every rank
+    std::vector<u64> snd(W * m);
+    for (size_t r = 0; r < W; r++) {
+      for (int j = 0; j < n; j++) snd[r * m + j] = mine[j];
+      snd[r * m + n] = code ? 1 : 0;
+    }
+    int rc = c->ex.exchange_counts(c->ex.user, (const uint64_t*)snd.data(), (uint64_t*)all.data(), (int)m);
+    if (rc) ex_fail("exchange_counts", rc);
+  }
+  bool other = false;
+  G.v.resize(W * (size_t)n);
+  for (size_t r = 0; r < W; r++) {
+    for (int j = 0; j < n; j++) G.v[r * n + j] = all[r * m + j];
+    if (all[r * m + n]) other = true;
+  }
+  if (code) throw Error(code, msg);
+  if (other) throw Error(CB_E_CAPACITY, "another rank of the sharded run failed (its cb_last_error has the reason)");
+  return G;
+}
+
 void ex_allreduce_max_u8(cb_ctx* c, uint8_t* dev, size_t n) {
   if (!distributed(c)) return;
   need_ex(c);
@@ -181,28 +241,6 @@ void ex_allreduce_max_u8(cb_ctx* c, uint8_t* dev, size_t n) {
   CB_CUDA(cudaStreamSynchronize(c->stream));
   int rc = c->ex.allreduce_max_u8_dev(c->ex.user, dev, (uint64_t)n);
   if (rc) ex_fail("allreduce_max_u8_dev", rc);
-}
-
-void ex_counts(cb_ctx* c, const u64* send, u64* recv, int n_per_rank) {
-  need_ex(c);
-  if (c->nccl_comm) {
-    // every rank's whole send vector is gathered; this rank's column is picked out on the host
-    const size_t W = (size_t)c->cfg.world, m = W * (size_t)n_per_rank;
-    if (m + W * m > c->ex_scratch_words) throw Error(CB_E_INVALID, "ex_counts: too many values");
-    u64* d_send = c->ex_scratch;
-    u64* d_all = c->ex_scratch + m;
-    CB_CUDA(cudaMemcpyAsync(d_send, send, m * 8, cudaMemcpyHostToDevice, c->stream));
-    CB_NCCL(nccl_api()->AllGather(d_send, d_all, m, ncclUint64, comm_of(c), c->stream));
-    std::vector<u64> all(W * m);
-    CB_CUDA(cudaMemcpyAsync(all.data(), d_all, W * m * 8, cudaMemcpyDeviceToHost, c->stream));
-    CB_CUDA(cudaStreamSynchronize(c->stream));
-    for (size_t r = 0; r < W; r++)
-      for (int j = 0; j < n_per_rank; j++)
-        recv[r * n_per_rank + j] = all[r * m + (size_t)c->cfg.rank * n_per_rank + j];
-    return;
-  }
-  int rc = c->ex.exchange_counts(c->ex.user, (const uint64_t*)send, (uint64_t*)recv, n_per_rank);
-  if (rc) ex_fail("exchange_counts", rc);
 }
 
 void ex_alltoallv(cb_ctx* c, const void* send, const u64* send_bytes, void* recv, const u64* recv_bytes) {
@@ -290,6 +328,220 @@ void ex_alltoallv2(cb_ctx* c, const void* send_a, void* recv_a, size_t elem_a, c
   ex_alltoallv(c, send_b, sb.data(), recv_b, rb.data());
 }
 
+// ---------------------------------------------------------------------------------------------
+// One-sided exchange over NVLink.  NCCL's grouped send/recv all-to-all reaches about 300 GB/s per GPU
+// here (it stages through its own FIFOs); the exchange below is one kernel of plain coalesced stores from
+// the send buffer into the peers' mailboxes, every peer at once, followed by a stream-ordered barrier.
+// Safety of the mailbox: a rank writes into a peer's mailbox only after a host-synchronous gather of the
+// same exchange (the count matrix), which the peer enters in stream order after everything that read
+// the mailbox's previous contents.
+// ---------------------------------------------------------------------------------------------
+static void p2p_unmap(cb_ctx* c) {
+  for (int r = 0; r < (int)c->p2p_peer.size(); r++)
+    if (r != c->cfg.rank && c->p2p_peer[r]) {
+      if (cudaIpcCloseMemHandle(c->p2p_peer[r]) != cudaSuccess) cudaGetLastError();
+    }
+  c->p2p_peer.clear();
+}
+
+void p2p_release(cb_ctx* c) {
+  p2p_unmap(c);
+  if (c->p2p_box) cudaFree(c->p2p_box);
+  c->p2p_box = nullptr;
+  c->p2p_cap = 0;
+  c->p2p_on = false;
+  c->p2p_tried = false;
+}
+
+// collective: allocates this rank's mailbox of `cap` bytes and maps every peer's; false (on every rank) if any step
+// fails on any rank
+static bool p2p_map(cb_ctx* c, size_t cap) {
+  const int W = c->cfg.world, me = c->cfg.rank;
+  u64 info[11] = {0};
+  char host[256] = {0};
+  gethostname(host, sizeof(host) - 1);
+  u64 hh = 1469598103934665603ull;
+  for (const char* q = host; *q; q++) hh = (hh ^ (unsigned char)*q) * 1099511628211ull;
+  int dev = 0;
+  cudaIpcMemHandle_t h;
+  memset(&h, 0, sizeof(h));
+  bool ok = cudaGetDevice(&dev) == cudaSuccess;
+  if (ok && cudaMalloc(&c->p2p_box, cap) != cudaSuccess) { cudaGetLastError(); c->p2p_box = nullptr; ok = false; }
+  if (ok && cudaIpcGetMemHandle(&h, c->p2p_box) != cudaSuccess) { cudaGetLastError(); ok = false; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  info[0] = ok ? 1 : 0;
+  info[1] = hh;
+  info[2] = (u64)dev;
+  memcpy(info + 3, &h, 64);
+  const Gathered G = ex_gather_checked(c, info, 11);
+  bool all = true;
+  for (int r = 0; r < W; r++) {
+    if (!G.at(r, 0) || G.at(r, 1) != hh) all = false;
+    for (int q = 0; q < r; q++)
+      if (G.at(q, 2) == G.at(r, 2)) all = false;  // two ranks on one device: not the layout this path is for
+  }
+  u64 ok2 = all ? 1 : 0;
+  if (all) {
+    c->p2p_peer.assign(W, nullptr);
+    c->p2p_peer[me] = c->p2p_box;
+    for (int r = 0; r < W && ok2; r++) {
+      if (r == me) continue;
+      cudaIpcMemHandle_t hr;
+      u64 words[8];
+      for (int j = 0; j < 8; j++) words[j] = G.at(r, 3 + j);
+      memcpy(&hr, words, 64);
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok2 = 0;
+      } else {
+        c->p2p_peer[r] = (char*)ptr;
+      }
+    }
+  }
+  const Gathered G2 = ex_gather_checked(c, &ok2, 1);
+  bool every = true;
+  for (int r = 0; r < W; r++)
+    if (!G2.at(r, 0)) every = false;
+  if (!every) {
+    p2p_unmap(c);
+    // (the peers may still hold this mailbox mapped until they pass the same point: one more gather orders the free)
+    u64 z = 0;
+    ex_gather_checked(c, &z, 1);
+    if (c->p2p_box) cudaFree(c->p2p_box);
+    c->p2p_box = nullptr;
+    return false;
+  }
+  c->p2p_cap = cap;
+  return true;
+}
+
+// collective (the same decision on every rank: need_max is computed from gathered data)
+static bool p2p_ensure(cb_ctx* c, u64 need_max) {
+  static const bool off = getenv("CB_NO_P2P") != nullptr;
+  if (off || !c->nccl_comm || c->cfg.world > 16) return false;
+  if (c->p2p_tried && !c->p2p_on) return false;
+  if (c->p2p_on && c->p2p_cap >= need_max) return true;
+  size_t cap = (size_t)need_max + (size_t)need_max / 8 + (1u << 20);
+  cap = (cap + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+  if (c->p2p_on) {  // grow: nobody may still have the old mailbox mapped when it is freed
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    p2p_unmap(c);
+    u64 z = 0;
+    ex_gather_checked(c, &z, 1);
+    cudaFree(c->p2p_box);
+    c->p2p_box = nullptr;
+    c->p2p_on = false;
+  }
+  c->p2p_tried = true;
+  c->p2p_on = p2p_map(c, cap);
+  return c->p2p_on;
+}
+
+constexpr int kPutSegs = 48;  // 16 ranks x 3 arrays
+struct PutTable {
+  int n;
+  unsigned long long chunks_max;
+  const char* src[kPutSegs];
+  char* dst[kPutSegs];
+  unsigned long long bytes[kPutSegs];
+};
+constexpr u64 kPutChunk = 64 << 10;
+
+// Chunk v of the exchange is chunk v / n of segment v % n: consecutive blocks store to different peers, so every
+// NVLink destination is busy from the first wave on.  The access width is what source, destination and length allow.
+template <class V>
+__device__ __forceinline__ void put_chunk(const char* __restrict__ src, char* __restrict__ dst, u64 bytes) {
+  const V* s = reinterpret_cast<const V*>(src);
+  V* d = reinterpret_cast<V*>(dst);
+  const u64 n = bytes / sizeof(V);
+  u64 i = threadIdx.x;
+  for (; i + 3 * (u64)blockDim.x < n; i += 4 * (u64)blockDim.x) {
+    const V a = s[i], b = s[i + blockDim.x], e = s[i + 2 * (u64)blockDim.x], f = s[i + 3 * (u64)blockDim.x];
+    d[i] = a;
+    d[i + blockDim.x] = b;
+    d[i + 2 * (u64)blockDim.x] = e;
+    d[i + 3 * (u64)blockDim.x] = f;
+  }
+  for (; i < n; i += blockDim.x) d[i] = s[i];
+}
+__global__ void __launch_bounds__(512) p2p_put_kernel(const PutTable T) {
+  const unsigned long long total = T.chunks_max * (unsigned long long)T.n;
+  for (unsigned long long v = blockIdx.x; v < total; v += gridDim.x) {
+    const int sg = (int)(v % (unsigned long long)T.n);
+    const u64 off = (v / (unsigned long long)T.n) * kPutChunk;
+    if (off >= T.bytes[sg]) continue;
+    const u64 len = T.bytes[sg] - off < kPutChunk ? T.bytes[sg] - off : kPutChunk;
+    const char* src = T.src[sg] + off;
+    char* dst = T.dst[sg] + off;
+    const u64 al = (u64)(uintptr_t)src | (u64)(uintptr_t)dst | len;
+    if ((al & 15) == 0) put_chunk<uint4>(src, dst, len);
+    else if ((al & 7) == 0) put_chunk<uint2>(src, dst, len);
+    else put_chunk<u32>(src, dst, len);  // every record of the path is a multiple of 4 bytes
+  }
+}
+
+bool p2p_exchange(cb_ctx* c, const Gathered& M, int narr, const void* const* send, const size_t* elem, void** recv) {
+  if (!distributed(c) || !c->nccl_comm) return false;
+  const int W = c->cfg.world, me = c->cfg.rank;
+  if (W * narr > kPutSegs) return false;
+  auto align = [](u64 b) { return (b + 255) & ~255ull; };
+  // what every rank receives, and the mailbox bytes that takes
+  std::vector<u64> trecv(W, 0);
+  u64 need_max = 0;
+  for (int d = 0; d < W; d++) {
+    for (int q = 0; q < W; q++) trecv[d] += M.at(q, d);
+    u64 need = 0;
+    for (int a = 0; a < narr; a++) need += align(trecv[d] * elem[a]);
+    if (need > need_max) need_max = need;
+  }
+  if (!p2p_ensure(c, need_max)) return false;
+  std::vector<u64> so(W + 1, 0);  // elements before destination d in the send arrays
+  for (int d = 0; d < W; d++) so[d + 1] = so[d] + M.at(me, d);
+  PutTable T;
+  T.n = 0;
+  T.chunks_max = 0;
+  for (int i = 0; i < W; i++) {
+    const int d = (me + 1 + i) % W;  // the ranks do not all start on rank 0; this rank's own part goes last
+    const u64 cnt = M.at(me, d);
+    u64 before = 0;  // elements the ranks below this one put into d's mailbox
+    for (int q = 0; q < me; q++) before += M.at(q, d);
+    u64 base = 0;
+    for (int a = 0; a < narr; a++) {
+      if (cnt) {
+        T.src[T.n] = (const char*)send[a] + so[d] * elem[a];
+        T.dst[T.n] = c->p2p_peer[d] + base + before * elem[a];
+        T.bytes[T.n] = cnt * elem[a];
+        const u64 ch = (T.bytes[T.n] + kPutChunk - 1) / kPutChunk;
+        if (ch > T.chunks_max) T.chunks_max = ch;
+        T.n++;
+      }
+      base += align(trecv[d] * elem[a]);
+    }
+  }
+  {
+    u64 base = 0;
+    for (int a = 0; a < narr; a++) {
+      recv[a] = c->p2p_box + base;
+      base += align(trecv[me] * elem[a]);
+    }
+  }
+  if (T.n) {
+    const unsigned long long total = T.chunks_max * (unsigned long long)T.n;
+    int grid = kNumSMs * 4;
+    if ((unsigned long long)grid > total) grid = (int)total;
+    c->lc.begin("p2p_put");
+    p2p_put_kernel<<<grid, 512, 0, c->stream>>>(T);
+    c->lc.end("p2p_put");
+    c->lc.n++;
+    CB_CUDA(cudaGetLastError());
+  }
+  // barrier in stream order: when it completes here, every rank's put kernel has completed (its stores have landed)
+  u64* bar = c->ex_scratch + c->ex_scratch_words - 1;
+  CB_NCCL(nccl_api()->AllReduce(bar, bar, 1, ncclUint64, ncclSum, comm_of(c), c->stream));
+  return true;
+}
+
 void wait_node_table(cb_ctx* c, bool rest) {
   if (c->gather_pending_seq) {
     CB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_seq, 0));
@@ -301,14 +553,15 @@ void wait_node_table(cb_ctx* c, bool rest) {
   }
 }
 
-void reduce_counters(cb_ctx* c) {
-  for (int i = 0; i < DC_COUNT; i++) c->gcount[i] = c->hcount[i];
-  if (!distributed(c)) return;
-  ex_allreduce(c, (u64*)c->gcount, DC_COUNT, 0);
-  u64 mx[2] = {c->hcount[DC_MAX_COV], c->hcount[DC_MAX_LIST]};
-  ex_allreduce(c, mx, 2, 1);
-  c->gcount[DC_MAX_COV] = mx[0];
-  c->gcount[DC_MAX_LIST] = mx[1];
+Gathered reduce_counters(cb_ctx* c, const u64* extra, int n_extra) {
+  std::vector<u64> mine(DC_COUNT + n_extra);
+  for (int i = 0; i < DC_COUNT; i++) mine[i] = c->hcount[i];
+  for (int j = 0; j < n_extra; j++) mine[DC_COUNT + j] = extra[j];
+  Gathered G = ex_gather_checked(c, mine.data(), DC_COUNT + n_extra);
+  for (int i = 0; i < DC_COUNT; i++) c->gcount[i] = G.sum(i);
+  c->gcount[DC_MAX_COV] = G.max(DC_MAX_COV);
+  c->gcount[DC_MAX_LIST] = G.max(DC_MAX_LIST);
+  return G;
 }
 
 __global__ void __launch_bounds__(256) dest_keys_kernel(const u32* __restrict__ dest, size_t n,
@@ -344,15 +597,15 @@ __global__ void __launch_bounds__(256) gather_records_kernel(const u32* __restri
 }
 
 void route_records(cb_ctx* c, const void* recs, size_t elem_bytes, const u32* dest, size_t n, DevBuf<char>& out,
-                   size_t& n_out) {
+                   size_t& n_out, u64* piggy, int n_piggy, bool big) {
   cudaStream_t s = c->stream;
   const int world = c->cfg.world;
   const int words = (int)(elem_bytes / 4);
   if (elem_bytes % 4) throw Error(CB_E_INVALID, "route_records: record size must be a multiple of 4");
   std::vector<u64> cnt(world + 1, 0), send_bytes(world), recv_bytes(world);
   DevBuf<char> send;
-  guarded(c, [&] {  // every rank reaches the exchange below, whatever happens locally
-    if (!n) { send.alloc(elem_bytes, s); return; }
+  guarded_defer(c, [&] {  // every rank reaches the exchange below, whatever happens locally
+    if (!n || failed_locally(c)) { send.alloc(elem_bytes, s); return; }
     DevBuf<u64> ka, kb;
     DevBuf<u32> va, vb;
     DevBuf<u64> dcnt;
@@ -376,13 +629,27 @@ void route_records(cb_ctx* c, const void* recs, size_t elem_bytes, const u32* de
     c->lc.n += 3;
     CB_CUDA(cudaGetLastError());
   });
-  std::vector<u64> rcnt(world);
-  ex_counts(c, cnt.data(), rcnt.data(), 1);
+  // one gather: the count matrix (row = source rank), the caller's piggy-backed sums, the failure flags
+  if (failed_locally(c)) std::fill(cnt.begin(), cnt.end(), 0);
+  std::vector<u64> mine(cnt.begin(), cnt.begin() + world);
+  for (int j = 0; j < n_piggy; j++) mine.push_back(piggy[j]);
+  const Gathered G = ex_gather_checked(c, mine.data(), world + n_piggy);
+  for (int j = 0; j < n_piggy; j++) piggy[j] = G.sum(world + j);
   n_out = 0;
   for (int r = 0; r < world; r++) {
     send_bytes[r] = cnt[r] * elem_bytes;
-    recv_bytes[r] = rcnt[r] * elem_bytes;
-    n_out += (size_t)rcnt[r];
+    recv_bytes[r] = G.at(r, c->cfg.rank) * elem_bytes;
+    n_out += (size_t)G.at(r, c->cfg.rank);
+  }
+  if (big) {  // stores into the peers' mailboxes when the one-sided path is there
+    const void* snd[1] = {send.p};
+    const size_t el[1] = {elem_bytes};
+    void* rcv[1] = {nullptr};
+    if (p2p_exchange(c, G, 1, snd, el, rcv)) {
+      out.borrow((char*)rcv[0], (n_out ? n_out : 1) * elem_bytes);
+      // (the send buffer goes back to the arena here: the barrier above is stream-ordered after the put kernel)
+      return;
+    }
   }
   out.alloc((n_out ? n_out : 1) * elem_bytes, s);
   ex_alltoallv(c, send.p, send_bytes.data(), out.p, recv_bytes.data());

@@ -1137,7 +1137,12 @@ void stage_build_overlap(cb_ctx* c) {
   const int world = c->cfg.world;
   const u32 wmask = (u32)world - 1;
   size_t Tmax = (size_t)n_own * W;  // tuple slots generated here
-  sync_error(c, Tmax >= (1ull << 32) ? CB_E_CAPACITY : 0, "more than 2^32 k-mer tuples per context");
+  c->carried_code = 0;
+  // (on several GPUs a rank-local failure up to the tuple exchange travels with the exchange's counts)
+  if (Tmax >= (1ull << 32)) {
+    defer_error(c, CB_E_CAPACITY, "more than 2^32 k-mer tuples per context");
+    Tmax = 0;
+  }
   c->lay.nb = nbits;
   c->lay.ob = bits_for((u64)(L - K + 1));
   c->lay.L = L;
@@ -1159,9 +1164,11 @@ void stage_build_overlap(cb_ctx* c) {
   timer_start(c, "keygen");
   DevBuf<u64> keys[2];
   DevBuf<u32> vals[2];
-  for (int i = 0; i < 2; i++) { keys[i].alloc(Tmax ? Tmax : 1, s); vals[i].alloc(Tmax ? Tmax : 1, s); }
+  guarded_defer(c, [&] {
+    for (int i = 0; i < 2; i++) { keys[i].alloc(Tmax ? Tmax : 1, s); vals[i].alloc(Tmax ? Tmax : 1, s); }
+  });
   CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_TUPLES_INVALID, 0, (DC_COUNT - DC_TUPLES_INVALID) * sizeof(u64), s));
-  if (n_own) {
+  if (n_own && !failed_locally(c)) {
     int blocks = div_up(Tmax, 256);
     int cap = kNumSMs * 8 * 4;
     if (blocks > cap) blocks = cap;
@@ -1184,32 +1191,57 @@ void stage_build_overlap(cb_ctx* c) {
     // all-to-all that replaces the MapReduce shuffle
     timer_start(c, "exchange_tuples");
     int w0 = 0;
-    guarded(c, [&] {
+    std::vector<u64> cnt(world, 0), rcnt(world);
+    guarded_defer(c, [&] {
+      if (failed_locally(c)) return;
       w0 = radix_sort(keys[0].p, keys[1].p, vals[0].p, vals[1].p, Tmax, c->pbit, c->pbit + c->lg_world, s, c->lc,
                       "partition");
+      DevBuf<u64> dcnt;
+      dcnt.alloc(world, s);
+      CB_CUDA(cudaMemsetAsync(dcnt.p, 0, world * sizeof(u64), s));
+      if (Tmax) {
+        int blocks = div_up(Tmax, 256 * 16);
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        tuple_dest_hist_kernel<<<blocks, 256, 0, s>>>(keys[w0].p, Tmax, c->pbit, wmask, (ull*)dcnt.p);
+        c->lc.n++;
+      }
+      CB_CUDA(cudaMemcpyAsync(cnt.data(), dcnt.p, world * sizeof(u64), cudaMemcpyDeviceToHost, s));
+      CB_CUDA(cudaStreamSynchronize(s));
     });
-    DevBuf<u64> dcnt;
-    dcnt.alloc(world, s);
-    CB_CUDA(cudaMemsetAsync(dcnt.p, 0, world * sizeof(u64), s));
-    if (Tmax) {
-      int blocks = div_up(Tmax, 256 * 16);
-      if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-      tuple_dest_hist_kernel<<<blocks, 256, 0, s>>>(keys[w0].p, Tmax, c->pbit, wmask, (ull*)dcnt.p);
-      c->lc.n++;
-    }
-    std::vector<u64> cnt(world), rcnt(world), sb(world), rb(world);
-    CB_CUDA(cudaMemcpyAsync(cnt.data(), dcnt.p, world * sizeof(u64), cudaMemcpyDeviceToHost, s));
-    CB_CUDA(cudaStreamSynchronize(s));
-    ex_counts(c, cnt.data(), rcnt.data(), 1);
+    // ONE gather: the whole count matrix (row = sender) and the failure flags.  Every rank sees what every
+    // rank will receive, so the capacity check and the choice of pipeline need no further round trips.
+    if (failed_locally(c)) std::fill(cnt.begin(), cnt.end(), 0);
+    const Gathered G = ex_gather_checked(c, cnt.data(), world);
     size_t Trecv = 0;
-    for (int r = 0; r < world; r++) Trecv += (size_t)rcnt[r];
-    sync_error(c, Trecv >= (1ull << 32) ? CB_E_CAPACITY : 0, "more than 2^32 k-mer tuples per context");
+    bool all_fit = true;
+    for (int r = 0; r < world; r++) {
+      u64 t = 0;
+      for (int q = 0; q < world; q++) t += G.at(q, r);
+      if (t >= (1ull << 32))
+        throw Error(CB_E_CAPACITY, "more than 2^32 k-mer tuples per context (rank " + std::to_string(r) + ")");
+      if (!make_bucket_plan((size_t)t).fits) all_fit = false;
+      if (r == c->cfg.rank) Trecv = (size_t)t;
+      rcnt[r] = G.at(r, c->cfg.rank);
+    }
     DevBuf<u64> rkeys;
     DevBuf<u32> rvals;
-    rkeys.alloc(Trecv ? Trecv : 1, s);
-    rvals.alloc(Trecv ? Trecv : 1, s);
     timer_start(c, "a2a_tuples");
-    ex_alltoallv2(c, keys[w0].p, rkeys.p, 8, vals[w0].p, rvals.p, 4, cnt.data(), rcnt.data());  // one transfer group
+    {
+      // one kernel of stores into the peers' mailboxes over NVLink; NCCL's grouped send/recv otherwise
+      const void* snd[2] = {keys[w0].p, vals[w0].p};
+      const size_t el[2] = {8, 4};
+      void* rcv[2] = {nullptr, nullptr};
+      if (p2p_exchange(c, G, 2, snd, el, rcv)) {
+        rkeys.borrow((u64*)rcv[0], Trecv ? Trecv : 1);
+        rvals.borrow((u32*)rcv[1], Trecv ? Trecv : 1);
+        c->counters["p2p_exchange"] = 1;
+      } else {
+        rkeys.alloc(Trecv ? Trecv : 1, s);
+        rvals.alloc(Trecv ? Trecv : 1, s);
+        ex_alltoallv2(c, keys[w0].p, rkeys.p, 8, vals[w0].p, rvals.p, 4, cnt.data(), rcnt.data());  // one transfer group
+        c->counters["p2p_exchange"] = 0;
+      }
+    }
     timer_stop(c, "a2a_tuples");
     Tmax = Trecv;
     keys[0] = std::move(rkeys);
@@ -1217,9 +1249,7 @@ void stage_build_overlap(cb_ctx* c) {
     keys[1].alloc(Tmax ? Tmax : 1, s);
     vals[1].alloc(Tmax ? Tmax : 1, s);
     plan = make_bucket_plan(Tmax);
-    u64 nofit = plan.fits ? 0 : 1;
-    ex_allreduce(c, &nofit, 1, 1);  // the same pipeline on every rank
-    if (nofit) bucket = false;
+    if (!all_fit) bucket = false;  // the same pipeline on every rank
     timer_stop(c, "exchange_tuples");
   }
 
@@ -1256,11 +1286,11 @@ void stage_build_overlap(cb_ctx* c) {
   if (bucket) {
     bstart.alloc((size_t)plan.NB + 1, s);
     d_total.alloc(1, s);
-    guarded(c, [&] {
+    guarded_defer(c, [&] {  // a failure here surfaces at the gather after the join attempt
       bucket_partition(keys[0].p, vals[0].p, keys[1].p, vals[1].p, Tmax, kmask, plan, fused_count ? cnt1.p : nullptr,
                        bstart.p, d_total.p, s, c->lc);
+      T = read_u32(c, d_total.p);
     });
-    T = read_u32(c, d_total.p);
     where = 0;
   }
   // the LSD sort of the flat pipeline over the first n_sort tuple slots (all-ones keys of windows that emit
@@ -1337,6 +1367,7 @@ void stage_build_overlap(cb_ctx* c) {
     // (DC_HKMER and DC_UPKMER_LISTS of the flat path were counted by group_walk_kernel and stay)
     CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGES_RAW, 0, (DC_UPKMER_LISTS - DC_EDGES_RAW) * sizeof(u64), s));
     CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_MAX_LIST, 0, sizeof(u64), s));
+    u64 x_over = 0;
     if (bucket) {
       slot_cursor.alloc(2, s);
       list_order.alloc(n_lists ? n_lists : 1, s);
@@ -1355,39 +1386,47 @@ void stage_build_overlap(cb_ctx* c) {
       P.slot_cursor = slot_cursor.p;
       P.slot_cap = slots1;
       P.list_order = list_order.p;
-      c->lc.begin("bucket_join");
-      static const bool force_m64 = getenv("CB_FORCE_M64") != nullptr;  // test hook: the wide-payload variant on small inputs
-      const bool m32 = nbits + pb + 1 <= 32 && !force_m64;  // node | window | dir fit the 32-bit payload
-      switch (c->NW) {
-        case 2: launch_bucket_join<2, 7, 1024>(P, plan.NB, m32, s); break;
-        case 4: launch_bucket_join<4, 4, 2048>(P, plan.NB, m32, s); break;
-        case 6: launch_bucket_join<6, 4, 2048>(P, plan.NB, m32, s); break;
-        case 8: launch_bucket_join<8, 4, 2048>(P, plan.NB, m32, s); break;
-        default: throw Error(CB_E_UNSUPPORTED, "read length above 256 bases");
-      }
-      c->lc.end("bucket_join");
-      c->lc.n++;
-      if (have_extra && n_lists) {
-        orphan_lists_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(extra_total.p, n_lists, adj.p, slots.p, slot_cursor.p,
-                                                                        (ull)slots1, list_order.p);
-        c->lc.n++;
-      }
-      CB_CUDA(cudaGetLastError());
-      download_counters(c);
       ull cur[2] = {0, 0};
-      CB_CUDA(cudaMemcpyAsync(cur, slot_cursor.p, 2 * sizeof(ull), cudaMemcpyDeviceToHost, s));
-      CB_CUDA(cudaStreamSynchronize(s));
+      if (!failed_locally(c)) {
+        c->lc.begin("bucket_join");
+        static const bool force_m64 = getenv("CB_FORCE_M64") != nullptr;  // test hook: the wide-payload variant on small inputs
+        const bool m32 = nbits + pb + 1 <= 32 && !force_m64;  // node | window | dir fit the 32-bit payload
+        switch (c->NW) {
+          case 2: launch_bucket_join<2, 7, 1024>(P, plan.NB, m32, s); break;
+          case 4: launch_bucket_join<4, 4, 2048>(P, plan.NB, m32, s); break;
+          case 6: launch_bucket_join<6, 4, 2048>(P, plan.NB, m32, s); break;
+          case 8: launch_bucket_join<8, 4, 2048>(P, plan.NB, m32, s); break;
+          default: throw Error(CB_E_UNSUPPORTED, "read length above 256 bases");
+        }
+        c->lc.end("bucket_join");
+        c->lc.n++;
+        if (have_extra && n_lists) {
+          orphan_lists_kernel<<<div_up((size_t)n_lists, 256), 256, 0, s>>>(extra_total.p, n_lists, adj.p, slots.p, slot_cursor.p,
+                                                                          (ull)slots1, list_order.p);
+          c->lc.n++;
+        }
+        CB_CUDA(cudaGetLastError());
+        CB_CUDA(cudaMemcpyAsync(cur, slot_cursor.p, 2 * sizeof(ull), cudaMemcpyDeviceToHost, s));
+        download_counters(c);
+      }
       const ull used = cur[0];
       n_list_order = (size_t)cur[1];
-      u64 flags[2] = {c->hcount[DC_BUCKET_OVER] ? 1ull : 0ull, used > slots1 ? 1ull : 0ull};
-      ex_allreduce(c, flags, 2, 1);  // every rank takes the same branch: collectives follow
+      n_x = c->hcount[DC_EDGES_RAW];
+      // every rank takes the same branch (collectives follow): one gather for the three retry conditions
+      // and whatever failed locally since the tuple exchange
+      u64 flags[3] = {c->hcount[DC_BUCKET_OVER] ? 1ull : 0ull, used > slots1 ? 1ull : 0ull, n_x > xcap ? 1ull : 0ull};
+      if (distributed(c)) {
+        const Gathered G = ex_gather_checked(c, flags, 3);
+        for (int j = 0; j < 3; j++) flags[j] = G.max(j);
+      }
+      x_over = flags[2];
       if (flags[0] && plan.b1 + plan.b2 < 20 && refine < 2) {
         // a bucket does not fit the kernel: cut the tuples (already compacted to the front of keys[0]) into
         // four times as many buckets first
         refine++;
         plan = make_bucket_plan_bits(plan.b1 + plan.b2 + 2 > 20 ? 20 : plan.b1 + plan.b2 + 2);
         bstart.alloc((size_t)plan.NB + 1, s);
-        guarded(c, [&] {
+        guarded_defer(c, [&] {
           bucket_partition(keys[0].p, vals[0].p, keys[1].p, vals[1].p, T, kmask, plan, nullptr, bstart.p, d_total.p, s, c->lc);
         });
         attempt = -1;
@@ -1405,6 +1444,7 @@ void stage_build_overlap(cb_ctx* c) {
       if (flags[1]) {  // more node entries per group than expected: the exact need is known now
         if (attempt >= 4) throw Error(CB_E_CAPACITY, "adjacency slot capacity");
         if (used > slots1) slots1 = (size_t)used + 1024;
+        if (n_x > xcap) xcap = n_x;  // (known already: saves an attempt)
         continue;
       }
       slots1 = (size_t)used;
@@ -1426,10 +1466,10 @@ void stage_build_overlap(cb_ctx* c) {
       c->lc.n += 2;
       CB_CUDA(cudaGetLastError());
       download_counters(c);
+      n_x = c->hcount[DC_EDGES_RAW];
+      x_over = n_x > xcap ? 1 : 0;
+      ex_allreduce(c, &x_over, 1, 1);  // every rank must take the same branch: collectives follow
     }
-    n_x = c->hcount[DC_EDGES_RAW];
-    u64 x_over = n_x > xcap ? 1 : 0;
-    ex_allreduce(c, &x_over, 1, 1);  // every rank must take the same branch: collectives follow
     if (x_over) {  // side buffer too small: its exact size is known now
       if (attempt >= 4) throw Error(CB_E_CAPACITY, "side buffer overflow");
       if (n_x > xcap) xcap = n_x;
@@ -1487,17 +1527,14 @@ void stage_build_overlap(cb_ctx* c) {
     }
   }
   timer_stop(c, "join_verify");
-  {
-    u64 tg = T;
-    ex_allreduce(c, &tg, 1, 0);
-    c->counters["tuples"] = (int64_t)tg;
-  }
   keys[0].release(); keys[1].release();
   vals[0].release(); vals[1].release();
   (void)sorted;
 
   // BuildHighKmerList's counter (poly-A/T k-mer handled through its global weight)
-  reduce_counters(c);
+  const u64 totals[2] = {T, slots1};
+  const Gathered GT = reduce_counters(c, totals, 2);
+  c->counters["tuples"] = (int64_t)GT.sum(DC_COUNT);
   int64_t hkmer = (int64_t)c->gcount[DC_HKMER] + ((long long)c->gcount[DC_POLYA_WEIGHT] > c->cfg.up_kmer ? 1 : 0);
   c->counters["hkmer"] = hkmer;
   c->counters["candidates_verified"] = (int64_t)c->gcount[DC_CAND_VERIFIED];
@@ -1505,13 +1542,10 @@ void stage_build_overlap(cb_ctx* c) {
   c->counters["upkmer_truncated_lists"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
   c->counters["order_dependent"] = (int64_t)c->gcount[DC_UPKMER_LISTS];
   c->counters["bucket_path"] = bucket ? 1 : 0;
+  c->counters["host_collectives"] = c->n_host_coll;
   c->counters["bucket_refine"] = refine;
   c->counters["bucket_bits"] = plan.b1 + plan.b2;
-  {
-    u64 sg = slots1;
-    ex_allreduce(c, &sg, 1, 0);
-    c->counters["slots"] = (int64_t)sg;
-  }
+  c->counters["slots"] = (int64_t)GT.sum(DC_COUNT + 1);
   if (c->gcount[DC_UPKMER_LISTS] > 0)
     throw Error(CB_E_UNSUPPORTED,
                 "a k-mer group with a node entry holds more than -kmerup tuples: the reference truncates its "

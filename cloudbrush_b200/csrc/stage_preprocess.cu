@@ -533,8 +533,12 @@ __global__ void __launch_bounds__(256) dd_scatter_kernel(const u32* __restrict__
 
 void stage_parse_and_pack(cb_ctx* c) {
   cudaStream_t s = c->stream;
-  const size_t n = c->text_n;
   const int world = c->cfg.world;
+  c->carried_code = 0;
+  c->n_host_coll = 0;
+  // (a shard of 4 GiB or more is treated as empty here and fails every rank at the first gather below)
+  if (c->text_n >= (1ull << 32)) defer_error(c, CB_E_CAPACITY, "SFA input of 4 GiB or more per context");
+  const size_t n = failed_locally(c) ? 0 : c->text_n;
   wait_node_table(c, true);  // a gather of the previous run still in flight: its buffers are reused below
   if (n == 0 && !distributed(c)) throw Error(CB_E_NOREADS, "No good reads");
   c->K = c->cfg.k;
@@ -546,7 +550,6 @@ void stage_parse_and_pack(cb_ctx* c) {
   if (world < 1 || (world & (world - 1)) || world > 256) throw Error(CB_E_UNSUPPORTED, "world must be a power of two <= 256");
   if (distributed(c) && !c->has_ex && !c->nccl_comm)
     throw Error(CB_E_INVALID, "cfg.world > 1 needs cb_init_nccl or cb_set_exchange before cb_preprocess");
-  sync_error(c, n >= (1ull << 32) ? CB_E_CAPACITY : 0, "SFA input of 4 GiB or more per context");
   c->lg_world = 0;
   while ((1 << c->lg_world) < world) c->lg_world++;
   c->pbit = c->K;  // owner of a k-mer group: bits [K, K + lg_world) of the canonical key (its middle bases)
@@ -581,19 +584,6 @@ void stage_parse_and_pack(cb_ctx* c) {
   set_u32_kernel<<<1, 1, 0, s>>>(c->line_start.p + c->n_lines, (u32)n);
   c->lc.n += 3;
 
-  // global line numbering: shards are consecutive line ranges in rank order
-  c->line_bases.assign(world + 1, 0);
-  c->line_base = 0;
-  if (distributed(c)) {
-    std::vector<u64> snd(world, (u64)c->n_lines), rcv(world, 0);
-    ex_counts(c, snd.data(), rcv.data(), 1);
-    for (int r = 0; r < world; r++) c->line_bases[r + 1] = c->line_bases[r] + rcv[r];
-    if (c->line_bases[world] >= (1ull << 32)) throw Error(CB_E_CAPACITY, "more than 2^32 SFA lines");  // same on every rank
-    c->line_base = (u32)c->line_bases[c->cfg.rank];
-  } else {
-    c->line_bases[1] = c->n_lines;
-  }
-
   const u32 nl = c->n_lines;
   const size_t nl1 = nl ? nl : 1;
   c->status.alloc(nl1, s);
@@ -613,7 +603,15 @@ void stage_parse_and_pack(cb_ctx* c) {
   }
   timer_stop(c, "parse");
   download_counters(c);
-  reduce_counters(c);
+  {
+    // one gather: the counters, and the global line numbering (shards are consecutive line ranges in rank order)
+    const u64 my_lines = c->n_lines;
+    const Gathered G = reduce_counters(c, &my_lines, 1);
+    c->line_bases.assign(world + 1, 0);
+    for (int r = 0; r < world; r++) c->line_bases[r + 1] = c->line_bases[r] + G.at(r, DC_COUNT);
+    if (c->line_bases[world] >= (1ull << 32)) throw Error(CB_E_CAPACITY, "more than 2^32 SFA lines");  // same on every rank
+    c->line_base = (u32)c->line_bases[c->cfg.rank];
+  }
   // decisions are taken on the global counters so that every rank takes the same branch
   if (c->gcount[DC_READS_GOOD] == 0) throw Error(CB_E_NOREADS, "No good reads");
   if (c->gcount[DC_LEN_MISMATCH])
@@ -664,7 +662,7 @@ void stage_parse_and_pack(cb_ctx* c) {
     }
     DevBuf<char> got;
     size_t n_got = 0;
-    route_records(c, recs.p, rec_words * 8, dest.p, nl, got, n_got);
+    route_records(c, recs.p, rec_words * 8, dest.p, nl, got, n_got, nullptr, 0, true);  // (a big exchange)
     recs.release();
     timer_stop(c, "dd_route");
     const size_t g1 = n_got ? n_got : 1;
@@ -676,13 +674,13 @@ void stage_parse_and_pack(cb_ctx* c) {
     CB_CUDA(cudaMemsetAsync(rsurv.p, 0, g1 * 4, s));
     CB_CUDA(cudaMemsetAsync(rcov.p, 0, g1 * 4, s));
     int where = 0;
-    guarded(c, [&] {  // a rank-local sort failure must not leave the peers blocked in the next exchange
+    guarded_defer(c, [&] {  // a rank-local sort failure travels with the next exchange's counts
       if (!n_got) return;
       CB_DISPATCH_NW(NW, (dd_unpack_kernel<NW_><<<div_up(n_got, 256), 256, 0, s>>>((const u64*)got.p, n_got, rk[0].p,
                                                                                   rv[0].p, rline.p, rid.p, rreads.p)));
       where = radix_sort(rk[0].p, rk[1].p, rv[0].p, rv[1].p, n_got, 0, hb, s, c->lc, "dedupe");
     });
-    if (n_got) {
+    if (n_got && !failed_locally(c)) {
       c->lc.begin("dedupe_runs");
       CB_DISPATCH_NW(NW, (dedupe_runs_kernel<NW_><<<min(div_up(n_got, 128), kNumSMs * 16), 128, 0, s>>>(
                              rk[where].p, rv[where].p, (u32)n_got, keymask, rreads.p, rid.p, c->L, rsurv.p, rcov.p,
@@ -697,7 +695,7 @@ void stage_parse_and_pack(cb_ctx* c) {
     DevBuf<u32> ret, rdest;
     ret.alloc(g1 * 2, s);
     rdest.alloc(g1, s);
-    if (n_got) {
+    if (n_got && !failed_locally(c)) {
       dd_return_kernel<<<div_up(n_got, 256), 256, 0, s>>>(rsurv.p, rcov.p, rline.p, n_got, dbases.p, world, ret.p,
                                                          rdest.p);
       c->lc.n++;
@@ -715,7 +713,8 @@ void stage_parse_and_pack(cb_ctx* c) {
     download_counters(c);
     n_local_nodes = (u32)n_back;
   }
-  reduce_counters(c);
+  const u64 my_nodes = n_local_nodes;
+  const Gathered GN = reduce_counters(c, &my_nodes, 1);  // the counters and every rank's node count in one gather
 
   // ---- nodes of this shard, in line order ----
   exclusive_scan_u32(surv_flag.p, surv_idx.p, nl1, s, c->lc);
@@ -744,8 +743,8 @@ void stage_parse_and_pack(cb_ctx* c) {
   } else {
     // the node table (packed reads, id keys, coverage) is small and replicated on every rank, so
     // every later gather of a neighbour's sequence is a local HBM read
-    std::vector<u64> snd(world, (u64)n_local_nodes), counts(world, 0);
-    ex_counts(c, snd.data(), counts.data(), 1);
+    std::vector<u64> counts(world, 0);
+    for (int r = 0; r < world; r++) counts[r] = GN.at(r, DC_COUNT);
     u64 total = 0, lo = 0;
     c->node_bases.assign(world + 1, 0);
     for (int r = 0; r < world; r++) {
@@ -799,6 +798,7 @@ void stage_parse_and_pack(cb_ctx* c) {
   C["contained"] = (int64_t)(c->gcount[DC_READS_GOOD] - c->n_nodes);
   C["redundant"] = C["contained"];
   C["nodes"] = (int64_t)c->n_nodes;
+  c->counters["host_collectives"] = c->n_host_coll;
   // free what later stages do not need (node arrays carry everything forward)
   c->reads.release();
   c->idkey.release();

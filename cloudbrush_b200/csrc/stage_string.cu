@@ -842,17 +842,19 @@ static u32 read_u32s(cb_ctx* c, const u32* p) {
 }
 
 // routes device keys to the owner rank of their adjacency list; returns the received keys
-static size_t route_keys(cb_ctx* c, const u64* keys, size_t n, DevBuf<char>& out) {
+static size_t route_keys(cb_ctx* c, const u64* keys, size_t n, DevBuf<char>& out, u64* piggy = nullptr,
+                         int n_piggy = 0) {
   cudaStream_t s = c->stream;
   DevBuf<u32> dest;
-  dest.alloc(n ? n : 1, s);
+  guarded_defer(c, [&] { dest.alloc(n ? n : 1, s); });
+  if (failed_locally(c)) n = 0;
   if (n) {
     CB_DISPATCH_NW(c->NW, (key_owner_s_kernel<NW_><<<div_up(n, 256), 256, 0, s>>>(
                               keys, n, c->lay, c->node_seq.p, c->L, c->K, c->pbit, (u32)c->cfg.world - 1, dest.p)));
     c->lc.n++;
   }
   size_t n_out = 0;
-  route_records(c, keys, 8, dest.p, n, out, n_out);
+  route_records(c, keys, 8, dest.p, n, out, n_out, piggy, n_piggy);
   return n_out;
 }
 
@@ -874,6 +876,7 @@ void stage_string_graph(cb_ctx* c) {
   const size_t nl = n_lists ? n_lists : 1;
   const size_t slots = c->slots ? c->slots : 1;
   const bool dist = distributed(c);
+  c->carried_code = 0;
   wait_node_table(c, true);  // id keys (CutChimericLinks tie-breaks) and SFA lines of every rank's nodes
   CB_CUDA(cudaMemsetAsync(c->dcount.p + DC_EDGE_REMOVAL, 0, (DC_COUNT - DC_EDGE_REMOVAL) * sizeof(u64), s));
   c->list_flag.alloc((nl + 3) & ~(size_t)3, s);
@@ -938,7 +941,8 @@ void stage_string_graph(cb_ctx* c) {
     u32 n_work = n_bad;
     for (int round = 1; round <= 2; round++) {
       u64 any_work = n_work;
-      ex_allreduce(c, &any_work, 1, 0);  // every rank must take the same branches (collectives below)
+      // every rank must take the same branches (collectives below); a cut-log failure of round 1 surfaces here too
+      if (dist) any_work = ex_gather_checked(c, &any_work, 1).sum(0);
       if (any_work == 0) break;
       u32* dirty = (round == 1) ? workB.p : workA.p;  // round 2 reuses A's storage: its list is consumed
       u32* n_dirty = nwork.p + round;
@@ -965,26 +969,35 @@ void stage_string_graph(cb_ctx* c) {
         CB_CUDA(cudaGetLastError());
       }
       size_t n_req_applied = 0;
+      u64 cuts = 0;
+      u32 nd = 0;
       if (dist) {  // removal requests for mirrors -> owner rank of the mirror's list
-        u32 nr = read_u32s(c, nwork.p + 4);
-        sync_error(c, nr > P.req_cap ? CB_E_CAPACITY : 0, "removal request buffer overflow");
-        if (nr > P.req_cap) nr = P.req_cap;
+        u32 nr = 0;
+        CB_CUDA(cudaMemcpyAsync(&nr, nwork.p + 4, 4, cudaMemcpyDeviceToHost, s));
+        download_counters(c);  // (the cut kernel is the only one that counts DC_EDGE_REMOVAL)
+        if (nr > P.req_cap) {
+          defer_error(c, CB_E_CAPACITY, "removal request buffer overflow");
+          nr = P.req_cap;
+        }
+        // the exchange's own gather also sums the cuts of the round and carries the failure flags
+        cuts = c->hcount[DC_EDGE_REMOVAL];
         DevBuf<char> got;
-        size_t n_got = route_keys(c, req.p, nr, got);
+        size_t n_got = route_keys(c, req.p, nr, got, &cuts, 1);
         n_req_applied = n_got;
         if (n_got) {
           apply_removal_requests_kernel<<<div_up(n_got, 256), 256, 0, s>>>(P, (const u64*)got.p, n_got);
           c->lc.n++;
           CB_CUDA(cudaGetLastError());
         }
+      } else {
+        CB_CUDA(cudaMemcpyAsync(&nd, n_dirty, 4, cudaMemcpyDeviceToHost, s));  // (one round trip with the counters)
+        download_counters(c);
+        cuts = c->hcount[DC_EDGE_REMOVAL];
       }
-      download_counters(c);
-      u64 cuts = c->hcount[DC_EDGE_REMOVAL];
-      ex_allreduce(c, &cuts, 1, 0);
       (round == 1 ? e1 : e2) = (int64_t)cuts;
       if (cuts == 0) break;
       // EdgeRemoval: the flagged slots of the lists that lost a record are emptied in place and logged
-      u32 nd = read_u32s(c, n_dirty);
+      if (dist) nd = read_u32s(c, n_dirty);  // (requests applied here have added to the list)
       {  // room for this round's removals: every local cut flags its record, plus the mirrors flagged here
         const size_t add = dist ? (size_t)c->hcount[DC_EDGE_REMOVAL] + n_req_applied : 2 * (size_t)c->hcount[DC_EDGE_REMOVAL];
         const size_t need = c->n_cut_log + add;
@@ -1005,10 +1018,16 @@ void stage_string_graph(cb_ctx* c) {
         c->lc.n++;
         CB_CUDA(cudaGetLastError());
       }
+      u32 n_log = 0;
+      CB_CUDA(cudaMemcpyAsync(&n_log, nwork.p + 7, 4, cudaMemcpyDeviceToHost, s));
       download_counters(c);
       cur_n -= (size_t)c->hcount[DC_EDGES_C];
-      c->n_cut_log = read_u32s(c, nwork.p + 7);
-      sync_error(c, c->n_cut_log > log_cap ? CB_E_CAPACITY : 0, "cut log overflow");
+      c->n_cut_log = n_log;
+      if (c->n_cut_log > log_cap) {  // (cannot happen: the log was sized from the exact counts above)
+        c->n_cut_log = log_cap;
+        c->overlapped = false;  // the slot array no longer restores to 01-overlap: cb_build_overlap must run again
+        defer_error(c, CB_E_CAPACITY, "cut log overflow");
+      }
       // round 2 only has to look at the lists that changed: an unchanged list cuts nothing again
       work = dirty;
       n_work = nd;
@@ -1018,11 +1037,6 @@ void stage_string_graph(cb_ctx* c) {
   c->counters["edge_removal_2"] = e2;
   c->counters["edge_removal"] = e1 > 0 ? e2 : e1;
   timer_stop(c, "cut");
-  {
-    u64 g = cur_n;
-    ex_allreduce(c, &g, 1, 0);
-    c->counters["edges_chl2"] = (int64_t)g;
-  }
 
   // ---- TransitiveReduction + EdgeRemoval (BrushAssembler.java:370-379) ----
   timer_start(c, "tr");
@@ -1070,9 +1084,12 @@ void stage_string_graph(cb_ctx* c) {
         c->lc.n++;
       }
       u32 nv = read_u32s(c, nwork.p + 5);
-      sync_error(c, nv > P.req_cap ? CB_E_CAPACITY : 0, "vote buffer overflow");
+      if (nv > P.req_cap) {
+        defer_error(c, CB_E_CAPACITY, "vote buffer overflow");
+        nv = P.req_cap;
+      }
       u64 any_votes = nv;
-      ex_allreduce(c, &any_votes, 1, 0);
+      any_votes = ex_gather_checked(c, &any_votes, 1).sum(0);  // (and every failure deferred since the cut rounds)
       if (any_votes) {
         DevBuf<char> got;
         size_t n_got = route_keys(c, req.p, nv, got);
@@ -1098,7 +1115,11 @@ void stage_string_graph(cb_ctx* c) {
   }
   timer_stop(c, "tr");
   download_counters(c);
-  reduce_counters(c);
+  {
+    const u64 left = cur_n;
+    const Gathered G = reduce_counters(c, &left, 1);
+    c->counters["edges_chl2"] = (int64_t)G.sum(DC_COUNT);
+  }
   c->ckB.n = (size_t)c->hcount[DC_EDGES_B];
   c->ckB.valid = true;
   c->n_edges_c = cur_n;
@@ -1107,6 +1128,7 @@ void stage_string_graph(cb_ctx* c) {
   c->counters["contained_edge"] = (int64_t)c->gcount[DC_CONTAINED_EDGE];
   c->counters["edges_re"] = (int64_t)c->gcount[DC_EDGES_B];
   c->counters["slow_lists"] = (int64_t)c->gcount[DC_SLOW_LISTS];
+  c->counters["host_collectives"] = c->n_host_coll;
 }
 
 }  // namespace cb
