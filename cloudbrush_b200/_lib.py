@@ -39,7 +39,8 @@ SYMBOLS = ["cb_default_config", "cb_create", "cb_destroy", "cb_last_error", "cb_
            "cb_get_counter", "cb_export_edges", "cb_export_nodes", "cb_write_nodes", "cb_get_time_ms",
            "cb_get_launch_count", "cb_borrow_sfa_device", "cb_set_profile", "cb_get_kernel_stat", "cb_set_exchange",
            "cb_nccl_get_unique_id", "cb_init_nccl", "cb_debug_sort", "cb_prefetch_sfa_buffer", "cb_nccl_last_error",
-           "cb_debug_bucket_plan", "cb_debug_partition", "cb_write_fasta"]
+           "cb_debug_bucket_plan", "cb_debug_partition", "cb_write_fasta", "cb_export_nodes_begin",
+           "cb_export_edges_begin", "cb_export_wait"]
 
 _lib = None
 
@@ -72,6 +73,9 @@ def load():
     L.cb_get_counter.argtypes = [P, C.c_char_p, C.POINTER(C.c_int64)]
     L.cb_export_edges.argtypes = [P, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.cb_export_nodes.argtypes = [P, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.cb_export_edges_begin.argtypes = [P, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.cb_export_nodes_begin.argtypes = [P, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.cb_export_wait.argtypes = [P]
     L.cb_write_nodes.argtypes = [P, C.c_int, C.c_char_p]
     L.cb_write_fasta.argtypes = [P, C.c_char_p]
     L.cb_get_time_ms.argtypes = [P, C.c_char_p, C.POINTER(C.c_double)]

@@ -195,6 +195,26 @@ class BrushGpu:
             self._check(self._L.cb_export_nodes(self._h, out.ctypes.data, len(out), C.byref(n)))
         return out[:n.value]
 
+    def edges_begin(self, checkpoint, out):
+        """Asynchronous edges(): `out` (EDGE_DTYPE view of PINNED host memory, large enough) holds the records
+        after export_wait(); the slice that will be valid is returned at once."""
+        n = C.c_size_t()
+        self._check(self._L.cb_export_edges_begin(self._h, checkpoint, out.ctypes.data, len(out), C.byref(n)))
+        if len(out) < n.value:
+            raise BrushGpuError(-1, f"edges_begin: buffer of {len(out)} records for {n.value}")
+        return out[:n.value]
+
+    def nodes_begin(self, out):
+        """Asynchronous nodes() (see edges_begin)."""
+        n = C.c_size_t()
+        self._check(self._L.cb_export_nodes_begin(self._h, out.ctypes.data, len(out), C.byref(n)))
+        if len(out) < n.value:
+            raise BrushGpuError(-1, f"nodes_begin: buffer of {len(out)} records for {n.value}")
+        return out[:n.value]
+
+    def export_wait(self):
+        self._check(self._L.cb_export_wait(self._h))
+
     def write_nodes(self, checkpoint, out_dir):
         self._check(self._L.cb_write_nodes(self._h, checkpoint, str(out_dir).encode()))
 

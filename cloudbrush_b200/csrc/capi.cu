@@ -28,8 +28,8 @@ void timer_stop(cb_ctx* c, const char* name) {
 }
 
 void download_counters(cb_ctx* c) {
-  CB_CUDA(cudaMemcpyAsync(c->hcount, c->dcount.p, DC_COUNT * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-  CB_CUDA(cudaStreamSynchronize(c->stream));
+  c->lc.rb.get(c->hcount, c->dcount.p, DC_COUNT * sizeof(u64), c->stream);
+  c->lc.rb.sync(c->stream);  // (delivers every small result enqueued before it as well)
 }
 
 // canonical export order (node, type, nbr, ov): compact the occupied slots, re-encode, sort, decode
@@ -127,20 +127,40 @@ static void export_encoded(cb_ctx* c, int ck, DevBuf<u64>& a) {
   }
 }
 
-static void export_edges_to(cb_ctx* c, int ck, cb_edge* out) {
+// the n > 0 records of a checkpoint in export order, on the device
+static void export_edges_dev(cb_ctx* c, int ck, DevBuf<cb_edge>& d) {
   cudaStream_t s = c->stream;
   const size_t n = (size_t)edge_count(c, ck);
-  if (n == 0) return;
   DevBuf<u64> a, b;
   export_encoded(c, ck, a);
   b.alloc(n, s);
   int w = radix_sort(a.p, b.p, nullptr, nullptr, n, 0, c->lay.total_bits(), s, c->lc, "export");
-  DevBuf<cb_edge> d;
   d.alloc(n, s);
   export_decode_kernel<<<div_up(n, 256), 256, 0, s>>>(w ? b.p : a.p, n, c->lay, c->K, c->node_line.p, d.p);
   c->lc.n++;
+}
+
+static void export_edges_to(cb_ctx* c, int ck, cb_edge* out) {
+  cudaStream_t s = c->stream;
+  const size_t n = (size_t)edge_count(c, ck);
+  if (n == 0) return;
+  DevBuf<cb_edge> d;
+  export_edges_dev(c, ck, d);
   CB_CUDA(cudaMemcpyAsync(out, d.p, n * sizeof(cb_edge), cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
+}
+
+// cb_export_*_begin: the copy of a staged result to the caller's memory, behind whatever the context's stream does next
+static void d2h_begin(cb_ctx* c, void* out, const void* dev, size_t bytes) {
+  if (!c->d2h_stream) {
+    CB_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    CB_CUDA(cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming));
+  }
+  CB_CUDA(cudaEventRecord(c->ev_d2h, c->stream));
+  CB_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->ev_d2h, 0));
+  // (the stage groups' own small read-backs do not queue behind this transfer: they do not use the copy engine, ReadBack)
+  CB_CUDA(cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, c->d2h_stream));
+  c->d2h_pending = true;
 }
 
 
@@ -280,6 +300,15 @@ static void read_file(const std::string& path, std::vector<char>& out) {
   if (!out.empty() && out.back() != '\n' && out.back() != '\r') out.push_back('\n');  // files are split separately
 }
 
+// a blocking load replaces whatever was prefetched and not consumed
+static void drop_prefetched(cb_ctx* c) {
+  if (c->next_q.empty()) return;
+  cudaStreamSynchronize(c->copy_stream);
+  for (auto& e : c->next_q)
+    if (e.done) cudaEventDestroy(e.done);
+  c->next_q.clear();
+}
+
 static void reset_after_load(cb_ctx* c) {
   c->loaded = true;
   c->preprocessed = c->overlapped = c->reduced = false;
@@ -363,10 +392,16 @@ void cb_destroy(cb_ctx* c) {
     if (kv.second.b) cudaEventDestroy(kv.second.b);
   }
   cb::nccl_shutdown(c);
+  if (c->d2h_stream) {
+    cudaStreamSynchronize(c->d2h_stream);
+    cudaStreamDestroy(c->d2h_stream);
+    cudaEventDestroy(c->ev_d2h);
+  }
   if (c->copy_stream) {
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamDestroy(c->copy_stream);
-    cudaEventDestroy(c->ev_copy);
+    for (auto& e : c->next_q)
+      if (e.done) cudaEventDestroy(e.done);
     cudaEventDestroy(c->ev_main);
   }
   cudaStream_t s = c->stream;
@@ -385,6 +420,7 @@ int cb_load_sfa_device(cb_ctx* c, const void* dev_buf, size_t n) {
   CB_CUDA(cudaMemsetAsync(c->text.p + n, 0, 32, c->stream));
   CB_CUDA(cudaStreamSynchronize(c->stream));  // the caller's buffer is only borrowed for the call
   c->text_ptr = c->text.p;
+  drop_prefetched(c);
   reset_after_load(c);
   CB_API_END(c)
 }
@@ -398,6 +434,7 @@ int cb_borrow_sfa_device(cb_ctx* c, const void* dev_buf, size_t n) {
   c->text.release();
   c->text_ptr = (const char*)dev_buf;
   c->text_n = n;
+  drop_prefetched(c);
   reset_after_load(c);
   CB_API_END(c)
 }
@@ -458,6 +495,7 @@ int cb_load_sfa_buffer(cb_ctx* c, const char* buf, size_t n) {
   CB_CUDA(cudaMemsetAsync(c->text.p + n, 0, 32, c->stream));
   CB_CUDA(cudaStreamSynchronize(c->stream));  // the caller's buffer is only borrowed for the call
   c->text_ptr = c->text.p;
+  drop_prefetched(c);
   reset_after_load(c);
   CB_API_END(c)
 }
@@ -467,19 +505,27 @@ int cb_prefetch_sfa_buffer(cb_ctx* c, const char* buf, size_t n) {
   if (!buf && n) throw Error(CB_E_INVALID, "null buffer");
   if (!c->copy_stream) {
     CB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CB_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
     CB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
   }
-  if (c->next_pending) CB_CUDA(cudaStreamSynchronize(c->copy_stream));  // a prefetch that was never consumed
-  c->text_next.alloc(n + 32, c->stream);
-  c->text_next_n = n;
-  // the block may have been used by work still queued on the context's stream: the copy starts after it
-  CB_CUDA(cudaEventRecord(c->ev_main, c->stream));
-  CB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
-  if (n) CB_CUDA(cudaMemcpyAsync(c->text_next.p, buf, n, cudaMemcpyHostToDevice, c->copy_stream));
-  CB_CUDA(cudaMemsetAsync(c->text_next.p + n, 0, 32, c->copy_stream));
-  CB_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
-  c->next_pending = true;
+  if (c->next_q.size() >= 2) throw Error(CB_E_INVALID, "cb_prefetch_sfa_buffer: two prefetched inputs are waiting already");
+  c->next_q.emplace_back();
+  cb_ctx::Prefetched& e = c->next_q.back();
+  try {
+    e.buf.alloc(n + 32, c->stream);
+    e.n = n;
+    CB_CUDA(cudaEventCreateWithFlags(&e.done, cudaEventDisableTiming));
+    // the block may have been used by work still queued on the context's stream: the copy starts after it
+    CB_CUDA(cudaEventRecord(c->ev_main, c->stream));
+    CB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+    if (n) CB_CUDA(cudaMemcpyAsync(e.buf.p, buf, n, cudaMemcpyHostToDevice, c->copy_stream));
+    CB_CUDA(cudaMemsetAsync(e.buf.p + n, 0, 32, c->copy_stream));
+    CB_CUDA(cudaEventRecord(e.done, c->copy_stream));
+  } catch (...) {
+    cudaStreamSynchronize(c->copy_stream);
+    if (e.done) cudaEventDestroy(e.done);
+    c->next_q.pop_back();
+    throw;
+  }
   CB_API_END(c)
 }
 
@@ -513,16 +559,15 @@ int cb_load_sfa(cb_ctx* c, const char* path) {
 
 int cb_preprocess(cb_ctx* c) {
   CB_API_BEGIN(c)
-  if (c->next_pending) {  // cb_prefetch_sfa_buffer: the prefetched input becomes the current one
-    c->next_pending = false;
-    std::swap(c->text.p, c->text_next.p);
-    std::swap(c->text.n, c->text_next.n);
-    std::swap(c->text.a, c->text_next.a);
-    c->text_next.release();
-    c->text_n = c->text_next_n;
+  if (!c->next_q.empty()) {  // cb_prefetch_sfa_buffer: the oldest prefetched input becomes the current one
+    cb_ctx::Prefetched& e = c->next_q.front();
+    c->text = std::move(e.buf);  // (the previous input's block goes back to the arena: stream-ordered)
+    c->text_n = e.n;
     c->text_ptr = c->text.p;
     reset_after_load(c);
-    CB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+    CB_CUDA(cudaStreamWaitEvent(c->stream, e.done, 0));
+    cudaEventDestroy(e.done);  // (released once the wait above has been satisfied)
+    c->next_q.pop_front();
   }
   if (!c->loaded) throw Error(CB_E_INVALID, "cb_preprocess: no input loaded");
   c->preprocessed = c->overlapped = c->reduced = false;
@@ -596,6 +641,60 @@ int cb_export_nodes(cb_ctx* c, cb_node* out, size_t cap, size_t* n) {
     c->lc.n++;
     CB_CUDA(cudaMemcpyAsync(out, d.p, (size_t)cnt * sizeof(cb_node), cudaMemcpyDeviceToHost, c->stream));
     CB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  CB_API_END(c)
+}
+
+int cb_export_nodes_begin(cb_ctx* c, cb_node* out, size_t cap, size_t* n) {
+  CB_API_BEGIN(c)
+  if (!n) throw Error(CB_E_INVALID, "null size pointer");
+  if (!c->preprocessed) throw Error(CB_E_INVALID, "nodes not available");
+  const u32 lo = distributed(c) ? c->node_lo : 0, hi = distributed(c) ? c->node_hi : c->n_nodes;
+  const u32 cnt = hi - lo;
+  *n = cnt;
+  if (out && cap >= cnt && cnt) {
+    // (a sharded context whose node table is still being gathered reads its own nodes from the send buffers
+    // instead of making the stream wait for the gather)
+    const u32* lines = c->node_line.p + lo;
+    const u32* covs = c->node_cov.p + lo;
+    if (c->gather_pending_rest && c->own_line_tmp.p && c->own_cov.p) {
+      lines = c->own_line_tmp.p;
+      covs = c->own_cov.p;
+    } else {
+      wait_node_table(c, true);
+    }
+    // a transfer out of the staging buffer may still be running: it is reused only after that
+    if (c->d2h_pending && c->stage_nodes.p) CB_CUDA(cudaStreamSynchronize(c->d2h_stream));
+    c->stage_nodes.alloc(cnt, c->stream);
+    export_nodes_kernel<<<div_up(cnt, 256), 256, 0, c->stream>>>(lines, covs, cnt, c->stage_nodes.p);
+    c->lc.n++;
+    CB_CUDA(cudaGetLastError());
+    d2h_begin(c, out, c->stage_nodes.p, (size_t)cnt * sizeof(cb_node));
+  }
+  CB_API_END(c)
+}
+
+int cb_export_edges_begin(cb_ctx* c, int checkpoint, cb_edge* out, size_t cap, size_t* n) {
+  CB_API_BEGIN(c)
+  if (!n) throw Error(CB_E_INVALID, "null size pointer");
+  const long long cnt = edge_count(c, checkpoint);
+  if (cnt < 0) throw Error(CB_E_INVALID, "checkpoint not available");
+  *n = (size_t)cnt;
+  if (out && cap >= (size_t)cnt && cnt) {
+    wait_node_table(c, true);
+    if (c->d2h_pending && c->stage_edges.p) CB_CUDA(cudaStreamSynchronize(c->d2h_stream));
+    export_edges_dev(c, checkpoint, c->stage_edges);
+    CB_CUDA(cudaGetLastError());
+    d2h_begin(c, out, c->stage_edges.p, (size_t)cnt * sizeof(cb_edge));
+  }
+  CB_API_END(c)
+}
+
+int cb_export_wait(cb_ctx* c) {
+  CB_API_BEGIN(c)
+  if (c->d2h_pending) {
+    CB_CUDA(cudaStreamSynchronize(c->d2h_stream));
+    c->d2h_pending = false;
   }
   CB_API_END(c)
 }

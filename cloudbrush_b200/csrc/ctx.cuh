@@ -1,6 +1,7 @@
 // ctx.cuh -- the context object behind the C ABI (include/cloudbrush_gpu.h) and the stage
 // entry points implemented in the stage_*.cu files.
 #pragma once
+#include <deque>
 #include <map>
 #include <string>
 #include <vector>
@@ -125,11 +126,22 @@ struct cb_ctx {
   uint64_t gcount[cb::DC_COUNT] = {0};  // counters reduced over the ranks
 
   // input text
-  cb::DevBuf<char> text_next;     // cb_prefetch_sfa_buffer: the NEXT input, copied on copy_stream while this one is processed
-  size_t text_next_n = 0;
-  bool next_pending = false;
+  // cb_prefetch_sfa_buffer: the NEXT inputs (at most two), copied on copy_stream while this one is processed
+  struct Prefetched {
+    cb::DevBuf<char> buf;
+    size_t n = 0;
+    cudaEvent_t done = nullptr;  // recorded on copy_stream behind the copy
+  };
+  std::deque<Prefetched> next_q;
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_copy = nullptr, ev_main = nullptr;
+  cudaEvent_t ev_main = nullptr;
+  // cb_export_*_begin: the records are produced on the context's stream into these buffers and copied to the
+  // caller's memory on d2h_stream (device-to-host, next to the prefetch's host-to-device copy)
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t ev_d2h = nullptr;
+  cb::DevBuf<cb_node> stage_nodes;
+  cb::DevBuf<cb_edge> stage_edges;
+  bool d2h_pending = false;
   cb::DevBuf<char> text;          // owned copy (cb_load_sfa / cb_load_sfa_buffer / cb_load_sfa_device)
   const char* text_ptr = nullptr; // what the kernels read: text.p or a borrowed device buffer
   size_t text_n = 0;

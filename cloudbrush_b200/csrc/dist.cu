@@ -619,8 +619,8 @@ void route_records(cb_ctx* c, const void* recs, size_t elem_bytes, const u32* de
     int blocks = div_up(n, 256 * 16);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     dest_hist_kernel<<<blocks, 256, 0, s>>>(w ? kb.p : ka.p, n, world + 1, (ull*)dcnt.p);
-    CB_CUDA(cudaMemcpyAsync(cnt.data(), dcnt.p, (world + 1) * sizeof(u64), cudaMemcpyDeviceToHost, s));
-    CB_CUDA(cudaStreamSynchronize(s));
+    c->lc.rb.get(cnt.data(), dcnt.p, (world + 1) * sizeof(u64), s);
+    c->lc.rb.sync(s);
     size_t n_send = n - (size_t)cnt[world];
     send.alloc((n_send ? n_send : 1) * elem_bytes, s);
     if (n_send)

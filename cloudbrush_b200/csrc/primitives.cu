@@ -17,9 +17,42 @@
 // HBM traffic per pass: 8 B (keys, histogram) + 12 B read + 12 B write per tuple.
 #include <cstdlib>
 
+#include <cstring>
+
 #include "primitives.cuh"
 
 namespace cb {
+
+__global__ void __launch_bounds__(128) read_back_kernel(char* __restrict__ dst, const char* __restrict__ src, int bytes) {
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+}
+
+void ReadBack::get(void* dst, const void* dev_src, size_t bytes, cudaStream_t s) {
+  if (!host) {
+    CB_CUDA(cudaHostAlloc((void**)&host, kCap, cudaHostAllocMapped));
+    CB_CUDA(cudaHostGetDevicePointer((void**)&dev, host, 0));
+  }
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (used + need > kCap) {  // (never on the path: a handful of words per round trip)
+    CB_CUDA(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, s));
+    return;
+  }
+  read_back_kernel<<<1, 128, 0, s>>>(dev + used, (const char*)dev_src, (int)bytes);
+  CB_CUDA(cudaGetLastError());
+  items.push_back({dst, used, bytes});
+  used += need;
+}
+
+void ReadBack::sync(cudaStream_t s) {
+  CB_CUDA(cudaStreamSynchronize(s));
+  for (const Item& it : items) memcpy(it.dst, host + it.off, it.bytes);
+  items.clear();
+  used = 0;
+}
+
+ReadBack::~ReadBack() {
+  if (host) cudaFreeHost(host);
+}
 
 // ------------------------------------------------------------------------------------------
 // exclusive scan
@@ -662,8 +695,8 @@ static int radix_sort_onesweep(u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_
     where ^= 1;
   }
   u32 err = 0;
-  CB_CUDA(cudaMemcpyAsync(&err, ctl.p + 1, 4, cudaMemcpyDeviceToHost, s));
-  CB_CUDA(cudaStreamSynchronize(s));
+  lc.rb.get(&err, ctl.p + 1, 4, s);
+  lc.rb.sync(s);
   if (err) throw Error(CB_E_CUDA, "radix sort: look-back spin limit exceeded");
   return where;
 }

@@ -8,6 +8,27 @@
 
 namespace cb {
 
+// Small results (counters, sizes, flags) come back to the host through a one-block kernel that stores them into
+// mapped pinned host memory, not through the copy engine: a device-to-host copy queues behind the multi-megabyte
+// transfers a pipelined caller keeps in flight (cb_prefetch_sfa_buffer, cb_export_*_begin) and stalled every
+// stage group by the length of such a transfer (tools/e2e_probe.py).
+struct ReadBack {
+  static constexpr size_t kCap = 8192;
+  char* host = nullptr;  // mapped pinned staging area
+  char* dev = nullptr;   // the same memory as the device sees it
+  size_t used = 0;
+  struct Item {
+    void* dst;
+    size_t off, bytes;
+  };
+  std::vector<Item> items;
+  // enqueue: dst[0..bytes) = dev_src[0..bytes) once sync() has returned
+  void get(void* dst, const void* dev_src, size_t bytes, cudaStream_t s);
+  // waits for the stream and delivers everything enqueued
+  void sync(cudaStream_t s);
+  ~ReadBack();
+};
+
 // Counts kernel launches and, in profile mode, brackets the instrumented kernels with CUDA
 // events on the launching stream (bench.py's roofline numbers come from these).
 struct KernelStat {
@@ -17,6 +38,7 @@ struct LaunchCounter {
   int64_t n = 0;
   bool profile = false;
   cudaStream_t stream = nullptr;
+  ReadBack rb;  // (lives here because every primitive already receives the launch counter)
   std::vector<cudaEvent_t> pool;
   size_t used = 0;
   std::map<std::string, KernelStat> stats;

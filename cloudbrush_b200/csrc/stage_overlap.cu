@@ -1029,8 +1029,8 @@ static int bits_for(u64 nvalues) {  // bits needed to store values 0 .. nvalues-
 
 static u32 read_u32(cb_ctx* c, const u32* p) {
   u32 v = 0;
-  CB_CUDA(cudaMemcpyAsync(&v, p, 4, cudaMemcpyDeviceToHost, c->stream));
-  CB_CUDA(cudaStreamSynchronize(c->stream));
+  c->lc.rb.get(&v, p, 4, c->stream);
+  c->lc.rb.sync(c->stream);
   return v;
 }
 
@@ -1205,8 +1205,8 @@ void stage_build_overlap(cb_ctx* c) {
         tuple_dest_hist_kernel<<<blocks, 256, 0, s>>>(keys[w0].p, Tmax, c->pbit, wmask, (ull*)dcnt.p);
         c->lc.n++;
       }
-      CB_CUDA(cudaMemcpyAsync(cnt.data(), dcnt.p, world * sizeof(u64), cudaMemcpyDeviceToHost, s));
-      CB_CUDA(cudaStreamSynchronize(s));
+      c->lc.rb.get(cnt.data(), dcnt.p, world * sizeof(u64), s);
+      c->lc.rb.sync(s);
     });
     // ONE gather: the whole count matrix (row = sender) and the failure flags.  Every rank sees what every
     // rank will receive, so the capacity check and the choice of pipeline need no further round trips.
@@ -1406,7 +1406,7 @@ void stage_build_overlap(cb_ctx* c) {
           c->lc.n++;
         }
         CB_CUDA(cudaGetLastError());
-        CB_CUDA(cudaMemcpyAsync(cur, slot_cursor.p, 2 * sizeof(ull), cudaMemcpyDeviceToHost, s));
+        c->lc.rb.get(cur, slot_cursor.p, 2 * sizeof(ull), s);
         download_counters(c);
       }
       const ull used = cur[0];

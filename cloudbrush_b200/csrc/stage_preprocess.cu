@@ -570,10 +570,10 @@ void stage_parse_and_pack(cb_ctx* c) {
     exclusive_scan_u32(bcnt.p, boff.p, nb, s, c->lc);
     u32 last_cnt = 0, last_off = 0;
     char last_byte = 0;
-    CB_CUDA(cudaMemcpyAsync(&last_cnt, bcnt.p + nb - 1, 4, cudaMemcpyDeviceToHost, s));
-    CB_CUDA(cudaMemcpyAsync(&last_off, boff.p + nb - 1, 4, cudaMemcpyDeviceToHost, s));
-    CB_CUDA(cudaMemcpyAsync(&last_byte, c->text_ptr + n - 1, 1, cudaMemcpyDeviceToHost, s));
-    CB_CUDA(cudaStreamSynchronize(s));
+    c->lc.rb.get(&last_cnt, bcnt.p + nb - 1, 4, s);
+    c->lc.rb.get(&last_off, boff.p + nb - 1, 4, s);
+    c->lc.rb.get(&last_byte, c->text_ptr + n - 1, 1, s);
+    c->lc.rb.sync(s);
     u32 terms = last_cnt + last_off;
     bool last_is_term = (last_byte == '\n' || last_byte == '\r');
     c->n_lines = terms + (last_is_term ? 0 : 1);

@@ -836,8 +836,8 @@ static int slot_grid(size_t slots) {
 
 static u32 read_u32s(cb_ctx* c, const u32* p) {
   u32 v = 0;
-  CB_CUDA(cudaMemcpyAsync(&v, p, 4, cudaMemcpyDeviceToHost, c->stream));
-  CB_CUDA(cudaStreamSynchronize(c->stream));
+  c->lc.rb.get(&v, p, 4, c->stream);
+  c->lc.rb.sync(c->stream);
   return v;
 }
 
@@ -973,7 +973,7 @@ void stage_string_graph(cb_ctx* c) {
       u32 nd = 0;
       if (dist) {  // removal requests for mirrors -> owner rank of the mirror's list
         u32 nr = 0;
-        CB_CUDA(cudaMemcpyAsync(&nr, nwork.p + 4, 4, cudaMemcpyDeviceToHost, s));
+        c->lc.rb.get(&nr, nwork.p + 4, 4, s);
         download_counters(c);  // (the cut kernel is the only one that counts DC_EDGE_REMOVAL)
         if (nr > P.req_cap) {
           defer_error(c, CB_E_CAPACITY, "removal request buffer overflow");
@@ -990,7 +990,7 @@ void stage_string_graph(cb_ctx* c) {
           CB_CUDA(cudaGetLastError());
         }
       } else {
-        CB_CUDA(cudaMemcpyAsync(&nd, n_dirty, 4, cudaMemcpyDeviceToHost, s));  // (one round trip with the counters)
+        c->lc.rb.get(&nd, n_dirty, 4, s);  // (one round trip with the counters)
         download_counters(c);
         cuts = c->hcount[DC_EDGE_REMOVAL];
       }
@@ -1019,7 +1019,7 @@ void stage_string_graph(cb_ctx* c) {
         CB_CUDA(cudaGetLastError());
       }
       u32 n_log = 0;
-      CB_CUDA(cudaMemcpyAsync(&n_log, nwork.p + 7, 4, cudaMemcpyDeviceToHost, s));
+      c->lc.rb.get(&n_log, nwork.p + 7, 4, s);
       download_counters(c);
       cur_n -= (size_t)c->hcount[DC_EDGES_C];
       c->n_cut_log = n_log;

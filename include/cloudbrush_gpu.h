@@ -120,11 +120,12 @@ int cb_load_sfa_device(cb_ctx* ctx, const void* dev_buf, size_t n);
 int cb_borrow_sfa_device(cb_ctx* ctx, const void* dev_buf, size_t n);
 
 /* Pipelined input for callers that process one batch after another: starts the host-to-device copy of
- * the NEXT input on a copy stream of the context's own and returns at once; the copy runs while the stage
- * groups of the current input execute.  The prefetched input becomes the current one at the next
- * cb_preprocess (which waits for the copy).  `buf` must be page-locked host memory and must stay valid
- * and unchanged until that cb_preprocess has returned.  Results of the current input stay available
- * until then. */
+ * a LATER input on a copy stream of the context's own and returns at once; the copy runs while the stage
+ * groups of the current input execute.  Up to two prefetched inputs wait in order (so that the copies run
+ * back to back, also during cb_preprocess; a third is CB_E_INVALID); the oldest becomes the current input
+ * at the next cb_preprocess (which waits for its copy).  `buf` must be page-locked host memory and must
+ * stay valid and unchanged until that cb_preprocess has returned.  Results of the current input stay
+ * available until then.  A blocking cb_load_* / cb_borrow_* discards what was prefetched. */
 int cb_prefetch_sfa_buffer(cb_ctx* ctx, const char* buf, size_t n);
 
 /* The three stage groups, run to completion on the calling thread (see top of file). */
@@ -143,6 +144,17 @@ int cb_get_counter(cb_ctx* ctx, const char* name, int64_t* value);
  * Edges come sorted by (node, type, nbr, ov); nodes by line. */
 int cb_export_edges(cb_ctx* ctx, int checkpoint, cb_edge* out, size_t cap, size_t* n);
 int cb_export_nodes(cb_ctx* ctx, cb_node* out, size_t cap, size_t* n);
+
+/* The same exports for a caller that processes batch after batch (the device-to-host counterpart of
+ * cb_prefetch_sfa_buffer): the records are produced on the context's stream and copied into `out` on a
+ * separate copy stream while the context goes on with its next stage group; *n is set at once, `out`
+ * (pinned host memory, or the copy is not asynchronous) holds the records after cb_export_wait.  One
+ * transfer of each kind may be in flight; a second cb_export_nodes_begin / cb_export_edges_begin first
+ * waits for the transfers before it.  Replaces the same reference steps as the blocking forms
+ * (the part files of TextOutputFormat, BrushAssembler.java:75-89). */
+int cb_export_nodes_begin(cb_ctx* ctx, cb_node* out, size_t cap, size_t* n);
+int cb_export_edges_begin(cb_ctx* ctx, int checkpoint, cb_edge* out, size_t cap, size_t* n);
+int cb_export_wait(cb_ctx* ctx);
 
 /* Writes <out_dir>/part-000<rank> in Node.toNodeMsg format (out_dir is emptied first, like
  * FileSystem.delete(outputPath, true) in every stage's run()): part-00000 on a single GPU.  On a sharded

@@ -252,5 +252,59 @@ def test_prefetch_next_input_while_the_current_one_is_processed():
     g.build_overlap()
     g.string_graph()
     assert np.array_equal(g.edge_rows(3), want_b)
+    # two inputs may wait (the copies then run back to back); they are consumed oldest first
+    g.prefetch_sfa_buffer(pin_a)
+    g.prefetch_sfa_buffer(pin_b)
+    with pytest.raises(IOError):
+        g.prefetch_sfa_buffer(pin_a)
+    g.preprocess()
+    g.build_overlap()
+    assert np.array_equal(g.edge_rows(1), want_a)
+    g.run()
+    assert np.array_equal(g.edge_rows(3), want_b)
+    # a blocking load discards what was prefetched
+    g.prefetch_sfa_buffer(pin_b)
+    g.load_sfa_buffer(a)
+    g.run()
+    assert np.array_equal(g.edge_rows(1), want_a)
+    for x in (g, ref_a, ref_b):
+        x.close()
+
+
+def test_exports_that_overlap_the_next_stage_group():
+    """cb_export_nodes_begin / cb_export_edges_begin / cb_export_wait: the same records as the blocking exports,
+    delivered into pinned host memory while the context already runs the next stage group (and the next input)."""
+    import torch
+    from cloudbrush_b200 import BrushConfig, BrushGpu
+    from cloudbrush_b200.api import EDGE_DTYPE, NODE_DTYPE
+    a, k, L = CASES["tiling_both_strands"]
+    b, _, _ = CASES["branch"]
+    ref_a, ref_b = run_gpu(a, k, L), run_gpu(b, k, L)
+    g = BrushGpu(BrushConfig(k=k, readlen=L))
+    pin_n = torch.zeros(4096 * NODE_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    pin_e = [torch.zeros(65536 * EDGE_DTYPE.itemsize, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    out_n = pin_n.numpy().view(NODE_DTYPE)
+    out_e = [p.numpy().view(EDGE_DTYPE) for p in pin_e]
+    g.load_sfa_buffer(a)
+    g.preprocess()
+    nd = g.nodes_begin(out_n)           # copied while the overlap stage group runs
+    g.build_overlap()
+    g.string_graph()
+    e_a = g.edges_begin(3, out_e[0])    # copied while the next input is loaded and preprocessed
+    g.load_sfa_buffer(b)
+    g.preprocess()
+    g.export_wait()
+    assert np.array_equal(nd, ref_a.nodes()) and np.array_equal(e_a, ref_a.edges(3))
+    nd = g.nodes_begin(out_n)
+    g.build_overlap()
+    e_b1 = g.edges_begin(1, out_e[1])
+    g.string_graph()
+    g.export_wait()
+    assert np.array_equal(nd, ref_b.nodes()) and np.array_equal(e_b1, ref_b.edges(1))
+    e_b3 = g.edges_begin(3, out_e[0])   # the staging buffer is reused only after its transfer
+    g.export_wait()
+    assert np.array_equal(e_b3, ref_b.edges(3))
+    with pytest.raises(IOError):
+        g.edges_begin(3, out_e[0][:1])   # too small: nothing is written, the size is reported
     for x in (g, ref_a, ref_b):
         x.close()
