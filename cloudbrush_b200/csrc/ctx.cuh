@@ -97,6 +97,8 @@ struct cb_ctx {
   cb_exchange ex = {};
   bool has_ex = false;
   void* nccl_comm = nullptr;      // native transport (cb_init_nccl); takes precedence over the callbacks
+  void* nccl_comm_side = nullptr; // a second communicator (ncclCommSplit) for the side stream: NCCL orders the operations
+                                  //   of ONE communicator, so the node-table gather would hold back the main stream's
   cudaStream_t side_stream = nullptr;  // the node-table all-gather runs here, behind keygen + tuple exchange + partition
   cudaStream_t ex_stream = nullptr;    // stream the transport calls are enqueued on (nullptr: the context's stream)
   cudaEvent_t ev_fork = nullptr, ev_seq = nullptr, ev_rest = nullptr;
@@ -264,6 +266,8 @@ void p2p_release(cb_ctx* c);
 // the main stream waits for the replicated node table (rest: id keys and SFA lines too)
 void wait_node_table(cb_ctx* c, bool rest);
 void ex_allgatherv(cb_ctx* c, const void* send, u64 send_bytes, void* recv, const u64* recv_bytes);
+// counts[d] = keys with digit (key >> shift) & mask == d, for keys sorted by that digit (device arrays)
+void sorted_digit_counts(const u64* keys, size_t n, int shift, u32 mask, int nbins, u64* counts, cudaStream_t s);
 // routes n records of elem_bytes (multiple of 4) to rank dest[i] (dest[i] == world: dropped);
 // out receives the records addressed to this rank, grouped by source rank
 // (a checked gather: deferred failures surface here; piggy[0..n_piggy) are summed over the ranks on the way)

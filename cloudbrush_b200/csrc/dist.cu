@@ -29,6 +29,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;  // optional (NCCL >= 2.18)
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -68,6 +69,7 @@ static NcclApi* nccl_api() {
   CB_NCCL_SYM(AllGather, "ncclAllGather")
   CB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef CB_NCCL_SYM
+  api.CommSplit = reinterpret_cast<decltype(api.CommSplit)>(dlsym(api.lib, "ncclCommSplit"));
   return &api;
 }
 
@@ -109,6 +111,11 @@ void nccl_init(cb_ctx* c, const void* id128) {
   ncclComm_t comm = nullptr;
   CB_NCCL(A->CommInitRank(&comm, c->cfg.world, id, c->cfg.rank));
   c->nccl_comm = comm;
+  static const bool one_comm = getenv("CB_ONE_COMM") != nullptr;  // experiment knob
+  if (A->CommSplit && !one_comm) {
+    ncclComm_t side = nullptr;
+    if (A->CommSplit(comm, 0, c->cfg.rank, &side, nullptr) == ncclSuccess && side) c->nccl_comm_side = side;
+  }
   if (!c->side_stream) {
     CB_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
     CB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -123,6 +130,8 @@ void nccl_init(cb_ctx* c, const void* id128) {
 }
 
 void nccl_shutdown(cb_ctx* c) {
+  if (c->nccl_comm_side && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)c->nccl_comm_side);
+  c->nccl_comm_side = nullptr;
   if (c->nccl_comm && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)c->nccl_comm);
   c->nccl_comm = nullptr;
   if (c->side_stream) {
@@ -141,6 +150,10 @@ void nccl_shutdown(cb_ctx* c) {
 }
 
 static inline ncclComm_t comm_of(cb_ctx* c) { return (ncclComm_t)c->nccl_comm; }
+// the communicator of the transfers enqueued on xs(c): the second one while they go to the side stream
+static inline ncclComm_t comm_x(cb_ctx* c) {
+  return (ncclComm_t)((c->ex_stream && c->ex_stream == c->side_stream && c->nccl_comm_side) ? c->nccl_comm_side : c->nccl_comm);
+}
 static inline cudaStream_t xs(cb_ctx* c) { return c->ex_stream ? c->ex_stream : c->stream; }
 
 static void need_ex(cb_ctx* c) {
@@ -256,8 +269,8 @@ void ex_alltoallv(cb_ctx* c, const void* send, const u64* send_bytes, void* recv
       if (r == me) {
         if (send_bytes[r]) CB_CUDA(cudaMemcpyAsync(rp, sp, send_bytes[r], cudaMemcpyDeviceToDevice, xs(c)));
       } else {
-        if (send_bytes[r]) CB_NCCL(A->Send(sp, send_bytes[r], ncclUint8, r, comm_of(c), xs(c)));
-        if (recv_bytes[r]) CB_NCCL(A->Recv(rp, recv_bytes[r], ncclUint8, r, comm_of(c), xs(c)));
+        if (send_bytes[r]) CB_NCCL(A->Send(sp, send_bytes[r], ncclUint8, r, comm_x(c), xs(c)));
+        if (recv_bytes[r]) CB_NCCL(A->Recv(rp, recv_bytes[r], ncclUint8, r, comm_x(c), xs(c)));
       }
       so += send_bytes[r];
       ro += recv_bytes[r];
@@ -282,8 +295,8 @@ void ex_allgatherv(cb_ctx* c, const void* send, u64 send_bytes, void* recv, cons
       if (r == me) {
         if (send_bytes) CB_CUDA(cudaMemcpyAsync(rp, send, send_bytes, cudaMemcpyDeviceToDevice, xs(c)));
       } else {
-        if (send_bytes) CB_NCCL(A->Send(send, send_bytes, ncclUint8, r, comm_of(c), xs(c)));
-        if (recv_bytes[r]) CB_NCCL(A->Recv(rp, recv_bytes[r], ncclUint8, r, comm_of(c), xs(c)));
+        if (send_bytes) CB_NCCL(A->Send(send, send_bytes, ncclUint8, r, comm_x(c), xs(c)));
+        if (recv_bytes[r]) CB_NCCL(A->Recv(rp, recv_bytes[r], ncclUint8, r, comm_x(c), xs(c)));
       }
       ro += recv_bytes[r];
     }
@@ -311,8 +324,8 @@ void ex_alltoallv2(cb_ctx* c, const void* send_a, void* recv_a, size_t elem_a, c
         if (r == me) {
           if (send_cnt[r]) CB_CUDA(cudaMemcpyAsync(rp[q], sp[q], send_cnt[r] * el[q], cudaMemcpyDeviceToDevice, xs(c)));
         } else {
-          if (send_cnt[r]) CB_NCCL(A->Send(sp[q], send_cnt[r] * el[q], ncclUint8, r, comm_of(c), xs(c)));
-          if (recv_cnt[r]) CB_NCCL(A->Recv(rp[q], recv_cnt[r] * el[q], ncclUint8, r, comm_of(c), xs(c)));
+          if (send_cnt[r]) CB_NCCL(A->Send(sp[q], send_cnt[r] * el[q], ncclUint8, r, comm_x(c), xs(c)));
+          if (recv_cnt[r]) CB_NCCL(A->Recv(rp[q], recv_cnt[r] * el[q], ncclUint8, r, comm_x(c), xs(c)));
         }
       }
       so += send_cnt[r];
@@ -527,11 +540,18 @@ bool p2p_exchange(cb_ctx* c, const Gathered& M, int narr, const void* const* sen
     }
   }
   if (T.n) {
+    static const int per_sm = getenv("CB_P2P_BLOCKS") ? atoi(getenv("CB_P2P_BLOCKS")) : 4;  // experiment knobs
+    static const bool use_ce = getenv("CB_P2P_CE") != nullptr;
     const unsigned long long total = T.chunks_max * (unsigned long long)T.n;
-    int grid = kNumSMs * 4;
+    int grid = kNumSMs * (per_sm > 0 ? per_sm : 4);
     if ((unsigned long long)grid > total) grid = (int)total;
     c->lc.begin("p2p_put");
-    p2p_put_kernel<<<grid, 512, 0, c->stream>>>(T);
+    if (use_ce) {  // the copy engines instead of the SMs
+      for (int j = 0; j < T.n; j++)
+        CB_CUDA(cudaMemcpyAsync(T.dst[j], T.src[j], T.bytes[j], cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+      p2p_put_kernel<<<grid, 512, 0, c->stream>>>(T);
+    }
     c->lc.end("p2p_put");
     c->lc.n++;
     CB_CUDA(cudaGetLastError());
@@ -570,19 +590,31 @@ __global__ void __launch_bounds__(256) dest_keys_kernel(const u32* __restrict__ 
   if (i < n) { keys[i] = dest[i]; vals[i] = (u32)i; }
 }
 
-// counts[d] = number of keys equal to d (d <= world), block-local histogram first
-__global__ void __launch_bounds__(256) dest_hist_kernel(const u64* __restrict__ keys, size_t n, int nbins,
-                                                        ull* __restrict__ counts) {
-  __shared__ u32 h[257];
-  for (int t = threadIdx.x; t < nbins; t += blockDim.x) h[t] = 0;
-  __syncthreads();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    u32 d = (u32)keys[i];
-    if ((int)d < nbins) atomicAdd(&h[d], 1u);
+// counts[d] = number of keys whose digit (key >> shift) & mask equals d, for keys SORTED by that digit: one
+// thread per bin finds its bounds by bisection.  (A histogram with a shared-memory atomic per key took 1 ms for
+// the 69 M tuples of config 2: a handful of bins means every lane of a warp hits the same few addresses.)
+__global__ void __launch_bounds__(256) sorted_digit_counts_kernel(const u64* __restrict__ keys, size_t n, int shift,
+                                                                  u32 mask, int nbins, ull* __restrict__ counts) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nbins) return;
+  size_t bound[2];
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const u32 want = (u32)d + q;  // first key with digit >= want
+    size_t a = 0, b = n;
+    while (a < b) {
+      const size_t m = a + ((b - a) >> 1);
+      if (((u32)(keys[m] >> shift) & mask) < want) a = m + 1;
+      else b = m;
+    }
+    bound[q] = a;
   }
-  __syncthreads();
-  for (int t = threadIdx.x; t < nbins; t += blockDim.x)
-    if (h[t]) atomicAdd(&counts[t], (ull)h[t]);
+  counts[d] = (ull)(bound[1] - bound[0]);
+}
+
+void sorted_digit_counts(const u64* keys, size_t n, int shift, u32 mask, int nbins, u64* counts, cudaStream_t s) {
+  sorted_digit_counts_kernel<<<div_up((size_t)nbins, 256), 256, 0, s>>>(keys, n, shift, mask, nbins, (ull*)counts);
+  CB_CUDA(cudaGetLastError());
 }
 
 __global__ void __launch_bounds__(256) gather_records_kernel(const u32* __restrict__ recs, int words,
@@ -616,9 +648,7 @@ void route_records(cb_ctx* c, const void* recs, size_t elem_bytes, const u32* de
     int bits = 1;
     while ((1 << bits) < world + 1) bits++;
     int w = radix_sort(ka.p, kb.p, va.p, vb.p, n, 0, bits, s, c->lc, "route");
-    int blocks = div_up(n, 256 * 16);
-    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    dest_hist_kernel<<<blocks, 256, 0, s>>>(w ? kb.p : ka.p, n, world + 1, (ull*)dcnt.p);
+    sorted_digit_counts(w ? kb.p : ka.p, n, 0, (1u << bits) - 1, world + 1, dcnt.p, s);
     c->lc.rb.get(cnt.data(), dcnt.p, (world + 1) * sizeof(u64), s);
     c->lc.rb.sync(s);
     size_t n_send = n - (size_t)cnt[world];

@@ -995,17 +995,6 @@ __global__ void __launch_bounds__(256) key_owner_kernel(const u64* __restrict__ 
   if (i < n) dest[i] = list_owner<NW>(node_seq, lay.list(keys[i]), L, K, pbit, wmask);
 }
 
-__global__ void __launch_bounds__(256) tuple_dest_hist_kernel(const u64* __restrict__ keys, size_t n, int pbit,
-                                                              u32 wmask, ull* __restrict__ counts) {
-  __shared__ u32 h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    atomicAdd(&h[(u32)(keys[i] >> pbit) & wmask], 1u);
-  __syncthreads();
-  if (threadIdx.x <= wmask && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (ull)h[threadIdx.x]);
-}
-
 __global__ void __launch_bounds__(256) count_invalid_kernel(const u64* __restrict__ keys, size_t n,
                                                             ull* __restrict__ out) {
   u32 c = 0;
@@ -1199,12 +1188,8 @@ void stage_build_overlap(cb_ctx* c) {
       DevBuf<u64> dcnt;
       dcnt.alloc(world, s);
       CB_CUDA(cudaMemsetAsync(dcnt.p, 0, world * sizeof(u64), s));
-      if (Tmax) {
-        int blocks = div_up(Tmax, 256 * 16);
-        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-        tuple_dest_hist_kernel<<<blocks, 256, 0, s>>>(keys[w0].p, Tmax, c->pbit, wmask, (ull*)dcnt.p);
-        c->lc.n++;
-      }
+      sorted_digit_counts(keys[w0].p, Tmax, c->pbit, wmask, world, dcnt.p, s);  // (the tuples are sorted by owner now)
+      c->lc.n++;
       c->lc.rb.get(cnt.data(), dcnt.p, world * sizeof(u64), s);
       c->lc.rb.sync(s);
     });
