@@ -39,6 +39,7 @@ void ReadBack::get(void* dst, const void* dev_src, size_t bytes, cudaStream_t s)
   }
   read_back_kernel<<<1, 128, 0, s>>>(dev + used, (const char*)dev_src, (int)bytes);
   CB_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
   items.push_back({dst, used, bytes});
   used += need;
 }

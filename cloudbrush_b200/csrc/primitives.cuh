@@ -17,6 +17,7 @@ struct ReadBack {
   char* host = nullptr;  // mapped pinned staging area
   char* dev = nullptr;   // the same memory as the device sees it
   size_t used = 0;
+  int64_t* launches = nullptr;  // the owner's launch count (the read-back kernel is one of the library's kernels)
   struct Item {
     void* dst;
     size_t off, bytes;
@@ -39,6 +40,9 @@ struct LaunchCounter {
   bool profile = false;
   cudaStream_t stream = nullptr;
   ReadBack rb;  // (lives here because every primitive already receives the launch counter)
+  LaunchCounter() { rb.launches = &n; }
+  LaunchCounter(const LaunchCounter&) = delete;
+  LaunchCounter& operator=(const LaunchCounter&) = delete;
   std::vector<cudaEvent_t> pool;
   size_t used = 0;
   std::map<std::string, KernelStat> stats;
