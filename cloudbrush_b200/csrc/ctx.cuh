@@ -109,7 +109,6 @@ struct cb_ctx {
   cb::DevBuf<cb::IdKey> own_id_tmp;
   u64* ex_scratch = nullptr;      // small device scratch of the native transport
   size_t ex_scratch_words = 0;
-  u64* ex_host = nullptr;         // its pinned host mirror (same size)
   // One-sided exchange (native transport, every rank on one NVLink domain): each rank owns a mailbox that
   // every other rank maps over CUDA IPC; the big exchanges of the path are stores into the peers' mailboxes.
   bool p2p_tried = false, p2p_on = false;

@@ -125,7 +125,6 @@ void nccl_init(cb_ctx* c, const void* id128) {
   const size_t W = (size_t)c->cfg.world;
   const size_t words = (W + 1) * (4 * W + (size_t)DC_COUNT + 64);  // a gather of that many values per rank fits
   CB_CUDA(cudaMalloc(&c->ex_scratch, words * sizeof(u64)));
-  CB_CUDA(cudaMallocHost(&c->ex_host, words * sizeof(u64)));
   c->ex_scratch_words = words;
 }
 
@@ -145,8 +144,6 @@ void nccl_shutdown(cb_ctx* c) {
   p2p_release(c);
   if (c->ex_scratch) cudaFree(c->ex_scratch);
   c->ex_scratch = nullptr;
-  if (c->ex_host) cudaFreeHost(c->ex_host);
-  c->ex_host = nullptr;
 }
 
 static inline ncclComm_t comm_of(cb_ctx* c) { return (ncclComm_t)c->nccl_comm; }
@@ -168,11 +165,12 @@ void ex_allreduce(cb_ctx* c, u64* vals, int n, int op) {
   if (c->nccl_comm) {
     if ((size_t)n > c->ex_scratch_words) throw Error(CB_E_INVALID, "ex_allreduce: too many values");
     NcclApi* A = nccl_api();
-    CB_CUDA(cudaMemcpyAsync(c->ex_scratch, vals, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    // (the few words travel through mapped pinned memory, not the copy engines: primitives.cuh, ReadBack)
+    c->lc.rb.put(c->ex_scratch, vals, (size_t)n * 8, c->stream);
     CB_NCCL(A->AllReduce(c->ex_scratch, c->ex_scratch, (size_t)n, ncclUint64, op == 0 ? ncclSum : ncclMax, comm_of(c),
                          c->stream));
-    CB_CUDA(cudaMemcpyAsync(vals, c->ex_scratch, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
-    CB_CUDA(cudaStreamSynchronize(c->stream));
+    c->lc.rb.get(vals, c->ex_scratch, (size_t)n * 8, c->stream);
+    c->lc.rb.sync(c->stream);
     return;
   }
   int rc = c->ex.allreduce_u64(c->ex.user, (uint64_t*)vals, n, op);
@@ -214,14 +212,14 @@ Gathered ex_gather_checked(cb_ctx* c, const u64* mine, int n) {
   std::vector<u64> all(W * m);
   if (c->nccl_comm) {
     if (m + W * m > c->ex_scratch_words) throw Error(CB_E_INVALID, "ex_gather_checked: too many values");
-    u64* h = c->ex_host;
-    for (int j = 0; j < n; j++) h[j] = mine[j];
-    h[n] = code ? 1 : 0;
-    CB_CUDA(cudaMemcpyAsync(c->ex_scratch, h, m * 8, cudaMemcpyHostToDevice, c->stream));
+    // (the few words travel through mapped pinned memory, not the copy engines -- a copy would queue behind the
+    // input prefetch / result transfers of a pipelined caller: primitives.cuh, ReadBack)
+    std::vector<u64> snd(mine, mine + n);
+    snd.push_back(code ? 1 : 0);
+    c->lc.rb.put(c->ex_scratch, snd.data(), m * 8, c->stream);
     CB_NCCL(nccl_api()->AllGather(c->ex_scratch, c->ex_scratch + m, m, ncclUint64, comm_of(c), c->stream));
-    CB_CUDA(cudaMemcpyAsync(h + m, c->ex_scratch + m, W * m * 8, cudaMemcpyDeviceToHost, c->stream));
-    CB_CUDA(cudaStreamSynchronize(c->stream));
-    memcpy(all.data(), h + m, W * m * 8);
+    c->lc.rb.get(all.data(), c->ex_scratch + m, W * m * 8, c->stream);
+    c->lc.rb.sync(c->stream);
   } else {
     // the callbacks have an all-to-all of counts: the same m values go to every rank
     std::vector<u64> snd(W * m);

@@ -44,6 +44,23 @@ void ReadBack::get(void* dst, const void* dev_src, size_t bytes, cudaStream_t s)
   used += need;
 }
 
+void ReadBack::put(void* dev_dst, const void* host_src, size_t bytes, cudaStream_t s) {
+  if (!host) {
+    CB_CUDA(cudaHostAlloc((void**)&host, kCap, cudaHostAllocMapped));
+    CB_CUDA(cudaHostGetDevicePointer((void**)&dev, host, 0));
+  }
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (used + need > kCap) {
+    CB_CUDA(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, s));
+    return;
+  }
+  memcpy(host + used, host_src, bytes);  // (the slot is not reused before the next sync())
+  read_back_kernel<<<1, 128, 0, s>>>((char*)dev_dst, dev + used, (int)bytes);
+  CB_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  used += need;
+}
+
 void ReadBack::sync(cudaStream_t s) {
   CB_CUDA(cudaStreamSynchronize(s));
   for (const Item& it : items) memcpy(it.dst, host + it.off, it.bytes);

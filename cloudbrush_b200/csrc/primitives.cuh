@@ -25,6 +25,8 @@ struct ReadBack {
   std::vector<Item> items;
   // enqueue: dst[0..bytes) = dev_src[0..bytes) once sync() has returned
   void get(void* dst, const void* dev_src, size_t bytes, cudaStream_t s);
+  // the other direction: dev_dst[0..bytes) = host_src[0..bytes) (read at the call), in stream order
+  void put(void* dev_dst, const void* host_src, size_t bytes, cudaStream_t s);
   // waits for the stream and delivers everything enqueued
   void sync(cudaStream_t s);
   ~ReadBack();

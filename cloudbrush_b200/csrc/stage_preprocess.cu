@@ -691,7 +691,7 @@ void stage_parse_and_pack(cb_ctx* c) {
     timer_start(c, "dd_return");
     DevBuf<u64> dbases;
     dbases.alloc(world + 1, s);
-    CB_CUDA(cudaMemcpyAsync(dbases.p, c->line_bases.data(), (world + 1) * sizeof(u64), cudaMemcpyHostToDevice, s));
+    c->lc.rb.put(dbases.p, c->line_bases.data(), (world + 1) * sizeof(u64), s);
     DevBuf<u32> ret, rdest;
     ret.alloc(g1 * 2, s);
     rdest.alloc(g1, s);
