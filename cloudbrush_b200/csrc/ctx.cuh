@@ -103,6 +103,8 @@ struct cb_ctx {
   cudaStream_t ex_stream = nullptr;    // stream the transport calls are enqueued on (nullptr: the context's stream)
   cudaEvent_t ev_fork = nullptr, ev_seq = nullptr, ev_rest = nullptr;
   bool gather_pending_seq = false, gather_pending_rest = false;
+  bool gather_deferred = false;   // the gather has not been enqueued yet (launch_node_gather)
+  std::vector<u64> gather_counts; // nodes built by every rank
   cb::DevBuf<u64> own_seq;        // packed reads / coverage of the nodes built from this shard (keygen reads these
   cb::DevBuf<u32> own_cov;        //   while the replicated table is still being gathered)
   cb::DevBuf<u32> own_line_tmp;   // send buffers of the pending gather
@@ -262,6 +264,11 @@ void ex_alltoallv2(cb_ctx* c, const void* send_a, void* recv_a, size_t elem_a, c
 // the caller then uses ex_alltoallv.  Collective: every rank takes the same branch.
 bool p2p_exchange(cb_ctx* c, const Gathered& M, int narr, const void* const* send, const size_t* elem, void** recv);
 void p2p_release(cb_ctx* c);
+// Enqueues the node-table gather that cb_preprocess left pending, on the side stream behind whatever the main
+// stream holds now.  The overlap stage group calls it right AFTER its tuple exchange: issued earlier (round 2,
+// first half) the 1.4 GB gather shared the NVLink with the tuple stores and the exchange could not finish before
+// it (a2a_tuples 2.4 ms for a 0.6 ms put kernel at N=4).  No-op when nothing is pending.
+void launch_node_gather(cb_ctx* c);
 // the main stream waits for the replicated node table (rest: id keys and SFA lines too)
 void wait_node_table(cb_ctx* c, bool rest);
 void ex_allgatherv(cb_ctx* c, const void* send, u64 send_bytes, void* recv, const u64* recv_bytes);

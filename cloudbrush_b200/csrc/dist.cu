@@ -560,7 +560,27 @@ bool p2p_exchange(cb_ctx* c, const Gathered& M, int narr, const void* const* sen
   return true;
 }
 
+void launch_node_gather(cb_ctx* c) {
+  if (!c->gather_deferred) return;
+  c->gather_deferred = false;
+  const size_t n_local = (size_t)(c->node_hi - c->node_lo);
+  CB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+  CB_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+  c->ex_stream = c->side_stream;
+  struct Unset {
+    cb_ctx* c;
+    ~Unset() { c->ex_stream = nullptr; }
+  } unset{c};
+  gather_all(c, c->own_seq.p, (size_t)c->NW * 8, n_local, c->gather_counts, c->node_seq.p);
+  gather_all(c, c->own_cov.p, 4, n_local, c->gather_counts, c->node_cov.p);
+  CB_CUDA(cudaEventRecord(c->ev_seq, c->side_stream));
+  gather_all(c, c->own_line_tmp.p, 4, n_local, c->gather_counts, c->node_line.p);
+  gather_all(c, c->own_id_tmp.p, sizeof(IdKey), n_local, c->gather_counts, c->node_idkey.p);
+  CB_CUDA(cudaEventRecord(c->ev_rest, c->side_stream));
+}
+
 void wait_node_table(cb_ctx* c, bool rest) {
+  launch_node_gather(c);  // (nobody has started it yet: every rank reaches this point in the same call)
   if (c->gather_pending_seq) {
     CB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_seq, 0));
     c->gather_pending_seq = false;

@@ -1228,6 +1228,7 @@ void stage_build_overlap(cb_ctx* c) {
       }
     }
     timer_stop(c, "a2a_tuples");
+    launch_node_gather(c);  // the replicated node table follows the tuples over the NVLink, behind the hash partition
     Tmax = Trecv;
     keys[0] = std::move(rkeys);
     vals[0] = std::move(rvals);

@@ -539,7 +539,12 @@ void stage_parse_and_pack(cb_ctx* c) {
   // (a shard of 4 GiB or more is treated as empty here and fails every rank at the first gather below)
   if (c->text_n >= (1ull << 32)) defer_error(c, CB_E_CAPACITY, "SFA input of 4 GiB or more per context");
   const size_t n = failed_locally(c) ? 0 : c->text_n;
-  wait_node_table(c, true);  // a gather of the previous run still in flight: its buffers are reused below
+  if (c->gather_deferred) {  // the previous run's node-table gather was never needed: it is not started at all
+    c->gather_deferred = false;
+    c->gather_pending_seq = c->gather_pending_rest = false;
+  } else {
+    wait_node_table(c, true);  // a gather of the previous run still in flight: its buffers are reused below
+  }
   if (n == 0 && !distributed(c)) throw Error(CB_E_NOREADS, "No good reads");
   c->K = c->cfg.k;
   c->L = c->cfg.readlen;
@@ -764,24 +769,20 @@ void stage_parse_and_pack(cb_ctx* c) {
     // partition; the join waits for the packed reads and coverage, the string stage for id keys and lines.
     const bool overlap = c->nccl_comm && c->side_stream;
     if (overlap) {
-      CB_CUDA(cudaEventRecord(c->ev_fork, s));
-      CB_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
-      c->ex_stream = c->side_stream;
-    }
-    gather_all(c, l_seq.p, (size_t)c->NW * 8, n_local_nodes, counts, c->node_seq.p);
-    gather_all(c, l_cov.p, 4, n_local_nodes, counts, c->node_cov.p);
-    if (overlap) CB_CUDA(cudaEventRecord(c->ev_seq, c->side_stream));
-    gather_all(c, l_line.p, 4, n_local_nodes, counts, c->node_line.p);
-    gather_all(c, l_id.p, sizeof(IdKey), n_local_nodes, counts, c->node_idkey.p);
-    if (overlap) {
-      CB_CUDA(cudaEventRecord(c->ev_rest, c->side_stream));
-      c->ex_stream = nullptr;
-      c->gather_pending_seq = c->gather_pending_rest = true;
-      // the send buffers must outlive the transfers: they stay with the context (keygen reads them too)
+      // enqueued later (launch_node_gather: behind the tuple exchange of the overlap stage group, or by whoever
+      // needs the table first); the send buffers stay with the context (keygen reads them too)
       c->own_seq = std::move(l_seq);
       c->own_cov = std::move(l_cov);
       c->own_line_tmp = std::move(l_line);
       c->own_id_tmp = std::move(l_id);
+      c->gather_counts = counts;
+      c->gather_deferred = true;
+      c->gather_pending_seq = c->gather_pending_rest = true;
+    } else {
+      gather_all(c, l_seq.p, (size_t)c->NW * 8, n_local_nodes, counts, c->node_seq.p);
+      gather_all(c, l_cov.p, 4, n_local_nodes, counts, c->node_cov.p);
+      gather_all(c, l_line.p, 4, n_local_nodes, counts, c->node_line.p);
+      gather_all(c, l_id.p, sizeof(IdKey), n_local_nodes, counts, c->node_idkey.p);
     }
     timer_stop(c, "node_gather");
   }
