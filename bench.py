@@ -585,13 +585,13 @@ def bench_ours(args):
     # n_it complete results out, the last export waited for inside the timed region.
     pin_e2 = torch.empty_like(pin_e).pin_memory()
     out_e2 = [out_e, pin_e2.numpy().view(EDGE_DTYPE)]
-    n_it = max(2, min(args.steps, 5))
+    n_it = max(4, min(args.steps, 10))
     # Two inputs are prefetched ahead, so the H2D copies run back to back (also during cb_preprocess).
     g.prefetch_sfa_buffer(host)
     for timed in (False, True):
         barrier()
         t1 = time.perf_counter()
-        for i in range(n_it if timed else 2):
+        for i in range(n_it if timed else 3):
             g.prefetch_sfa_buffer(host)  # batch i+1; batch i was prefetched one iteration ago
             g.preprocess()
             g.export_wait()  # the previous batch's edges are in host memory now
