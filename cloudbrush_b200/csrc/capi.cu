@@ -628,16 +628,26 @@ int cb_export_nodes(cb_ctx* c, cb_node* out, size_t cap, size_t* n) {
   CB_API_BEGIN(c)
   if (!n) throw Error(CB_E_INVALID, "null size pointer");
   if (!c->preprocessed) throw Error(CB_E_INVALID, "nodes not available");
-  wait_node_table(c, true);
   // a sharded context exports the nodes built from ITS shard of the SFA lines (the union over the
   // ranks, in rank order, is the node table sorted by line)
   const u32 lo = distributed(c) ? c->node_lo : 0, hi = distributed(c) ? c->node_hi : c->n_nodes;
   const u32 cnt = hi - lo;
   *n = cnt;
   if (out && cap >= cnt && cnt) {
+    // While the replicated table is still being gathered (or its gather has not even been enqueued: that happens
+    // collectively, in cb_build_overlap) the rank's own nodes are read from the gather's send buffers, so this
+    // call never depends on the other ranks.
+    const u32* lines = c->node_line.p + lo;
+    const u32* covs = c->node_cov.p + lo;
+    if (c->gather_pending_rest && c->own_line_tmp.p && c->own_cov.p) {
+      lines = c->own_line_tmp.p;
+      covs = c->own_cov.p;
+    } else {
+      wait_node_table(c, true);
+    }
     DevBuf<cb_node> d;
     d.alloc(cnt, c->stream);
-    export_nodes_kernel<<<div_up(cnt, 256), 256, 0, c->stream>>>(c->node_line.p + lo, c->node_cov.p + lo, cnt, d.p);
+    export_nodes_kernel<<<div_up(cnt, 256), 256, 0, c->stream>>>(lines, covs, cnt, d.p);
     c->lc.n++;
     CB_CUDA(cudaMemcpyAsync(out, d.p, (size_t)cnt * sizeof(cb_node), cudaMemcpyDeviceToHost, c->stream));
     CB_CUDA(cudaStreamSynchronize(c->stream));

@@ -229,7 +229,10 @@ typedef struct cb_exchange {
 /* Must be called before cb_preprocess when cfg.world > 1 (or cb_init_nccl, below).  On a sharded
  * context counters are global sums, cb_export_nodes returns the nodes built from this rank's shard
  * of the SFA lines (in rank order their union is the node table sorted by line) and
- * cb_export_edges the adjacency lists this rank owns (their union over the ranks is the checkpoint). */
+ * cb_export_edges the adjacency lists this rank owns (their union over the ranks is the checkpoint).
+ * cb_preprocess, cb_build_overlap, cb_string_graph, cb_write_nodes and cb_write_fasta are COLLECTIVE on a
+ * sharded context: every rank calls them, in the same order.  The exports (blocking and *_begin) are local:
+ * a rank may call them on its own. */
 int cb_set_exchange(cb_ctx* ctx, const cb_exchange* ex);
 
 /* Native transport: NCCL over NVLink / NVSwitch, driven by the library on its own stream (no host
