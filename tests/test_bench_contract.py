@@ -32,3 +32,16 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 def test_reference_arm_other_ranks_print_nothing():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_numa_binding_is_a_no_op_without_nvml():
+    """bench.bind_to_gpu_numa: without a GPU (NVML cannot initialise) the process affinity is left alone."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    before = os.sched_getaffinity(0)
+    got = bench.bind_to_gpu_numa(0)
+    after = os.sched_getaffinity(0)
+    assert got is None or got == len(after)
+    assert after <= before and len(after) > 0
