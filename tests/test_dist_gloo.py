@@ -15,6 +15,14 @@ def _exchange_worker(rank, world):
     # two values per destination
     got = ex.exchange_counts([100 * rank + 2 * d + j for d in range(world) for j in range(2)])
     assert got.tolist() == [100 * s + 2 * rank + j for s in range(world) for j in range(2)]
+    # the gather the library builds on this call (dist.cu ex_gather_checked): every rank sends the SAME m words
+    # (n values + its failure flag) to every rank and receives every rank's words, here m = 4 with rank 1 "failing"
+    mine = [7 * rank + 1, 1000 + rank, 5, 1 if rank == 1 else 0]
+    got = ex.exchange_counts(mine * world)
+    assert got.tolist() == [v for s in range(world) for v in (7 * s + 1, 1000 + s, 5, 1 if s == 1 else 0)]
+    # ... also for more words than a count matrix has (the counters travel this way: 31 words per rank)
+    got = ex.exchange_counts([rank * 100 + j for j in range(31)] * world)
+    assert got.tolist() == [s * 100 + j for s in range(world) for j in range(31)]
     # alltoallv with ragged (and one empty) blocks: block r->d has (r + 2*d) bytes of value 16*r + d
     send_bytes = [rank + 2 * d for d in range(world)]
     recv_bytes = [s + 2 * rank for s in range(world)]
